@@ -1,0 +1,71 @@
+"""ctypes binding of the C-ABI library (include/pbe_b200.h). Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpbe_b200.so"
+_lib = None
+
+
+class PbeError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load libpbe_b200.so (building it in-tree with nvcc if absent). No CPU fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        if not build_if_missing:
+            raise PbeError(f"{_LIB_PATH} is missing: run `python -m pbe_b200.build` (nvcc, sm_100a)")
+        from .build import build_native
+        build_native()
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    lib.pbe_last_error.restype = c_char_p
+    lib.pbe_last_error.argtypes = []
+    lib.pbe_op_conv_gemm.restype = c_int
+    lib.pbe_op_conv_gemm.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p]
+    for name, sig in _OPTIONAL_SIGS.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = sig
+
+
+_OPTIONAL_SIGS: dict = {}
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().pbe_last_error().decode(errors="replace")
+        raise PbeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C-ABI expects contiguous tensors"
+    return t.data_ptr()
+
+
+def exported_symbols() -> list[str]:
+    """Function names declared in include/pbe_b200.h."""
+    import re
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "pbe_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pbe_[a-z0-9_]+)\s*\(", hdr)))

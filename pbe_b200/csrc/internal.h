@@ -1,0 +1,178 @@
+// Internal host-side API shared by the kernels, the engine and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+namespace pbe {
+
+typedef __nv_bfloat16 bf16;
+
+// Thread-local error string (also copied into the handle by the C-ABI layer).
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define PBE_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      ::pbe::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + __FILE__ + \
+                       ":" + std::to_string(__LINE__));                                               \
+      return -2;                                                                                      \
+    }                                                                                                 \
+  } while (0)
+
+#define PBE_REQUIRE(cond, msg)                                                              \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      ::pbe::set_error(std::string("requirement failed: ") + #cond + " — " + (msg) + " at " + \
+                       __FILE__ + ":" + std::to_string(__LINE__));                          \
+      return -1;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (cuTensorMapEncodeTiled resolved through the runtime; no -lcuda link dependency)
+// ------------------------------------------------------------------------------------------------
+// dims[0] is the innermost (contiguous) dimension. strides_bytes has rank-1 entries (for dims 1..rank-1).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128);
+
+// ------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution / linear on tcgen05 (gemm_tc.cu)
+//   out[m, n] = epilogue( sum_{tap, c} act[pixel(m) shifted by tap, c] * wt[tap][n][c] )
+// ------------------------------------------------------------------------------------------------
+enum EpiMode : int { EPI_STD = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
+
+struct ConvGemmParams {
+  // M-tile geometry: 128 rows = tn x th x tw output pixels (w fastest)
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_n;
+  int Wo, Ho, Nb;          // output extents
+  int num_taps, k_chunks;  // K loop = num_taps * k_chunks chunks of 64 channels
+  int n_total;             // number of GEMM columns (Cout)
+  int8_t tap_dw[9], tap_dh[9], tap_ph[9];
+  int tap_coff[9];
+  // epilogue
+  int mode;
+  const float* bias;      // [n_total] or null
+  const float* rowbias;   // [Nb, n_total] or null (timestep-embedding / folded cross-attention term)
+  const float* residual;  // [M, ld_out] fp32 or null
+  float* out_f32;         // [M, ld_out] or null
+  bf16* out_bf16;         // [M, ld_out] or null
+  int ld_out;
+  // EPI_QKV: columns [0, qk_cols) go to out_bf16 (ld_out), columns >= qk_cols go transposed to out_vt[b][c][token]
+  bf16* out_vt;
+  int qk_cols;
+};
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  ConvGemmParams p;
+  int block_n;
+  dim3 grid;
+  size_t smem;
+};
+
+struct ConvGemmDesc {
+  const bf16* act;  // NHWC activations [Nb, H, W, C]
+  int Nb, H, W, C;  // input geometry (C % 64 == 0)
+  int ksize;        // 1 or 3 (pad = ksize/2)
+  int stride;       // 1 or 2
+  const bf16* wt;   // [ksize*ksize][Cout][C]
+  int Cout;
+  int mode;
+  const float* bias;
+  const float* rowbias;
+  const float* residual;
+  float* out_f32;
+  bf16* out_bf16;
+  int ld_out;  // 0 -> Cout (or Cout/2 for GEGLU)
+  bf16* out_vt;
+  int qk_cols;
+  int block_n;  // 0 -> auto
+};
+
+int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan);
+int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Flash self-attention on tcgen05 (attn_tc.cu)
+//   qk: [B, N, 2C] bf16 (Q in cols [0,C), K in cols [C,2C)), vt: [B, C, N] bf16, out: [B, N, C] bf16
+// ------------------------------------------------------------------------------------------------
+struct AttnPlan {
+  CUtensorMap tmQ, tmK, tmV;
+  int B, N, heads, d;
+  float scale_log2;
+  bf16* out;
+  dim3 grid;
+  size_t smem;
+};
+int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan);
+int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Normalisation / elementwise kernels (norm.cu, misc.cu)
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(32 groups) over NHWC fp32 input that may be the channel-concat of two tensors (x0: C0 ch, x1: C1 ch).
+// Writes y = [silu](gn(x)) as bf16 [M, C0+C1]; optionally also the raw concat as bf16 (for 1x1 skip convs).
+struct GroupNormArgs {
+  const float* x0; int C0;
+  const float* x1; int C1;   // x1 may be null (C1 = 0)
+  int Nb, HW;
+  const float* gamma; const float* beta;
+  float eps; int silu;
+  bf16* y; bf16* raw;        // raw may be null
+  float* partial;            // workspace: [Nb][slabs][32][2] floats, slabs = gn_num_slabs(HW)
+};
+int gn_num_slabs(int HW);
+int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream);
+
+// LayerNorm over the last dim of fp32 [M, C] -> bf16 [M, C]
+int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16* y, int M, int C, float eps,
+                     cudaStream_t stream);
+
+// nearest 2x upsample, fp32 NHWC [Nb,H,W,C] -> bf16 NHWC [Nb,2H,2W,C]
+int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
+// fp32 -> bf16 cast of a flat buffer
+int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
+
+// x NCHW fp32 [Nb, Cin, H, W] -> NHWC bf16 [Nb, H, W, Cpad] (channels >= Cin zero)
+int launch_pack_input(const float* x, bf16* y, int Nb, int Cin, int H, int W, int Cpad, cudaStream_t stream);
+// y NHWC fp32 [Nb, H, W, ld] (first Cout channels) -> NCHW fp32 [Nb, Cout, H, W]
+int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, int W, int ld, cudaStream_t stream);
+
+// Small dense layers on CUDA cores (M = batch rows only): y[b, o] = act_in(x[b, :]) . W[o, :] + bias[o]
+// pre_silu applies SiLU to x on load. W is fp32 [O, K] row-major.
+int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
+                        int post_silu, cudaStream_t stream);
+// sinusoidal timestep embedding [B, dim] (cos || sin), reference util.py:151-171
+int launch_timestep_embedding(const int64_t* t, float* out, int B, int dim, cudaStream_t stream);
+// y[b, n] = a[n] + v[b, n]
+int launch_add_rowvec(const float* a, const float* v, float* y, int B, int N, cudaStream_t stream);
+
+// Fused sampler update (sampler.cu): CFG combine + PLMS/DDIM multistep + x_prev / pred_x0.
+struct SamplerStepArgs {
+  const float* eps_uc;   // [B, 4, H, W] NCHW (unconditional half) — or the only eps when cfg == 0
+  const float* eps_c;    // conditional half (null when cfg == 0)
+  float scale;           // guidance scale
+  int cfg;
+  int order;             // 0: e' = e ; 1: (3e - h1)/2 ; 2: (23e-16h1+5h2)/12 ; 3: (55e-59h1+37h2-9h3)/24 ;
+                         // 4: e' = (e_prev_first + e)/2  (PLMS first-step second evaluation, h1 = first eps)
+  const float* h1; const float* h2; const float* h3;
+  const float* x;        // current latent [B,4,H,W]
+  float a_t, a_prev, sigma_t, sqrt_one_minus_at;
+  const float* noise;    // optional [B,4,H,W], multiplied by sigma_t (null when sigma_t == 0)
+  float* e_out;          // CFG-combined eps (history entry); may be null
+  float* x_prev;         // may alias nothing else
+  float* pred_x0;        // may be null
+  size_t n;              // elements
+};
+int launch_sampler_step(const SamplerStepArgs& a, cudaStream_t stream);
+// x9[b] = cat(x[b], z[b], mask[b]) duplicated for both CFG halves: out [2B or B, 9, H, W]
+int launch_build_unet_input(const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup,
+                            cudaStream_t stream);
+
+}  // namespace pbe

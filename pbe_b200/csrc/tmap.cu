@@ -1,0 +1,62 @@
+// Error string plumbing and TMA tensor-map construction.
+#include "internal.h"
+
+#include <mutex>
+
+namespace pbe {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn resolve_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn fn = resolve_encode();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled could not be resolved from the CUDA driver");
+    return -3;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
+                  gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string m = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " rank " +
+                    std::to_string(rank) + " dims[";
+    for (int i = 0; i < rank; ++i) m += std::to_string(dims[i]) + (i + 1 < rank ? "," : "] box[");
+    for (int i = 0; i < rank; ++i) m += std::to_string(box[i]) + (i + 1 < rank ? "," : "] strides[");
+    for (int i = 0; i + 1 < rank; ++i) m += std::to_string(strides_bytes[i]) + (i + 2 < rank ? "," : "]");
+    set_error(m);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace pbe
