@@ -1,0 +1,347 @@
+// Flash-style self-attention for the SpatialTransformer blocks, on tcgen05 / TMEM (sm_100a).
+//
+//   O = softmax(Q K^T * d^-1/2) V        per (sample, head), N tokens, no mask, never materialising the N x N matrix.
+//
+// Replaces CrossAttention.forward with context=None (ldm/modules/attention.py:207-230), where the reference builds
+// sim[(B*8), N, N] in fp32 (1 GB per layer at N=4096, B=2).
+//
+// One CTA = one (sample, head, 128-query tile).  warp 0: TMA producer; warp 1: MMA issuer; warps 2..5: softmax
+// (one query row per thread).  S = Q K^T lands in a double-buffered 128x128 fp32 TMEM tile, the softmax warps read it
+// with tcgen05.ld, keep running max / sum in registers, write P (bf16) into 128B-swizzled shared memory, and the MMA
+// warp accumulates O += P V into a third TMEM region.  Q and K come from the fused projection output [B, N, 2C];
+// V arrives transposed ([B, C, N], written by the projection GEMM's epilogue) so both MMAs take K-major operands.
+// Head dims that are not a multiple of 64 (40, 80, 160) rely on TMA out-of-bounds zero fill.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace pbe {
+
+namespace {
+
+constexpr int ATT_THREADS = 192;
+constexpr int QT = 128;   // queries per CTA
+constexpr int KT = 128;   // keys per tile
+constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16
+
+struct AttnParams {
+  int N, heads, d, dv, ksteps, C;
+  float scale_log2;
+  bf16* out;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DK_CHUNKS, int KV_STAGES>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                  const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int v_chunk_bytes = p.dv * 128;  // one 64-key chunk of V^T: dv rows x 128 B
+  const uint32_t sQ = smem_base;
+  const uint32_t sK = sQ + DK_CHUNKS * CHUNK_BYTES;                     // KV_STAGES x DK_CHUNKS chunks
+  const uint32_t sV = sK + KV_STAGES * DK_CHUNKS * CHUNK_BYTES;         // KV_STAGES x 2 chunks of (dv x 64)
+  const uint32_t sP = sV + KV_STAGES * 2 * 160 * 128;                   // 2 chunks of (128 x 64); V region sized for dv<=160
+  const uint32_t sBar = sP + 2 * CHUNK_BYTES;
+  uint8_t* bar_gen = smem_gen + (sBar - smem_base);
+  uint8_t* p_gen = smem_gen + (sP - smem_base);
+
+  const uint32_t q_full = sBar;
+  auto k_full = [&](int s) { return sBar + 8u * (1 + s); };
+  auto v_full = [&](int s) { return sBar + 8u * (1 + KV_STAGES + s); };
+  auto kv_empty = [&](int s) { return sBar + 8u * (1 + 2 * KV_STAGES + s); };
+  auto s_full = [&](int b) { return sBar + 8u * (1 + 3 * KV_STAGES + b); };
+  auto s_free = [&](int b) { return sBar + 8u * (3 + 3 * KV_STAGES + b); };
+  const uint32_t p_full = sBar + 8u * (5 + 3 * KV_STAGES);
+  const uint32_t pv_done = sBar + 8u * (6 + 3 * KV_STAGES);
+  const uint32_t tmem_ptr_addr = sBar + 8u * (7 + 3 * KV_STAGES);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (7 + 3 * KV_STAGES));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int T = (p.N + KT - 1) / KT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(s_free(i), 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, DK_CHUNKS * CHUNK_BYTES);
+      for (int kc = 0; kc < DK_CHUNKS; ++kc)
+        tma_load_4d(sQ + kc * CHUNK_BYTES, &tmQK, q_full, kc * 64, head, q0, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(kv_empty(st), ph ^ 1u);
+        mbar_expect_tx(k_full(st), DK_CHUNKS * CHUNK_BYTES);
+        for (int kc = 0; kc < DK_CHUNKS; ++kc)
+          tma_load_4d(sK + (st * DK_CHUNKS + kc) * CHUNK_BYTES, &tmQK, k_full(st), kc * 64, p.heads + head, j * KT, b);
+        mbar_expect_tx(v_full(st), 2 * v_chunk_bytes);
+        for (int jj = 0; jj < 2; ++jj)
+          tma_load_3d(sV + st * 2 * 160 * 128 + jj * v_chunk_bytes, &tmV, v_full(st), j * KT + jj * 64, head * p.d, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc_qk = umma_idesc_bf16(128, KT);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, p.dv);
+    auto issue_qk = [&](int j) {
+      const int st = j % KV_STAGES;
+      const int sb = j & 1;
+      mbar_wait(k_full(st), (j / KV_STAGES) & 1);
+      mbar_wait(s_free(sb), ((j >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint64_t adesc = umma_desc_sw128(sQ + (ks >> 2) * CHUNK_BYTES) + 2u * (ks & 3);
+          const uint64_t bdesc = umma_desc_sw128(sK + (st * DK_CHUNKS + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
+          umma_bf16_ss(tmem_base + sb * 128, adesc, bdesc, idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(sb));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < T; ++j) {
+      if (KV_STAGES >= 2 && j + 1 < T) issue_qk(j + 1);
+      const int st = j % KV_STAGES;
+      mbar_wait(v_full(st), (j / KV_STAGES) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks) {
+          const uint64_t adesc = umma_desc_sw128(sP + (ks >> 2) * CHUNK_BYTES) + 2u * (ks & 3);
+          const uint64_t bdesc = umma_desc_sw128(sV + st * 2 * 160 * 128 + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
+          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(kv_empty(st));
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+      if (KV_STAGES < 2 && j + 1 < T) issue_qk(j + 1);
+    }
+  } else {
+    // ================= softmax / correction / output (warps 2..5) =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    float m_run = -INFINITY;  // running max of raw scores
+    float l_run = 0.0f;
+    const float sl2 = p.scale_log2;
+
+    for (int j = 0; j < T; ++j) {
+      const int sb = j & 1;
+      mbar_wait(s_full(sb), (j >> 1) & 1);
+      tc_fence_after();
+      float s[KT];
+#pragma unroll
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_off + sb * 128 + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(sb));
+
+      const int kvalid = p.N - j * KT;  // keys valid in this tile
+      float mx = m_run;
+      if (kvalid >= KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) mx = fmaxf(mx, s[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+          if (i >= kvalid) s[i] = -INFINITY;
+          mx = fmaxf(mx, s[i]);
+        }
+      }
+      const float alpha = ex2((m_run - mx) * sl2);  // first tile: ex2(-inf) = 0
+      const float mneg = -mx * sl2;
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < KT; ++i) {
+        s[i] = ex2(fmaf(s[i], sl2, mneg));
+        sum += s[i];
+      }
+      l_run = l_run * alpha + sum;
+      m_run = mx;
+
+      if (j > 0) {
+        // previous PV must have landed before O is rescaled and before P is overwritten
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          for (int c = 0; c < p.dv; c += 16) {
+            uint32_t o[16];
+            tmem_ld_x16(tmem_O + lane_off + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(tmem_O + lane_off + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P -> shared memory, K-major, 128B swizzle (16-byte unit index XOR row%8)
+      {
+        uint8_t* prow = p_gen + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < KT; c += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(s[c + 0], s[c + 1]);
+          pk.y = pack_bf16x2(s[c + 2], s[c + 3]);
+          pk.z = pack_bf16x2(s[c + 4], s[c + 5]);
+          pk.w = pack_bf16x2(s[c + 6], s[c + 7]);
+          const int chunk = c >> 6;
+          const int u = (c & 63) >> 3;
+          *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((u ^ (row & 7)) << 4)) = pk;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    // ---- final: O / l -> out[b, q0+row, head*d + :] ----
+    mbar_wait(pv_done, (T - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int tok = q0 + row;
+    bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
+    for (int c = 0; c < p.dv; c += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tmem_O + lane_off + c, o);
+      tmem_ld_wait();
+      if (tok < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < p.d) {  // d % 8 == 0
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + i) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int DK_CHUNKS, int KV_STAGES>
+constexpr size_t attn_smem_bytes() {
+  return 1024 + DK_CHUNKS * CHUNK_BYTES + KV_STAGES * DK_CHUNKS * CHUNK_BYTES + KV_STAGES * 2 * 160 * 128 +
+         2 * CHUNK_BYTES + 8 * (8 + 3 * KV_STAGES);
+}
+
+template <int DK_CHUNKS, int KV_STAGES>
+int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  constexpr size_t smem = attn_smem_bytes<DK_CHUNKS, KV_STAGES>();
+  static_assert(smem <= 227 * 1024, "attention smem");
+  if (!attr_set) {
+    PBE_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<DK_CHUNKS, KV_STAGES>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.N = plan.N; p.heads = plan.heads; p.d = plan.d;
+  p.dv = (plan.d + 15) / 16 * 16;
+  p.ksteps = (plan.d + 15) / 16;
+  p.C = plan.heads * plan.d;
+  p.scale_log2 = plan.scale_log2;
+  p.out = plan.out;
+  flash_attn_kernel<DK_CHUNKS, KV_STAGES><<<plan.grid, ATT_THREADS, smem, stream>>>(plan.tmQ, plan.tmV, p);
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan) {
+  PBE_REQUIRE(d % 8 == 0 && d <= 160, "head dim must be a multiple of 8, <= 160");
+  PBE_REQUIRE(N % 8 == 0, "token count must be a multiple of 8");
+  const int C = heads * d;
+  plan->B = B; plan->N = N; plan->heads = heads; plan->d = d;
+  plan->scale_log2 = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(d)));
+  plan->out = out;
+  plan->grid = dim3((N + QT - 1) / QT, heads, B);
+  const int dv = (d + 15) / 16 * 16;
+  {
+    // Q|K: (d, 2*heads, N, B) over [B, N, 2C]
+    const uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(2 * heads), static_cast<uint64_t>(N),
+                              static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(2 * C) * 2,
+                                 static_cast<uint64_t>(N) * 2 * C * 2};
+    const uint32_t box[4] = {64u, 1u, 128u, 1u};
+    int rc = make_tmap_bf16(&plan->tmQ, qk, 4, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    // V^T: (N, C, B) over [B, C, N]
+    const uint64_t dims[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(N) * 2, static_cast<uint64_t>(C) * N * 2};
+    const uint32_t box[3] = {64u, static_cast<uint32_t>(dv), 1u};
+    int rc = make_tmap_bf16(&plan->tmV, vt, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  plan->smem = 0;
+  return 0;
+}
+
+int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream) {
+  const int chunks = (plan.d + 63) / 64;
+  switch (chunks) {
+    case 1: return launch_attn_t<1, 2>(plan, stream);
+    case 2: return launch_attn_t<2, 2>(plan, stream);
+    case 3: return launch_attn_t<3, 1>(plan, stream);
+    default: set_error("launch_attn_plan: head dim too large"); return -1;
+  }
+}
+
+}  // namespace pbe
