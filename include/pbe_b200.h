@@ -33,6 +33,77 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
                      int Cout, int mode, const float* bias, const float* rowbias, const float* residual,
                      float* out_f32, void* out_bf16, void* out_vt, int qk_cols, int block_n, void* stream);
 
+/* Flash self-attention on tcgen05. Replaces CrossAttention.forward with context=None, ldm/modules/attention.py:207-230.
+ *   qk_bf16 [B,N,2C] (Q | K), vt_bf16 [B,C,N], out_bf16 [B,N,C]; C = heads*d, scale = d^-1/2. */
+int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
+                          void* stream);
+
+/* GroupNorm(32 groups)(+SiLU) of the channel-concat of x0 [Nb,HW,C0] and x1 [Nb,HW,C1] (fp32 NHWC; x1 may be NULL)
+ * -> y_bf16 [Nb,HW,C0+C1] (+ optional raw bf16 copy). Replaces GroupNorm32/Normalize (+SiLU, + th.cat):
+ * ldm/modules/diffusionmodules/util.py:199-216, ldm/modules/attention.py:77-78, openaimodel.py:883.
+ * workspace: at least pbe_op_groupnorm_workspace_bytes(Nb, HW) bytes. */
+int pbe_op_groupnorm(const float* x0, int C0, const float* x1, int C1, int Nb, int HW, const float* gamma,
+                     const float* beta, float eps, int silu, void* y_bf16, void* raw_bf16, void* workspace,
+                     void* stream);
+int64_t pbe_op_groupnorm_workspace_bytes(int Nb, int HW);
+
+/* LayerNorm over the last dim of fp32 [M,C] -> bf16. Replaces norm1/norm3, ldm/modules/attention.py:240-242. */
+int pbe_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int C, float eps,
+                     void* stream);
+
+/* nearest-2x upsample fp32 NHWC -> bf16 NHWC. Replaces F.interpolate in Upsample.forward, openaimodel.py:109-119. */
+int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C, void* stream);
+
+/* Fused CFG combine + PLMS/DDIM multistep + x_prev/pred_x0 update over n fp32 elements (K11).
+ * Replaces plms.py:185-189,202-219,230-246 and ddim.py:209-242.  order: 0 DDIM/plain, 1..3 Adams-Bashforth with
+ * h1 (most recent) .. h3, 4 = PLMS first-step average (h1 = first eps, eps_* = second evaluation).
+ * eps_c may be NULL when cfg == 0; noise may be NULL when sigma_t == 0; e_out / pred_x0 may be NULL. */
+int pbe_sampler_step(const float* eps_uc, const float* eps_c, float scale, int cfg, int order, const float* h1,
+                     const float* h2, const float* h3, const float* x, float a_t, float a_prev, float sigma_t,
+                     float sqrt_one_minus_at, const float* noise, float* e_out, float* x_prev, float* pred_x0,
+                     int64_t n, void* stream);
+
+/* out[dup*B, 9, H*W] = cat(x[B,4,HW], z_inpaint[B,4,HW], mask[B,1,HW]) repeated `dup` (1 or 2) times along batch.
+ * Replaces torch_cat((x, images_inpaint, images_mask), 1) and torch_cat([x]*2): plms.py:185-186,225; ddim.py:200,209. */
+int pbe_build_unet_input(const float* x, const float* z_inpaint, const float* mask, float* out, int B, int HW, int dup,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Engine: the whole UNetModel.forward (ldm/modules/diffusionmodules/openaimodel.py:852-889) behind
+ * LatentDiffusion.apply_model (ldm/models/diffusion/latent_diffusion.py:646-743)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct pbe_config {
+  int32_t in_channels;     /* 9  (configs/v1.yaml:34) */
+  int32_t out_channels;    /* 4 */
+  int32_t model_channels;  /* 320, multiple of 64 */
+  int32_t num_res_blocks;  /* 2 */
+  int32_t num_levels;      /* len(channel_mult) */
+  int32_t channel_mult[8]; /* 1,2,4,4 */
+  int32_t num_attention_resolutions;
+  int32_t attention_resolutions[8]; /* 4,2,1 */
+  int32_t num_heads;                /* 8 */
+  int32_t context_dim;              /* 768 */
+} pbe_config;
+
+typedef struct pbe_engine* pbe_handle;
+
+int pbe_create(const pbe_config* cfg, pbe_handle* out);
+void pbe_destroy(pbe_handle h);
+/* name = reference state-dict key relative to the U-Net (e.g. "input_blocks.0.0.weight", i.e. the part after
+ * "model.diffusion_model."); host fp32 data; the library repacks and owns its copy. */
+int pbe_load_weight(pbe_handle h, const char* name, const float* host_data, const int64_t* shape, int rank);
+/* Repack + upload everything loaded so far; errors name the first missing / mis-shaped tensor. */
+int pbe_finalize_weights(pbe_handle h);
+/* Fold the single-key cross-attention for context ctx [Bc, context_dim] fp32 (device): v = to_out(to_v(ctx)) per
+ * SpatialTransformer (attention.py:207-230 with a 1-token context). Call whenever the context changes. */
+int pbe_set_context(pbe_handle h, const float* ctx, int Bc, void* stream);
+/* eps[Bc,out_ch,H,W] = UNet(x[Bc,in_ch,H,W] fp32 NCHW, t[Bc] int64, context set by pbe_set_context). */
+int pbe_unet_forward(pbe_handle h, const float* x, const int64_t* t, float* eps, int Bc, int H, int W, void* stream);
+/* 1 = replay a captured CUDA graph per forward (default), 0 = launch kernels one by one. */
+int pbe_set_use_graph(pbe_handle h, int enable);
+/* number of kernels one pbe_unet_forward launches for the current shape (0 before the first forward). */
+int pbe_launches_per_forward(pbe_handle h);
+
 #ifdef __cplusplus
 }
 #endif

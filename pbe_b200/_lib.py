@@ -46,7 +46,24 @@ def _declare(lib: ctypes.CDLL) -> None:
             fn.restype, fn.argtypes = sig
 
 
-_OPTIONAL_SIGS: dict = {}
+_f, _i, _p, _i64 = c_float, c_int, c_void_p, c_int64
+_OPTIONAL_SIGS: dict = {
+    "pbe_op_self_attention": (c_int, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "pbe_op_groupnorm": (c_int, [_p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p]),
+    "pbe_op_groupnorm_workspace_bytes": (c_int64, [_i, _i]),
+    "pbe_op_layernorm": (c_int, [_p, _p, _p, _p, _i, _i, _f, _p]),
+    "pbe_op_upsample2x": (c_int, [_p, _p, _i, _i, _i, _i, _p]),
+    "pbe_sampler_step": (c_int, [_p, _p, _f, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p, _i64, _p]),
+    "pbe_build_unet_input": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "pbe_create": (c_int, [_p, _p]),
+    "pbe_destroy": (None, [_p]),
+    "pbe_load_weight": (c_int, [_p, c_char_p, _p, _p, _i]),
+    "pbe_finalize_weights": (c_int, [_p]),
+    "pbe_set_context": (c_int, [_p, _p, _i, _p]),
+    "pbe_unet_forward": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "pbe_set_use_graph": (c_int, [_p, _i]),
+    "pbe_launches_per_forward": (c_int, [_p]),
+}
 
 
 def check(rc: int, what: str = "") -> None:

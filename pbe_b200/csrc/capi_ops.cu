@@ -32,3 +32,63 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
+                          void* stream) {
+  AttnPlan plan;
+  int rc = build_attn_plan(static_cast<const bf16*>(qk_bf16), static_cast<const bf16*>(vt_bf16),
+                           static_cast<bf16*>(out_bf16), B, N, heads, d, &plan);
+  if (rc) return rc;
+  return launch_attn_plan(plan, static_cast<cudaStream_t>(stream));
+}
+
+int64_t pbe_op_groupnorm_workspace_bytes(int Nb, int HW) {
+  return static_cast<int64_t>(Nb) * gn_num_slabs(HW) * 64 * sizeof(float);
+}
+
+int pbe_op_groupnorm(const float* x0, int C0, const float* x1, int C1, int Nb, int HW, const float* gamma,
+                     const float* beta, float eps, int silu, void* y_bf16, void* raw_bf16, void* workspace,
+                     void* stream) {
+  GroupNormArgs a{};
+  a.x0 = x0; a.C0 = C0; a.x1 = x1; a.C1 = C1; a.Nb = Nb; a.HW = HW; a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.silu = silu; a.y = static_cast<bf16*>(y_bf16); a.raw = static_cast<bf16*>(raw_bf16);
+  a.partial = static_cast<float*>(workspace);
+  return launch_groupnorm(a, static_cast<cudaStream_t>(stream));
+}
+
+int pbe_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int C, float eps,
+                     void* stream) {
+  return launch_layernorm(x, gamma, beta, static_cast<bf16*>(y_bf16), M, C, eps, static_cast<cudaStream_t>(stream));
+}
+
+int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C, void* stream) {
+  return launch_upsample2x_bf16(x, static_cast<bf16*>(y_bf16), Nb, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+int pbe_sampler_step(const float* eps_uc, const float* eps_c, float scale, int cfg, int order, const float* h1,
+                     const float* h2, const float* h3, const float* x, float a_t, float a_prev, float sigma_t,
+                     float sqrt_one_minus_at, const float* noise, float* e_out, float* x_prev, float* pred_x0,
+                     int64_t n, void* stream) {
+  SamplerStepArgs a{};
+  a.eps_uc = eps_uc; a.eps_c = eps_c; a.scale = scale; a.cfg = cfg; a.order = order;
+  a.h1 = h1; a.h2 = h2; a.h3 = h3; a.x = x; a.a_t = a_t; a.a_prev = a_prev; a.sigma_t = sigma_t;
+  a.sqrt_one_minus_at = sqrt_one_minus_at; a.noise = noise; a.e_out = e_out; a.x_prev = x_prev; a.pred_x0 = pred_x0;
+  a.n = static_cast<size_t>(n);
+  if (cfg && eps_c == nullptr) { set_error("pbe_sampler_step: cfg set but eps_c is NULL"); return -1; }
+  if (order >= 1 && h1 == nullptr) { set_error("pbe_sampler_step: history missing"); return -1; }
+  if ((order == 2 || order == 3) && h2 == nullptr) { set_error("pbe_sampler_step: history missing"); return -1; }
+  if (order == 3 && h3 == nullptr) { set_error("pbe_sampler_step: history missing"); return -1; }
+  if (sigma_t != 0.0f && noise == nullptr) { set_error("pbe_sampler_step: sigma_t != 0 needs noise"); return -1; }
+  return launch_sampler_step(a, static_cast<cudaStream_t>(stream));
+}
+
+int pbe_build_unet_input(const float* x, const float* z_inpaint, const float* mask, float* out, int B, int HW, int dup,
+                         void* stream) {
+  if (dup != 1 && dup != 2) { set_error("pbe_build_unet_input: dup must be 1 or 2"); return -1; }
+  return launch_build_unet_input(x, z_inpaint, mask, out, B, HW, dup, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

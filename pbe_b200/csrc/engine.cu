@@ -1,0 +1,749 @@
+// U-Net engine implementation.  See engine.h.
+//
+// Data layout in HBM: activations are NHWC.  The residual stream between blocks is fp32 (statistics for
+// GroupNorm / LayerNorm are computed from it in fp32); every GEMM operand is bf16 (written by the norm kernels or by
+// the previous GEMM's epilogue); accumulation is fp32 in TMEM.  Weights are repacked once at load:
+// conv OIHW fp32 -> [tap][O][I] bf16, Linear [O,I] -> bf16, q/k/v fused to one [3C,C] matrix, GEGLU value/gate rows
+// interleaved per 128-column tile, all 22 ResBlock emb_layers concatenated into one fp32 matrix.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace pbe {
+
+namespace {
+
+constexpr int MAX_BC = 128;
+
+uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+
+Prepared::~Prepared() {
+  if (graph) cudaGraphExecDestroy(graph);
+  if (persist.base_) cudaFree(persist.base_);
+  if (scratch.base_) cudaFree(scratch.base_);
+}
+
+Engine::~Engine() {
+  prepared_.clear();
+  if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  for (void* p : dev_allocs_) cudaFree(p);
+}
+
+int Engine::load_weight(const char* name, const float* host, const int64_t* shape, int rank) {
+  PBE_REQUIRE(!finalized_, "weights already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < rank; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  t.data.assign(host, host + n);
+  host_[name] = std::move(t);
+  return 0;
+}
+
+const HostTensor* Engine::find(const std::string& name) {
+  auto it = host_.find(name);
+  return it == host_.end() ? nullptr : &it->second;
+}
+
+int Engine::get(const std::string& name, const HostTensor** out) {
+  *out = find(name);
+  if (*out == nullptr) {
+    set_error("missing weight: " + name);
+    return -4;
+  }
+  return 0;
+}
+
+int Engine::upload_f32(const std::vector<float>& v, float** dst) {
+  void* p = nullptr;
+  PBE_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  dev_allocs_.push_back(p);
+  PBE_CHECK_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *dst = static_cast<float*>(p);
+  return 0;
+}
+
+int Engine::upload_bf16(const std::vector<float>& v, bf16** dst) {
+  std::vector<uint16_t> h(v.size());
+  for (size_t i = 0; i < v.size(); ++i) h[i] = f32_to_bf16_rn(v[i]);
+  void* p = nullptr;
+  PBE_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(h.size(), 1) * sizeof(uint16_t)));
+  dev_allocs_.push_back(p);
+  PBE_CHECK_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  *dst = static_cast<bf16*>(p);
+  return 0;
+}
+
+// conv / linear weight `prefix.weight` ([O,I,k,k] or [O,I]) (+ `prefix.bias`) -> [k*k][O][I_pad] bf16
+int Engine::make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad) {
+  const HostTensor* W;
+  int rc = get(prefix + ".weight", &W);
+  if (rc) return rc;
+  if (cin_pad == 0) cin_pad = cin;
+  const size_t expect = static_cast<size_t>(cout) * cin * k * k;
+  if (W->data.size() != expect) {
+    set_error("weight " + prefix + ".weight has " + std::to_string(W->data.size()) + " elements, expected " +
+              std::to_string(expect));
+    return -4;
+  }
+  std::vector<float> packed(static_cast<size_t>(k) * k * cout * cin_pad, 0.0f);
+  for (int o = 0; o < cout; ++o)
+    for (int i = 0; i < cin; ++i)
+      for (int t = 0; t < k * k; ++t)
+        packed[(static_cast<size_t>(t) * cout + o) * cin_pad + i] = W->data[(static_cast<size_t>(o) * cin + i) * k * k + t];
+  rc = upload_bf16(packed, &w->w);
+  if (rc) return rc;
+  w->cin = cin; w->cin_pad = cin_pad; w->cout = cout; w->k = k;
+  const HostTensor* B = find(prefix + ".bias");
+  if (B) {
+    if (static_cast<int>(B->data.size()) != cout) {
+      set_error("bias " + prefix + ".bias has wrong size");
+      return -4;
+    }
+    rc = upload_f32(B->data, &w->b);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int Engine::make_norm(const std::string& prefix, int c, NormW* n) {
+  const HostTensor *G, *B;
+  int rc = get(prefix + ".weight", &G);
+  if (rc) return rc;
+  rc = get(prefix + ".bias", &B);
+  if (rc) return rc;
+  if (static_cast<int>(G->data.size()) != c || static_cast<int>(B->data.size()) != c) {
+    set_error("norm " + prefix + " has wrong size");
+    return -4;
+  }
+  rc = upload_f32(G->data, &n->g);
+  if (rc) return rc;
+  rc = upload_f32(B->data, &n->b);
+  if (rc) return rc;
+  n->c = c;
+  return 0;
+}
+
+// Mirrors UNetModel.__init__ (openaimodel.py:558-834) for use_spatial_transformer=True, transformer_depth=1,
+// resblock_updown=False, conv_resample=True, legacy=False.
+int Engine::finalize() {
+  PBE_REQUIRE(!finalized_, "already finalized");
+  const int mc = cfg_.model_channels;
+  const int ted = 4 * mc;
+  PBE_REQUIRE(mc % 64 == 0, "model_channels must be a multiple of 64");
+  PBE_REQUIRE(cfg_.num_levels >= 1 && cfg_.num_levels <= 8, "num_levels");
+  PBE_REQUIRE(cfg_.in_channels <= 64, "in_channels <= 64");
+  int rc;
+
+  std::vector<float> emb_w, emb_b;  // concatenated emb_layers
+  auto add_res = [&](const std::string& pfx, int cin, int cout) -> int {
+    ResW r;
+    r.cin = cin; r.cout = cout;
+    int e;
+    if ((e = make_norm(pfx + ".in_layers.0", cin, &r.gn1))) return e;
+    if ((e = make_conv(pfx + ".in_layers.2", 3, cin, cout, &r.conv1))) return e;
+    if ((e = make_norm(pfx + ".out_layers.0", cout, &r.gn2))) return e;
+    if ((e = make_conv(pfx + ".out_layers.3", 3, cout, cout, &r.conv2))) return e;
+    r.has_skip = (cin != cout);
+    if (r.has_skip && (e = make_conv(pfx + ".skip_connection", 1, cin, cout, &r.skip))) return e;
+    const HostTensor *EW, *EB;
+    if ((e = get(pfx + ".emb_layers.1.weight", &EW))) return e;
+    if ((e = get(pfx + ".emb_layers.1.bias", &EB))) return e;
+    if (EW->data.size() != static_cast<size_t>(cout) * ted || EB->data.size() != static_cast<size_t>(cout)) {
+      set_error("emb_layers of " + pfx + " have wrong size");
+      return -4;
+    }
+    r.emb_off = static_cast<int>(emb_b.size());
+    emb_w.insert(emb_w.end(), EW->data.begin(), EW->data.end());
+    emb_b.insert(emb_b.end(), EB->data.begin(), EB->data.end());
+    res_.push_back(r);
+    return 0;
+  };
+  auto add_st = [&](const std::string& pfx, int c) -> int {
+    STW s;
+    s.c = c; s.heads = cfg_.num_heads; s.d = c / cfg_.num_heads;
+    PBE_REQUIRE(c % cfg_.num_heads == 0 && s.d % 8 == 0, "head dim must be a multiple of 8");
+    const std::string tb = pfx + ".transformer_blocks.0";
+    int e;
+    if ((e = make_norm(pfx + ".norm", c, &s.gn))) return e;
+    if ((e = make_conv(pfx + ".proj_in", 1, c, c, &s.proj_in))) return e;
+    if ((e = make_norm(tb + ".norm1", c, &s.ln1))) return e;
+    if ((e = make_norm(tb + ".norm3", c, &s.ln3))) return e;
+    {  // fused q|k|v projection [3C, C]
+      const HostTensor *Q, *K, *V;
+      if ((e = get(tb + ".attn1.to_q.weight", &Q))) return e;
+      if ((e = get(tb + ".attn1.to_k.weight", &K))) return e;
+      if ((e = get(tb + ".attn1.to_v.weight", &V))) return e;
+      const size_t cc = static_cast<size_t>(c) * c;
+      if (Q->data.size() != cc || K->data.size() != cc || V->data.size() != cc) {
+        set_error("attn1 q/k/v of " + pfx + " have wrong size");
+        return -4;
+      }
+      std::vector<float> w;
+      w.reserve(3 * cc);
+      w.insert(w.end(), Q->data.begin(), Q->data.end());
+      w.insert(w.end(), K->data.begin(), K->data.end());
+      w.insert(w.end(), V->data.begin(), V->data.end());
+      if ((e = upload_bf16(w, &s.qkv.w))) return e;
+      s.qkv.cin = s.qkv.cin_pad = c; s.qkv.cout = 3 * c; s.qkv.k = 1;
+    }
+    if ((e = make_conv(tb + ".attn1.to_out.0", 1, c, c, &s.to_out))) return e;
+    {  // GEGLU projection [8C, C]: rows [0,4C) value, [4C,8C) gate -> interleave per 128-column tile (64 value + 64 gate)
+      const HostTensor *W, *B;
+      if ((e = get(tb + ".ff.net.0.proj.weight", &W))) return e;
+      if ((e = get(tb + ".ff.net.0.proj.bias", &B))) return e;
+      const int inner = 4 * c;
+      if (W->data.size() != static_cast<size_t>(2 * inner) * c || B->data.size() != static_cast<size_t>(2 * inner)) {
+        set_error("GEGLU proj of " + pfx + " has wrong size");
+        return -4;
+      }
+      PBE_REQUIRE(inner % 64 == 0, "GEGLU inner dim % 64");
+      std::vector<float> w(W->data.size()), b(B->data.size());
+      for (int t = 0; t < inner / 64; ++t)
+        for (int j = 0; j < 64; ++j) {
+          const int src_v = t * 64 + j, src_g = inner + t * 64 + j;
+          const int dst_v = t * 128 + j, dst_g = t * 128 + 64 + j;
+          memcpy(&w[static_cast<size_t>(dst_v) * c], &W->data[static_cast<size_t>(src_v) * c], c * sizeof(float));
+          memcpy(&w[static_cast<size_t>(dst_g) * c], &W->data[static_cast<size_t>(src_g) * c], c * sizeof(float));
+          b[dst_v] = B->data[src_v];
+          b[dst_g] = B->data[src_g];
+        }
+      if ((e = upload_bf16(w, &s.ff1.w))) return e;
+      if ((e = upload_f32(b, &s.ff1.b))) return e;
+      s.ff1.cin = s.ff1.cin_pad = c; s.ff1.cout = 2 * inner; s.ff1.k = 1;
+    }
+    if ((e = make_conv(tb + ".ff.net.2", 1, 4 * c, c, &s.ff2))) return e;
+    if ((e = make_conv(pfx + ".proj_out", 1, c, c, &s.proj_out))) return e;
+    {  // single-key cross-attention folds to to_out(to_v(ctx)); to_q / to_k / norm2 are dead (attention.py:207-230)
+      const HostTensor *V2, *O2, *B2;
+      if ((e = get(tb + ".attn2.to_v.weight", &V2))) return e;
+      if ((e = get(tb + ".attn2.to_out.0.weight", &O2))) return e;
+      if ((e = get(tb + ".attn2.to_out.0.bias", &B2))) return e;
+      if (V2->data.size() != static_cast<size_t>(c) * cfg_.context_dim || O2->data.size() != static_cast<size_t>(c) * c) {
+        set_error("attn2 weights of " + pfx + " have wrong size");
+        return -4;
+      }
+      if ((e = upload_f32(V2->data, &s.wv2))) return e;
+      if ((e = upload_f32(O2->data, &s.wo2))) return e;
+      if ((e = upload_f32(B2->data, &s.bo2))) return e;
+    }
+    s.ctx_vec_off = ctx_total_;
+    ctx_total_ += c;
+    st_.push_back(s);
+    return 0;
+  };
+  auto is_attn = [&](int ds) {
+    for (int i = 0; i < cfg_.num_attention_resolutions; ++i)
+      if (cfg_.attention_resolutions[i] == ds) return true;
+    return false;
+  };
+
+  // time_embed
+  {
+    const HostTensor *W0, *B0, *W1, *B1;
+    if ((rc = get("time_embed.0.weight", &W0))) return rc;
+    if ((rc = get("time_embed.0.bias", &B0))) return rc;
+    if ((rc = get("time_embed.2.weight", &W1))) return rc;
+    if ((rc = get("time_embed.2.bias", &B1))) return rc;
+    PBE_REQUIRE(W0->data.size() == static_cast<size_t>(ted) * mc && W1->data.size() == static_cast<size_t>(ted) * ted,
+                "time_embed sizes");
+    if ((rc = upload_f32(W0->data, &te_w0_))) return rc;
+    if ((rc = upload_f32(B0->data, &te_b0_))) return rc;
+    if ((rc = upload_f32(W1->data, &te_w1_))) return rc;
+    if ((rc = upload_f32(B1->data, &te_b1_))) return rc;
+  }
+
+  // input blocks
+  {
+    ConvW c;
+    if ((rc = make_conv("input_blocks.0.0", 3, cfg_.in_channels, mc, &c, 64))) return rc;
+    convs_.push_back(c);
+    modules_.push_back({Module::CONV_IN, static_cast<int>(convs_.size()) - 1, false, true});
+  }
+  std::vector<int> chans = {mc};
+  int ch = mc, ds = 1, ib = 1;
+  for (int level = 0; level < cfg_.num_levels; ++level) {
+    const int mult = cfg_.channel_mult[level];
+    for (int r = 0; r < cfg_.num_res_blocks; ++r) {
+      const std::string pfx = "input_blocks." + std::to_string(ib);
+      if ((rc = add_res(pfx + ".0", ch, mult * mc))) return rc;
+      ch = mult * mc;
+      const bool attn = is_attn(ds);
+      modules_.push_back({Module::RES, static_cast<int>(res_.size()) - 1, false, !attn});
+      if (attn) {
+        if ((rc = add_st(pfx + ".1", ch))) return rc;
+        modules_.push_back({Module::ST, static_cast<int>(st_.size()) - 1, false, true});
+      }
+      chans.push_back(ch);
+      ++ib;
+    }
+    if (level != cfg_.num_levels - 1) {
+      ConvW c;
+      if ((rc = make_conv("input_blocks." + std::to_string(ib) + ".0.op", 3, ch, ch, &c))) return rc;
+      convs_.push_back(c);
+      modules_.push_back({Module::DOWN, static_cast<int>(convs_.size()) - 1, false, true});
+      chans.push_back(ch);
+      ++ib;
+      ds *= 2;
+    }
+  }
+  // middle
+  if ((rc = add_res("middle_block.0", ch, ch))) return rc;
+  modules_.push_back({Module::RES, static_cast<int>(res_.size()) - 1, false, false});
+  if ((rc = add_st("middle_block.1", ch))) return rc;
+  modules_.push_back({Module::ST, static_cast<int>(st_.size()) - 1, false, false});
+  if ((rc = add_res("middle_block.2", ch, ch))) return rc;
+  modules_.push_back({Module::RES, static_cast<int>(res_.size()) - 1, false, false});
+  // output blocks
+  int ob = 0;
+  for (int level = cfg_.num_levels - 1; level >= 0; --level) {
+    const int mult = cfg_.channel_mult[level];
+    for (int i = 0; i <= cfg_.num_res_blocks; ++i) {
+      const int ich = chans.back();
+      chans.pop_back();
+      const std::string pfx = "output_blocks." + std::to_string(ob);
+      if ((rc = add_res(pfx + ".0", ch + ich, mc * mult))) return rc;
+      ch = mc * mult;
+      modules_.push_back({Module::RES, static_cast<int>(res_.size()) - 1, true, false});
+      int sub = 1;
+      if (is_attn(ds)) {
+        if ((rc = add_st(pfx + ".1", ch))) return rc;
+        modules_.push_back({Module::ST, static_cast<int>(st_.size()) - 1, false, false});
+        sub = 2;
+      }
+      if (level && i == cfg_.num_res_blocks) {
+        ConvW c;
+        if ((rc = make_conv(pfx + "." + std::to_string(sub) + ".conv", 3, ch, ch, &c))) return rc;
+        convs_.push_back(c);
+        modules_.push_back({Module::UP, static_cast<int>(convs_.size()) - 1, false, false});
+        ds /= 2;
+      }
+      ++ob;
+    }
+  }
+  // out
+  if ((rc = make_norm("out.0", ch, &out_norm_))) return rc;
+  {
+    ConvW c;
+    if ((rc = make_conv("out.2", 3, mc, cfg_.out_channels, &c))) return rc;
+    convs_.push_back(c);
+    modules_.push_back({Module::OUT, static_cast<int>(convs_.size()) - 1, false, false});
+  }
+  emb_total_ = static_cast<int>(emb_b.size());
+  if ((rc = upload_f32(emb_w, &emb_w_))) return rc;
+  if ((rc = upload_f32(emb_b, &emb_b_))) return rc;
+
+  {
+    void* p = nullptr;
+    PBE_CHECK_CUDA(cudaMalloc(&p, static_cast<size_t>(MAX_BC) * ctx_total_ * sizeof(float)));
+    dev_allocs_.push_back(p);
+    ctx_vecs_ = static_cast<float*>(p);
+    PBE_CHECK_CUDA(cudaMemset(p, 0, static_cast<size_t>(MAX_BC) * ctx_total_ * sizeof(float)));
+    int cmax = 0;
+    for (const auto& s : st_) cmax = std::max(cmax, s.c);
+    PBE_CHECK_CUDA(cudaMalloc(&p, static_cast<size_t>(MAX_BC) * cmax * sizeof(float)));
+    dev_allocs_.push_back(p);
+    ctx_tmp_ = static_cast<float*>(p);
+  }
+  host_.clear();
+  finalized_ = true;
+  return 0;
+}
+
+// K4: v[b] = to_out(to_v(ctx[b])) + bias for every SpatialTransformer; constant over all timesteps of a sample() call.
+int Engine::set_context(const float* ctx_dev, int Bc, cudaStream_t stream) {
+  PBE_REQUIRE(finalized_, "weights not finalized");
+  PBE_REQUIRE(Bc >= 1 && Bc <= MAX_BC, "context batch out of range");
+  for (const auto& s : st_) {
+    int rc = launch_small_linear(ctx_dev, s.wv2, nullptr, ctx_tmp_, Bc, cfg_.context_dim, s.c, 0, 0, stream);
+    if (rc) return rc;
+    // rows of ctx_vecs_ have stride ctx_total_: write through a strided view by launching per-ST into a packed tmp
+    // then scattering is avoided by letting small_linear write with O = s.c into a [Bc, s.c] block and the GEMM
+    // epilogue reading it with rowbias_ld = s.c; blocks are laid out back to back: offset = MAX_BC * ctx_vec_off.
+    rc = launch_small_linear(ctx_tmp_, s.wo2, s.bo2, ctx_vecs_ + static_cast<size_t>(MAX_BC) * s.ctx_vec_off, Bc, s.c,
+                             s.c, 0, 0, stream);
+    if (rc) return rc;
+  }
+  ctx_Bc_ = Bc;
+  return 0;
+}
+
+int Engine::build(Prepared& P, bool dry) {
+  const int Bc = P.Bc, H0 = P.H, W0 = P.W;
+  const int mc = cfg_.model_channels, ted = 4 * mc;
+  P.persist.reset(dry);
+  P.scratch.reset(dry);
+  P.ops.clear();
+  P.op_names.clear();
+  int launches = 0;
+  auto PA = [&](size_t bytes) { return P.persist.alloc(bytes); };
+  auto SA = [&](size_t bytes) { return P.scratch.alloc(bytes); };
+  auto add_op = [&](const std::string& name, int nlaunch, std::function<int(cudaStream_t)> fn) {
+    if (!dry) {
+      P.ops.push_back(std::move(fn));
+      P.op_names.push_back(name);
+    }
+    launches += nlaunch;
+  };
+  int err = 0;
+  auto add_gemm = [&](const std::string& name, ConvGemmDesc d) {
+    if (dry) { launches += 1; return; }
+    auto plan = std::make_shared<GemmPlan>();
+    int rc = build_gemm_plan(d, plan.get());
+    if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + name + "]"; }
+    add_op(name, 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); });
+  };
+  auto add_gn = [&](const std::string& name, GroupNormArgs a) {
+    a.partial = static_cast<float*>(SA(static_cast<size_t>(a.Nb) * gn_num_slabs(a.HW) * 64 * sizeof(float)));
+    add_op(name, 2, [a](cudaStream_t s) { return launch_groupnorm(a, s); });
+  };
+
+  P.x_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.in_channels * H0 * W0 * sizeof(float)));
+  P.t_stage = static_cast<int64_t*>(PA(static_cast<size_t>(Bc) * sizeof(int64_t)));
+  P.eps_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.out_channels * H0 * W0 * sizeof(float)));
+
+  // ---- timestep embedding path (K8) ----
+  float* t_emb = static_cast<float*>(PA(static_cast<size_t>(Bc) * mc * sizeof(float)));
+  float* t_hid = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
+  float* emb = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
+  float* emb_all = static_cast<float*>(PA(static_cast<size_t>(Bc) * emb_total_ * sizeof(float)));
+  {
+    const int64_t* tp = P.t_stage;
+    float *w0 = te_w0_, *b0 = te_b0_, *w1 = te_w1_, *b1 = te_b1_, *ew = emb_w_, *eb = emb_b_;
+    const int et = emb_total_;
+    add_op("timestep_embedding", 1, [=](cudaStream_t s) { return launch_timestep_embedding(tp, t_emb, Bc, mc, s); });
+    add_op("time_embed.0+silu", 1,
+           [=](cudaStream_t s) { return launch_small_linear(t_emb, w0, b0, t_hid, Bc, mc, ted, 0, 1, s); });
+    add_op("time_embed.2", 1,
+           [=](cudaStream_t s) { return launch_small_linear(t_hid, w1, b1, emb, Bc, ted, ted, 0, 0, s); });
+    add_op("emb_layers(all)", 1,
+           [=](cudaStream_t s) { return launch_small_linear(emb, ew, eb, emb_all, Bc, ted, et, 1, 0, s); });
+  }
+
+  struct Act {
+    float* f32;
+    bf16* b16;  // optional bf16 copy
+    int C, H, W;
+  };
+  std::vector<Act> hs;
+  Act h{nullptr, nullptr, 0, H0, W0};
+
+  for (size_t mi = 0; mi < modules_.size(); ++mi) {
+    const Module& m = modules_[mi];
+    const size_t smark = P.scratch.mark();
+    const std::string tag = "m" + std::to_string(mi);
+    // does the next module consume a raw bf16 copy of this module's output? (stride-2 conv reads raw activations)
+    const bool next_is_down = (mi + 1 < modules_.size() && modules_[mi + 1].kind == Module::DOWN);
+    switch (m.kind) {
+      case Module::CONV_IN: {
+        const ConvW& c = convs_[m.idx];
+        const size_t M = static_cast<size_t>(Bc) * H0 * W0;
+        bf16* xin = static_cast<bf16*>(SA(M * 64 * sizeof(bf16)));
+        const float* xs = P.x_stage;
+        const int cin = cfg_.in_channels;
+        add_op(tag + ".pack_input", 1, [=](cudaStream_t s) { return launch_pack_input(xs, xin, Bc, cin, H0, W0, 64, s); });
+        Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, H0, W0};
+        ConvGemmDesc d{};
+        d.act = xin; d.Nb = Bc; d.H = H0; d.W = W0; d.C = 64; d.ksize = 3; d.stride = 1;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        add_gemm(tag + ".conv_in", d);
+        h = o;
+        break;
+      }
+      case Module::RES: {
+        const ResW& r = res_[m.idx];
+        Act skip{nullptr, nullptr, 0, 0, 0};
+        if (m.pop_skip) {
+          skip = hs.back();
+          hs.pop_back();
+        }
+        const size_t M = static_cast<size_t>(Bc) * h.H * h.W;
+        const int cin = h.C + skip.C;
+        if (cin != r.cin) {
+          err = -5;
+          last_error = "channel mismatch at " + tag;
+          return err;
+        }
+        bf16* a1 = static_cast<bf16*>(SA(M * cin * sizeof(bf16)));
+        bf16* raw = r.has_skip ? static_cast<bf16*>(SA(M * cin * sizeof(bf16))) : nullptr;
+        GroupNormArgs g1{};
+        g1.x0 = h.f32; g1.C0 = h.C; g1.x1 = skip.f32; g1.C1 = skip.C; g1.Nb = Bc; g1.HW = h.H * h.W;
+        g1.gamma = r.gn1.g; g1.beta = r.gn1.b; g1.eps = 1e-5f; g1.silu = 1; g1.y = a1; g1.raw = raw;
+        add_gn(tag + ".gn1", g1);
+        float* h1 = static_cast<float*>(SA(M * r.cout * sizeof(float)));
+        {
+          ConvGemmDesc d{};
+          d.act = a1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 3; d.stride = 1;
+          d.wt = r.conv1.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv1.b;
+          d.rowbias = emb_all + r.emb_off; d.rowbias_ld = emb_total_;
+          d.out_f32 = h1;
+          add_gemm(tag + ".conv1", d);
+        }
+        bf16* a2 = static_cast<bf16*>(SA(M * r.cout * sizeof(bf16)));
+        GroupNormArgs g2{};
+        g2.x0 = h1; g2.C0 = r.cout; g2.x1 = nullptr; g2.C1 = 0; g2.Nb = Bc; g2.HW = h.H * h.W;
+        g2.gamma = r.gn2.g; g2.beta = r.gn2.b; g2.eps = 1e-5f; g2.silu = 1; g2.y = a2; g2.raw = nullptr;
+        add_gn(tag + ".gn2", g2);
+        const float* resid = h.f32;
+        if (r.has_skip) {
+          float* sk = static_cast<float*>(SA(M * r.cout * sizeof(float)));
+          ConvGemmDesc d{};
+          d.act = raw; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 1; d.stride = 1;
+          d.wt = r.skip.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.skip.b; d.out_f32 = sk;
+          add_gemm(tag + ".skip", d);
+          resid = sk;
+        }
+        Act o{static_cast<float*>(PA(M * r.cout * sizeof(float))), nullptr, r.cout, h.H, h.W};
+        if (next_is_down) o.b16 = static_cast<bf16*>(PA(M * r.cout * sizeof(bf16)));
+        {
+          ConvGemmDesc d{};
+          d.act = a2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = r.cout; d.ksize = 3; d.stride = 1;
+          d.wt = r.conv2.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv2.b; d.residual = resid;
+          d.out_f32 = o.f32; d.out_bf16 = o.b16;
+          add_gemm(tag + ".conv2", d);
+        }
+        h = o;
+        break;
+      }
+      case Module::ST: {
+        const STW& s = st_[m.idx];
+        const int C = s.c, N = h.H * h.W;
+        const size_t M = static_cast<size_t>(Bc) * N;
+        if (C != h.C) { err = -5; last_error = "channel mismatch at " + tag; return err; }
+        bf16* a = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        GroupNormArgs g{};
+        g.x0 = h.f32; g.C0 = C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = N;
+        g.gamma = s.gn.g; g.beta = s.gn.b; g.eps = 1e-6f; g.silu = 0; g.y = a; g.raw = nullptr;
+        add_gn(tag + ".norm", g);
+        float* t0 = static_cast<float*>(SA(M * C * sizeof(float)));
+        {
+          ConvGemmDesc d{};
+          d.act = a; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
+          d.wt = s.proj_in.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_in.b; d.out_f32 = t0;
+          add_gemm(tag + ".proj_in", d);
+        }
+        bf16* n1 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        {
+          const float *gg = s.ln1.g, *bb = s.ln1.b;
+          const int Mi = static_cast<int>(M);
+          add_op(tag + ".ln1", 1, [=](cudaStream_t st) { return launch_layernorm(t0, gg, bb, n1, Mi, C, 1e-5f, st); });
+        }
+        bf16* qk = static_cast<bf16*>(SA(M * 2 * C * sizeof(bf16)));
+        bf16* vt = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        {
+          ConvGemmDesc d{};
+          d.act = n1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
+          d.wt = s.qkv.w; d.Cout = 3 * C; d.mode = EPI_QKV; d.out_bf16 = qk; d.ld_out = 2 * C; d.out_vt = vt;
+          d.qk_cols = 2 * C;
+          d.block_n = (C % 160 == 0) ? 160 : ((C % 128 == 0) ? 128 : 64);
+          add_gemm(tag + ".qkv", d);
+        }
+        bf16* ao = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        if (!dry) {
+          auto plan = std::make_shared<AttnPlan>();
+          int rc = build_attn_plan(qk, vt, ao, Bc, N, s.heads, s.d, plan.get());
+          if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + tag + ".attn]"; }
+          add_op(tag + ".attn1", 1, [plan](cudaStream_t st) { return launch_attn_plan(*plan, st); });
+        } else {
+          launches += 1;
+        }
+        float* t1 = static_cast<float*>(SA(M * C * sizeof(float)));
+        {
+          // x1 = to_out(attn) + b + x ; x2 = x1 + to_out2(to_v2(ctx))  (single-key cross-attention, folded)
+          ConvGemmDesc d{};
+          d.act = ao; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
+          d.wt = s.to_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.to_out.b;
+          d.rowbias = ctx_vecs_ + static_cast<size_t>(MAX_BC) * s.ctx_vec_off; d.rowbias_ld = C;
+          d.residual = t0; d.out_f32 = t1;
+          add_gemm(tag + ".attn1.to_out+attn2", d);
+        }
+        bf16* n3 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        {
+          const float *gg = s.ln3.g, *bb = s.ln3.b;
+          const int Mi = static_cast<int>(M);
+          add_op(tag + ".ln3", 1, [=](cudaStream_t st) { return launch_layernorm(t1, gg, bb, n3, Mi, C, 1e-5f, st); });
+        }
+        bf16* gg = static_cast<bf16*>(SA(M * 4 * C * sizeof(bf16)));
+        {
+          ConvGemmDesc d{};
+          d.act = n3; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
+          d.wt = s.ff1.w; d.Cout = 8 * C; d.mode = EPI_GEGLU; d.bias = s.ff1.b; d.out_bf16 = gg; d.ld_out = 4 * C;
+          add_gemm(tag + ".ff.geglu", d);
+        }
+        bf16* t2 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        {
+          ConvGemmDesc d{};
+          d.act = gg; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = 4 * C; d.ksize = 1; d.stride = 1;
+          d.wt = s.ff2.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.ff2.b; d.residual = t1; d.out_bf16 = t2;
+          add_gemm(tag + ".ff.out", d);
+        }
+        Act o{static_cast<float*>(PA(M * C * sizeof(float))), nullptr, C, h.H, h.W};
+        if (next_is_down) o.b16 = static_cast<bf16*>(PA(M * C * sizeof(bf16)));
+        {
+          ConvGemmDesc d{};
+          d.act = t2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
+          d.wt = s.proj_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_out.b; d.residual = h.f32;
+          d.out_f32 = o.f32; d.out_bf16 = o.b16;
+          add_gemm(tag + ".proj_out", d);
+        }
+        h = o;
+        break;
+      }
+      case Module::DOWN: {
+        const ConvW& c = convs_[m.idx];
+        if (h.b16 == nullptr || (h.H & 1) || (h.W & 1)) {
+          err = -5;
+          last_error = "downsample needs a bf16 copy and even H, W at " + tag;
+          return err;
+        }
+        const size_t M = static_cast<size_t>(Bc) * (h.H / 2) * (h.W / 2);
+        Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, h.H / 2, h.W / 2};
+        ConvGemmDesc d{};
+        d.act = h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = h.C; d.ksize = 3; d.stride = 2;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        add_gemm(tag + ".downsample", d);
+        h = o;
+        break;
+      }
+      case Module::UP: {
+        const ConvW& c = convs_[m.idx];
+        const size_t M = static_cast<size_t>(Bc) * (2 * h.H) * (2 * h.W);
+        bf16* up = static_cast<bf16*>(SA(M * h.C * sizeof(bf16)));
+        {
+          const float* src = h.f32;
+          const int hh = h.H, ww = h.W, cc = h.C;
+          add_op(tag + ".upsample2x", 1,
+                 [=](cudaStream_t st) { return launch_upsample2x_bf16(src, up, Bc, hh, ww, cc, st); });
+        }
+        Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, 2 * h.H, 2 * h.W};
+        ConvGemmDesc d{};
+        d.act = up; d.Nb = Bc; d.H = 2 * h.H; d.W = 2 * h.W; d.C = h.C; d.ksize = 3; d.stride = 1;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        add_gemm(tag + ".upsample.conv", d);
+        h = o;
+        break;
+      }
+      case Module::OUT: {
+        const ConvW& c = convs_[m.idx];
+        const size_t M = static_cast<size_t>(Bc) * h.H * h.W;
+        bf16* a = static_cast<bf16*>(SA(M * h.C * sizeof(bf16)));
+        GroupNormArgs g{};
+        g.x0 = h.f32; g.C0 = h.C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = h.H * h.W;
+        g.gamma = out_norm_.g; g.beta = out_norm_.b; g.eps = 1e-5f; g.silu = 1; g.y = a; g.raw = nullptr;
+        add_gn(tag + ".out.norm", g);
+        float* y = static_cast<float*>(SA(M * c.cout * sizeof(float)));
+        ConvGemmDesc d{};
+        d.act = a; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = h.C; d.ksize = 3; d.stride = 1;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = y; d.block_n = 32;
+        add_gemm(tag + ".out.conv", d);
+        float* dst = P.eps_stage;
+        const int co = c.cout, hh = h.H, ww = h.W;
+        add_op(tag + ".unpack_output", 1,
+               [=](cudaStream_t st) { return launch_unpack_output(y, dst, Bc, co, hh, ww, co, st); });
+        break;
+      }
+    }
+    if (m.push_skip) hs.push_back(h);
+    P.scratch.rewind(smark);
+    if (err) return err;
+  }
+  if (!hs.empty()) {
+    last_error = "skip stack not empty after build";
+    return -5;
+  }
+  P.launches = launches;
+  return 0;
+}
+
+int Engine::prepare(int Bc, int H, int W) {
+  PBE_REQUIRE(finalized_, "weights not finalized");
+  PBE_REQUIRE(Bc >= 1 && Bc <= MAX_BC, "batch out of range");
+  int down = 1;
+  for (int i = 1; i < cfg_.num_levels; ++i) down *= 2;
+  PBE_REQUIRE(H % down == 0 && W % down == 0, "latent size must be divisible by 2^(levels-1)");
+  auto key = std::make_tuple(Bc, H, W);
+  auto it = prepared_.find(key);
+  if (it != prepared_.end()) {
+    cur_ = it->second.get();
+    return 0;
+  }
+  auto P = std::make_unique<Prepared>();
+  P->Bc = Bc; P->H = H; P->W = W;
+  int rc = build(*P, true);
+  if (rc) { set_error(last_error); return rc; }
+  const size_t pbytes = P->persist.high() + 4096, sbytes = P->scratch.high() + 4096;
+  void* p = nullptr;
+  PBE_CHECK_CUDA(cudaMalloc(&p, pbytes));
+  P->persist.base_ = static_cast<char*>(p);
+  P->persist.cap_ = pbytes;
+  PBE_CHECK_CUDA(cudaMalloc(&p, sbytes));
+  P->scratch.base_ = static_cast<char*>(p);
+  P->scratch.cap_ = sbytes;
+  rc = build(*P, false);
+  if (rc) { set_error(last_error); return rc; }
+  cur_ = P.get();
+  prepared_[key] = std::move(P);
+  return 0;
+}
+
+int Engine::forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream) {
+  int rc = prepare(Bc, H, W);
+  if (rc) return rc;
+  Prepared& P = *cur_;
+  PBE_REQUIRE(ctx_Bc_ == Bc, "set_context must be called with the same batch before forward");
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.x_stage, x, static_cast<size_t>(Bc) * cfg_.in_channels * H * W * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, stream));
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage, t, static_cast<size_t>(Bc) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                                 stream));
+  if (use_graph) {
+    if (P.graph == nullptr) {
+      // warm every kernel once eagerly (sets function attributes outside capture), then capture
+      for (size_t i = 0; i < P.ops.size(); ++i) {
+        rc = P.ops[i](stream);
+        if (rc) { set_error(std::string(get_error()) + " [" + P.op_names[i] + "]"); return rc; }
+      }
+      PBE_CHECK_CUDA(cudaStreamSynchronize(stream));
+      // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
+      // the instantiated graph is then launched on the caller's stream.
+      if (cap_stream_ == nullptr) PBE_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+      cudaGraph_t g = nullptr;
+      PBE_CHECK_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+      for (size_t i = 0; i < P.ops.size(); ++i) {
+        rc = P.ops[i](cap_stream_);
+        if (rc) {
+          cudaStreamEndCapture(cap_stream_, &g);
+          if (g) cudaGraphDestroy(g);
+          return rc;
+        }
+      }
+      PBE_CHECK_CUDA(cudaStreamEndCapture(cap_stream_, &g));
+      PBE_CHECK_CUDA(cudaGraphInstantiate(&P.graph, g, 0));
+      cudaGraphDestroy(g);
+    }
+    PBE_CHECK_CUDA(cudaGraphLaunch(P.graph, stream));
+  } else {
+    for (size_t i = 0; i < P.ops.size(); ++i) {
+      rc = P.ops[i](stream);
+      if (rc) { set_error(std::string(get_error()) + " [" + P.op_names[i] + "]"); return rc; }
+    }
+  }
+  PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+}  // namespace pbe

@@ -1,0 +1,136 @@
+// U-Net engine: owns repacked weights, per-shape launch plans and workspaces; runs UNetModel.forward
+// (ldm/modules/diffusionmodules/openaimodel.py:852-889) as a fixed list of sm_100a kernel launches (CUDA-graph replayed).
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pbe_b200.h"
+#include "internal.h"
+
+namespace pbe {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct ConvW {
+  bf16* w = nullptr;   // [k*k][cout][cin_pad]
+  float* b = nullptr;  // [cout]
+  int cin = 0, cin_pad = 0, cout = 0, k = 1;
+};
+struct NormW {
+  float* g = nullptr;
+  float* b = nullptr;
+  int c = 0;
+};
+struct ResW {
+  int cin = 0, cout = 0, emb_off = 0;
+  NormW gn1, gn2;
+  ConvW conv1, conv2, skip;
+  bool has_skip = false;
+};
+struct STW {
+  int c = 0, heads = 0, d = 0;
+  NormW gn, ln1, ln3;
+  ConvW proj_in, qkv, to_out, ff1, ff2, proj_out;
+  float* wv2 = nullptr;  // attn2.to_v  [c, ctx]
+  float* wo2 = nullptr;  // attn2.to_out.0.weight [c, c]
+  float* bo2 = nullptr;  // attn2.to_out.0.bias
+  int ctx_vec_off = 0;   // offset of this block's folded cross-attention vector inside ctx_vecs rows
+};
+
+struct Module {
+  enum Kind { CONV_IN, RES, ST, DOWN, UP, OUT } kind;
+  int idx = 0;             // index into the kind's weight table
+  bool pop_skip = false;   // RES in output blocks: input = cat(h, hs.pop())
+  bool push_skip = false;  // push the result onto hs after this module
+};
+
+class Arena {
+ public:
+  void reset(bool dry) { dry_ = dry; off_ = 0; if (dry) high_ = 0; }
+  void* alloc(size_t bytes) {
+    off_ = (off_ + 255) & ~static_cast<size_t>(255);
+    void* p = dry_ ? nullptr : static_cast<void*>(base_ + off_);
+    off_ += bytes;
+    if (off_ > high_) high_ = off_;
+    return p;
+  }
+  size_t mark() const { return off_; }
+  void rewind(size_t m) { off_ = m; }
+  size_t high() const { return high_; }
+  char* base_ = nullptr;
+  size_t cap_ = 0;
+
+ private:
+  bool dry_ = true;
+  size_t off_ = 0, high_ = 0;
+};
+
+struct Prepared {
+  int Bc = 0, H = 0, W = 0;
+  Arena persist, scratch;
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<std::string> op_names;
+  float* x_stage = nullptr;    // [Bc, in_ch, H, W]
+  int64_t* t_stage = nullptr;  // [Bc]
+  float* eps_stage = nullptr;  // [Bc, out_ch, H, W]
+  cudaGraphExec_t graph = nullptr;
+  int launches = 0;  // kernels per forward
+  ~Prepared();
+};
+
+class Engine {
+ public:
+  explicit Engine(const pbe_config& cfg) : cfg_(cfg) {}
+  ~Engine();
+  int load_weight(const char* name, const float* host, const int64_t* shape, int rank);
+  int finalize();
+  int set_context(const float* ctx_dev, int Bc, cudaStream_t stream);
+  int forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream);
+  int launches_per_forward() const { return cur_ ? cur_->launches : 0; }
+  bool use_graph = true;
+  std::string last_error;
+
+ private:
+  int prepare(int Bc, int H, int W);
+  int build(Prepared& P, bool dry);
+  const HostTensor* find(const std::string& name);
+  int get(const std::string& name, const HostTensor** out);
+  int make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad = 0);
+  int make_norm(const std::string& prefix, int c, NormW* n);
+  int upload_f32(const std::vector<float>& v, float** dst);
+  int upload_bf16(const std::vector<float>& v, bf16** dst);
+
+  pbe_config cfg_;
+  std::unordered_map<std::string, HostTensor> host_;
+  bool finalized_ = false;
+  std::vector<void*> dev_allocs_;
+
+  // network description
+  std::vector<Module> modules_;
+  std::vector<ResW> res_;
+  std::vector<STW> st_;
+  std::vector<ConvW> convs_;  // conv_in, downsample, upsample, out convs
+  NormW out_norm_;
+  float *te_w0_ = nullptr, *te_b0_ = nullptr, *te_w1_ = nullptr, *te_b1_ = nullptr;  // time_embed
+  float *emb_w_ = nullptr, *emb_b_ = nullptr;  // all ResBlock emb_layers concatenated [emb_total, 4*mc]
+  int emb_total_ = 0;
+  int ctx_total_ = 0;  // sum of C over SpatialTransformers
+
+  // context-dependent state (folded single-key cross-attention, K4)
+  float* ctx_vecs_ = nullptr;  // [ctx_Bc, ctx_total_]
+  float* ctx_tmp_ = nullptr;
+  int ctx_Bc_ = 0;
+
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Prepared>> prepared_;
+  Prepared* cur_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr;
+};
+
+}  // namespace pbe

@@ -200,7 +200,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int vb = __shfl_sync(0xffffffffu, my_valid ? on : -1, r);
           if (vb >= 0 && colv) {
             float x = stg[r * STAGE_LD + lane] + bias_v;
-            if (p.rowbias != nullptr) x += __ldg(p.rowbias + static_cast<long long>(vb) * p.n_total + col);
+            if (p.rowbias != nullptr) x += __ldg(p.rowbias + static_cast<long long>(vb) * p.rowbias_ld + col);
             const long long o = m * p.ld_out + col;
             if (p.residual != nullptr) x += __ldg(p.residual + o);
             if (p.out_f32 != nullptr) p.out_f32[o] = x;
@@ -296,6 +296,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.mode = d.mode;
   p.bias = d.bias;
   p.rowbias = d.rowbias;
+  p.rowbias_ld = d.rowbias_ld ? d.rowbias_ld : d.Cout;
   p.residual = d.residual;
   p.out_f32 = d.out_f32;
   p.out_bf16 = d.out_bf16;

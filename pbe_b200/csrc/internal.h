@@ -58,7 +58,8 @@ struct ConvGemmParams {
   // epilogue
   int mode;
   const float* bias;      // [n_total] or null
-  const float* rowbias;   // [Nb, n_total] or null (timestep-embedding / folded cross-attention term)
+  const float* rowbias;   // [Nb, rowbias_ld] or null (timestep-embedding / folded cross-attention term)
+  int rowbias_ld;
   const float* residual;  // [M, ld_out] fp32 or null
   float* out_f32;         // [M, ld_out] or null
   bf16* out_bf16;         // [M, ld_out] or null
@@ -86,6 +87,7 @@ struct ConvGemmDesc {
   int mode;
   const float* bias;
   const float* rowbias;
+  int rowbias_ld;  // 0 -> Cout
   const float* residual;
   float* out_f32;
   bf16* out_bf16;

@@ -1,0 +1,103 @@
+"""The oracle (oracle/*.py) is pinned two ways: against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py; runs anywhere) and, where /root/reference is mounted, against the live reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_bridge as R
+from oracle import sampler_ref as S
+from oracle import unet_ref as U
+
+
+def _golden(golden_dir, name):
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    a = np.load(os.path.join(golden_dir, name + ".npy"))
+    assert hashlib.sha256(a.astype(np.float32).tobytes()).hexdigest() == idx[name]["sha256"], "golden file corrupted"
+    return torch.from_numpy(a), idx[name]
+
+
+@pytest.fixture(scope="module")
+def small():
+    cfg = U.SMALL_CFG
+    sd = U.make_state_dict(cfg, 321)
+    req = S.synthetic_request(2, 32, 32, seed=321)
+    return cfg, sd, req
+
+
+def _cfg_inputs(req, B):
+    x9 = torch.cat((req["x_T"], req["z_inpaint"], req["mask"]), 1)
+    return torch.cat([x9] * 2), torch.cat((req["uc"].expand(B, 1, 768), req["c"]))
+
+
+def test_state_dict_keys_match_reference(golden_dir, small):
+    cfg, sd, _ = small
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    assert sorted(sd.keys()) == idx["state_dict_keys"]["keys"]
+    assert len(U.param_shapes(U.V1_CFG)) == 686  # 686 tensors
+    assert sum(int(np.prod(s)) for s in U.param_shapes(U.V1_CFG).values()) == 859_535_364
+
+
+@pytest.mark.parametrize("tval", [981, 1])
+def test_unet_oracle_matches_reference_golden(golden_dir, small, tval):
+    cfg, sd, req = small
+    x_in, c_in = _cfg_inputs(req, 2)
+    e = U.unet_forward(sd, cfg, x_in, torch.full((4,), tval, dtype=torch.int64), c_in)
+    g, _ = _golden(golden_dir, f"small_unet_eps_t{tval}")
+    assert torch.allclose(e, g, atol=2e-5, rtol=0), (e - g).abs().max()
+
+
+def test_plms_oracle_matches_reference_golden(golden_dir, small):
+    cfg, sd, req = small
+    om = S.OracleModel(sd, cfg)
+    out = S.plms_sample(om, 8, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"])
+    g, _ = _golden(golden_dir, "small_plms8_final")
+    assert om.calls == 9  # S + 1: the first step evaluates twice (plms.py:230-235)
+    assert torch.allclose(out, g, atol=5e-4, rtol=0), (out - g).abs().max()
+
+
+def test_ddim_oracle_matches_reference_golden(golden_dir, small):
+    cfg, sd, req = small
+    om = S.OracleModel(sd, cfg)
+    out = S.ddim_sample(om, 5, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"])
+    g, _ = _golden(golden_dir, "small_ddim5_final")
+    assert om.calls == 5
+    assert torch.allclose(out, g, atol=5e-4, rtol=0), (out - g).abs().max()
+
+
+def test_schedule_anchors():
+    """SURVEY.md Appendix A anchors, computed there with the reference's own functions."""
+    buf = S.make_schedule_buffers()
+    ac = buf["alphas_cumprod"]
+    assert abs(ac[0].item() - 0.99915) < 1e-6 and abs(ac[999].item() - 0.0046601) < 1e-7
+    tab = S.ddim_tables(ac, 50)
+    assert list(tab["timesteps"][:3]) == [1, 21, 41] and tab["timesteps"][-1] == 981
+    assert abs(tab["alphas"][49].item() - 0.00577550009) < 1e-9
+    assert abs(tab["alphas_prev"][49].item() - 0.00728172716) < 1e-9
+    assert abs(tab["alphas"][0].item() - 0.99829602) < 1e-7
+    tab20 = S.ddim_tables(ac, 20)
+    assert list(tab20["timesteps"][:2]) == [1, 51] and tab20["timesteps"][-1] == 951
+    assert abs(tab20["alphas"][19].item() - 0.00815500412) < 1e-9
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
+def test_oracle_bit_equals_live_reference(small):
+    cfg, sd, req = small
+    ref = R.build_reference_unet(cfg, sd)
+    x_in, c_in = _cfg_inputs(req, 2)
+    t = torch.full((4,), 501, dtype=torch.int64)
+    with torch.no_grad():
+        e_ref = ref(x_in, t, context=c_in)
+    e = U.unet_forward(sd, cfg, x_in, t, c_in)
+    assert torch.equal(e, e_ref)
+    model = R.StubLatentDiffusion(ref)
+    smp = R.reference_sampler("plms", model)
+    out_ref, _ = smp.sample(S=4, conditioning=req["c"], batch_size=2, shape=[4, 32, 32], verbose=False,
+                            unconditional_guidance_scale=5.0, unconditional_conditioning=req["uc"].expand(2, 1, 768),
+                            eta=0.0, x_T=req["x_T"],
+                            test_model_kwargs=dict(images_inpaint=req["z_inpaint"], images_mask=req["mask"]))
+    out = S.plms_sample(S.OracleModel(sd, cfg), 4, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"])
+    assert torch.equal(out, out_ref)
