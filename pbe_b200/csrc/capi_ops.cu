@@ -24,6 +24,7 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
   d.out_bf16 = static_cast<bf16*>(out_bf16);
   d.out_vt = static_cast<bf16*>(out_vt);
   d.qk_cols = qk_cols;
+  d.ld_out = (mode == EPI_QKV) ? qk_cols : 0;
   d.block_n = block_n;
   GemmPlan plan;
   int rc = build_gemm_plan(d, &plan);

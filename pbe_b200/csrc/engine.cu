@@ -438,6 +438,7 @@ int Engine::build(Prepared& P, bool dry) {
     float* f32;
     bf16* b16;  // optional bf16 copy
     int C, H, W;
+    bool has16 = false;
   };
   std::vector<Act> hs;
   Act h{nullptr, nullptr, 0, H0, W0};
@@ -508,7 +509,7 @@ int Engine::build(Prepared& P, bool dry) {
           resid = sk;
         }
         Act o{static_cast<float*>(PA(M * r.cout * sizeof(float))), nullptr, r.cout, h.H, h.W};
-        if (next_is_down) o.b16 = static_cast<bf16*>(PA(M * r.cout * sizeof(bf16)));
+        if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * r.cout * sizeof(bf16))); o.has16 = true; }
         {
           ConvGemmDesc d{};
           d.act = a2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = r.cout; d.ksize = 3; d.stride = 1;
@@ -592,7 +593,7 @@ int Engine::build(Prepared& P, bool dry) {
           add_gemm(tag + ".ff.out", d);
         }
         Act o{static_cast<float*>(PA(M * C * sizeof(float))), nullptr, C, h.H, h.W};
-        if (next_is_down) o.b16 = static_cast<bf16*>(PA(M * C * sizeof(bf16)));
+        if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * C * sizeof(bf16))); o.has16 = true; }
         {
           ConvGemmDesc d{};
           d.act = t2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
@@ -605,7 +606,7 @@ int Engine::build(Prepared& P, bool dry) {
       }
       case Module::DOWN: {
         const ConvW& c = convs_[m.idx];
-        if (h.b16 == nullptr || (h.H & 1) || (h.W & 1)) {
+        if (!h.has16 || (h.H & 1) || (h.W & 1)) {
           err = -5;
           last_error = "downsample needs a bf16 copy and even H, W at " + tag;
           return err;
