@@ -101,6 +101,12 @@ int pbe_set_context(pbe_handle h, const float* ctx, int Bc, void* stream);
 int pbe_unet_forward(pbe_handle h, const float* x, const int64_t* t, float* eps, int Bc, int H, int W, void* stream);
 /* 1 = replay a captured CUDA graph per forward (default), 0 = launch kernels one by one. */
 int pbe_set_use_graph(pbe_handle h, int enable);
+/* Measurement aid: one eager forward with a CUDA-event pair around every op of the launch plan. Fills ms_out[i]
+ * (device time of op i, ms) and returns the number of ops (<0 on error). pbe_op_info describes op i of the current
+ * shape: name, kernel family, algorithmic FLOPs (2*MAC, unpadded) and algorithmic HBM bytes. */
+int pbe_profile_forward(pbe_handle h, const float* x, const int64_t* t, float* eps, int Bc, int H, int W, void* stream,
+                        float* ms_out, int max_ops);
+int pbe_op_info(pbe_handle h, int i, const char** name, const char** family, double* flops, double* bytes);
 /* number of kernels one pbe_unet_forward launches for the current shape (0 before the first forward). */
 int pbe_launches_per_forward(pbe_handle h);
 

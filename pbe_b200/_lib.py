@@ -63,6 +63,8 @@ _OPTIONAL_SIGS: dict = {
     "pbe_unet_forward": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "pbe_set_use_graph": (c_int, [_p, _i]),
     "pbe_launches_per_forward": (c_int, [_p]),
+    "pbe_profile_forward": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i]),
+    "pbe_op_info": (c_int, [_p, _i, _p, _p, _p, _p]),
 }
 
 

@@ -55,6 +55,20 @@ int pbe_set_use_graph(pbe_handle h, int enable) {
   h->e->use_graph = enable != 0;
   return 0;
 }
+int pbe_profile_forward(pbe_handle h, const float* x, const int64_t* t, float* eps, int Bc, int H, int W, void* stream,
+                        float* ms_out, int max_ops) {
+  PBE_GUARD(h->e->profile_forward(x, t, eps, Bc, H, W, static_cast<cudaStream_t>(stream), ms_out, max_ops));
+}
+int pbe_op_info(pbe_handle h, int i, const char** name, const char** family, double* flops, double* bytes) {
+  if (h == nullptr || h->e->current() == nullptr) { set_error("no prepared shape"); return -1; }
+  const Prepared* P = h->e->current();
+  if (i < 0 || i >= static_cast<int>(P->ops.size())) { set_error("op index out of range"); return -1; }
+  if (name) *name = P->op_names[i].c_str();
+  if (family) *family = P->op_family[i].c_str();
+  if (flops) *flops = P->op_flops[i];
+  if (bytes) *bytes = P->op_bytes[i];
+  return 0;
+}
 int pbe_launches_per_forward(pbe_handle h) {
   if (h == nullptr) return 0;
   return h->e->launches_per_forward();

@@ -392,12 +392,22 @@ int Engine::build(Prepared& P, bool dry) {
   int launches = 0;
   auto PA = [&](size_t bytes) { return P.persist.alloc(bytes); };
   auto SA = [&](size_t bytes) { return P.scratch.alloc(bytes); };
-  auto add_op = [&](const std::string& name, int nlaunch, std::function<int(cudaStream_t)> fn) {
+  P.op_family.clear();
+  P.op_flops.clear();
+  P.op_bytes.clear();
+  auto add_op_meta = [&](const std::string& name, int nlaunch, std::function<int(cudaStream_t)> fn,
+                         const std::string& family, double flops, double bytes) {
     if (!dry) {
       P.ops.push_back(std::move(fn));
       P.op_names.push_back(name);
+      P.op_family.push_back(family);
+      P.op_flops.push_back(flops);
+      P.op_bytes.push_back(bytes);
     }
     launches += nlaunch;
+  };
+  auto add_op = [&](const std::string& name, int nlaunch, std::function<int(cudaStream_t)> fn) {
+    add_op_meta(name, nlaunch, std::move(fn), "misc", 0.0, 0.0);
   };
   int err = 0;
   auto add_gemm = [&](const std::string& name, ConvGemmDesc d) {
@@ -405,11 +415,21 @@ int Engine::build(Prepared& P, bool dry) {
     auto plan = std::make_shared<GemmPlan>();
     int rc = build_gemm_plan(d, plan.get());
     if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + name + "]"; }
-    add_op(name, 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); });
+    const double Mrows = static_cast<double>(d.Nb) * (d.H / d.stride) * (d.W / d.stride);
+    const double kreal = static_cast<double>(d.c_real ? d.c_real : d.C) * d.ksize * d.ksize;
+    const double flops = 2.0 * Mrows * d.Cout * kreal;
+    const double out_cols = (d.mode == EPI_GEGLU) ? d.Cout / 2.0 : d.Cout;
+    double bytes = static_cast<double>(d.Nb) * d.H * d.W * d.C * 2.0 + static_cast<double>(d.Cout) * d.C * d.ksize * d.ksize * 2.0;
+    if (d.out_f32) bytes += Mrows * out_cols * 4.0;
+    if (d.out_bf16 || d.out_vt) bytes += Mrows * out_cols * 2.0;
+    if (d.residual) bytes += Mrows * out_cols * 4.0;
+    add_op_meta(name, 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); }, "conv_gemm", flops, bytes);
   };
   auto add_gn = [&](const std::string& name, GroupNormArgs a) {
     a.partial = static_cast<float*>(SA(static_cast<size_t>(a.Nb) * gn_num_slabs(a.HW) * 64 * sizeof(float)));
-    add_op(name, 2, [a](cudaStream_t s) { return launch_groupnorm(a, s); });
+    const double n = static_cast<double>(a.Nb) * a.HW * (a.C0 + a.C1);
+    add_op_meta(name, 2, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
+                n * (4.0 + 4.0 + 2.0 + (a.raw ? 2.0 : 0.0)));
   };
 
   P.x_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.in_channels * H0 * W0 * sizeof(float)));
@@ -459,7 +479,7 @@ int Engine::build(Prepared& P, bool dry) {
         add_op(tag + ".pack_input", 1, [=](cudaStream_t s) { return launch_pack_input(xs, xin, Bc, cin, H0, W0, 64, s); });
         Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, H0, W0};
         ConvGemmDesc d{};
-        d.act = xin; d.Nb = Bc; d.H = H0; d.W = W0; d.C = 64; d.ksize = 3; d.stride = 1;
+        d.act = xin; d.Nb = Bc; d.H = H0; d.W = W0; d.C = 64; d.c_real = cin; d.ksize = 3; d.stride = 1;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
         add_gemm(tag + ".conv_in", d);
         h = o;
@@ -541,7 +561,8 @@ int Engine::build(Prepared& P, bool dry) {
         {
           const float *gg = s.ln1.g, *bb = s.ln1.b;
           const int Mi = static_cast<int>(M);
-          add_op(tag + ".ln1", 1, [=](cudaStream_t st) { return launch_layernorm(t0, gg, bb, n1, Mi, C, 1e-5f, st); });
+          add_op_meta(tag + ".ln1", 1, [=](cudaStream_t st) { return launch_layernorm(t0, gg, bb, n1, Mi, C, 1e-5f, st); },
+                      "layernorm", 0.0, static_cast<double>(M) * C * 6.0);
         }
         bf16* qk = static_cast<bf16*>(SA(M * 2 * C * sizeof(bf16)));
         bf16* vt = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
@@ -558,7 +579,8 @@ int Engine::build(Prepared& P, bool dry) {
           auto plan = std::make_shared<AttnPlan>();
           int rc = build_attn_plan(qk, vt, ao, Bc, N, s.heads, s.d, plan.get());
           if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + tag + ".attn]"; }
-          add_op(tag + ".attn1", 1, [plan](cudaStream_t st) { return launch_attn_plan(*plan, st); });
+          add_op_meta(tag + ".attn1", 1, [plan](cudaStream_t st) { return launch_attn_plan(*plan, st); }, "attention",
+                      4.0 * Bc * static_cast<double>(N) * N * C, static_cast<double>(M) * C * 2.0 * 4.0);
         } else {
           launches += 1;
         }
@@ -576,7 +598,8 @@ int Engine::build(Prepared& P, bool dry) {
         {
           const float *gg = s.ln3.g, *bb = s.ln3.b;
           const int Mi = static_cast<int>(M);
-          add_op(tag + ".ln3", 1, [=](cudaStream_t st) { return launch_layernorm(t1, gg, bb, n3, Mi, C, 1e-5f, st); });
+          add_op_meta(tag + ".ln3", 1, [=](cudaStream_t st) { return launch_layernorm(t1, gg, bb, n3, Mi, C, 1e-5f, st); },
+                      "layernorm", 0.0, static_cast<double>(M) * C * 6.0);
         }
         bf16* gg = static_cast<bf16*>(SA(M * 4 * C * sizeof(bf16)));
         {
@@ -627,8 +650,9 @@ int Engine::build(Prepared& P, bool dry) {
         {
           const float* src = h.f32;
           const int hh = h.H, ww = h.W, cc = h.C;
-          add_op(tag + ".upsample2x", 1,
-                 [=](cudaStream_t st) { return launch_upsample2x_bf16(src, up, Bc, hh, ww, cc, st); });
+          add_op_meta(tag + ".upsample2x", 1,
+                      [=](cudaStream_t st) { return launch_upsample2x_bf16(src, up, Bc, hh, ww, cc, st); }, "upsample",
+                      0.0, static_cast<double>(Bc) * hh * ww * cc * (4.0 + 8.0));
         }
         Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, 2 * h.H, 2 * h.W};
         ConvGemmDesc d{};
@@ -699,6 +723,33 @@ int Engine::prepare(int Bc, int H, int W) {
   cur_ = P.get();
   prepared_[key] = std::move(P);
   return 0;
+}
+
+int Engine::profile_forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream,
+                            float* ms, int max_ops) {
+  int rc = prepare(Bc, H, W);
+  if (rc) return rc;
+  Prepared& P = *cur_;
+  PBE_REQUIRE(ctx_Bc_ == Bc, "set_context must be called with the same batch before forward");
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.x_stage, x, static_cast<size_t>(Bc) * cfg_.in_channels * H * W * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, stream));
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage, t, static_cast<size_t>(Bc) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                                 stream));
+  const size_t n = P.ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) PBE_CHECK_CUDA(cudaEventCreate(&e));
+  PBE_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < n; ++i) {
+    rc = P.ops[i](stream);
+    if (rc) return rc;
+    PBE_CHECK_CUDA(cudaEventRecord(ev[i + 1], stream));
+  }
+  PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, stream));
+  PBE_CHECK_CUDA(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < n && static_cast<int>(i) < max_ops; ++i) PBE_CHECK_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return static_cast<int>(n);
 }
 
 int Engine::forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream) {

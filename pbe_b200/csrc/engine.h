@@ -77,6 +77,9 @@ struct Prepared {
   Arena persist, scratch;
   std::vector<std::function<int(cudaStream_t)>> ops;
   std::vector<std::string> op_names;
+  std::vector<std::string> op_family;  // kernel family: conv_gemm, attention, groupnorm, layernorm, ...
+  std::vector<double> op_flops;        // algorithmic FLOPs (2*MAC) of the op, 0 for non-GEMM ops
+  std::vector<double> op_bytes;        // algorithmic HBM bytes of the op
   float* x_stage = nullptr;    // [Bc, in_ch, H, W]
   int64_t* t_stage = nullptr;  // [Bc]
   float* eps_stage = nullptr;  // [Bc, out_ch, H, W]
@@ -94,6 +97,10 @@ class Engine {
   int set_context(const float* ctx_dev, int Bc, cudaStream_t stream);
   int forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream);
   int launches_per_forward() const { return cur_ ? cur_->launches : 0; }
+  // Eager forward with a CUDA event pair around every op; fills ms[i] for op i (returns number of ops, <0 on error).
+  int profile_forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream,
+                      float* ms, int max_ops);
+  const Prepared* current() const { return cur_; }
   bool use_graph = true;
   std::string last_error;
 

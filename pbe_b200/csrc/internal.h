@@ -80,6 +80,7 @@ struct GemmPlan {
 struct ConvGemmDesc {
   const bf16* act;  // NHWC activations [Nb, H, W, C]
   int Nb, H, W, C;  // input geometry (C % 64 == 0)
+  int c_real;       // channels that carry data (0 -> C); only used for FLOP accounting
   int ksize;        // 1 or 3 (pad = ksize/2)
   int stride;       // 1 or 2
   const bf16* wt;   // [ksize*ksize][Cout][C]

@@ -251,6 +251,30 @@ class UNetModel(nn.Module):
         self.set_context(context)
         return self.run(x, timesteps).to(x.dtype)
 
+    def profile(self, x: torch.Tensor, timesteps: torch.Tensor):
+        """Per-op device times of one eager forward: list of dicts(name, family, ms, flops, bytes)."""
+        self._ensure_engine(x.device)
+        lib = _lib.load()
+        x = x.detach().to(torch.float32).contiguous()
+        t = timesteps.detach().to(device=x.device, dtype=torch.int64).contiguous()
+        Bc, _, H, W = x.shape
+        out = torch.empty((Bc, self.out_channels, H, W), device=x.device, dtype=torch.float32)
+        ms = (ctypes.c_float * 4096)()
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            n = lib.pbe_profile_forward(self._engine, x.data_ptr(), t.data_ptr(), out.data_ptr(), Bc, H, W, st, ms, 4096)
+        if n < 0:
+            _lib.check(n, "pbe_profile_forward")
+        rows = []
+        for i in range(n):
+            name, fam = ctypes.c_char_p(), ctypes.c_char_p()
+            fl, by = ctypes.c_double(), ctypes.c_double()
+            _lib.check(lib.pbe_op_info(self._engine, i, ctypes.byref(name), ctypes.byref(fam), ctypes.byref(fl),
+                                       ctypes.byref(by)), "pbe_op_info")
+            rows.append(dict(name=name.value.decode(), family=fam.value.decode(), ms=float(ms[i]), flops=fl.value,
+                             bytes=by.value))
+        return rows
+
     def launches_per_forward(self) -> int:
         return int(_lib.load().pbe_launches_per_forward(self._engine)) if self._engine is not None else 0
 
