@@ -47,7 +47,7 @@ int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf
 }
 
 int64_t pbe_op_groupnorm_workspace_bytes(int Nb, int HW) {
-  return static_cast<int64_t>(Nb) * gn_num_slabs(HW) * 64 * sizeof(float);
+  return static_cast<int64_t>(gn_workspace_floats(Nb, HW, 2560)) * sizeof(float);
 }
 
 int pbe_op_groupnorm(const float* x0, int C0, const float* x1, int C1, int Nb, int HW, const float* gamma,

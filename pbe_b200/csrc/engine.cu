@@ -426,9 +426,9 @@ int Engine::build(Prepared& P, bool dry) {
     add_op_meta(name, 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); }, "conv_gemm", flops, bytes);
   };
   auto add_gn = [&](const std::string& name, GroupNormArgs a) {
-    a.partial = static_cast<float*>(SA(static_cast<size_t>(a.Nb) * gn_num_slabs(a.HW) * 64 * sizeof(float)));
+    a.partial = static_cast<float*>(SA(static_cast<size_t>(gn_workspace_floats(a.Nb, a.HW, a.C0 + a.C1)) * sizeof(float)));
     const double n = static_cast<double>(a.Nb) * a.HW * (a.C0 + a.C1);
-    add_op_meta(name, 2, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
+    add_op_meta(name, 3, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
                 n * (4.0 + 4.0 + 2.0 + (a.raw ? 2.0 : 0.0)));
   };
 
@@ -440,6 +440,7 @@ int Engine::build(Prepared& P, bool dry) {
   float* t_emb = static_cast<float*>(PA(static_cast<size_t>(Bc) * mc * sizeof(float)));
   float* t_hid = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
   float* emb = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
+  float* emb_silu = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
   float* emb_all = static_cast<float*>(PA(static_cast<size_t>(Bc) * emb_total_ * sizeof(float)));
   {
     const int64_t* tp = P.t_stage;
@@ -449,9 +450,10 @@ int Engine::build(Prepared& P, bool dry) {
     add_op("time_embed.0+silu", 1,
            [=](cudaStream_t s) { return launch_small_linear(t_emb, w0, b0, t_hid, Bc, mc, ted, 0, 1, s); });
     add_op("time_embed.2", 1,
-           [=](cudaStream_t s) { return launch_small_linear(t_hid, w1, b1, emb, Bc, ted, ted, 0, 0, s); });
+           [=](cudaStream_t s) { return launch_small_linear(t_hid, w1, b1, emb, Bc, ted, ted, 0, 0, s, emb_silu); });
+    // every ResBlock's emb_layers = Linear(SiLU(emb)) (openaimodel.py:218-224): SiLU once, all 22 Linears in one launch
     add_op("emb_layers(all)", 1,
-           [=](cudaStream_t s) { return launch_small_linear(emb, ew, eb, emb_all, Bc, ted, et, 1, 0, s); });
+           [=](cudaStream_t s) { return launch_small_linear(emb_silu, ew, eb, emb_all, Bc, ted, et, 0, 0, s); });
   }
 
   struct Act {

@@ -26,11 +26,26 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_THREADS = 192;
-constexpr int STAGE_LD = 33;  // epilogue transpose buffer row pitch (floats)
+constexpr int STAGE_LD = 36;  // epilogue transpose buffer row pitch (floats); 16-B aligned rows
+constexpr int STAGE_LD4 = STAGE_LD / 4;
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU (torch.nn.functional.gelu default). erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
+// the bf16 resolution of the stored result): 1 MUFU.RCP + 1 MUFU.EX2 + ~10 FMA instead of libdevice erff.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erfv = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erfv);
+}
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -143,6 +158,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
+    // Coalesced output pass shared by all modes: the 32x32 fp32 block staged in shared memory (thread = row) is
+    // re-read with lane = (row quad, 4 consecutive columns): every instruction touches 4 rows x 128 contiguous bytes.
+    const int rq = lane >> 3;           // row within a group of 4
+    const int cq = (lane & 7) * 4;      // first of my 4 columns inside the 32-column chunk
+    float4* stg4 = reinterpret_cast<float4*>(stg);
+
     if (p.mode == EPI_GEGLU) {
       // tile-local columns [0, BLOCK_N/2) = value half, [BLOCK_N/2, BLOCK_N) = gate half (weights pre-interleaved)
       constexpr int HALF = BLOCK_N / 2;
@@ -154,22 +175,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_x32(taddr + HALF + c0, vg);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float a = __uint_as_float(va[j]) + __ldg(p.bias + n_base + c0 + j);
-          const float g = __uint_as_float(vg[j]) + __ldg(p.bias + n_base + HALF + c0 + j);
-          stg[lane * STAGE_LD + j] = a * gelu_erf(g);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c0 + j));
+          const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + HALF + c0 + j));
+          float4 o;
+          o.x = (__uint_as_float(va[j + 0]) + ba.x) * gelu_erf(__uint_as_float(vg[j + 0]) + bg.x);
+          o.y = (__uint_as_float(va[j + 1]) + ba.y) * gelu_erf(__uint_as_float(vg[j + 1]) + bg.y);
+          o.z = (__uint_as_float(va[j + 2]) + ba.z) * gelu_erf(__uint_as_float(vg[j + 2]) + bg.z);
+          o.w = (__uint_as_float(va[j + 3]) + ba.w) * gelu_erf(__uint_as_float(vg[j + 3]) + bg.w);
+          stg4[lane * STAGE_LD4 + (j >> 2)] = o;
         }
         __syncwarp();
-        const int col = out_col0 + c0 + lane;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
+        const int col = out_col0 + c0 + cq;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rq;
           const long long m = __shfl_sync(0xffffffffu, my_m, r);
-          const bool v = __shfl_sync(0xffffffffu, my_valid ? 1 : 0, r);
-          if (v) p.out_bf16[m * p.ld_out + col] = __float2bfloat16(stg[r * STAGE_LD + lane]);
+          const int vb = __shfl_sync(0xffffffffu, my_valid ? 1 : 0, r);
+          if (vb) {
+            const float4 x = stg4[r * STAGE_LD4 + (cq >> 2)];
+            uint2 pk;
+            pk.x = pack_bf16x2(x.x, x.y);
+            pk.y = pack_bf16x2(x.z, x.w);
+            *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + col) = pk;
+          }
         }
         __syncwarp();
       }
     } else {
+      const float* __restrict__ residual = p.residual;
+      const float* __restrict__ rowbias = p.rowbias;
+      float* __restrict__ out_f32 = p.out_f32;
+      bf16* __restrict__ out_bf16 = p.out_bf16;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         if (n_base + c0 >= p.n_total) break;
@@ -189,22 +226,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           continue;
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * STAGE_LD + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; j += 4)
+          stg4[lane * STAGE_LD4 + (j >> 2)] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         __syncwarp();
-        const int col = n_base + c0 + lane;
-        const bool colv = col < p.n_total;
-        const float bias_v = (p.bias != nullptr && colv) ? __ldg(p.bias + col) : 0.0f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
+        const int col = n_base + c0 + cq;
+        const bool colv = col < p.n_total;  // n_total % 4 == 0
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && colv) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        // issue every global read of this chunk before the first dependent use (8 independent 16-B loads per lane)
+        long long moff[8];
+        float4 add4[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rq;
           const long long m = __shfl_sync(0xffffffffu, my_m, r);
           const int vb = __shfl_sync(0xffffffffu, my_valid ? on : -1, r);
-          if (vb >= 0 && colv) {
-            float x = stg[r * STAGE_LD + lane] + bias_v;
-            if (p.rowbias != nullptr) x += __ldg(p.rowbias + static_cast<long long>(vb) * p.rowbias_ld + col);
-            const long long o = m * p.ld_out + col;
-            if (p.residual != nullptr) x += __ldg(p.residual + o);
-            if (p.out_f32 != nullptr) p.out_f32[o] = x;
-            if (p.out_bf16 != nullptr) p.out_bf16[o] = __float2bfloat16(x);
+          moff[it] = (vb >= 0 && colv) ? m * p.ld_out + col : -1;
+          float4 a = bias4;
+          if (moff[it] >= 0) {
+            if (residual != nullptr) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + moff[it]));
+              a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+            }
+            if (rowbias != nullptr) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(rowbias + static_cast<long long>(vb) * p.rowbias_ld + col));
+              a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
+            }
+          }
+          add4[it] = a;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (moff[it] >= 0) {
+            const int r = it * 4 + rq;
+            float4 x = stg4[r * STAGE_LD4 + (cq >> 2)];
+            x.x += add4[it].x; x.y += add4[it].y; x.z += add4[it].z; x.w += add4[it].w;
+            if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + moff[it]) = x;
+            if (out_bf16 != nullptr) {
+              uint2 pk;
+              pk.x = pack_bf16x2(x.x, x.y);
+              pk.y = pack_bf16x2(x.z, x.w);
+              *reinterpret_cast<uint2*>(out_bf16 + moff[it]) = pk;
+            }
           }
         }
         __syncwarp();
@@ -260,6 +324,7 @@ void pick_tile(int Wo, int Ho, int Nb, int* tw, int* th, int* tn) {
 int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   PBE_REQUIRE(d.C % 64 == 0, "activation channels must be a multiple of 64");
   PBE_REQUIRE(d.ksize == 1 || d.ksize == 3, "kernel size 1 or 3");
+  PBE_REQUIRE(d.Cout % 4 == 0 && d.ld_out % 4 == 0 && d.rowbias_ld % 4 == 0, "output columns / leading dims % 4");
   PBE_REQUIRE(d.stride == 1 || d.stride == 2, "stride 1 or 2");
   PBE_REQUIRE(d.stride == 1 || (d.H % 2 == 0 && d.W % 2 == 0 && d.ksize == 3), "stride-2 conv needs even H, W, k=3");
   ConvGemmParams& p = plan->p;

@@ -128,9 +128,10 @@ struct GroupNormArgs {
   const float* gamma; const float* beta;
   float eps; int silu;
   bf16* y; bf16* raw;        // raw may be null
-  float* partial;            // workspace: [Nb][slabs][32][2] floats, slabs = gn_num_slabs(HW)
+  float* partial;            // workspace of gn_workspace_floats(Nb, HW, C0+C1) floats (16-B aligned)
 };
 int gn_num_slabs(int HW);
+int gn_workspace_floats(int Nb, int HW, int C);
 int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream);
 
 // LayerNorm over the last dim of fp32 [M, C] -> bf16 [M, C]
@@ -149,8 +150,9 @@ int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, in
 
 // Small dense layers on CUDA cores (M = batch rows only): y[b, o] = act_in(x[b, :]) . W[o, :] + bias[o]
 // pre_silu applies SiLU to x on load. W is fp32 [O, K] row-major.
+// y_silu (optional) additionally receives silu(y) so consumers that all start with SiLU apply it once.
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
-                        int post_silu, cudaStream_t stream);
+                        int post_silu, cudaStream_t stream, float* y_silu = nullptr);
 // sinusoidal timestep embedding [B, dim] (cos || sin), reference util.py:151-171
 int launch_timestep_embedding(const int64_t* t, float* out, int B, int dim, cudaStream_t stream);
 // y[b, n] = a[n] + v[b, n]

@@ -85,7 +85,8 @@ __device__ __forceinline__ float silu_f(float t) { return t / (1.0f + expf(-t));
 // one warp per output feature; batch rows processed 8 at a time
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ y,
-                                                           int B, int K, int O, int pre_silu, int post_silu) {
+                                                           float* __restrict__ y_silu, int B, int K, int O,
+                                                           int pre_silu, int post_silu) {
   const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= O) return;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
           float v = acc[i] + (bias ? bias[o] : 0.0f);
           if (post_silu) v = silu_f(v);
           y[static_cast<long long>(b0 + i) * O + o] = v;
+          if (y_silu) y_silu[static_cast<long long>(b0 + i) * O + o] = silu_f(v);
         }
       }
     }
@@ -181,9 +183,9 @@ int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, in
 }
 
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
-                        int post_silu, cudaStream_t stream) {
+                        int post_silu, cudaStream_t stream, float* y_silu) {
   PBE_REQUIRE(K % 4 == 0, "small_linear K % 4");
-  small_linear_kernel<<<(O + 7) / 8, 256, 0, stream>>>(x, W, bias, y, B, K, O, pre_silu, post_silu);
+  small_linear_kernel<<<(O + 7) / 8, 256, 0, stream>>>(x, W, bias, y, y_silu, B, K, O, pre_silu, post_silu);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

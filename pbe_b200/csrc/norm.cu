@@ -13,56 +13,89 @@ namespace pbe {
 
 namespace {
 
-constexpr int GN_THREADS = 256;
-constexpr int GN_MAX_COLS = 5;  // float2 columns per thread: C/2 <= 5*256 -> C <= 2560
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
-__device__ __forceinline__ float2 ld2(const float* x0, int C0, const float* x1, int C1, long long pix, int c) {
-  // c even; C0 even
-  if (c < C0) return *reinterpret_cast<const float2*>(x0 + pix * C0 + c);
-  return *reinterpret_cast<const float2*>(x1 + pix * C1 + (c - C0));
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_C = 2560;
+
+__device__ __forceinline__ float4 ld4(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                                      long long pix, int c) {
+  // c % 4 == 0, C0 % 4 == 0: a float4 never straddles the concat seam
+  if (c < C0) return __ldg(reinterpret_cast<const float4*>(x0 + pix * C0 + c));
+  return __ldg(reinterpret_cast<const float4*>(x1 + pix * C1 + (c - C0)));
 }
 
 // grid (slabs, Nb). partial[b][slab][g] = (sum, sumsq) over the slab's pixels and the group's channels.
+// Threads own float4 channel columns (per-CHANNEL accumulators, so group boundaries that are not multiples of 4
+// channels - 10, 30 channels per group - need no special casing); narrow tensors split the block over several pixel
+// rows; four pixels are in flight per thread.
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x0, int C0,
                                                               const float* __restrict__ x1, int C1, int HW, int slabs,
                                                               float* __restrict__ partial) {
-  __shared__ float s_sum[GN_THREADS * GN_MAX_COLS];
-  __shared__ float s_sq[GN_THREADS * GN_MAX_COLS];
+  __shared__ float s_sum[GN_MAX_C];
+  __shared__ float s_sq[GN_MAX_C];
   const int C = C0 + C1;
-  const int ncols = C / 2;
+  const int ncol4 = C / 4;
   const int b = blockIdx.y;
   const int slab = blockIdx.x;
   const int pix_per = (HW + slabs - 1) / slabs;
   const int p0 = slab * pix_per;
   const int p1 = min(HW, p0 + pix_per);
-  float sum[GN_MAX_COLS], sq[GN_MAX_COLS];
-#pragma unroll
-  for (int i = 0; i < GN_MAX_COLS; ++i) sum[i] = sq[i] = 0.0f;
-  for (int pix = p0; pix < p1; ++pix) {
-    const long long gp = static_cast<long long>(b) * HW + pix;
-#pragma unroll
-    for (int i = 0; i < GN_MAX_COLS; ++i) {
-      const int col = threadIdx.x + i * GN_THREADS;
-      if (col < ncols) {
-        const float2 v = ld2(x0, C0, x1, C1, gp, col * 2);
-        sum[i] += v.x + v.y;
-        sq[i] += v.x * v.x + v.y * v.y;
+  const int rows_par = ncol4 <= GN_THREADS ? GN_THREADS / ncol4 : 1;
+  const int ncols_thr = ncol4 <= GN_THREADS ? 1 : (ncol4 + GN_THREADS - 1) / GN_THREADS;  // <= 3
+  const int prow = ncol4 <= GN_THREADS ? threadIdx.x / ncol4 : 0;
+  const int col0 = ncol4 <= GN_THREADS ? threadIdx.x % ncol4 : threadIdx.x;
+  const bool active = prow < rows_par;
+  const long long base = static_cast<long long>(b) * HW;
+  for (int ci = 0; ci < ncols_thr; ++ci) {
+    const int col = col0 + ci * GN_THREADS;
+    float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
+    if (active && col < ncol4) {
+      const int c = col * 4;
+      int pix = p0 + prow;
+      for (; pix + 3 * rows_par < p1; pix += 4 * rows_par) {
+        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c);
+        const float4 a1 = ld4(x0, C0, x1, C1, base + pix + rows_par, c);
+        const float4 a2 = ld4(x0, C0, x1, C1, base + pix + 2 * rows_par, c);
+        const float4 a3 = ld4(x0, C0, x1, C1, base + pix + 3 * rows_par, c);
+        sx += (a0.x + a1.x) + (a2.x + a3.x); qx += (a0.x * a0.x + a1.x * a1.x) + (a2.x * a2.x + a3.x * a3.x);
+        sy += (a0.y + a1.y) + (a2.y + a3.y); qy += (a0.y * a0.y + a1.y * a1.y) + (a2.y * a2.y + a3.y * a3.y);
+        sz += (a0.z + a1.z) + (a2.z + a3.z); qz += (a0.z * a0.z + a1.z * a1.z) + (a2.z * a2.z + a3.z * a3.z);
+        sw += (a0.w + a1.w) + (a2.w + a3.w); qw += (a0.w * a0.w + a1.w * a1.w) + (a2.w * a2.w + a3.w * a3.w);
+      }
+      for (; pix < p1; pix += rows_par) {
+        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c);
+        sx += a0.x; qx += a0.x * a0.x;
+        sy += a0.y; qy += a0.y * a0.y;
+        sz += a0.z; qz += a0.z * a0.z;
+        sw += a0.w; qw += a0.w * a0.w;
       }
     }
+    // cross-row reduction in a fixed order: row r adds into the channel slot after rows < r
+    for (int r = 0; r < rows_par; ++r) {
+      if (active && prow == r && col < ncol4) {
+        const int c = col * 4;
+        if (r == 0) {
+          s_sum[c] = sx; s_sum[c + 1] = sy; s_sum[c + 2] = sz; s_sum[c + 3] = sw;
+          s_sq[c] = qx; s_sq[c + 1] = qy; s_sq[c + 2] = qz; s_sq[c + 3] = qw;
+        } else {
+          s_sum[c] += sx; s_sum[c + 1] += sy; s_sum[c + 2] += sz; s_sum[c + 3] += sw;
+          s_sq[c] += qx; s_sq[c + 1] += qy; s_sq[c + 2] += qz; s_sq[c + 3] += qw;
+        }
+      }
+      __syncthreads();
+    }
   }
-#pragma unroll
-  for (int i = 0; i < GN_MAX_COLS; ++i) {
-    s_sum[threadIdx.x + i * GN_THREADS] = sum[i];
-    s_sq[threadIdx.x + i * GN_THREADS] = sq[i];
-  }
-  __syncthreads();
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
-    const int cols_per_group = ncols / 32;
+    const int cpg = C / 32;
     float a = 0.0f, q = 0.0f;
-    for (int i = 0; i < cols_per_group; ++i) {
-      a += s_sum[g * cols_per_group + i];
-      q += s_sq[g * cols_per_group + i];
+    for (int i = 0; i < cpg; ++i) {
+      a += s_sum[g * cpg + i];
+      q += s_sq[g * cpg + i];
     }
     float* dst = partial + ((static_cast<long long>(b) * slabs + slab) * 32 + g) * 2;
     dst[0] = a;
@@ -70,18 +103,13 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
   }
 }
 
-// grid (pixel blocks, Nb)
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x0, int C0,
-                                                              const float* __restrict__ x1, int C1, int HW, int slabs,
-                                                              const float* __restrict__ partial,
-                                                              const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, float eps, int silu,
-                                                              bf16* __restrict__ y, bf16* __restrict__ raw,
-                                                              int pix_per_block) {
-  extern __shared__ float s_ab[];  // a[C], b[C]
+// grid (Nb): per-(sample, channel) affine y = x * a + b with a = gamma * rstd, b = beta - mean * a.
+__global__ void __launch_bounds__(GN_THREADS) gn_finalize_kernel(const float* __restrict__ partial, int slabs, int HW,
+                                                                 int C, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps,
+                                                                 float2* __restrict__ ab) {
   __shared__ float s_mean[32], s_rstd[32];
-  const int C = C0 + C1;
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
     double a = 0.0, q = 0.0;
@@ -102,42 +130,40 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
   for (int c = threadIdx.x; c < C; c += GN_THREADS) {
     const int g = c / cpg;
     const float a = gamma[c] * s_rstd[g];
-    s_ab[c] = a;
-    s_ab[C + c] = beta[c] - s_mean[g] * a;
+    ab[static_cast<long long>(b) * C + c] = make_float2(a, beta[c] - s_mean[g] * a);
   }
-  __syncthreads();
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
+}
+
+// pure streaming pass: one float4 of x per thread-iteration
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x0, int C0,
+                                                              const float* __restrict__ x1, int C1, int HW,
+                                                              long long total_vec, const float2* __restrict__ ab,
+                                                              int silu, bf16* __restrict__ y, bf16* __restrict__ raw) {
+  const int C = C0 + C1;
   const int vec_per_pix = C / 4;
-  const int total = (p1 - p0) * vec_per_pix;
-  for (int idx = threadIdx.x; idx < total; idx += GN_THREADS) {
-    const int pix = p0 + idx / vec_per_pix;
-    const int c = (idx % vec_per_pix) * 4;
-    const long long gp = static_cast<long long>(b) * HW + pix;
-    float4 v;
-    if (c < C0) v = *reinterpret_cast<const float4*>(x0 + gp * C0 + c);
-    else v = *reinterpret_cast<const float4*>(x1 + gp * C1 + (c - C0));
-    float r[4] = {v.x, v.y, v.z, v.w};
-    float o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float t = r[i] * s_ab[c + i] + s_ab[C + c + i];
-      if (silu) t = t / (1.0f + __expf(-t));
-      o[i] = t;
+  for (long long idx = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; idx < total_vec;
+       idx += static_cast<long long>(gridDim.x) * GN_THREADS) {
+    const long long gp = idx / vec_per_pix;
+    const int c = static_cast<int>(idx - gp * vec_per_pix) * 4;
+    const int b = static_cast<int>(gp / HW);
+    const float4 v = ld4(x0, C0, x1, C1, gp, c);
+    const float4 ab01 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c));
+    const float4 ab23 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
+    float o0 = fmaf(v.x, ab01.x, ab01.y), o1 = fmaf(v.y, ab01.z, ab01.w);
+    float o2 = fmaf(v.z, ab23.x, ab23.y), o3 = fmaf(v.w, ab23.z, ab23.w);
+    if (silu) {
+      o0 = o0 / (1.0f + __expf(-o0)); o1 = o1 / (1.0f + __expf(-o1));
+      o2 = o2 / (1.0f + __expf(-o2)); o3 = o3 / (1.0f + __expf(-o3));
     }
     const long long off = gp * C + c;
-    __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]);
-    __nv_bfloat162 hi = __floats2bfloat162_rn(o[2], o[3]);
     uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    pk.x = pack2(o0, o1);
+    pk.y = pack2(o2, o3);
     *reinterpret_cast<uint2*>(y + off) = pk;
     if (raw != nullptr) {
-      __nv_bfloat162 rlo = __floats2bfloat162_rn(r[0], r[1]);
-      __nv_bfloat162 rhi = __floats2bfloat162_rn(r[2], r[3]);
       uint2 rk;
-      rk.x = *reinterpret_cast<uint32_t*>(&rlo);
-      rk.y = *reinterpret_cast<uint32_t*>(&rhi);
+      rk.x = pack2(v.x, v.y);
+      rk.y = pack2(v.z, v.w);
       *reinterpret_cast<uint2*>(raw + off) = rk;
     }
   }
@@ -205,18 +231,26 @@ int gn_num_slabs(int HW) {
   return s;
 }
 
+int gn_workspace_floats(int Nb, int HW, int C) {
+  return Nb * gn_num_slabs(HW) * 64 + Nb * C * 2 + 64;
+}
+
 int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   const int C = a.C0 + a.C1;
-  PBE_REQUIRE(C % 64 == 0 && C <= 2 * GN_THREADS * GN_MAX_COLS, "GroupNorm channels must be a multiple of 64, <= 2560");
+  PBE_REQUIRE(C % 64 == 0 && C <= GN_MAX_C, "GroupNorm channels must be a multiple of 64, <= 2560");
   PBE_REQUIRE(a.C0 % 4 == 0 && a.C1 % 4 == 0, "GroupNorm concat halves must be multiples of 4 channels");
   const int slabs = gn_num_slabs(a.HW);
-  gn_stats_kernel<<<dim3(slabs, a.Nb), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, slabs, a.partial);
+  float* partial = a.partial;
+  float2* ab = reinterpret_cast<float2*>(a.partial + ((static_cast<size_t>(a.Nb) * slabs * 64 + 3) & ~static_cast<size_t>(3)));
+  gn_stats_kernel<<<dim3(slabs, a.Nb), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial);
   PBE_CHECK_CUDA(cudaGetLastError());
-  int pix_per_block = (64 * 1024) / (C * 4);  // ~64 KB of input per block
-  if (pix_per_block < 1) pix_per_block = 1;
-  const int blocks = (a.HW + pix_per_block - 1) / pix_per_block;
-  gn_apply_kernel<<<dim3(blocks, a.Nb), GN_THREADS, 2 * C * sizeof(float), stream>>>(
-      a.x0, a.C0, a.x1, a.C1, a.HW, slabs, a.partial, a.gamma, a.beta, a.eps, a.silu, a.y, a.raw, pix_per_block);
+  gn_finalize_kernel<<<a.Nb, GN_THREADS, 0, stream>>>(partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab);
+  PBE_CHECK_CUDA(cudaGetLastError());
+  const long long total_vec = static_cast<long long>(a.Nb) * a.HW * (C / 4);
+  long long blocks = (total_vec + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
+  if (blocks < 1) blocks = 1;
+  gn_apply_kernel<<<static_cast<unsigned>(blocks), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, total_vec, ab,
+                                                                         a.silu, a.y, a.raw);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
