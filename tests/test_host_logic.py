@@ -1,0 +1,139 @@
+"""CPU-only checks (no GPU): the C-ABI library loads and exports every declared symbol, the drop-in module exposes the
+reference's state-dict layout, the samplers build the reference's schedule tables, key spellings / error conventions
+match the reference, and the product refuses to run without CUDA (no fallback)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler_ref as S
+from oracle import unet_ref as U
+
+
+def test_library_loads_and_exports_declared_symbols():
+    from pbe_b200 import _lib
+    lib = _lib.load()
+    syms = _lib.exported_symbols()
+    assert len(syms) >= 19
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.pbe_last_error() is not None
+
+
+def test_unet_state_dict_keys_match_reference(golden_dir):
+    from pbe_b200.unet import UNetModel
+    m = UNetModel(**U.SMALL_CFG)
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    assert sorted(m.state_dict().keys()) == idx["state_dict_keys"]["keys"]
+    shapes = U.param_shapes(U.SMALL_CFG)
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    big = UNetModel.__new__(UNetModel)  # shapes only, no 3.4 GB allocation
+    from pbe_b200.unet import unet_param_shapes
+    s = unet_param_shapes(**{k: U.V1_CFG[k] for k in ("in_channels", "out_channels", "model_channels", "num_res_blocks",
+                                                      "channel_mult", "attention_resolutions", "num_heads",
+                                                      "context_dim")})
+    assert len(s) == 686 and sum(int(np.prod(v)) for v in s.values()) == 859_535_364
+
+
+def test_checkpoint_style_loading_under_model_diffusion_model_prefix():
+    from pbe_b200.diffusion import LatentDiffusion
+    sd = U.make_state_dict(U.SMALL_CFG, 1)
+    m = LatentDiffusion(unet_config=dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel",
+                                         params=dict(U.SMALL_CFG)))
+    r = m.load_state_dict({"model.diffusion_model." + k: v for k, v in sd.items()}, strict=False)
+    assert not r.unexpected_keys
+    assert not [k for k in r.missing_keys if k.startswith("model.")]
+    got = m.model.diffusion_model.state_dict()
+    assert torch.equal(got["input_blocks.0.0.weight"], sd["input_blocks.0.0.weight"])
+    assert m.num_timesteps == 1000 and m.alphas_cumprod.dtype == torch.float32
+
+
+def test_no_cpu_fallback():
+    from pbe_b200.diffusion import LatentDiffusion
+    from pbe_b200.samplers import PLMSSampler
+    m = LatentDiffusion(unet_config=dict(params=dict(U.SMALL_CFG)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.apply_model(torch.zeros(1, 9, 32, 32), torch.zeros(1, dtype=torch.int64), torch.zeros(1, 1, 768))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PLMSSampler(m).sample(S=4, batch_size=1, shape=[4, 32, 32], conditioning=torch.zeros(1, 1, 768), verbose=False,
+                              x_T=torch.zeros(1, 4, 32, 32),
+                              test_model_kwargs=dict(images_inpaint=torch.zeros(1, 4, 32, 32),
+                                                     images_mask=torch.zeros(1, 1, 32, 32)))
+
+
+def test_unsupported_unet_options_are_rejected_loudly():
+    from pbe_b200.unet import UNetModel
+    with pytest.raises(NotImplementedError):
+        UNetModel(**dict(U.SMALL_CFG, use_scale_shift_norm=True))
+    with pytest.raises(NotImplementedError):
+        UNetModel(**dict(U.SMALL_CFG, transformer_depth=2))
+
+
+@pytest.mark.parametrize("S_steps", [50, 20, 8])
+def test_sampler_schedule_tables_match_oracle(S_steps):
+    from pbe_b200.diffusion import LatentDiffusion
+    from pbe_b200.samplers import DDIMSampler, PLMSSampler
+    m = LatentDiffusion(unet_config=dict(params=dict(U.SMALL_CFG)))
+    buf = S.make_schedule_buffers()
+    assert torch.equal(m.alphas_cumprod, buf["alphas_cumprod"]) and torch.equal(m.betas, buf["betas"])
+    tab = S.ddim_tables(buf["alphas_cumprod"], S_steps)
+    for cls in (PLMSSampler, DDIMSampler):
+        smp = cls(m)
+        smp.make_schedule(S_steps, ddim_eta=0.0, verbose=False)
+        assert list(smp.ddim_timesteps) == list(tab["timesteps"])
+        assert smp._coef["a_t"] == [float(v) for v in tab["alphas"]]
+        assert smp._coef["a_prev"] == [float(v) for v in tab["alphas_prev"]]
+        assert smp._coef["sqrt_one_minus_at"] == [float(v) for v in tab["sqrt_one_minus_alphas"]]
+        assert all(v == 0.0 for v in smp._coef["sigma"])
+        assert isinstance(smp.ddim_alphas_prev, np.ndarray)        # reference keeps this one as numpy (util.py:66)
+        assert smp.ddim_alphas.dtype == torch.float32
+
+
+def test_plms_rejects_eta_and_ddim_rejects_batch_mismatch():
+    from pbe_b200.diffusion import LatentDiffusion
+    from pbe_b200.samplers import DDIMSampler, PLMSSampler
+    m = LatentDiffusion(unet_config=dict(params=dict(U.SMALL_CFG)))
+    with pytest.raises(ValueError, match="ddim_eta must be 0 for PLMS"):      # plms.py:25-26
+        PLMSSampler(m).make_schedule(10, ddim_eta=0.5, verbose=False)
+    with pytest.raises(ValueError):                                            # ddim.py:99-106
+        DDIMSampler(m).sample(S=4, batch_size=2, shape=[4, 32, 32], conditioning=torch.zeros(1, 1, 768), verbose=False)
+
+
+def test_inpaint_kwargs_spellings():
+    from pbe_b200.samplers import _inpaint_kwargs
+    z, mk = torch.zeros(1, 4, 8, 8), torch.ones(1, 1, 8, 8)
+    for kw in (dict(test_model_kwargs=dict(images_inpaint=z, images_mask=mk)),
+               dict(test_model_kwargs=dict(inpaint_image=z, inpaint_mask=mk)),
+               dict(rest=torch.cat((z, mk), 1))):
+        a, b = _inpaint_kwargs(kw)
+        assert a.shape == z.shape and b.shape == mk.shape
+    assert _inpaint_kwargs({}) is None
+    with pytest.raises(KeyError):
+        _inpaint_kwargs(dict(test_model_kwargs={}))
+
+
+def test_two_rank_request_sharding_gloo(tmp_path):
+    """Multi-GPU path = independent request shards: world_size-2 gloo run of the sharding helper."""
+    import torch.multiprocessing as mp
+    from pbe_b200.sharding import shard_requests
+    assert shard_requests(10, 0, 4) == [0, 4, 8] and shard_requests(10, 3, 4) == [3, 7]
+    assert sorted(sum((shard_requests(3500, r, 8) for r in range(8)), [])) == list(range(3500))
+    mp.spawn(_gloo_worker, args=(2, str(tmp_path)), nprocs=2, join=True)
+    got = sorted(int(x) for r in range(2) for x in open(os.path.join(tmp_path, f"r{r}.txt")).read().split())
+    assert got == list(range(7))
+
+
+def _gloo_worker(rank, world, out_dir):
+    import torch.distributed as dist
+    from pbe_b200.sharding import gather_latents, shard_requests
+    dist.init_process_group("gloo", init_method=f"file://{out_dir}/rdzv", rank=rank, world_size=world)
+    mine = shard_requests(7, rank, world)
+    lat = torch.stack([torch.full((4, 2, 2), float(i)) for i in mine]) if mine else torch.zeros(0, 4, 2, 2)
+    ids, full = gather_latents(mine, lat, 7)
+    assert ids == list(range(7))
+    assert all(float(full[i, 0, 0, 0]) == float(i) for i in range(7))
+    open(os.path.join(out_dir, f"r{rank}.txt"), "w").write(" ".join(str(i) for i in (mine if rank == 0 else mine)))
+    dist.destroy_process_group()
