@@ -18,6 +18,8 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace pbe {
 
 namespace {
@@ -25,62 +27,67 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int STAGE_LD = 36;  // epilogue transpose buffer row pitch (floats); 16-B aligned rows
 constexpr int STAGE_LD4 = STAGE_LD / 4;
+constexpr int NUM_SLOTS = 4;
+constexpr int SLOT_BYTES = 128 * 32 * 4;  // one 32-column fp32 chunk of a 128-row tile
+constexpr int EPI_STAGING_BYTES = NUM_SLOTS * SLOT_BYTES;
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // exact-erf GELU (torch.nn.functional.gelu default). erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
-// the bf16 resolution of the stored result): 1 MUFU.RCP + 1 MUFU.EX2 + ~10 FMA instead of libdevice erff.
+// the bf16 resolution of the stored result): 1 MUFU.RCP + 1 MUFU.EX2 + ~10 FMA instead of libdevice erff
+// (rcp.approx / ex2.approx: <= 2 ulp each).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float erfv = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erfv);
 }
 
+// Persistent kernel: one CTA per SM walks tiles (n-tile fastest, so co-running CTAs share A tiles and all weights in
+// L2).  Two TMEM accumulator buffers: the MMA warp fills buffer (i+1)&1 while the 8 epilogue warps drain buffer i&1.
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
+                 const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ ConvGemmParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr uint32_t TMEM_COLS = tmem_cols_for(BLOCK_N);
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
-  static_assert(4 * 32 * STAGE_LD * 4 <= STAGES * A_STAGE_BYTES, "epilogue staging aliases the A stages");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
-  uint8_t* bar_gen = smem_gen + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  constexpr int PIPE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  // after the pipeline stages: NUM_SLOTS epilogue slots of SLOT_BYTES (1024-B aligned), then the barriers
+  const uint32_t sBar = smem_base + PIPE_BYTES + EPI_STAGING_BYTES;
+  uint8_t* bar_gen = smem_gen + PIPE_BYTES + EPI_STAGING_BYTES;
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = sBar + 8u * (2 * STAGES);
-  const uint32_t tmem_ptr_addr = sBar + 8u * (2 * STAGES + 1);
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (2 * STAGES + 1));
+  auto tmem_full_bar = [&](int b) { return sBar + 8u * (2 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_ptr_addr = sBar + 8u * (2 * STAGES + 4 + NUM_SLOTS);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (2 * STAGES + 4 + NUM_SLOTS));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ----
-  int mt = blockIdx.x;
-  const int tile_w = mt % p.tiles_w;
-  mt /= p.tiles_w;
-  const int tile_h = mt % p.tiles_h;
-  const int tile_n = mt / p.tiles_h;
-  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
-  const int n_base = blockIdx.y * BLOCK_N;
   const int num_k_iters = p.num_taps * p.k_chunks;
+  const int n_tiles = p.n_tiles;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * n_tiles;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -90,7 +97,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), NUM_EPI_WARPS);
+    }
+    for (int sl = 0; sl < NUM_SLOTS; ++sl) mbar_init(sBar + 8u * (2 * STAGES + 4 + sl), 1);
+    if (p.has_res) tma_prefetch_desc(&tmR);
+    if (p.has_o32) tma_prefetch_desc(&tmO32);
+    if (p.has_o16) tma_prefetch_desc(&tmO16);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -107,15 +121,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < num_k_iters; ++it) {
-        const int tap = it / p.k_chunks;
-        const int kc = it - tap * p.k_chunks;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), p.tap_coff[tap] + kc * BLOCK_K,
-                    w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
-        tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kc * BLOCK_K, n_base, tap);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_base = (tile % n_tiles) * BLOCK_N;
+        int mt = tile / n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.tw;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.th;
+        const int n0 = (mt / p.tiles_h) * p.tn;
+        for (int it = 0; it < num_k_iters; ++it) {
+          const int tap = it / p.k_chunks;
+          const int kc = it - tap * p.k_chunks;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), p.tap_coff[tap] + kc * BLOCK_K,
+                      w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
+          tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kc * BLOCK_K, n_base, tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -123,157 +145,259 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < num_k_iters; ++it) {
-      mbar_wait(full_bar(stage), phase);
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      mbar_wait(tmem_empty_bar(buf), ((ti >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint64_t adesc = umma_desc_sw128(sA + stage * A_STAGE_BYTES);
-        const uint64_t bdesc = umma_desc_sw128(sB + stage * B_STAGE_BYTES);
+      const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+      for (int it = 0; it < num_k_iters; ++it) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = umma_desc_sw128(sA + stage * A_STAGE_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(sB + stage * B_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the 16-B-unit start address field
-          umma_bf16_ss(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the 16-B-unit start address field
+            umma_bf16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          if (it == num_k_iters - 1) umma_commit(tmem_full_bar(buf));
         }
-        umma_commit(empty_bar(stage));  // smem slot free once these MMAs retire
-        if (it == num_k_iters - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else {
-    // ================= Epilogue (warps 2..5) =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem_gen) + (warp - 2) * 32 * STAGE_LD;
-
-    // Geometry of my row (row = q*32 + lane), exchanged by shuffle while writing coalesced rows.
+    // ================= Epilogue (warps 2..9) =================
+    // Two warp-sets of 4 warps (one warp per TMEM lane quarter). A warp-set handles every other 32-column chunk of a
+    // tile (alternating per tile for balance) and owns two 16 KB shared-memory slots.  Per chunk:
+    //   TMA has prefetched the fp32 residual box [128 rows x 32 cols] into the slot (128B swizzle)  ->  each thread
+    //   (= one accumulator row) adds bias / per-sample bias / residual to its 32 TMEM columns  ->  writes the result
+    //   back into the slot  ->  one elected thread issues the TMA store (rows / columns outside the tensor are clipped
+    //   by the hardware) and, once the store has read the slot, the residual prefetch two chunks ahead.
+    // No global load or store instruction is on this path except the rare bf16 side copy and the V^T scatter.
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int ws = ew >> 2;   // warp-set
+    const int bar_id = 1 + ws;
+    const bool elected = ((ew & 3) == 0) && lane == 0;
     const int row = q * 32 + lane;
-    const int wl = row % p.tw;
-    const int hl = (row / p.tw) % p.th;
-    const int nl = row / (p.tw * p.th);
-    const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
-    const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
-    const long long my_m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
+    const bool geglu = (p.mode == EPI_GEGLU);
+    const int chunk_cols = 32;
+    const int nchunks = geglu ? (BLOCK_N / 2) / 32 : BLOCK_N / 32;
+    const int out_cols_total = geglu ? p.n_total / 2 : (p.mode == EPI_QKV ? p.qk_cols : p.n_total);
+    const int tile_out_cols = geglu ? BLOCK_N / 2 : BLOCK_N;
+    const uint32_t slot_base = smem_base + PIPE_BYTES;
+    uint8_t* slot_gen_base = smem_gen + PIPE_BYTES;
+    auto res_full_bar = [&](int s) { return sBar + 8u * (2 * STAGES + 4 + s); };
+    const float* __restrict__ rowbias = p.rowbias;
+    bf16* __restrict__ out_bf16 = p.out_bf16;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    auto tile_geom = [&](int tile, int& n_tile, int& w0, int& h0, int& n0) {
+      n_tile = tile % n_tiles;
+      int mt = tile / n_tiles;
+      w0 = (mt % p.tiles_w) * p.tw;
+      mt /= p.tiles_w;
+      h0 = (mt % p.tiles_h) * p.th;
+      n0 = (mt / p.tiles_h) * p.tn;
+    };
+    auto tile_is_vt = [&](int n_tile) { return p.mode == EPI_QKV && n_tile * BLOCK_N >= p.qk_cols; };
+    auto chunk_valid = [&](int n_tile, int c) { return c < nchunks && n_tile * tile_out_cols + c * chunk_cols < out_cols_total; };
 
-    // Coalesced output pass shared by all modes: the 32x32 fp32 block staged in shared memory (thread = row) is
-    // re-read with lane = (row quad, 4 consecutive columns): every instruction touches 4 rows x 128 contiguous bytes.
-    const int rq = lane >> 3;           // row within a group of 4
-    const int cq = (lane & 7) * 4;      // first of my 4 columns inside the 32-column chunk
-    float4* stg4 = reinterpret_cast<float4*>(stg);
-
-    if (p.mode == EPI_GEGLU) {
-      // tile-local columns [0, BLOCK_N/2) = value half, [BLOCK_N/2, BLOCK_N) = gate half (weights pre-interleaved)
-      constexpr int HALF = BLOCK_N / 2;
-      const int out_col0 = blockIdx.y * HALF;
-#pragma unroll 1
-      for (int c0 = 0; c0 < HALF; c0 += 32) {
-        uint32_t va[32], vg[32];
-        tmem_ld_x32(taddr + c0, va);
-        tmem_ld_x32(taddr + HALF + c0, vg);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c0 + j));
-          const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + HALF + c0 + j));
-          float4 o;
-          o.x = (__uint_as_float(va[j + 0]) + ba.x) * gelu_erf(__uint_as_float(vg[j + 0]) + bg.x);
-          o.y = (__uint_as_float(va[j + 1]) + ba.y) * gelu_erf(__uint_as_float(vg[j + 1]) + bg.y);
-          o.z = (__uint_as_float(va[j + 2]) + ba.z) * gelu_erf(__uint_as_float(vg[j + 2]) + bg.z);
-          o.w = (__uint_as_float(va[j + 3]) + ba.w) * gelu_erf(__uint_as_float(vg[j + 3]) + bg.w);
-          stg4[lane * STAGE_LD4 + (j >> 2)] = o;
-        }
-        __syncwarp();
-        const int col = out_col0 + c0 + cq;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rq;
-          const long long m = __shfl_sync(0xffffffffu, my_m, r);
-          const int vb = __shfl_sync(0xffffffffu, my_valid ? 1 : 0, r);
-          if (vb) {
-            const float4 x = stg4[r * STAGE_LD4 + (cq >> 2)];
-            uint2 pk;
-            pk.x = pack_bf16x2(x.x, x.y);
-            pk.y = pack_bf16x2(x.z, x.w);
-            *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + col) = pk;
+    // ---- prefetch iterator (elected thread): walks the chunks this warp-set will consume, in order ----
+    int pf_ti = 0, pf_tile = blockIdx.x, pf_c = ws & 1, pf_seq = 0;
+    auto pf_issue_next = [&]() {
+      // find the next valid chunk at or after (pf_ti, pf_c)
+      while (pf_tile < total_tiles) {
+        int n_tile, w0, h0, n0;
+        tile_geom(pf_tile, n_tile, w0, h0, n0);
+        if (!tile_is_vt(n_tile) && chunk_valid(n_tile, pf_c)) {
+          const int slot = ws * 2 + (pf_seq & 1);
+          if (p.has_res) {
+            mbar_expect_tx(res_full_bar(slot), SLOT_BYTES);
+            tma_load_4d(slot_base + slot * SLOT_BYTES, &tmR, res_full_bar(slot), n_tile * tile_out_cols + pf_c * chunk_cols,
+                        w0, h0, n0);
+          } else {
+            mbar_arrive(res_full_bar(slot));
           }
+          ++pf_seq;
+          pf_c += 2;
+          return;
         }
-        __syncwarp();
+        // advance to the next tile
+        ++pf_ti;
+        pf_tile += gridDim.x;
+        pf_c = (ws + pf_ti) & 1;
       }
-    } else {
-      const float* __restrict__ residual = p.residual;
-      const float* __restrict__ rowbias = p.rowbias;
-      float* __restrict__ out_f32 = p.out_f32;
-      bf16* __restrict__ out_bf16 = p.out_bf16;
+    };
+    if (elected) {
+      pf_issue_next();
+      pf_issue_next();
+    }
+
+    int ti = 0;
+    int seq = 0;  // chunks consumed by this warp-set
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      int n_tile, w0, h0, n0;
+      tile_geom(tile, n_tile, w0, h0, n0);
+      const int n_base = n_tile * BLOCK_N;
+      const int wl = row % p.tw;
+      const int hl = (row / p.tw) % p.th;
+      const int nl = row / (p.tw * p.th);
+      const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
+      const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
+      const long long my_m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
+
+      mbar_wait(tmem_full_bar(buf), (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      const int c_first = (ws + ti) & 1;
+
+      if (tile_is_vt(n_tile)) {
+        // V^T scatter: out_vt[b][c][token]; lanes are consecutive tokens -> 64-B contiguous per column
+        int last_c = -1;
+        for (int c = c_first; c < nchunks; c += 2) last_c = c;
+        if (last_c < 0 && lane == 0) mbar_arrive(tmem_empty_bar(buf));
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        if (n_base + c0 >= p.n_total) break;
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c0, v);
-        tmem_ld_wait();
-        if (p.mode == EPI_QKV && n_base + c0 >= p.qk_cols) {
-          // V^T store: out_vt[b][c][token]; lanes are consecutive tokens -> 64-B contiguous per column
+        for (int c = c_first; c <= last_c; c += 2) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == last_c) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+          }
           if (my_valid) {
             const long long tokens = static_cast<long long>(p.Ho) * p.Wo;
             const long long tok = static_cast<long long>(oh) * p.Wo + ow;
             const int vC = p.n_total - p.qk_cols;
-            bf16* dst = p.out_vt + (static_cast<long long>(on) * vC + (n_base + c0 - p.qk_cols)) * tokens + tok;
+            bf16* dst = p.out_vt + (static_cast<long long>(on) * vC + (n_base + c * 32 - p.qk_cols)) * tokens + tok;
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[j * tokens] = __float2bfloat16(__uint_as_float(v[j]));
           }
-          continue;
         }
+        continue;
+      }
+
+      int last_c = -1;
+      for (int c = c_first; chunk_valid(n_tile, c); c += 2) last_c = c;
+      if (last_c < 0 && lane == 0) mbar_arrive(tmem_empty_bar(buf));
+#pragma unroll 1
+      for (int c = c_first; c <= last_c; c += 2, ++seq) {
+        const int slot = ws * 2 + (seq & 1);
+        const uint32_t slot_addr = slot_base + slot * SLOT_BYTES;
+        uint8_t* slot_gen = slot_gen_base + slot * SLOT_BYTES;
+        float o[32];
+        if (geglu) {
+          constexpr int HALF = BLOCK_N / 2;
+          uint32_t va[32], vg[32];
+          tmem_ld_x32(taddr + c * 32, va);
+          tmem_ld_x32(taddr + HALF + c * 32, vg);
+          tmem_ld_wait();
+          if (c == last_c) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+          }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          stg4[lane * STAGE_LD4 + (j >> 2)] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        __syncwarp();
-        const int col = n_base + c0 + cq;
-        const bool colv = col < p.n_total;  // n_total % 4 == 0
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && colv) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        // issue every global read of this chunk before the first dependent use (8 independent 16-B loads per lane)
-        long long moff[8];
-        float4 add4[8];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c * 32 + j));
+            const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + HALF + c * 32 + j));
+            o[j + 0] = (__uint_as_float(va[j + 0]) + ba.x) * gelu_erf(__uint_as_float(vg[j + 0]) + bg.x);
+            o[j + 1] = (__uint_as_float(va[j + 1]) + ba.y) * gelu_erf(__uint_as_float(vg[j + 1]) + bg.y);
+            o[j + 2] = (__uint_as_float(va[j + 2]) + ba.z) * gelu_erf(__uint_as_float(vg[j + 2]) + bg.z);
+            o[j + 3] = (__uint_as_float(va[j + 3]) + ba.w) * gelu_erf(__uint_as_float(vg[j + 3]) + bg.w);
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == last_c) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+          }
+          const int col = n_base + c * 32;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rq;
-          const long long m = __shfl_sync(0xffffffffu, my_m, r);
-          const int vb = __shfl_sync(0xffffffffu, my_valid ? on : -1, r);
-          moff[it] = (vb >= 0 && colv) ? m * p.ld_out + col : -1;
-          float4 a = bias4;
-          if (moff[it] >= 0) {
-            if (residual != nullptr) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + moff[it]));
-              a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
-            }
-            if (rowbias != nullptr) {
-              const float4 rb = __ldg(reinterpret_cast<const float4*>(rowbias + static_cast<long long>(vb) * p.rowbias_ld + col));
+          for (int j = 0; j < 32; j += 4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && col + j < p.n_total) a = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+            if (rowbias != nullptr && my_valid && col + j < p.n_total) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(rowbias + static_cast<long long>(on) * p.rowbias_ld + col + j));
               a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
             }
+            o[j + 0] = __uint_as_float(v[j + 0]) + a.x;
+            o[j + 1] = __uint_as_float(v[j + 1]) + a.y;
+            o[j + 2] = __uint_as_float(v[j + 2]) + a.z;
+            o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
           }
-          add4[it] = a;
         }
+        // the slot is ours once the residual prefetch (or the plain arrive that stands in for it) has landed
+        mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
+        uint8_t* my_row128 = slot_gen + row * 128;
+        if (p.has_res) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (moff[it] >= 0) {
-            const int r = it * 4 + rq;
-            float4 x = stg4[r * STAGE_LD4 + (cq >> 2)];
-            x.x += add4[it].x; x.y += add4[it].y; x.z += add4[it].z; x.w += add4[it].w;
-            if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + moff[it]) = x;
-            if (out_bf16 != nullptr) {
-              uint2 pk;
-              pk.x = pack_bf16x2(x.x, x.y);
-              pk.y = pack_bf16x2(x.z, x.w);
-              *reinterpret_cast<uint2*>(out_bf16 + moff[it]) = pk;
+          for (int u = 0; u < 8; ++u) {
+            const float4 rr = *reinterpret_cast<const float4*>(my_row128 + ((u ^ (row & 7)) << 4));
+            o[4 * u + 0] += rr.x; o[4 * u + 1] += rr.y; o[4 * u + 2] += rr.z; o[4 * u + 3] += rr.w;
+          }
+        }
+        if (p.has_o32) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(my_row128 + ((u ^ (row & 7)) << 4)) =
+                make_float4(o[4 * u + 0], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+          if (p.has_o16 && my_valid) {  // rare side copy (feeds a stride-2 conv): direct 64-B row store
+            const int col = n_base + c * 32;
+            bf16* dst = out_bf16 + my_m * p.ld_out + col;
+            if (((p.n_total | p.ld_out) & 7) != 0) {  // narrow / unaligned rows: scalar stores
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.n_total) dst[j] = __float2bfloat16(o[j]);
+            } else
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (col + 8 * u < p.n_total) {
+                uint4 pk;
+                pk.x = pack_bf16x2(o[8 * u + 0], o[8 * u + 1]);
+                pk.y = pack_bf16x2(o[8 * u + 2], o[8 * u + 3]);
+                pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
+                pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
+                *reinterpret_cast<uint4*>(dst + 8 * u) = pk;
+              }
             }
           }
+        } else {
+          // bf16-only output: compact [128 rows x 64 B] layout (64B swizzle) overlaps other rows' fp32 residual
+          if (p.has_res) named_bar_sync(bar_id, 128);
+          uint8_t* my_row64 = slot_gen + row * 64;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 pk;
+            pk.x = pack_bf16x2(o[8 * u + 0], o[8 * u + 1]);
+            pk.y = pack_bf16x2(o[8 * u + 2], o[8 * u + 3]);
+            pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
+            pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
+            *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+          }
         }
-        __syncwarp();
+        fence_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (elected) {
+          const int ocol = n_tile * tile_out_cols + c * chunk_cols;
+          if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0);
+          else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
+          tma_store_commit();
+          tma_store_wait_read0();  // slot may be overwritten again
+          pf_issue_next();         // residual prefetch (or hand-back) for the chunk two ahead, same slot
+        }
       }
     }
+    if (elected) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -283,7 +407,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BLOCK_N, int STAGES>
 constexpr size_t smem_bytes_for() {
-  return 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * STAGES + 2);
+  return 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + EPI_STAGING_BYTES + 8 * (2 * STAGES + 6 + NUM_SLOTS);
 }
 
 template <int BLOCK_N, int STAGES>
@@ -295,9 +419,22 @@ int launch_t(const GemmPlan& plan, cudaStream_t stream) {
                                         static_cast<int>(smem)));
     attr_set = true;
   }
-  conv_gemm_kernel<BLOCK_N, STAGES><<<plan.grid, NUM_THREADS, smem, stream>>>(plan.tmA, plan.tmB, plan.p);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  conv_gemm_kernel<BLOCK_N, STAGES><<<plan.grid, NUM_THREADS, smem, stream>>>(plan.tmA, plan.tmB, plan.tmR, plan.tmO32,
+                                                                              plan.tmO16, plan.p);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 void pick_tile(int Wo, int Ho, int Nb, int* tw, int* th, int* tn) {
@@ -382,7 +519,11 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   if (d.mode == EPI_GEGLU) PBE_REQUIRE(bn == 128 && d.Cout % 128 == 0, "GEGLU needs BLOCK_N=128 | Cout");
   if (d.mode == EPI_QKV) PBE_REQUIRE(d.qk_cols % bn == 0 && d.Cout % bn == 0, "QKV split must align with BLOCK_N");
   plan->block_n = bn;
-  plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, (d.Cout + bn - 1) / bn, 1);
+  p.n_tiles = (d.Cout + bn - 1) / bn;
+  {
+    const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+    plan->grid = dim3(std::min(total, num_sms()), 1, 1);
+  }
 
   // A: 5-D view (c, w, phase, h, n)
   {
@@ -400,6 +541,31 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     int rc = make_tmap_bf16(&plan->tmA, d.act, 5, dims, strides, box, true);
     if (rc) return rc;
   }
+  // Epilogue maps: residual (fp32 load), fp32 store, bf16 store; geometry = output pixels, box = 32 columns x tile
+  {
+    const int out_cols = (d.mode == EPI_GEGLU) ? d.Cout / 2 : (d.mode == EPI_QKV ? d.qk_cols : d.Cout);
+    const uint64_t ld = static_cast<uint64_t>(p.ld_out);
+    const uint64_t Wo = p.Wo, Ho = p.Ho, Nb = p.Nb;
+    const uint64_t dims[4] = {static_cast<uint64_t>(out_cols), Wo, Ho, Nb};
+    const uint32_t box[4] = {32u, static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.tn)};
+    p.has_res = d.residual != nullptr;
+    p.has_o32 = d.out_f32 != nullptr;
+    p.has_o16 = d.out_bf16 != nullptr;
+    PBE_REQUIRE(p.has_o32 || p.has_o16, "GEMM needs an output");
+    PBE_REQUIRE(!(d.mode != EPI_STD && (p.has_res || p.has_o32)), "GEGLU / QKV epilogues write bf16 only");
+    const uint64_t s32[3] = {ld * 4, Wo * ld * 4, Ho * Wo * ld * 4};
+    const uint64_t s16[3] = {ld * 2, Wo * ld * 2, Ho * Wo * ld * 2};
+    int rc = 0;
+    if (p.has_res) rc = make_tmap(&plan->tmR, d.residual, true, 4, dims, s32, box, 128);
+    if (rc) return rc;
+    if (p.has_o32) rc = make_tmap(&plan->tmO32, d.out_f32, true, 4, dims, s32, box, 128);
+    if (rc) return rc;
+    if (p.has_o16) rc = make_tmap(&plan->tmO16, d.out_bf16, false, 4, dims, s16, box, 64);
+    if (rc) return rc;
+    if (!p.has_res) plan->tmR = p.has_o32 ? plan->tmO32 : plan->tmO16;
+    if (!p.has_o32) plan->tmO32 = p.has_o16 ? plan->tmO16 : plan->tmR;
+    if (!p.has_o16) plan->tmO16 = plan->tmO32;
+  }
   // B: 3-D (cin, cout, tap)
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(d.C), static_cast<uint64_t>(d.Cout),
@@ -414,11 +580,11 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
 
 int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.block_n) {
-    case 32: return launch_t<32, 4>(plan, stream);
-    case 64: return launch_t<64, 4>(plan, stream);
-    case 128: return launch_t<128, 3>(plan, stream);
-    case 160: return launch_t<160, 3>(plan, stream);
-    case 256: return launch_t<256, 4>(plan, stream);
+    case 32: return launch_t<32, 6>(plan, stream);
+    case 64: return launch_t<64, 6>(plan, stream);
+    case 128: return launch_t<128, 4>(plan, stream);
+    case 160: return launch_t<160, 4>(plan, stream);
+    case 256: return launch_t<256, 3>(plan, stream);
     default: set_error("launch_gemm_plan: bad block_n"); return -1;
   }
 }

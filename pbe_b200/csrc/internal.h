@@ -39,6 +39,8 @@ const char* get_error();
 // dims[0] is the innermost (contiguous) dimension. strides_bytes has rank-1 entries (for dims 1..rank-1).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128);
+int make_tmap(CUtensorMap* out, const void* base, bool is_f32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ------------------------------------------------------------------------------------------------
 // Implicit-GEMM convolution / linear on tcgen05 (gemm_tc.cu)
@@ -53,6 +55,8 @@ struct ConvGemmParams {
   int Wo, Ho, Nb;          // output extents
   int num_taps, k_chunks;  // K loop = num_taps * k_chunks chunks of 64 channels
   int n_total;             // number of GEMM columns (Cout)
+  int n_tiles;             // ceil(n_total / BLOCK_N)
+  int has_res, has_o32, has_o16;  // which epilogue tensor maps are live
   int8_t tap_dw[9], tap_dh[9], tap_ph[9];
   int tap_coff[9];
   // epilogue
@@ -71,6 +75,7 @@ struct ConvGemmParams {
 
 struct GemmPlan {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmR, tmO32, tmO16;  // residual (fp32 load), fp32 output store, bf16 output store (epilogue TMA)
   ConvGemmParams p;
   int block_n;
   dim3 grid;

@@ -28,6 +28,11 @@ static EncodeTiledFn resolve_encode() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128) {
+  return make_tmap(out, base, /*is_f32=*/false, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, bool is_f32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = resolve_encode();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled could not be resolved from the CUDA driver");
@@ -43,9 +48,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     estr[i] = 1;
     if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
-                  gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::string m = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " rank " +

@@ -1,0 +1,40 @@
+"""Run a few representative GEMM shapes of the U-Net (CFG batch 16) through pbe_op_conv_gemm; used under ncu."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pbe_b200 import _lib
+lib = _lib.load()
+dev = torch.device("cuda:0")
+st = torch.cuda.current_stream().cuda_stream
+
+def case(name, Nb, H, W, C, k, Cout, mode=0, residual=False, rowbias=False, f32=True, b16=False, bn=0, iters=3):
+    x = torch.randn(Nb, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(k * k, Cout, C, device=dev) / (C * k * k) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device=dev)
+    ncol = Cout // 2 if mode == 1 else Cout
+    res = torch.randn(Nb, H, W, ncol, device=dev) if residual else None
+    rb = torch.randn(Nb, Cout, device=dev) if rowbias else None
+    of = torch.empty(Nb, H, W, ncol, device=dev) if f32 else None
+    ob = torch.empty(Nb, H, W, ncol, device=dev, dtype=torch.bfloat16) if (b16 or mode == 1) else None
+    p = _lib.ptr
+    for _ in range(iters):
+        rc = lib.pbe_op_conv_gemm(p(x), Nb, H, W, C, k, 1, p(w), Cout, mode, p(bias), p(rb), p(res), p(of), p(ob), None, 0, bn, st)
+        assert rc == 0, lib.pbe_last_error()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        lib.pbe_op_conv_gemm(p(x), Nb, H, W, C, k, 1, p(w), Cout, mode, p(bias), p(rb), p(res), p(of), p(ob), None, 0, bn, st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = 2.0 * Nb * H * W * Cout * C * k * k
+    print(f"{name:28s} {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TF/s", flush=True)
+
+which = sys.argv[1:] or ["proj_out", "geglu", "conv2", "conv1", "ffout", "lowres"]
+if "proj_out" in which: case("proj_out 64^2 320->320 +res", 16, 64, 64, 320, 1, 320, residual=True)
+if "geglu" in which: case("geglu 64^2 320->2560", 16, 64, 64, 320, 1, 2560, mode=1, f32=False)
+if "conv2" in which: case("conv2 64^2 320->320 +res", 16, 64, 64, 320, 3, 320, residual=True)
+if "conv1" in which: case("conv1 64^2 320->320 +rb", 16, 64, 64, 320, 3, 320, rowbias=True)
+if "ffout" in which: case("ff.out 64^2 1280->320 +res", 16, 64, 64, 1280, 1, 320, residual=True, f32=False, b16=True)
+if "lowres" in which: case("conv 8^2 1280->1280 +res", 16, 8, 8, 1280, 3, 1280, residual=True)
+if "nores" in which: case("proj 64^2 320->320 no res", 16, 64, 64, 320, 1, 320)
