@@ -273,6 +273,266 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two-warpgroup variant for head dims <= 64 (the 64x64-latent level: N = 4096, d = 40 — 92 % of all attention time).
+// One CTA = one (sample, head, 256-query pair of tiles).  Softmax is MUFU(ex2)-bound at d = 40, so the point is to keep
+// two softmax warps resident per scheduler: warpgroup A works on S_A(j) while the tensor core produces S_B(j) and the
+// P·V products; K/V tiles are loaded once for both query tiles.
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int ATT2_THREADS = 64 + 2 * 128;
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int V_STAGE_BYTES = 2 * 64 * 128;  // two 64-key chunks of up to 64 rows
+  const int v_chunk_bytes = p.dv * 128;
+  const uint32_t sQ = smem_base;                          // 2 query tiles
+  const uint32_t sK = sQ + 2 * CHUNK_BYTES;               // 2 stages
+  const uint32_t sV = sK + 2 * CHUNK_BYTES;               // 2 stages
+  const uint32_t sP = sV + 2 * V_STAGE_BYTES;             // 2 warpgroups x 2 chunks
+  const uint32_t sBar = sP + 4 * CHUNK_BYTES;
+  uint8_t* bar_gen = smem_gen + (sBar - smem_base);
+  uint8_t* p_gen = smem_gen + (sP - smem_base);
+  const uint32_t q_full = sBar;
+  auto k_full = [&](int s) { return sBar + 8u * (1 + s); };
+  auto v_full = [&](int s) { return sBar + 8u * (3 + s); };
+  auto kv_empty = [&](int s) { return sBar + 8u * (5 + s); };
+  auto s_full = [&](int g) { return sBar + 8u * (7 + g); };
+  auto p_full = [&](int g) { return sBar + 8u * (9 + g); };
+  auto pv_done = [&](int g) { return sBar + 8u * (11 + g); };
+  const uint32_t tmem_ptr_addr = sBar + 8u * 13;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * QT;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int T = (p.N + KT - 1) / KT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 4);
+      mbar_init(pv_done(s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * CHUNK_BYTES);
+      tma_load_4d(sQ, &tmQK, q_full, 0, head, q0, b);
+      tma_load_4d(sQ + CHUNK_BYTES, &tmQK, q_full, 0, head, q0 + QT, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        mbar_wait(kv_empty(st), ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(k_full(st), CHUNK_BYTES);
+        tma_load_4d(sK + st * CHUNK_BYTES, &tmQK, k_full(st), 0, p.heads + head, j * KT, b);
+        mbar_expect_tx(v_full(st), 2 * v_chunk_bytes);
+        for (int jj = 0; jj < 2; ++jj)
+          tma_load_3d(sV + st * V_STAGE_BYTES + jj * v_chunk_bytes, &tmV, v_full(st), j * KT + jj * 64, head * p.d, b);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_qk = umma_idesc_bf16(128, KT);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, p.dv);
+    auto issue_qk = [&](int g, int j) {
+      const int st = j & 1;
+      if (lane == 0) {
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint64_t adesc = umma_desc_sw128(sQ + g * CHUNK_BYTES) + 2u * ks;
+          const uint64_t bdesc = umma_desc_sw128(sK + st * CHUNK_BYTES) + 2u * ks;
+          umma_bf16_ss(tmem_base + g * 128, adesc, bdesc, idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(g));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(k_full(0), 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    for (int j = 0; j < T; ++j) {
+      const int st = j & 1;
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(p_full(g), j & 1);
+        if (j + 1 < T) {
+          if (g == 0) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_qk(g, j + 1);
+        }
+        if (g == 0) mbar_wait(v_full(st), (j >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < KT / 16; ++ks) {
+            const uint64_t adesc = umma_desc_sw128(sP + (g * 2 + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
+            const uint64_t bdesc = umma_desc_sw128(sV + st * V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
+            umma_bf16_ss(tmem_base + 256 + g * 64, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(pv_done(g));
+          if (g == 1) umma_commit(kv_empty(st));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;  // warpgroup: query tile g
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tmem_S = tmem_base + g * 128;
+    const uint32_t tmem_O = tmem_base + 256 + g * 64;
+    uint8_t* pg = p_gen + g * 2 * CHUNK_BYTES;
+    float m_run = -INFINITY;
+    float l_run = 0.0f;
+    const float sl2 = p.scale_log2;
+
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full(g), j & 1);
+      tc_fence_after();
+      float s[KT];
+#pragma unroll
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
+      }
+      const int kvalid = p.N - j * KT;
+      float mx = m_run;
+      if (kvalid >= KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) mx = fmaxf(mx, s[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+          if (i >= kvalid) s[i] = -INFINITY;
+          mx = fmaxf(mx, s[i]);
+        }
+      }
+      const float alpha = ex2((m_run - mx) * sl2);
+      const float mneg = -mx * sl2;
+      float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < KT; i += 2) {
+        s[i] = ex2(fmaf(s[i], sl2, mneg));
+        s[i + 1] = ex2(fmaf(s[i + 1], sl2, mneg));
+        sum0 += s[i];
+        sum1 += s[i + 1];
+      }
+      l_run = l_run * alpha + (sum0 + sum1);
+      m_run = mx;
+
+      if (j > 0) {
+        mbar_wait(pv_done(g), (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          for (int c = 0; c < p.dv; c += 16) {
+            uint32_t o[16];
+            tmem_ld_x16(tmem_O + lane_off + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(tmem_O + lane_off + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      {
+        uint8_t* prow = pg + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < KT; c += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(s[c + 0], s[c + 1]);
+          pk.y = pack_bf16x2(s[c + 2], s[c + 3]);
+          pk.z = pack_bf16x2(s[c + 4], s[c + 5]);
+          pk.w = pack_bf16x2(s[c + 6], s[c + 7]);
+          const int chunk = c >> 6;
+          const int u = (c & 63) >> 3;
+          *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((u ^ (row & 7)) << 4)) = pk;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(g));
+    }
+
+    mbar_wait(pv_done(g), (T - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int tok = q0 + g * QT + row;
+    bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
+    for (int c = 0; c < p.dv; c += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tmem_O + lane_off + c, o);
+      tmem_ld_wait();
+      if (tok < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < p.d) {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + i) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t ATT2_SMEM = 1024 + 2 * CHUNK_BYTES + 2 * CHUNK_BYTES + 2 * (2 * 64 * 128) + 4 * CHUNK_BYTES + 8 * 16;
+
+int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  static_assert(ATT2_SMEM <= 227 * 1024, "attention smem");
+  if (!attr_set) {
+    PBE_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(ATT2_SMEM)));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.N = plan.N; p.heads = plan.heads; p.d = plan.d;
+  p.dv = (plan.d + 15) / 16 * 16;
+  p.ksteps = (plan.d + 15) / 16;
+  p.C = plan.heads * plan.d;
+  p.scale_log2 = plan.scale_log2;
+  p.out = plan.out;
+  dim3 grid((plan.N + 2 * QT - 1) / (2 * QT), plan.heads, plan.B);
+  flash_attn2_kernel<<<grid, ATT2_THREADS, ATT2_SMEM, stream>>>(plan.tmQ, plan.tmV, p);
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int DK_CHUNKS, int KV_STAGES>
 constexpr size_t attn_smem_bytes() {
   return 1024 + DK_CHUNKS * CHUNK_BYTES + KV_STAGES * DK_CHUNKS * CHUNK_BYTES + KV_STAGES * 2 * 160 * 128 +
@@ -336,6 +596,7 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
 
 int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream) {
   const int chunks = (plan.d + 63) / 64;
+  if (chunks == 1 && plan.N > QT) return launch_attn2(plan, stream);
   switch (chunks) {
     case 1: return launch_attn_t<1, 2>(plan, stream);
     case 2: return launch_attn_t<2, 2>(plan, stream);

@@ -560,11 +560,12 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     if (rc) return rc;
     if (p.has_o32) rc = make_tmap(&plan->tmO32, d.out_f32, true, 4, dims, s32, box, 128);
     if (rc) return rc;
-    if (p.has_o16) rc = make_tmap(&plan->tmO16, d.out_bf16, false, 4, dims, s16, box, 64);
+    const bool o16_tma = p.has_o16 && !p.has_o32;  // with both outputs the bf16 copy is a direct row store
+    if (o16_tma) rc = make_tmap(&plan->tmO16, d.out_bf16, false, 4, dims, s16, box, 64);
     if (rc) return rc;
     if (!p.has_res) plan->tmR = p.has_o32 ? plan->tmO32 : plan->tmO16;
-    if (!p.has_o32) plan->tmO32 = p.has_o16 ? plan->tmO16 : plan->tmR;
-    if (!p.has_o16) plan->tmO16 = plan->tmO32;
+    if (!p.has_o32) plan->tmO32 = plan->tmO16;
+    if (!o16_tma) plan->tmO16 = plan->tmO32;
   }
   // B: 3-D (cin, cout, tap)
   {
