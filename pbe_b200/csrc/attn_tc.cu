@@ -14,6 +14,10 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
+#include <type_traits>
+
 namespace pbe {
 
 namespace {
@@ -27,6 +31,9 @@ struct AttnParams {
   int N, heads, d, dv, ksteps, C;
   float scale_log2;
   bf16* out;
+  int exp_mode;    // 0 normal; 1 = experiment: skip MUFU (p = 1)
+  int wg_skew;     // cycles warpgroup 1 starts after warpgroup 0 (flash_attn4)
+  long long* dbg;  // optional: per-tile clock64 stamps of CTA (0,0,0), softmax warp 2 lane 0 (tools/attn_probe.py)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -63,7 +70,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   const uint32_t tmem_ptr_addr = sBar + 8u * (7 + 3 * KV_STAGES);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (7 + 3 * KV_STAGES));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT;
   const int head = blockIdx.y;
@@ -94,7 +101,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
   const uint32_t tmem_O = tmem_base + 256;
 
   if (warp == 0) {
@@ -125,13 +132,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       mbar_wait(k_full(st), (j / KV_STAGES) & 1);
       mbar_wait(s_free(sb), ((j >> 1) & 1) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {
         for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint64_t adesc = umma_desc_sw128(sQ + (ks >> 2) * CHUNK_BYTES) + 2u * (ks & 3);
           const uint64_t bdesc = umma_desc_sw128(sK + (st * DK_CHUNKS + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
-          umma_bf16_ss(tmem_base + sb * 128, adesc, bdesc, idesc_qk, ks > 0 ? 1u : 0u);
+          umma_bf16_ss_elect(tmem_base + sb * 128, adesc, bdesc, idesc_qk, ks > 0 ? 1u : 0u);
         }
-        umma_commit(s_full(sb));
+        umma_commit_elect(s_full(sb));
       }
       __syncwarp();
     };
@@ -143,15 +150,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       mbar_wait(v_full(st), (j / KV_STAGES) & 1);
       mbar_wait(p_full, j & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
           const uint64_t adesc = umma_desc_sw128(sP + (ks >> 2) * CHUNK_BYTES) + 2u * (ks & 3);
           const uint64_t bdesc = umma_desc_sw128(sV + st * 2 * 160 * 128 + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
-          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16_ss_elect(tmem_O, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(kv_empty(st));
-        umma_commit(pv_done);
+        umma_commit_elect(kv_empty(st));
+        umma_commit_elect(pv_done);
       }
       __syncwarp();
       if (KV_STAGES < 2 && j + 1 < T) issue_qk(j + 1);
@@ -280,8 +287,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 // P·V products; K/V tiles are loaded once for both query tiles.
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 64 + 2 * 128;
+constexpr int ATT2_THREADS = 64 + 2 * 256;   // 2 MMA(+TMA) warps, 2 warpgroups x 8 softmax warps (18 warps: 112 regs/thread)
 
+// 128-key tiles, 256 queries per CTA, SIXTEEN softmax warps: every query row is shared by two threads (64 keys each),
+// so each scheduler always has four softmax warps to pick from.  Findings that shaped this (clock64 traces, ncu):
+//  * the softmax is issue/latency bound, not MUFU bound: with two softmax warps per scheduler IPC was ~0.4;
+//  * eager rescaling of O waited for the tensor core in ~half of all tiles on random data -> lazy rescaling (the
+//    reference maximum only moves when exceeded by 2^8);
+//  * one MMA-issuing warp per warpgroup (mbarrier round trips serialise otherwise);
+//  * exponentials are computed in place first, sums / bf16 packing / stores afterwards.
+// warps: 0, 1 MMA issue for warpgroup 0, 1 (warp 0 also drives the K/V TMA ring) | 2..9 softmax wg 0 | 10..17 softmax wg 1
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ AttnParams p) {
@@ -294,161 +309,168 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const uint32_t sK = sQ + 2 * CHUNK_BYTES;               // 2 stages
   const uint32_t sV = sK + 2 * CHUNK_BYTES;               // 2 stages
   const uint32_t sP = sV + 2 * V_STAGE_BYTES;             // 2 warpgroups x 2 chunks
-  const uint32_t sBar = sP + 4 * CHUNK_BYTES;
+  const uint32_t sX = sP + 4 * CHUNK_BYTES;               // row-max / row-sum exchange: [2 wg][2 halves][128] floats
+  const uint32_t sBar = sX + 2 * 2 * 128 * 4;
   uint8_t* bar_gen = smem_gen + (sBar - smem_base);
   uint8_t* p_gen = smem_gen + (sP - smem_base);
+  float* x_gen = reinterpret_cast<float*>(smem_gen + (sX - smem_base));
   const uint32_t q_full = sBar;
-  auto k_full = [&](int s) { return sBar + 8u * (1 + s); };
-  auto v_full = [&](int s) { return sBar + 8u * (3 + s); };
-  auto kv_empty = [&](int s) { return sBar + 8u * (5 + s); };
-  auto s_full = [&](int g) { return sBar + 8u * (7 + g); };
-  auto p_full = [&](int g) { return sBar + 8u * (9 + g); };
-  auto pv_done = [&](int g) { return sBar + 8u * (11 + g); };
-  const uint32_t tmem_ptr_addr = sBar + 8u * 13;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 13);
+  auto kv_full = [&](int s) { return sBar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return sBar + 8u * (3 + s); };
+  auto s_full = [&](int g) { return sBar + 8u * (5 + g); };
+  auto p_full = [&](int g) { return sBar + 8u * (7 + g); };
+  auto pv_done = [&](int g) { return sBar + 8u * (9 + g); };
+  const uint32_t tmem_ptr_addr = sBar + 8u * 11;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 11);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * QT;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int T = (p.N + KT - 1) / KT;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(k_full(s), 1);
-      mbar_init(v_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 2);   // one tcgen05.commit arrival per MMA warp
       mbar_init(s_full(s), 1);
-      mbar_init(p_full(s), 4);
+      mbar_init(p_full(s), 8);
       mbar_init(pv_done(s), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 0) {
     tmem_alloc(tmem_ptr_addr, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * CHUNK_BYTES);
-      tma_load_4d(sQ, &tmQK, q_full, 0, head, q0, b);
-      tma_load_4d(sQ + CHUNK_BYTES, &tmQK, q_full, 0, head, q0 + QT, b);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        mbar_wait(kv_empty(st), ((j >> 1) & 1) ^ 1u);
-        mbar_expect_tx(k_full(st), CHUNK_BYTES);
-        tma_load_4d(sK + st * CHUNK_BYTES, &tmQK, k_full(st), 0, p.heads + head, j * KT, b);
-        mbar_expect_tx(v_full(st), 2 * v_chunk_bytes);
-        for (int jj = 0; jj < 2; ++jj)
-          tma_load_3d(sV + st * V_STAGE_BYTES + jj * v_chunk_bytes, &tmV, v_full(st), j * KT + jj * 64, head * p.d, b);
-      }
-    }
-  } else if (warp == 1) {
+  if (warp <= 1) {
+    // ================= MMA issue for warpgroup g (uniform code, elect.sync issues) =================
+    const int g = warp;
     const uint32_t idesc_qk = umma_idesc_bf16(128, KT);
     const uint32_t idesc_pv = umma_idesc_bf16(128, p.dv);
-    auto issue_qk = [&](int g, int j) {
-      const int st = j & 1;
+    const uint64_t qdesc = umma_desc_sw128(sQ + g * CHUNK_BYTES);
+    const uint32_t tmem_S = tmem_base + g * 128;
+    const uint32_t tmem_O = tmem_base + 256 + g * 64;
+    auto issue_qk = [&](int j) {
+      const uint64_t kdesc = umma_desc_sw128(sK + (j & 1) * CHUNK_BYTES);
+      for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16_ss_elect(tmem_S, qdesc + 2u * ks, kdesc + 2u * ks, idesc_qk, ks > 0 ? 1u : 0u);
+      umma_commit_elect(s_full(g));
+    };
+    // K/V TMA ring (2 stages), driven by MMA warp 0: tile t goes to stage t & 1 once P·V of tile t-2 (both
+    // warpgroups) has released it
+    auto load_kv = [&](int t) {
       if (lane == 0) {
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          const uint64_t adesc = umma_desc_sw128(sQ + g * CHUNK_BYTES) + 2u * ks;
-          const uint64_t bdesc = umma_desc_sw128(sK + st * CHUNK_BYTES) + 2u * ks;
-          umma_bf16_ss(tmem_base + g * 128, adesc, bdesc, idesc_qk, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(s_full(g));
+        const int st = t & 1;
+        mbar_expect_tx(kv_full(st), CHUNK_BYTES + 2 * v_chunk_bytes);
+        tma_load_4d(sK + st * CHUNK_BYTES, &tmQK, kv_full(st), 0, p.heads + head, t * KT, b);
+        for (int jj = 0; jj < 2; ++jj)
+          tma_load_3d(sV + st * V_STAGE_BYTES + jj * v_chunk_bytes, &tmV, kv_full(st), t * KT + jj * 64, head * p.d, b);
       }
       __syncwarp();
     };
+    if (g == 0) {
+      if (lane == 0) {
+        mbar_expect_tx(q_full, 2 * CHUNK_BYTES);
+        tma_load_4d(sQ, &tmQK, q_full, 0, head, q0, b);
+        tma_load_4d(sQ + CHUNK_BYTES, &tmQK, q_full, 0, head, q0 + QT, b);
+      }
+      __syncwarp();
+      load_kv(0);
+      if (T > 1) load_kv(1);
+    }
     mbar_wait(q_full, 0);
-    mbar_wait(k_full(0), 0);
+    mbar_wait(kv_full(0), 0);
     tc_fence_after();
-    issue_qk(0, 0);
-    issue_qk(1, 0);
+    issue_qk(0);
     for (int j = 0; j < T; ++j) {
       const int st = j & 1;
-      for (int g = 0; g < 2; ++g) {
-        mbar_wait(p_full(g), j & 1);
-        if (j + 1 < T) {
-          if (g == 0) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_qk(g, j + 1);
-        }
-        if (g == 0) mbar_wait(v_full(st), (j >> 1) & 1);
+      mbar_wait(p_full(g), j & 1);   // P(j) published => S(j) fully read
+      if (j + 1 < T) {
+        mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        issue_qk(j + 1);
+      }
+      tc_fence_after();
+      {
 #pragma unroll
-          for (int ks = 0; ks < KT / 16; ++ks) {
-            const uint64_t adesc = umma_desc_sw128(sP + (g * 2 + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
-            const uint64_t bdesc = umma_desc_sw128(sV + st * V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
-            umma_bf16_ss(tmem_base + 256 + g * 64, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(pv_done(g));
-          if (g == 1) umma_commit(kv_empty(st));
+        for (int ks = 0; ks < KT / 16; ++ks) {
+          const uint64_t pdesc = umma_desc_sw128(sP + (g * 2 + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
+          const uint64_t vdesc = umma_desc_sw128(sV + st * V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
+          umma_bf16_ss_elect(tmem_O, pdesc, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit_elect(pv_done(g));
+        umma_commit_elect(kv_empty(st));
+      }
+      if (g == 0 && j + 2 < T) {
+        mbar_wait(kv_empty(st), (j >> 1) & 1);   // P·V(j) of both warpgroups has retired
+        load_kv(j + 2);
       }
     }
   } else {
-    const int g = (warp - 2) >> 2;  // warpgroup: query tile g
-    const int q = warp & 3;
+    const int sw = warp - 2;            // 0..15
+    const int g = sw >> 3;              // warpgroup = query tile
+    const int sub = (sw >> 2) & 1;      // which 64-key half of the row this thread owns
+    const int q = warp & 3;             // TMEM lane quarter
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tmem_S = tmem_base + g * 128;
+    const uint32_t tmem_S = tmem_base + g * 128 + sub * 64;
     const uint32_t tmem_O = tmem_base + 256 + g * 64;
-    uint8_t* pg = p_gen + g * 2 * CHUNK_BYTES;
-    float m_run = -INFINITY;
-    float l_run = 0.0f;
+    uint8_t* prow = p_gen + (g * 2 + sub) * CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    float* xmine = x_gen + (g * 2 + sub) * 128 + row;
+    float* xpeer = x_gen + (g * 2 + (sub ^ 1)) * 128 + row;
+    const int bar_id = 1 + g;
+    float m_run = -INFINITY;   // reference maximum used by the exponentials (lazy)
+    float l_run = 0.0f;        // partial row sum over this thread's columns
     const float sl2 = p.scale_log2;
 
-    for (int j = 0; j < T; ++j) {
+    auto tile = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       mbar_wait(s_full(g), j & 1);
       tc_fence_after();
-      float s[KT];
+      // pass 1: partial row maximum over my 64 columns, 32 at a time (values are re-read from TMEM in pass 2:
+      // 32 live registers instead of 64 keeps the 18-warp CTA free of spills)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < KT; c += 32) {
+      for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
-        tmem_ld_x32(tmem_S + lane_off + c, v);
+        tmem_ld_x32(tmem_S + lane_off + h * 32, v);
         tmem_ld_wait();
+        if (MASKED) {
+          const int kvalid = p.N - j * KT - sub * 64 - h * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
-      }
-      const int kvalid = p.N - j * KT;
-      float mx = m_run;
-      if (kvalid >= KT) {
+          for (int i = 0; i < 32; ++i)
+            if (i >= kvalid) v[i] = 0xff800000u;  // -inf
+        }
 #pragma unroll
-        for (int i = 0; i < KT; ++i) mx = fmaxf(mx, s[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < KT; ++i) {
-          if (i >= kvalid) s[i] = -INFINITY;
-          mx = fmaxf(mx, s[i]);
+        for (int i = 0; i < 32; i += 8) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 4])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[i + 1]), __uint_as_float(v[i + 5])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 6])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[i + 3]), __uint_as_float(v[i + 7])));
         }
       }
-      const float alpha = ex2((m_run - mx) * sl2);
-      const float mneg = -mx * sl2;
-      float sum0 = 0.0f, sum1 = 0.0f;
-#pragma unroll
-      for (int i = 0; i < KT; i += 2) {
-        s[i] = ex2(fmaf(s[i], sl2, mneg));
-        s[i + 1] = ex2(fmaf(s[i + 1], sl2, mneg));
-        sum0 += s[i];
-        sum1 += s[i + 1];
-      }
-      l_run = l_run * alpha + (sum0 + sum1);
-      m_run = mx;
-
-      if (j > 0) {
-        mbar_wait(pv_done(g), (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+      const float mpart = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      *xmine = mpart;
+      named_bar_sync(bar_id, 256);
+      const float mx = fmaxf(mpart, *xpeer);   // identical in both halves of the row
+      // lazy rescaling: both halves of a row take the same decision
+      float alpha = 1.0f;
+      if (__any_sync(0xffffffffu, (mx - m_run) * sl2 > 8.0f)) {
+        const float m_new = fmaxf(m_run, mx);
+        alpha = ex2((m_run - m_new) * sl2);  // first tile: ex2(-inf) = 0
+        m_run = m_new;
+        if (j > 0 && sub == 0) {
+          mbar_wait(pv_done(g), (j - 1) & 1);
+          tc_fence_after();
           for (int c = 0; c < p.dv; c += 16) {
             uint32_t o[16];
             tmem_ld_x16(tmem_O + lane_off + c, o);
@@ -460,45 +482,75 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           tmem_st_wait();
         }
       }
-      {
-        uint8_t* prow = pg + (row >> 3) * 1024 + (row & 7) * 128;
+      const float mneg = -m_run * sl2;
+      // P is single-buffered: P·V of tile j-1 must have read it (issued right after P(j-1) was published)
+      if (j > 0) mbar_wait(pv_done(g), (j - 1) & 1);
+      // pass 2: exponentials, partial row sum, bf16 P -> shared memory (chunk `sub`, K-major, 128B swizzle)
+      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
 #pragma unroll
-        for (int c = 0; c < KT; c += 8) {
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_off + h * 32, v);
+        tmem_ld_wait();
+        if (MASKED) {
+          const int kvalid = p.N - j * KT - sub * 64 - h * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= kvalid) v[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2(fmaf(__uint_as_float(v[i]), sl2, mneg)));
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          sum0 += __uint_as_float(v[c + 0]) + __uint_as_float(v[c + 4]);
+          sum1 += __uint_as_float(v[c + 1]) + __uint_as_float(v[c + 5]);
+          sum2 += __uint_as_float(v[c + 2]) + __uint_as_float(v[c + 6]);
+          sum3 += __uint_as_float(v[c + 3]) + __uint_as_float(v[c + 7]);
           uint4 pk;
-          pk.x = pack_bf16x2(s[c + 0], s[c + 1]);
-          pk.y = pack_bf16x2(s[c + 2], s[c + 3]);
-          pk.z = pack_bf16x2(s[c + 4], s[c + 5]);
-          pk.w = pack_bf16x2(s[c + 6], s[c + 7]);
-          const int chunk = c >> 6;
-          const int u = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((u ^ (row & 7)) << 4)) = pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
+          const int u = (h * 32 + c) >> 3;
+          *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = pk;
         }
       }
+      l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(g));
-    }
+    };
+    const int T_full = p.N / KT;
+    for (int j = 0; j < T_full; ++j) tile(j, std::false_type{});
+    if (T_full < T) tile(T_full, std::true_type{});
 
+    // combine the two partial row sums, then the `sub == 0` thread of each row writes O / l
+    named_bar_sync(bar_id, 256);   // all reads of the max-exchange slots are done
+    *xmine = l_run;
+    named_bar_sync(bar_id, 256);
+    const float l_tot = l_run + *xpeer;
     mbar_wait(pv_done(g), (T - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int tok = q0 + g * QT + row;
-    bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
-    for (int c = 0; c < p.dv; c += 16) {
-      uint32_t o[16];
-      tmem_ld_x16(tmem_O + lane_off + c, o);
-      tmem_ld_wait();
-      if (tok < p.N) {
+    if (sub == 0) {
+      const float inv_l = 1.0f / l_tot;
+      const int tok = q0 + g * QT + row;
+      bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
+      for (int c = 0; c < p.dv; c += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(tmem_O + lane_off + c, o);
+        tmem_ld_wait();
+        if (tok < p.N) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 8) {
-          if (c + i < p.d) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-            pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-            pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c + i) = pk;
+          for (int i = 0; i < 16; i += 8) {
+            if (c + i < p.d) {
+              uint4 pk;
+              pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+              pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+              pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+              pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c + i) = pk;
+            }
           }
         }
       }
@@ -507,10 +559,10 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr size_t ATT2_SMEM = 1024 + 2 * CHUNK_BYTES + 2 * CHUNK_BYTES + 2 * (2 * 64 * 128) + 4 * CHUNK_BYTES + 8 * 16;
+constexpr size_t ATT2_SMEM = 1024 + 2 * CHUNK_BYTES + 2 * CHUNK_BYTES + 2 * (2 * 64 * 128) + 4 * CHUNK_BYTES + 2048 + 8 * 16;
 
 int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
@@ -527,6 +579,9 @@ int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   p.C = plan.heads * plan.d;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
+  p.dbg = plan.dbg;
+  p.exp_mode = 0;
+  p.wg_skew = 0;
   dim3 grid((plan.N + 2 * QT - 1) / (2 * QT), plan.heads, plan.B);
   flash_attn2_kernel<<<grid, ATT2_THREADS, ATT2_SMEM, stream>>>(plan.tmQ, plan.tmV, p);
   PBE_CHECK_CUDA(cudaGetLastError());
@@ -556,6 +611,9 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   p.C = plan.heads * plan.d;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
+  p.dbg = nullptr;
+  p.exp_mode = 0;
+  p.wg_skew = 0;
   flash_attn_kernel<DK_CHUNKS, KV_STAGES><<<plan.grid, ATT_THREADS, smem, stream>>>(plan.tmQ, plan.tmV, p);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -570,6 +628,7 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
   plan->B = B; plan->N = N; plan->heads = heads; plan->d = d;
   plan->scale_log2 = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(d)));
   plan->out = out;
+  plan->dbg = nullptr;
   plan->grid = dim3((N + QT - 1) / QT, heads, B);
   const int dv = (d + 15) / 16 * 16;
   {
@@ -580,6 +639,9 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
                                  static_cast<uint64_t>(N) * 2 * C * 2};
     const uint32_t box[4] = {64u, 1u, 128u, 1u};
     int rc = make_tmap_bf16(&plan->tmQ, qk, 4, dims, strides, box, true);
+    if (rc) return rc;
+    const uint32_t box64[4] = {64u, 1u, 64u, 1u};
+    rc = make_tmap_bf16(&plan->tmK, qk, 4, dims, strides, box64, true);
     if (rc) return rc;
   }
   {

@@ -26,6 +26,19 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
   d.qk_cols = qk_cols;
   d.ld_out = (mode == EPI_QKV) ? qk_cols : 0;
   d.block_n = block_n;
+  {  // split-K workspace for small grids (grown on demand, owned by the library; op-level API only)
+    static float* ws = nullptr;
+    static size_t ws_bytes = 0;
+    const size_t need = gemm_splitk_ws_bytes(d);
+    if (need > ws_bytes) {
+      if (ws) cudaFree(ws);
+      ws = nullptr;
+      ws_bytes = 0;
+      if (cudaMalloc(&ws, need) != cudaSuccess) { set_error("split-K workspace allocation failed"); return -2; }
+      ws_bytes = need;
+    }
+    d.splitk_ws = need ? ws : nullptr;
+  }
   GemmPlan plan;
   int rc = build_gemm_plan(d, &plan);
   if (rc) return rc;
@@ -37,14 +50,19 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" {
 
+static long long* g_attn_dbg = nullptr;
+
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
                           void* stream) {
   AttnPlan plan;
   int rc = build_attn_plan(static_cast<const bf16*>(qk_bf16), static_cast<const bf16*>(vt_bf16),
                            static_cast<bf16*>(out_bf16), B, N, heads, d, &plan);
   if (rc) return rc;
+  plan.dbg = g_attn_dbg;
   return launch_attn_plan(plan, static_cast<cudaStream_t>(stream));
 }
+
+void pbe_debug_set_attention_trace(void* dev_buffer) { g_attn_dbg = static_cast<long long*>(dev_buffer); }
 
 int64_t pbe_op_groupnorm_workspace_bytes(int Nb, int HW) {
   return static_cast<int64_t>(gn_workspace_floats(Nb, HW, 2560)) * sizeof(float);

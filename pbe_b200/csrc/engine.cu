@@ -411,7 +411,9 @@ int Engine::build(Prepared& P, bool dry) {
   };
   int err = 0;
   auto add_gemm = [&](const std::string& name, ConvGemmDesc d) {
-    if (dry) { launches += 1; return; }
+    const size_t ws_bytes = gemm_splitk_ws_bytes(d);
+    d.splitk_ws = ws_bytes ? static_cast<float*>(SA(ws_bytes)) : nullptr;
+    if (dry) { launches += ws_bytes ? 2 : 1; return; }
     auto plan = std::make_shared<GemmPlan>();
     int rc = build_gemm_plan(d, plan.get());
     if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + name + "]"; }
@@ -423,7 +425,8 @@ int Engine::build(Prepared& P, bool dry) {
     if (d.out_f32) bytes += Mrows * out_cols * 4.0;
     if (d.out_bf16 || d.out_vt) bytes += Mrows * out_cols * 2.0;
     if (d.residual) bytes += Mrows * out_cols * 4.0;
-    add_op_meta(name, 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); }, "conv_gemm", flops, bytes);
+    add_op_meta(name, ws_bytes ? 2 : 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); }, "conv_gemm", flops,
+                bytes);
   };
   auto add_gn = [&](const std::string& name, GroupNormArgs a) {
     a.partial = static_cast<float*>(SA(static_cast<size_t>(gn_workspace_floats(a.Nb, a.HW, a.C0 + a.C1)) * sizeof(float)));

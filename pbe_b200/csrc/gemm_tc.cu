@@ -83,11 +83,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_ptr_addr = sBar + 8u * (2 * STAGES + 4 + NUM_SLOTS);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (2 * STAGES + 4 + NUM_SLOTS));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   const int num_k_iters = p.num_taps * p.k_chunks;
   const int n_tiles = p.n_tiles;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * n_tiles;
+  const int split_k = p.split_k;                                  // >1: partial sums go to a workspace slice
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * n_tiles * split_k;  // work units (tile x split)
+  auto k_range = [&](int unit, int& k_begin, int& k_end) {
+    const int sidx = unit % split_k;
+    k_begin = static_cast<int>(static_cast<long long>(num_k_iters) * sidx / split_k);
+    k_end = static_cast<int>(static_cast<long long>(num_k_iters) * (sidx + 1) / split_k);
+  };
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -114,21 +120,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
+        const int tile = unit / split_k;
+        int k_begin, k_end;
+        k_range(unit, k_begin, k_end);
         const int n_base = (tile % n_tiles) * BLOCK_N;
         int mt = tile / n_tiles;
         const int w0 = (mt % p.tiles_w) * p.tw;
         mt /= p.tiles_w;
         const int h0 = (mt % p.tiles_h) * p.th;
         const int n0 = (mt / p.tiles_h) * p.tn;
-        for (int it = 0; it < num_k_iters; ++it) {
+        for (int it = k_begin; it < k_end; ++it) {
           const int tap = it / p.k_chunks;
           const int kc = it - tap * p.k_chunks;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -146,26 +155,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++ti) {
       const int buf = ti & 1;
+      int k_begin, k_end;
+      k_range(unit, k_begin, k_end);
       mbar_wait(tmem_empty_bar(buf), ((ti >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
-      for (int it = 0; it < num_k_iters; ++it) {
+      for (int it = k_begin; it < k_end; ++it) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint64_t adesc = umma_desc_sw128(sA + stage * A_STAGE_BYTES);
           const uint64_t bdesc = umma_desc_sw128(sB + stage * B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the 16-B-unit start address field
-            umma_bf16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss_elect(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > k_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // smem slot free once these MMAs retire
-          if (it == num_k_iters - 1) umma_commit(tmem_full_bar(buf));
+          umma_commit_elect(empty_bar(stage));  // smem slot free once these MMAs retire
+          if (it == k_end - 1) umma_commit_elect(tmem_full_bar(buf));
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -195,7 +205,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float* __restrict__ rowbias = p.rowbias;
     bf16* __restrict__ out_bf16 = p.out_bf16;
 
-    auto tile_geom = [&](int tile, int& n_tile, int& w0, int& h0, int& n0) {
+    // unit -> tile geometry; n_store = batch coordinate used by the TMA store (split-K slices are stacked along n)
+    auto tile_geom = [&](int unit, int& n_tile, int& w0, int& h0, int& n0) {
+      const int tile = unit / split_k;
       n_tile = tile % n_tiles;
       int mt = tile / n_tiles;
       w0 = (mt % p.tiles_w) * p.tw;
@@ -203,6 +215,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       h0 = (mt % p.tiles_h) * p.th;
       n0 = (mt / p.tiles_h) * p.tn;
     };
+    const int nb_pad = p.tiles_n * p.tn;
     auto tile_is_vt = [&](int n_tile) { return p.mode == EPI_QKV && n_tile * BLOCK_N >= p.qk_cols; };
     auto chunk_valid = [&](int n_tile, int c) { return c < nchunks && n_tile * tile_out_cols + c * chunk_cols < out_cols_total; };
 
@@ -389,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         named_bar_sync(bar_id, 128);
         if (elected) {
           const int ocol = n_tile * tile_out_cols + c * chunk_cols;
-          if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0);
+          if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + (tile % split_k) * nb_pad);
           else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
           tma_store_commit();
           tma_store_wait_read0();  // slot may be overwritten again
@@ -456,7 +469,77 @@ void pick_tile(int Wo, int Ho, int Nb, int* tw, int* th, int* tn) {
   (void)Nb;
 }
 
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitKReduce r) {
+  const long long n4 = r.M * (r.N / 4);
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  const long long m = idx / (r.N / 4);
+  const int col = static_cast<int>(idx - m * (r.N / 4)) * 4;
+  float4 acc = *reinterpret_cast<const float4*>(r.ws + m * r.N + col);
+  for (int s = 1; s < r.S; ++s) {  // fixed order -> bit-reproducible
+    const float4 v = *reinterpret_cast<const float4*>(r.ws + s * r.slice_stride + m * r.N + col);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (r.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(r.bias + col);
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  if (r.rowbias) {
+    const long long smp = m / r.HW;
+    const float4 b = *reinterpret_cast<const float4*>(r.rowbias + smp * r.rowbias_ld + col);
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  const long long o = m * r.ld_out + col;
+  if (r.residual) {
+    const float4 b = *reinterpret_cast<const float4*>(r.residual + o);
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  if (r.out_f32) *reinterpret_cast<float4*>(r.out_f32 + o) = acc;
+  if (r.out_bf16) {
+    uint2 pk;
+    pk.x = pack_bf16x2(acc.x, acc.y);
+    pk.y = pack_bf16x2(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(r.out_bf16 + o) = pk;
+  }
+}
+
+int auto_block_n(const ConvGemmDesc& d) {
+  if (d.block_n) return d.block_n;
+  if (d.mode == EPI_GEGLU) return 128;
+  if (d.Cout % 160 == 0) return 160;
+  if (d.Cout % 128 == 0) return 128;
+  if (d.Cout <= 32) return 32;
+  if (d.Cout <= 64) return 64;
+  return 128;
+}
+
 }  // namespace
+
+int gemm_split_k(const ConvGemmDesc& d) {
+  if (d.mode != EPI_STD || d.Cout % 4 != 0) return 1;
+  int tw, th, tn;
+  const int Wo = d.W / d.stride, Ho = d.H / d.stride;
+  pick_tile(Wo, Ho, d.Nb, &tw, &th, &tn);
+  const int bn = auto_block_n(d);
+  const int tiles = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((d.Nb + tn - 1) / tn) * ((d.Cout + bn - 1) / bn);
+  const int k_iters = d.ksize * d.ksize * (d.C / 64);
+  const int sms = num_sms();
+  if (tiles * 2 > sms) return 1;
+  int S = sms / tiles;
+  S = std::min(S, std::max(1, k_iters / 8));
+  S = std::min(S, 16);
+  return std::max(S, 1);
+}
+
+size_t gemm_splitk_ws_bytes(const ConvGemmDesc& d) {
+  const int S = gemm_split_k(d);
+  if (S <= 1) return 0;
+  int tw, th, tn;
+  const int Wo = d.W / d.stride, Ho = d.H / d.stride;
+  pick_tile(Wo, Ho, d.Nb, &tw, &th, &tn);
+  const size_t nb_pad = static_cast<size_t>((d.Nb + tn - 1) / tn) * tn;
+  return static_cast<size_t>(S) * nb_pad * Ho * Wo * d.Cout * sizeof(float);
+}
 
 int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   PBE_REQUIRE(d.C % 64 == 0, "activation channels must be a multiple of 64");
@@ -506,22 +589,17 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.qk_cols = d.qk_cols;
   p.ld_out = d.ld_out ? d.ld_out : (d.mode == EPI_GEGLU ? d.Cout / 2 : d.Cout);
 
-  int bn = d.block_n;
-  if (bn == 0) {
-    if (d.mode == EPI_GEGLU) bn = 128;
-    else if (d.Cout % 160 == 0) bn = 160;
-    else if (d.Cout % 128 == 0) bn = 128;
-    else if (d.Cout <= 32) bn = 32;
-    else if (d.Cout <= 64) bn = 64;
-    else bn = 128;
-  }
+  const int bn = auto_block_n(d);
+  p.split_k = (d.splitk_ws != nullptr) ? gemm_split_k(d) : 1;
+  plan->red = SplitKReduce{};
+  plan->red.S = p.split_k;
   PBE_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
   if (d.mode == EPI_GEGLU) PBE_REQUIRE(bn == 128 && d.Cout % 128 == 0, "GEGLU needs BLOCK_N=128 | Cout");
   if (d.mode == EPI_QKV) PBE_REQUIRE(d.qk_cols % bn == 0 && d.Cout % bn == 0, "QKV split must align with BLOCK_N");
   plan->block_n = bn;
   p.n_tiles = (d.Cout + bn - 1) / bn;
   {
-    const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+    const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.split_k;
     plan->grid = dim3(std::min(total, num_sms()), 1, 1);
   }
 
@@ -552,6 +630,28 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     p.has_o32 = d.out_f32 != nullptr;
     p.has_o16 = d.out_bf16 != nullptr;
     PBE_REQUIRE(p.has_o32 || p.has_o16, "GEMM needs an output");
+    if (p.split_k > 1) {
+      // main kernel: raw fp32 partial tiles into the workspace, slices stacked along the batch coordinate
+      const uint64_t nb_pad = static_cast<uint64_t>(p.tiles_n) * p.tn;
+      SplitKReduce& r = plan->red;
+      r.ws = d.splitk_ws;
+      r.slice_stride = static_cast<long long>(nb_pad) * p.Ho * p.Wo * d.Cout;
+      r.M = static_cast<long long>(p.Nb) * p.Ho * p.Wo;
+      r.N = d.Cout;
+      r.HW = p.Ho * p.Wo;
+      r.bias = d.bias; r.rowbias = d.rowbias; r.rowbias_ld = p.rowbias_ld; r.residual = d.residual;
+      r.out_f32 = d.out_f32; r.out_bf16 = d.out_bf16; r.ld_out = p.ld_out;
+      p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr; p.out_bf16 = nullptr;
+      p.out_f32 = d.splitk_ws;
+      p.has_res = 0; p.has_o32 = 1; p.has_o16 = 0;
+      const uint64_t wdims[4] = {static_cast<uint64_t>(d.Cout), Wo, Ho, nb_pad * p.split_k};
+      const uint64_t wld = static_cast<uint64_t>(d.Cout);
+      const uint64_t ws32[3] = {wld * 4, Wo * wld * 4, Ho * Wo * wld * 4};
+      int rcw = make_tmap(&plan->tmO32, d.splitk_ws, true, 4, wdims, ws32, box, 128);
+      if (rcw) return rcw;
+      plan->tmR = plan->tmO32;
+      plan->tmO16 = plan->tmO32;
+    } else {
     PBE_REQUIRE(!(d.mode != EPI_STD && (p.has_res || p.has_o32)), "GEGLU / QKV epilogues write bf16 only");
     const uint64_t s32[3] = {ld * 4, Wo * ld * 4, Ho * Wo * ld * 4};
     const uint64_t s16[3] = {ld * 2, Wo * ld * 2, Ho * Wo * ld * 2};
@@ -566,6 +666,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     if (!p.has_res) plan->tmR = p.has_o32 ? plan->tmO32 : plan->tmO16;
     if (!p.has_o32) plan->tmO32 = plan->tmO16;
     if (!o16_tma) plan->tmO16 = plan->tmO32;
+    }
   }
   // B: 3-D (cin, cout, tap)
   {
@@ -579,7 +680,20 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   return 0;
 }
 
+static int launch_main(const GemmPlan& plan, cudaStream_t stream);
+
 int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream) {
+  int rc = launch_main(plan, stream);
+  if (rc) return rc;
+  if (plan.red.S > 1) {
+    const long long n4 = plan.red.M * (plan.red.N / 4);
+    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(plan.red);
+    PBE_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+static int launch_main(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.block_n) {
     case 32: return launch_t<32, 6>(plan, stream);
     case 64: return launch_t<64, 6>(plan, stream);

@@ -57,6 +57,7 @@ struct ConvGemmParams {
   int n_total;             // number of GEMM columns (Cout)
   int n_tiles;             // ceil(n_total / BLOCK_N)
   int has_res, has_o32, has_o16;  // which epilogue tensor maps are live
+  int split_k;                    // >1: K range split over work units, partial sums to a workspace
   int8_t tap_dw[9], tap_dh[9], tap_ph[9];
   int tap_coff[9];
   // epilogue
@@ -73,7 +74,17 @@ struct ConvGemmParams {
   int qk_cols;
 };
 
+// Deterministic split-K: slice s of the K range writes its partial tile to ws[s]; a second small kernel sums the
+// slices in fixed order and applies the fused epilogue terms.
+struct SplitKReduce {
+  const float* ws; int S; long long slice_stride;  // floats between slices
+  long long M; int N; int HW;                      // rows, columns, rows per sample
+  const float* bias; const float* rowbias; int rowbias_ld; const float* residual;
+  float* out_f32; bf16* out_bf16; int ld_out;
+};
+
 struct GemmPlan {
+  SplitKReduce red;
   CUtensorMap tmA, tmB;
   CUtensorMap tmR, tmO32, tmO16;  // residual (fp32 load), fp32 output store, bf16 output store (epilogue TMA)
   ConvGemmParams p;
@@ -101,7 +112,11 @@ struct ConvGemmDesc {
   bf16* out_vt;
   int qk_cols;
   int block_n;  // 0 -> auto
+  float* splitk_ws;        // optional workspace enabling split-K (size from gemm_splitk_ws_bytes)
 };
+// Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
+int gemm_split_k(const ConvGemmDesc& d);
+size_t gemm_splitk_ws_bytes(const ConvGemmDesc& d);
 
 int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan);
 int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream);
@@ -115,6 +130,7 @@ struct AttnPlan {
   int B, N, heads, d;
   float scale_log2;
   bf16* out;
+  long long* dbg;
   dim3 grid;
   size_t smem;
 };
