@@ -411,7 +411,7 @@ int Engine::build(Prepared& P, bool dry) {
   };
   int err = 0;
   auto add_gemm = [&](const std::string& name, ConvGemmDesc d) {
-    const size_t ws_bytes = gemm_splitk_ws_bytes(d);
+    const size_t ws_bytes = d.stats_out ? 0 : gemm_splitk_ws_bytes(d);
     d.splitk_ws = ws_bytes ? static_cast<float*>(SA(ws_bytes)) : nullptr;
     if (dry) { launches += ws_bytes ? 2 : 1; return; }
     auto plan = std::make_shared<GemmPlan>();
@@ -431,8 +431,9 @@ int Engine::build(Prepared& P, bool dry) {
   auto add_gn = [&](const std::string& name, GroupNormArgs a) {
     a.partial = static_cast<float*>(SA(static_cast<size_t>(gn_workspace_floats(a.Nb, a.HW, a.C0 + a.C1)) * sizeof(float)));
     const double n = static_cast<double>(a.Nb) * a.HW * (a.C0 + a.C1);
-    add_op_meta(name, 3, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
-                n * (4.0 + 4.0 + 2.0 + (a.raw ? 2.0 : 0.0)));
+    const bool fused_stats = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
+    add_op_meta(name, fused_stats ? 2 : 3, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
+                n * ((fused_stats ? 4.0 : 8.0) + 2.0 + (a.raw ? 2.0 : 0.0)));
   };
 
   P.x_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.in_channels * H0 * W0 * sizeof(float)));
@@ -464,6 +465,18 @@ int Engine::build(Prepared& P, bool dry) {
     bf16* b16;  // optional bf16 copy
     int C, H, W;
     bool has16 = false;
+    float* stats = nullptr;   // fused GroupNorm statistics written by the producing GEMM (or null)
+    bool has_stats = false;
+  };
+  // Attach fused GroupNorm statistics to a GEMM whose fp32 output `o` is normalised by the next op.
+  auto want_stats = [&](ConvGemmDesc& d, Act& o, bool persistent) {
+    d.splitk_ws = nullptr;
+    if (!gemm_can_fuse_stats(d)) return;
+    const size_t rows = static_cast<size_t>(d.Nb) * (d.H / d.stride) * (d.W / d.stride);
+    const size_t bytes = rows / 32 * d.Cout * 2 * sizeof(float);
+    o.stats = static_cast<float*>(persistent ? PA(bytes) : SA(bytes));
+    o.has_stats = true;
+    d.stats_out = o.stats;
   };
   std::vector<Act> hs;
   Act h{nullptr, nullptr, 0, H0, W0};
@@ -486,6 +499,7 @@ int Engine::build(Prepared& P, bool dry) {
         ConvGemmDesc d{};
         d.act = xin; d.Nb = Bc; d.H = H0; d.W = W0; d.C = 64; d.c_real = cin; d.ksize = 3; d.stride = 1;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        want_stats(d, o, true);
         add_gemm(tag + ".conv_in", d);
         h = o;
         break;
@@ -509,20 +523,26 @@ int Engine::build(Prepared& P, bool dry) {
         GroupNormArgs g1{};
         g1.x0 = h.f32; g1.C0 = h.C; g1.x1 = skip.f32; g1.C1 = skip.C; g1.Nb = Bc; g1.HW = h.H * h.W;
         g1.gamma = r.gn1.g; g1.beta = r.gn1.b; g1.eps = 1e-5f; g1.silu = 1; g1.y = a1; g1.raw = raw;
+        g1.stats0 = h.has_stats ? h.stats : nullptr;
+        g1.stats1 = (skip.C > 0 && skip.has_stats) ? skip.stats : nullptr;
+        if (skip.C > 0 && !(h.has_stats && skip.has_stats)) g1.stats0 = g1.stats1 = nullptr;
         add_gn(tag + ".gn1", g1);
         float* h1 = static_cast<float*>(SA(M * r.cout * sizeof(float)));
+        Act h1act{h1, nullptr, r.cout, h.H, h.W};
         {
           ConvGemmDesc d{};
           d.act = a1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 3; d.stride = 1;
           d.wt = r.conv1.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv1.b;
           d.rowbias = emb_all + r.emb_off; d.rowbias_ld = emb_total_;
           d.out_f32 = h1;
+          want_stats(d, h1act, false);
           add_gemm(tag + ".conv1", d);
         }
         bf16* a2 = static_cast<bf16*>(SA(M * r.cout * sizeof(bf16)));
         GroupNormArgs g2{};
         g2.x0 = h1; g2.C0 = r.cout; g2.x1 = nullptr; g2.C1 = 0; g2.Nb = Bc; g2.HW = h.H * h.W;
         g2.gamma = r.gn2.g; g2.beta = r.gn2.b; g2.eps = 1e-5f; g2.silu = 1; g2.y = a2; g2.raw = nullptr;
+        g2.stats0 = h1act.has_stats ? h1act.stats : nullptr;
         add_gn(tag + ".gn2", g2);
         const float* resid = h.f32;
         if (r.has_skip) {
@@ -540,6 +560,7 @@ int Engine::build(Prepared& P, bool dry) {
           d.act = a2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = r.cout; d.ksize = 3; d.stride = 1;
           d.wt = r.conv2.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv2.b; d.residual = resid;
           d.out_f32 = o.f32; d.out_bf16 = o.b16;
+          want_stats(d, o, true);
           add_gemm(tag + ".conv2", d);
         }
         h = o;
@@ -554,6 +575,7 @@ int Engine::build(Prepared& P, bool dry) {
         GroupNormArgs g{};
         g.x0 = h.f32; g.C0 = C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = N;
         g.gamma = s.gn.g; g.beta = s.gn.b; g.eps = 1e-6f; g.silu = 0; g.y = a; g.raw = nullptr;
+        g.stats0 = h.has_stats ? h.stats : nullptr;
         add_gn(tag + ".norm", g);
         float* t0 = static_cast<float*>(SA(M * C * sizeof(float)));
         {
@@ -627,6 +649,7 @@ int Engine::build(Prepared& P, bool dry) {
           d.act = t2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.proj_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_out.b; d.residual = h.f32;
           d.out_f32 = o.f32; d.out_bf16 = o.b16;
+          want_stats(d, o, true);
           add_gemm(tag + ".proj_out", d);
         }
         h = o;
@@ -644,6 +667,7 @@ int Engine::build(Prepared& P, bool dry) {
         ConvGemmDesc d{};
         d.act = h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = h.C; d.ksize = 3; d.stride = 2;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        want_stats(d, o, true);
         add_gemm(tag + ".downsample", d);
         h = o;
         break;
@@ -663,6 +687,7 @@ int Engine::build(Prepared& P, bool dry) {
         ConvGemmDesc d{};
         d.act = up; d.Nb = Bc; d.H = 2 * h.H; d.W = 2 * h.W; d.C = h.C; d.ksize = 3; d.stride = 1;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        want_stats(d, o, true);
         add_gemm(tag + ".upsample.conv", d);
         h = o;
         break;
@@ -674,6 +699,7 @@ int Engine::build(Prepared& P, bool dry) {
         GroupNormArgs g{};
         g.x0 = h.f32; g.C0 = h.C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = h.H * h.W;
         g.gamma = out_norm_.g; g.beta = out_norm_.b; g.eps = 1e-5f; g.silu = 1; g.y = a; g.raw = nullptr;
+        g.stats0 = h.has_stats ? h.stats : nullptr;
         add_gn(tag + ".out.norm", g);
         float* y = static_cast<float*>(SA(M * c.cout * sizeof(float)));
         ConvGemmDesc d{};

@@ -364,6 +364,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int u = 0; u < 8; ++u)
             *reinterpret_cast<float4*>(my_row128 + ((u ^ (row & 7)) << 4)) =
                 make_float4(o[4 * u + 0], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+          if (p.stats_out != nullptr) {
+            // GroupNorm statistics of the tensor being written: lane = column, walk my warp's 32 rows of the slot
+            // (conflict-free: one 128-B row per step).  Fixed order, no atomics -> bit-reproducible.
+            __syncwarp();
+            const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
+            const long long m_first = __shfl_sync(0xffffffffu, my_m, 0);
+            const int col = n_base + c * 32 + lane;
+            if (vmask != 0u && col < p.n_total) {
+              float sm = 0.0f, sq = 0.0f;
+              const uint8_t* wrow = slot_gen + (q * 32) * 128;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const float x = *reinterpret_cast<const float*>(wrow + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                if ((vmask >> r) & 1u) { sm += x; sq = fmaf(x, x, sq); }
+              }
+              *reinterpret_cast<float2*>(p.stats_out + ((m_first >> 5) * p.n_total + col) * 2) = make_float2(sm, sq);
+            }
+          }
           if (p.has_o16 && my_valid) {  // rare side copy (feeds a stride-2 conv): direct 64-B row store
             const int col = n_base + c * 32;
             bf16* dst = out_bf16 + my_m * p.ld_out + col;
@@ -531,6 +549,17 @@ int gemm_split_k(const ConvGemmDesc& d) {
   return std::max(S, 1);
 }
 
+bool gemm_can_fuse_stats(const ConvGemmDesc& d) {
+  if (d.mode != EPI_STD || gemm_split_k(d) > 1) return false;
+  int tw, th, tn;
+  const int Wo = d.W / d.stride, Ho = d.H / d.stride;
+  pick_tile(Wo, Ho, d.Nb, &tw, &th, &tn);
+  if (Wo % tw != 0 || Ho % th != 0) return false;          // no partial tiles inside a sample
+  if (!(tw % 32 == 0 || (tw == Wo && 32 % tw == 0))) return false;  // a warp's 32 rows are 32 consecutive pixels
+  if ((tw * th) % 32 != 0 || (Ho * Wo) % 32 != 0) return false;     // ... of one sample
+  return true;
+}
+
 size_t gemm_splitk_ws_bytes(const ConvGemmDesc& d) {
   const int S = gemm_split_k(d);
   if (S <= 1) return 0;
@@ -591,6 +620,11 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
 
   const int bn = auto_block_n(d);
   p.split_k = (d.splitk_ws != nullptr) ? gemm_split_k(d) : 1;
+  p.stats_out = nullptr;
+  if (d.stats_out != nullptr) {
+    PBE_REQUIRE(gemm_can_fuse_stats(d) && p.split_k == 1 && d.out_f32 != nullptr, "fused GroupNorm statistics not available for this GEMM");
+    p.stats_out = d.stats_out;
+  }
   plan->red = SplitKReduce{};
   plan->red.S = p.split_k;
   PBE_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");

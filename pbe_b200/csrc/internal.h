@@ -58,6 +58,7 @@ struct ConvGemmParams {
   int n_tiles;             // ceil(n_total / BLOCK_N)
   int has_res, has_o32, has_o16;  // which epilogue tensor maps are live
   int split_k;                    // >1: K range split over work units, partial sums to a workspace
+  float* stats_out;               // optional [M/32][n_total][2] per-32-row (sum, sumsq) of the fp32 output (GroupNorm)
   int8_t tap_dw[9], tap_dh[9], tap_ph[9];
   int tap_coff[9];
   // epilogue
@@ -113,9 +114,12 @@ struct ConvGemmDesc {
   int qk_cols;
   int block_n;  // 0 -> auto
   float* splitk_ws;        // optional workspace enabling split-K (size from gemm_splitk_ws_bytes)
+  float* stats_out;        // optional fused GroupNorm statistics of out_f32 (see gemm_can_fuse_stats)
 };
 // Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
 int gemm_split_k(const ConvGemmDesc& d);
+// True when the epilogue can emit per-32-row column statistics for this geometry (no split-K, aligned tiles).
+bool gemm_can_fuse_stats(const ConvGemmDesc& d);
 size_t gemm_splitk_ws_bytes(const ConvGemmDesc& d);
 
 int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan);
@@ -150,6 +154,9 @@ struct GroupNormArgs {
   float eps; int silu;
   bf16* y; bf16* raw;        // raw may be null
   float* partial;            // workspace of gn_workspace_floats(Nb, HW, C0+C1) floats (16-B aligned)
+  // optional statistics fused into the producers' GEMM epilogues: [Nb*HW/32][C_i][2]; when every live source has
+  // them the stats pass over x is skipped
+  const float* stats0; const float* stats1;
 };
 int gn_num_slabs(int HW);
 int gn_workspace_floats(int Nb, int HW, int C);

@@ -134,6 +134,69 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_kernel(const float* __
   }
 }
 
+// grid (32 groups, Nb): same result as gn_finalize_kernel, but from the per-32-row column statistics the producing
+// GEMM epilogues wrote ([Nb*HW/32][C_i][2] per source): no pass over x at all.  One small CTA per (sample, group):
+// threads = (channel of the group) x (interleaved subsets of the row blocks); fixed-order double reduction.
+constexpr int GNF_THREADS = 128;
+__global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const float* __restrict__ st0, int C0,
+                                                                        const float* __restrict__ st1, int C1, int HW,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, float eps,
+                                                                        float2* __restrict__ ab) {
+  __shared__ double s_a[GNF_THREADS], s_q[GNF_THREADS];
+  __shared__ float s_mean, s_rstd;
+  const int C = C0 + C1;
+  const int cpg = C / 32;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int blocks = HW / 32;
+  const int nsub = GNF_THREADS / cpg;          // >= 1 (cpg <= 80)
+  const int t = threadIdx.x;
+  const int ci = t % cpg, sub = t / cpg;
+  double a = 0.0, q = 0.0;
+  if (sub < nsub) {
+    const int c = g * cpg + ci;
+    const float* src = (c < C0) ? st0 + (static_cast<long long>(b) * blocks * C0 + c) * 2
+                                : st1 + (static_cast<long long>(b) * blocks * C1 + (c - C0)) * 2;
+    const long long ld = static_cast<long long>((c < C0) ? C0 : C1) * 2;
+    int k = sub;
+    for (; k + 3 * nsub < blocks; k += 4 * nsub) {   // four independent loads in flight
+      const float2 v0 = *reinterpret_cast<const float2*>(src + k * ld);
+      const float2 v1 = *reinterpret_cast<const float2*>(src + (k + nsub) * ld);
+      const float2 v2 = *reinterpret_cast<const float2*>(src + (k + 2 * nsub) * ld);
+      const float2 v3 = *reinterpret_cast<const float2*>(src + (k + 3 * nsub) * ld);
+      a += (static_cast<double>(v0.x) + static_cast<double>(v1.x)) + (static_cast<double>(v2.x) + static_cast<double>(v3.x));
+      q += (static_cast<double>(v0.y) + static_cast<double>(v1.y)) + (static_cast<double>(v2.y) + static_cast<double>(v3.y));
+    }
+    for (; k < blocks; k += nsub) {
+      const float2 v = *reinterpret_cast<const float2*>(src + k * ld);
+      a += static_cast<double>(v.x);
+      q += static_cast<double>(v.y);
+    }
+  }
+  s_a[t] = a;
+  s_q[t] = q;
+  __syncthreads();
+  if (t == 0) {
+    double sa = 0.0, sq = 0.0;
+    for (int i = 0; i < cpg * nsub; ++i) {
+      sa += s_a[i];
+      sq += s_q[i];
+    }
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = sa / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean = static_cast<float>(mean);
+    s_rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  if (t < cpg) {
+    const int c = g * cpg + t;
+    const float sc = gamma[c] * s_rstd;
+    ab[static_cast<long long>(b) * C + c] = make_float2(sc, beta[c] - s_mean * sc);
+  }
+}
+
 // pure streaming pass: one float4 of x per thread-iteration
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x0, int C0,
                                                               const float* __restrict__ x1, int C1, int HW,
@@ -242,10 +305,17 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   const int slabs = gn_num_slabs(a.HW);
   float* partial = a.partial;
   float2* ab = reinterpret_cast<float2*>(a.partial + ((static_cast<size_t>(a.Nb) * slabs * 64 + 3) & ~static_cast<size_t>(3)));
-  gn_stats_kernel<<<dim3(slabs, a.Nb), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial);
-  PBE_CHECK_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<a.Nb, GN_THREADS, 0, stream>>>(partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab);
-  PBE_CHECK_CUDA(cudaGetLastError());
+  const bool fused = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
+  if (fused) {
+    gn_finalize_fused_kernel<<<dim3(32, a.Nb), GNF_THREADS, 0, stream>>>(a.stats0, a.C0, a.stats1, a.C1, a.HW, a.gamma,
+                                                                        a.beta, a.eps, ab);
+    PBE_CHECK_CUDA(cudaGetLastError());
+  } else {
+    gn_stats_kernel<<<dim3(slabs, a.Nb), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial);
+    PBE_CHECK_CUDA(cudaGetLastError());
+    gn_finalize_kernel<<<a.Nb, GN_THREADS, 0, stream>>>(partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab);
+    PBE_CHECK_CUDA(cudaGetLastError());
+  }
   const long long total_vec = static_cast<long long>(a.Nb) * a.HW * (C / 4);
   long long blocks = (total_vec + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
   if (blocks < 1) blocks = 1;
