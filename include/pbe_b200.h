@@ -26,7 +26,7 @@ const char* pbe_last_error(void);
  * ldm/modules/diffusionmodules/openaimodel.py:107-119,150-160,201-241 and ldm/modules/attention.py:38-65,198-230,270-297.
  *   act_bf16 : NHWC bf16 [Nb,H,W,C], C % 64 == 0        wt_bf16 : [ksize*ksize][Cout][C] bf16
  *   mode 0 (STD)  : out = acc + bias[n] + rowbias[b,n] + residual[m,n]  -> out_f32 and/or out_bf16 (row-major [M,Cout])
- *   mode 1 (GEGLU): out_bf16[m, j] = (acc_a+b_a) * gelu_erf(acc_g+b_g); weight rows interleaved per 128-col tile
+ *   mode 1 (GEGLU): out_bf16[m, j] = (acc_a+b_a) * gelu_erf(acc_g+b_g); weight rows interleaved per 256-col tile
  *   mode 2 (QKV)  : cols < qk_cols -> out_bf16 [M, qk_cols]; cols >= qk_cols -> out_vt [Nb][Cout-qk_cols][H*W]
  */
 int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksize, int stride, const void* wt_bf16,

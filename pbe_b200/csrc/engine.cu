@@ -211,12 +211,12 @@ int Engine::finalize() {
         set_error("GEGLU proj of " + pfx + " has wrong size");
         return -4;
       }
-      PBE_REQUIRE(inner % 64 == 0, "GEGLU inner dim % 64");
+      PBE_REQUIRE(inner % 128 == 0, "GEGLU inner dim % 128");
       std::vector<float> w(W->data.size()), b(B->data.size());
-      for (int t = 0; t < inner / 64; ++t)
-        for (int j = 0; j < 64; ++j) {
-          const int src_v = t * 64 + j, src_g = inner + t * 64 + j;
-          const int dst_v = t * 128 + j, dst_g = t * 128 + 64 + j;
+      for (int t = 0; t < inner / 128; ++t)
+        for (int j = 0; j < 128; ++j) {
+          const int src_v = t * 128 + j, src_g = inner + t * 128 + j;
+          const int dst_v = t * 256 + j, dst_g = t * 256 + 128 + j;
           memcpy(&w[static_cast<size_t>(dst_v) * c], &W->data[static_cast<size_t>(src_v) * c], c * sizeof(float));
           memcpy(&w[static_cast<size_t>(dst_g) * c], &W->data[static_cast<size_t>(src_g) * c], c * sizeof(float));
           b[dst_v] = B->data[src_v];

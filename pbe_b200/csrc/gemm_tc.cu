@@ -29,35 +29,82 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int STAGE_LD = 36;  // epilogue transpose buffer row pitch (floats); 16-B aligned rows
-constexpr int STAGE_LD4 = STAGE_LD / 4;
 constexpr int NUM_SLOTS = 4;
 constexpr int SLOT_BYTES = 128 * 32 * 4;  // one 32-column fp32 chunk of a 128-row tile
 constexpr int EPI_STAGING_BYTES = NUM_SLOTS * SLOT_BYTES;
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-// exact-erf GELU (torch.nn.functional.gelu default). erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
-// the bf16 resolution of the stored result): 1 MUFU.RCP + 1 MUFU.EX2 + ~10 FMA instead of libdevice erff
-// (rcp.approx / ex2.approx: <= 2 ulp each).
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erfv = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erfv);
+// exact-erf GELU (torch.nn.functional.gelu default): erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
+// the bf16 resolution of the stored result): 1 MUFU.RCP + 1 MUFU.EX2 + a handful of FMAs instead of libdevice erff
+// (rcp.approx / ex2.approx: <= 2 ulp each).  See geglu2() below.
+
+// ---- packed fp32x2 arithmetic (FFMA2 on sm_100): two GEGLU outputs per instruction stream ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// (a0, a1) * gelu_erf((g0, g1)) with the same Abramowitz-Stegun 7.1.26 erf as gelu_erf(), two lanes per FFMA2.
+// The GEGLU epilogue is ALU-issue bound (K = C is short, 64 GELUs per thread per tile): ~11 issue slots per output
+// instead of ~20.
+__device__ __forceinline__ f32x2 geglu2(f32x2 a, f32x2 g) {
+  const f32x2 az = g & 0x7fffffff7fffffffull;                                   // |g|
+  const f32x2 z = mul2(az, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+  const f32x2 d = fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.0f, 1.0f));
+  float d0, d1;
+  upk2(d, d0, d1);
+  const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
+  // -poly(t): constants negated so that erf_abs = fma(-poly * t, e, 1)
+  f32x2 np = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));
+  np = fma2(np, t, pk2(-1.421413741f, -1.421413741f));
+  np = fma2(np, t, pk2(0.284496736f, 0.284496736f));
+  np = fma2(np, t, pk2(-0.254829592f, -0.254829592f));
+  np = mul2(np, t);
+  const f32x2 arg = mul2(mul2(z, z), pk2(-1.4426950408889634f, -1.4426950408889634f));
+  float x0, x1;
+  upk2(arg, x0, x1);
+  const f32x2 e = pk2(ex2_approx(x0), ex2_approx(x1));
+  const f32x2 erf_abs = fma2(np, e, pk2(1.0f, 1.0f));                            // >= 0
+  const f32x2 erfv = erf_abs | (g & 0x8000000080000000ull);                      // copysign(erf_abs, g)
+  const f32x2 h = fma2(erfv, pk2(0.5f, 0.5f), pk2(0.5f, 0.5f));                  // 0.5 (1 + erf)
+  return mul2(a, mul2(g, h));
 }
 
-// Persistent kernel: one CTA per SM walks tiles (n-tile fastest, so co-running CTAs share A tiles and all weights in
-// L2).  Two TMEM accumulator buffers: the MMA warp fills buffer (i+1)&1 while the 8 epilogue warps drain buffer i&1.
+// Work-unit coordinates (split slice, n tile, w / h / batch tile) advanced incrementally: unit += gridDim.x is a
+// mixed-radix addition with carries (a dozen integer ops) instead of five runtime divisions per tile and role
+// (ncu on the short-K GEMMs: index arithmetic was ~half of the epilogue's instruction stream).
+struct TileCoord {
+  int s, nt, wi, hi, ni;
+};
+struct TileStep {
+  int S, NT, TW, TH;           // radices
+  int ds, dnt, dwi, dhi, dni;  // digits of the stride gridDim.x
+};
+__device__ __forceinline__ TileCoord tile_coord_from_unit(int unit, const TileStep& r) {
+  TileCoord c;
+  c.s = unit % r.S; unit /= r.S;
+  c.nt = unit % r.NT; unit /= r.NT;
+  c.wi = unit % r.TW; unit /= r.TW;
+  c.hi = unit % r.TH;
+  c.ni = unit / r.TH;
+  return c;
+}
+__device__ __forceinline__ void tile_coord_advance(TileCoord& c, const TileStep& r) {
+  int carry;
+  c.s += r.ds; carry = c.s >= r.S; c.s -= carry ? r.S : 0;
+  c.nt += r.dnt + carry; carry = c.nt >= r.NT; c.nt -= carry ? r.NT : 0;
+  c.wi += r.dwi + carry; carry = c.wi >= r.TW; c.wi -= carry ? r.TW : 0;
+  c.hi += r.dhi + carry; carry = c.hi >= r.TH; c.hi -= carry ? r.TH : 0;
+  c.ni += r.dni + carry;
+}
+
+// Persistent kernel: one CTA per SM walks work units (n-tile fastest, so co-running CTAs share A tiles and all weights
+// in L2).  Two TMEM accumulator buffers: the MMA warp fills buffer (i+1)&1 while the 8 epilogue warps drain buffer i&1.
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -89,10 +136,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_tiles = p.n_tiles;
   const int split_k = p.split_k;                                  // >1: partial sums go to a workspace slice
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * n_tiles * split_k;  // work units (tile x split)
-  auto k_range = [&](int unit, int& k_begin, int& k_end) {
-    const int sidx = unit % split_k;
-    k_begin = static_cast<int>(static_cast<long long>(num_k_iters) * sidx / split_k);
-    k_end = static_cast<int>(static_cast<long long>(num_k_iters) * (sidx + 1) / split_k);
+  TileStep tstep;
+  tstep.S = split_k; tstep.NT = n_tiles; tstep.TW = p.tiles_w; tstep.TH = p.tiles_h;
+  {
+    const TileCoord d = tile_coord_from_unit(static_cast<int>(gridDim.x), tstep);
+    tstep.ds = d.s; tstep.dnt = d.nt; tstep.dwi = d.wi; tstep.dhi = d.hi; tstep.dni = d.ni;
+  }
+  auto k_range = [&](int sidx, int& k_begin, int& k_end) {
+    k_begin = (num_k_iters * sidx) / split_k;
+    k_end = (num_k_iters * (sidx + 1)) / split_k;
   };
 
   // ---- one-time setup ----
@@ -127,16 +179,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
-        const int tile = unit / split_k;
+      TileCoord tc = tile_coord_from_unit(blockIdx.x, tstep);
+      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, tile_coord_advance(tc, tstep)) {
         int k_begin, k_end;
-        k_range(unit, k_begin, k_end);
-        const int n_base = (tile % n_tiles) * BLOCK_N;
-        int mt = tile / n_tiles;
-        const int w0 = (mt % p.tiles_w) * p.tw;
-        mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * p.th;
-        const int n0 = (mt / p.tiles_h) * p.tn;
+        k_range(tc.s, k_begin, k_end);
+        const int n_base = tc.nt * BLOCK_N;
+        const int w0 = tc.wi * p.tw;
+        const int h0 = tc.hi * p.th;
+        const int n0 = tc.ni * p.tn;
         for (int it = k_begin; it < k_end; ++it) {
           const int tap = it / p.k_chunks;
           const int kc = it - tap * p.k_chunks;
@@ -155,10 +205,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int ti = 0;
+    int s_idx = static_cast<int>(blockIdx.x % split_k);
+    const int s_step = static_cast<int>(gridDim.x % split_k);
     for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++ti) {
       const int buf = ti & 1;
       int k_begin, k_end;
-      k_range(unit, k_begin, k_end);
+      k_range(s_idx, k_begin, k_end);
+      s_idx += s_step;
+      if (s_idx >= split_k) s_idx -= split_k;
       mbar_wait(tmem_empty_bar(buf), ((ti >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
@@ -205,27 +259,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float* __restrict__ rowbias = p.rowbias;
     bf16* __restrict__ out_bf16 = p.out_bf16;
 
-    // unit -> tile geometry; n_store = batch coordinate used by the TMA store (split-K slices are stacked along n)
-    auto tile_geom = [&](int unit, int& n_tile, int& w0, int& h0, int& n0) {
-      const int tile = unit / split_k;
-      n_tile = tile % n_tiles;
-      int mt = tile / n_tiles;
-      w0 = (mt % p.tiles_w) * p.tw;
-      mt /= p.tiles_w;
-      h0 = (mt % p.tiles_h) * p.th;
-      n0 = (mt / p.tiles_h) * p.tn;
-    };
     const int nb_pad = p.tiles_n * p.tn;
     auto tile_is_vt = [&](int n_tile) { return p.mode == EPI_QKV && n_tile * BLOCK_N >= p.qk_cols; };
     auto chunk_valid = [&](int n_tile, int c) { return c < nchunks && n_tile * tile_out_cols + c * chunk_cols < out_cols_total; };
 
     // ---- prefetch iterator (elected thread): walks the chunks this warp-set will consume, in order ----
     int pf_ti = 0, pf_tile = blockIdx.x, pf_c = ws & 1, pf_seq = 0;
+    TileCoord pf_tc = tile_coord_from_unit(blockIdx.x, tstep);
     auto pf_issue_next = [&]() {
       // find the next valid chunk at or after (pf_ti, pf_c)
       while (pf_tile < total_tiles) {
-        int n_tile, w0, h0, n0;
-        tile_geom(pf_tile, n_tile, w0, h0, n0);
+        const int n_tile = pf_tc.nt, w0 = pf_tc.wi * p.tw, h0 = pf_tc.hi * p.th, n0 = pf_tc.ni * p.tn;
         if (!tile_is_vt(n_tile) && chunk_valid(n_tile, pf_c)) {
           const int slot = ws * 2 + (pf_seq & 1);
           if (p.has_res) {
@@ -242,6 +286,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // advance to the next tile
         ++pf_ti;
         pf_tile += gridDim.x;
+        tile_coord_advance(pf_tc, tstep);
         pf_c = (ws + pf_ti) & 1;
       }
     };
@@ -252,14 +297,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     int ti = 0;
     int seq = 0;  // chunks consumed by this warp-set
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    // position of my accumulator row inside a tile: constant over all tiles
+    const int wl = row % p.tw;
+    const int hl = (row / p.tw) % p.th;
+    const int nl = row / (p.tw * p.th);
+    TileCoord tc = tile_coord_from_unit(blockIdx.x, tstep);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, tile_coord_advance(tc, tstep)) {
       const int buf = ti & 1;
-      int n_tile, w0, h0, n0;
-      tile_geom(tile, n_tile, w0, h0, n0);
+      const int n_tile = tc.nt, w0 = tc.wi * p.tw, h0 = tc.hi * p.th, n0 = tc.ni * p.tn;
       const int n_base = n_tile * BLOCK_N;
-      const int wl = row % p.tw;
-      const int hl = (row / p.tw) % p.th;
-      const int nl = row / (p.tw * p.th);
       const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
       const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
       const long long my_m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
@@ -320,10 +366,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; j += 4) {
             const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c * 32 + j));
             const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + HALF + c * 32 + j));
-            o[j + 0] = (__uint_as_float(va[j + 0]) + ba.x) * gelu_erf(__uint_as_float(vg[j + 0]) + bg.x);
-            o[j + 1] = (__uint_as_float(va[j + 1]) + ba.y) * gelu_erf(__uint_as_float(vg[j + 1]) + bg.y);
-            o[j + 2] = (__uint_as_float(va[j + 2]) + ba.z) * gelu_erf(__uint_as_float(vg[j + 2]) + bg.z);
-            o[j + 3] = (__uint_as_float(va[j + 3]) + ba.w) * gelu_erf(__uint_as_float(vg[j + 3]) + bg.w);
+            const f32x2 a01 = add2(pk2(__uint_as_float(va[j + 0]), __uint_as_float(va[j + 1])), pk2(ba.x, ba.y));
+            const f32x2 a23 = add2(pk2(__uint_as_float(va[j + 2]), __uint_as_float(va[j + 3])), pk2(ba.z, ba.w));
+            const f32x2 g01 = add2(pk2(__uint_as_float(vg[j + 0]), __uint_as_float(vg[j + 1])), pk2(bg.x, bg.y));
+            const f32x2 g23 = add2(pk2(__uint_as_float(vg[j + 2]), __uint_as_float(vg[j + 3])), pk2(bg.z, bg.w));
+            upk2(geglu2(a01, g01), o[j + 0], o[j + 1]);
+            upk2(geglu2(a23, g23), o[j + 2], o[j + 3]);
           }
         } else {
           uint32_t v[32];
@@ -420,7 +468,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         named_bar_sync(bar_id, 128);
         if (elected) {
           const int ocol = n_tile * tile_out_cols + c * chunk_cols;
-          if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + (tile % split_k) * nb_pad);
+          if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
           else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
           tma_store_commit();
           tma_store_wait_read0();  // slot may be overwritten again
@@ -523,7 +571,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitKReduce r) {
 
 int auto_block_n(const ConvGemmDesc& d) {
   if (d.block_n) return d.block_n;
-  if (d.mode == EPI_GEGLU) return 128;
+  if (d.mode == EPI_GEGLU) return 256;
   if (d.Cout % 160 == 0) return 160;
   if (d.Cout % 128 == 0) return 128;
   if (d.Cout <= 32) return 32;
@@ -628,7 +676,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   plan->red = SplitKReduce{};
   plan->red.S = p.split_k;
   PBE_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
-  if (d.mode == EPI_GEGLU) PBE_REQUIRE(bn == 128 && d.Cout % 128 == 0, "GEGLU needs BLOCK_N=128 | Cout");
+  if (d.mode == EPI_GEGLU) PBE_REQUIRE(bn == 256 && d.Cout % 256 == 0, "GEGLU needs BLOCK_N=256 | Cout");
   if (d.mode == EPI_QKV) PBE_REQUIRE(d.qk_cols % bn == 0 && d.Cout % bn == 0, "QKV split must align with BLOCK_N");
   plan->block_n = bn;
   p.n_tiles = (d.Cout + bn - 1) / bn;

@@ -197,39 +197,53 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const fl
   }
 }
 
-// pure streaming pass: one float4 of x per thread-iteration
+// pure streaming pass: four float4 of x per thread, all loads issued before the first use
+__device__ __forceinline__ void gn_apply_one(const float4 v, const float4 ab01, const float4 ab23, int silu,
+                                             bf16* __restrict__ y, bf16* __restrict__ raw, long long off) {
+  float o0 = fmaf(v.x, ab01.x, ab01.y), o1 = fmaf(v.y, ab01.z, ab01.w);
+  float o2 = fmaf(v.z, ab23.x, ab23.y), o3 = fmaf(v.w, ab23.z, ab23.w);
+  if (silu) {
+    o0 = o0 / (1.0f + __expf(-o0)); o1 = o1 / (1.0f + __expf(-o1));
+    o2 = o2 / (1.0f + __expf(-o2)); o3 = o3 / (1.0f + __expf(-o3));
+  }
+  uint2 pk;
+  pk.x = pack2(o0, o1);
+  pk.y = pack2(o2, o3);
+  *reinterpret_cast<uint2*>(y + off) = pk;
+  if (raw != nullptr) {
+    uint2 rk;
+    rk.x = pack2(v.x, v.y);
+    rk.y = pack2(v.z, v.w);
+    *reinterpret_cast<uint2*>(raw + off) = rk;
+  }
+}
+
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x0, int C0,
                                                               const float* __restrict__ x1, int C1, int HW,
                                                               long long total_vec, const float2* __restrict__ ab,
                                                               int silu, bf16* __restrict__ y, bf16* __restrict__ raw) {
   const int C = C0 + C1;
   const int vec_per_pix = C / 4;
-  for (long long idx = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; idx < total_vec;
-       idx += static_cast<long long>(gridDim.x) * GN_THREADS) {
-    const long long gp = idx / vec_per_pix;
-    const int c = static_cast<int>(idx - gp * vec_per_pix) * 4;
-    const int b = static_cast<int>(gp / HW);
-    const float4 v = ld4(x0, C0, x1, C1, gp, c);
-    const float4 ab01 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c));
-    const float4 ab23 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
-    float o0 = fmaf(v.x, ab01.x, ab01.y), o1 = fmaf(v.y, ab01.z, ab01.w);
-    float o2 = fmaf(v.z, ab23.x, ab23.y), o3 = fmaf(v.w, ab23.z, ab23.w);
-    if (silu) {
-      o0 = o0 / (1.0f + __expf(-o0)); o1 = o1 / (1.0f + __expf(-o1));
-      o2 = o2 / (1.0f + __expf(-o2)); o3 = o3 / (1.0f + __expf(-o3));
-    }
-    const long long off = gp * C + c;
-    uint2 pk;
-    pk.x = pack2(o0, o1);
-    pk.y = pack2(o2, o3);
-    *reinterpret_cast<uint2*>(y + off) = pk;
-    if (raw != nullptr) {
-      uint2 rk;
-      rk.x = pack2(v.x, v.y);
-      rk.y = pack2(v.z, v.w);
-      *reinterpret_cast<uint2*>(raw + off) = rk;
+  const long long base = static_cast<long long>(blockIdx.x) * (GN_THREADS * 4) + threadIdx.x;
+  float4 v[4], a01[4], a23[4];
+  long long off[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long idx = base + u * GN_THREADS;
+    off[u] = -1;
+    if (idx < total_vec) {
+      const long long gp = idx / vec_per_pix;
+      const int c = static_cast<int>(idx - gp * vec_per_pix) * 4;
+      const int b = static_cast<int>(gp / HW);
+      v[u] = ld4(x0, C0, x1, C1, gp, c);
+      a01[u] = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c));
+      a23[u] = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
+      off[u] = gp * C + c;
     }
   }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (off[u] >= 0) gn_apply_one(v[u], a01[u], a23[u], silu, y, raw, off[u]);
 }
 
 // One warp per row; row held in registers (C <= 1280).

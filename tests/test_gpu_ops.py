@@ -91,10 +91,10 @@ def test_gemm_geglu_epilogue(lib):
     x = torch.randn(M, C, generator=g).to(dev).bfloat16()
     w = (torch.randn(2 * inner, C, generator=g) / math.sqrt(C)).to(dev).bfloat16()
     b = torch.randn(2 * inner, generator=g).to(dev)
-    # interleave: tile t = 64 value rows then 64 gate rows (engine.cu add_st)
-    wv, wg = w[:inner].view(inner // 64, 64, C), w[inner:].view(inner // 64, 64, C)
+    # interleave: tile t = 128 value rows then 128 gate rows (engine.cu add_st)
+    wv, wg = w[:inner].view(inner // 128, 128, C), w[inner:].view(inner // 128, 128, C)
     wi = torch.cat((wv, wg), dim=1).reshape(2 * inner, C).contiguous()
-    bi = torch.cat((b[:inner].view(-1, 64), b[inner:].view(-1, 64)), dim=1).reshape(-1).contiguous()
+    bi = torch.cat((b[:inner].view(-1, 128), b[inner:].view(-1, 128)), dim=1).reshape(-1).contiguous()
     out = torch.zeros(M, inner, device=dev, dtype=torch.bfloat16)
     rc = lib.pbe_op_conv_gemm(x.data_ptr(), 1, 1, M, C, 1, 1, wi.data_ptr(), 2 * inner, 1, bi.data_ptr(), None, None,
                               None, out.data_ptr(), None, 0, 0, _stream())
