@@ -23,6 +23,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+
 import torch
 
 F64_MIN = 771.3e9   # algorithmic FLOPs per sample-eval at 64x64 with the dead cross-attention work elided

@@ -33,6 +33,10 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
                      int Cout, int mode, const float* bias, const float* rowbias, const float* residual,
                      float* out_f32, void* out_bf16, void* out_vt, int qk_cols, int block_n, void* stream);
 
+/* Debug aid (env PBE_GEMM_DEBUG=1): wait-time counters of CTA 0 of the last conv_gemm launch: [0] MMA-warp cycles,
+ * [1] cycles waiting for TMA stages, [2] cycles waiting for a free TMEM buffer, [4] K iterations. Host array of 8. */
+int pbe_debug_gemm_counters(long long* out8);
+
 /* Flash self-attention on tcgen05. Replaces CrossAttention.forward with context=None, ldm/modules/attention.py:207-230.
  *   qk_bf16 [B,N,2C] (Q | K), vt_bf16 [B,C,N], out_bf16 [B,N,C]; C = heads*d, scale = d^-1/2. */
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,

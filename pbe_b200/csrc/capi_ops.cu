@@ -52,6 +52,8 @@ extern "C" {
 
 static long long* g_attn_dbg = nullptr;
 
+int pbe_debug_gemm_counters(long long* out8) { return gemm_read_debug_counters(out8); }
+
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
                           void* stream) {
   AttnPlan plan;

@@ -24,6 +24,10 @@
 
 namespace pbe {
 
+// Debug counters of CTA 0 (tools/gemm_probe.py): [0] MMA-warp cycles total, [1] waiting for smem stages (TMA),
+// [2] waiting for a free TMEM buffer (epilogue), [3] producer cycles waiting for free stages, [4] k iterations.
+__device__ long long g_gemm_dbg[8];
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -203,17 +207,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int ti = 0;
     int s_idx = static_cast<int>(blockIdx.x % split_k);
     const int s_step = static_cast<int>(gridDim.x % split_k);
+    const bool dbg = p.debug != 0 && blockIdx.x == 0;
+    long long t_all = dbg ? clock64() : 0, t_full = 0, t_tmem = 0, n_it = 0;
     for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++ti) {
       const int buf = ti & 1;
       int k_begin, k_end;
       k_range(s_idx, k_begin, k_end);
       s_idx += s_step;
       if (s_idx >= split_k) s_idx -= split_k;
+      long long tw = dbg ? clock64() : 0;
       mbar_wait(tmem_empty_bar(buf), ((ti >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
+      if (dbg) t_tmem += clock64() - tw;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
       for (int it = k_begin; it < k_end; ++it) {
+        if (dbg) { tw = clock64(); ++n_it; }
         mbar_wait(full_bar(stage), phase);
+        if (dbg) t_full += clock64() - tw;
         tc_fence_after();
         {
           const uint64_t adesc = umma_desc_sw128(sA + stage * A_STAGE_BYTES);
@@ -228,6 +238,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+    }
+    if (dbg && lane == 0) {
+      g_gemm_dbg[0] = clock64() - t_all;
+      g_gemm_dbg[1] = t_full;
+      g_gemm_dbg[2] = t_tmem;
+      g_gemm_dbg[4] = n_it;
     }
   } else {
     // ================= Epilogue (warps 2..9) =================
@@ -577,6 +593,11 @@ int auto_block_n(const ConvGemmDesc& d) {
 
 }  // namespace
 
+int gemm_read_debug_counters(long long* out8) {
+  PBE_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(long long) * 8));
+  return 0;
+}
+
 int gemm_split_k(const ConvGemmDesc& d) {
   if (d.mode != EPI_STD || d.Cout % 4 != 0) return 1;
   int tw, th, tn;
@@ -664,6 +685,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
 
   const int bn = auto_block_n(d);
   p.split_k = (d.splitk_ws != nullptr) ? gemm_split_k(d) : 1;
+  p.debug = getenv("PBE_GEMM_DEBUG") ? 1 : 0;
   p.stats_out = nullptr;
   if (d.stats_out != nullptr) {
     PBE_REQUIRE(gemm_can_fuse_stats(d) && p.split_k == 1 && d.out_f32 != nullptr, "fused GroupNorm statistics not available for this GEMM");

@@ -57,6 +57,7 @@ struct ConvGemmParams {
   int n_total;             // number of GEMM columns (Cout)
   int n_tiles;             // ceil(n_total / BLOCK_N)
   int has_res, has_o32, has_o16;  // which epilogue tensor maps are live
+  int debug;                      // 1: CTA 0 records wait-time counters (PBE_GEMM_DEBUG)
   int split_k;                    // >1: K range split over work units, partial sums to a workspace
   float* stats_out;               // optional [M/32][n_total][2] per-32-row (sum, sumsq) of the fp32 output (GroupNorm)
   int8_t tap_dw[9], tap_dh[9], tap_ph[9];
@@ -117,6 +118,7 @@ struct ConvGemmDesc {
   float* stats_out;        // optional fused GroupNorm statistics of out_f32 (see gemm_can_fuse_stats)
 };
 // Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
+int gemm_read_debug_counters(long long* out8);
 int gemm_split_k(const ConvGemmDesc& d);
 // True when the epilogue can emit per-32-row column statistics for this geometry (no split-K, aligned tiles).
 bool gemm_can_fuse_stats(const ConvGemmDesc& d);

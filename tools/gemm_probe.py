@@ -28,7 +28,14 @@ def case(name, Nb, H, W, C, k, Cout, mode=0, residual=False, rowbias=False, f32=
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     fl = 2.0 * Nb * H * W * Cout * C * k * k
-    print(f"{name:28s} {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TF/s", flush=True)
+    extra = ""
+    if os.environ.get("PBE_GEMM_DEBUG"):
+        import ctypes
+        c = (ctypes.c_longlong * 8)()
+        lib.pbe_debug_gemm_counters(c)
+        if c[0] > 0:
+            extra = f"  | CTA0 MMA warp: {c[0]} cyc, wait TMA {100*c[1]/c[0]:.0f}%, wait TMEM {100*c[2]/c[0]:.0f}%, {c[4]} k-iters, {c[0]/max(c[4],1):.0f} cyc/iter"
+    print(f"{name:28s} {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TF/s{extra}", flush=True)
 
 which = sys.argv[1:] or ["proj_out", "geglu", "conv2", "conv1", "ffout", "lowres"]
 if "proj_out" in which: case("proj_out 64^2 320->320 +res", 16, 64, 64, 320, 1, 320, residual=True)
