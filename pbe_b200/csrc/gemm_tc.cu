@@ -18,6 +18,7 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -105,12 +106,24 @@ __device__ __forceinline__ void tile_coord_advance(TileCoord& c, const TileStep&
 
 // Persistent kernel: one CTA per SM walks work units (n-tile fastest, so co-running CTAs share A tiles and all weights
 // in L2).  Two TMEM accumulator buffers: the MMA warp fills buffer (i+1)&1 while the 8 epilogue warps drain buffer i&1.
-template <int BLOCK_N, int STAGES>
+//
+// CL == 2: the kernel runs as CTA pairs (2-CTA clusters, tcgen05 cta_group::2).  Both CTAs of a pair work on the same
+// (split slice, n tile) and on two neighbouring m tiles (p.pair_dim picks the tile dimension that is paired): one
+// M = 256 MMA, issued by the leader (rank 0), reads 128 activation rows and HALF of the weight tile from each CTA's
+// shared memory and accumulates into both CTAs' TMEM.  Why: a B200 SM ingests ~64 B/clk from L2; a 128 x 160 tile needs
+// (128 + 160) * 128 B per 64-deep k step = 576 clk of ingest for 320 clk of MMA (measured 555 clk per step, the MMA warp
+// waiting on TMA 60 % of the time, tools/gemm_probe.py).  With the weight tile split over the pair each SM ingests
+// (128 + 80) * 128 B = 416 clk per step, and the smaller stages allow a deeper ring.  (Multicasting the weight tile to
+// both CTAs instead was measured slower than no cluster at all: it does not reduce what each SM has to ingest.)
+//   full[stage]   lives in the leader: both producers' TMA loads complete_tx on it
+//   empty[stage], tmem_full[buf]  exist in both CTAs: the leader's commits are multicast to the pair
+//   tmem_empty[buf] lives in the leader: the epilogue warps of both CTAs arrive on it
+template <int BLOCK_N, int STAGES, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
                  const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ ConvGemmParams p) {
-  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_STAGE_BYTES = (BLOCK_N / CL) * BLOCK_K * 2;  // a CTA pair splits the weight tile
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 
@@ -135,11 +148,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_k_iters = p.num_taps * p.k_chunks;
   const int n_tiles = p.n_tiles;
   const int split_k = p.split_k;                                  // >1: partial sums go to a workspace slice
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * n_tiles * split_k;  // work units (tile x split)
+  // cluster-level work units: CTA `crank` of cluster `vblock` takes tile 2 * digit + crank along the paired dimension
+  const int crank = CL == 2 ? static_cast<int>(blockIdx.x & 1u) : 0;
+  const int vblock = static_cast<int>(blockIdx.x) / CL;
+  const int vgrid = static_cast<int>(gridDim.x) / CL;
+  const int mw = (CL == 2 && p.pair_dim == 0) ? 2 : 1, mh = (CL == 2 && p.pair_dim == 1) ? 2 : 1,
+            mn = (CL == 2 && p.pair_dim == 2) ? 2 : 1;
+  const int cw = mw == 2 ? crank : 0, ch = mh == 2 ? crank : 0, cn = mn == 2 ? crank : 0;
+  const int total_tiles = (p.tiles_w * p.tiles_h * p.tiles_n / CL) * n_tiles * split_k;  // work units (tile x split)
   TileStep tstep;
-  tstep.S = split_k; tstep.NT = n_tiles; tstep.TW = p.tiles_w; tstep.TH = p.tiles_h;
+  tstep.S = split_k; tstep.NT = n_tiles; tstep.TW = p.tiles_w / mw; tstep.TH = p.tiles_h / mh;
   {
-    const TileCoord d = tile_coord_from_unit(static_cast<int>(gridDim.x), tstep);
+    const TileCoord d = tile_coord_from_unit(vgrid, tstep);
     tstep.ds = d.s; tstep.dnt = d.nt; tstep.dwi = d.wi; tstep.dhi = d.hi; tstep.dni = d.ni;
   }
   auto k_range = [&](int sidx, int& k_begin, int& k_end) {
@@ -157,7 +177,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), NUM_EPI_WARPS);
+      mbar_init(tmem_empty_bar(b), CL * NUM_EPI_WARPS);
     }
     for (int sl = 0; sl < NUM_SLOTS; ++sl) mbar_init(sBar + 8u * (2 * STAGES + 4 + sl), 1);
     if (p.has_res) tma_prefetch_desc(&tmR);
@@ -166,50 +186,71 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_addr, TMEM_COLS);
-    tmem_relinquish();
+    if (CL == 2) {
+      tmem_alloc_pair(tmem_ptr_addr, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      TileCoord tc = tile_coord_from_unit(blockIdx.x, tstep);
-      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, tile_coord_advance(tc, tstep)) {
-        int k_begin, k_end;
-        k_range(tc.s, k_begin, k_end);
-        const int n_base = tc.nt * BLOCK_N;
-        const int w0 = tc.wi * p.tw;
-        const int h0 = tc.hi * p.th;
-        const int n0 = tc.ni * p.tn;
-        for (int it = k_begin; it < k_end; ++it) {
-          const int tap = it / p.k_chunks;
-          const int kc = it - tap * p.k_chunks;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), p.tap_coff[tap] + kc * BLOCK_K,
-                      w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
-          tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kc * BLOCK_K, n_base, tap);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    // The whole warp runs this loop with warp-uniform values and one elected lane issues: no divisions, no table
+    // look-ups and no divergent single-lane region per k step (that version cost ~550 clk of dependent latency per
+    // step -- more than the 320 clk of MMA it feeds -- and was THE bound of every long-K GEMM here).
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t lead_full0 = CL == 2 ? map_to_cta(full_bar(0), 0) : full_bar(0);  // barriers are 8 B apart
+    const bool dbg = p.debug != 0 && blockIdx.x == 0;
+    long long t_empty = 0;
+    TileCoord tc = tile_coord_from_unit(vblock, tstep);
+    for (int unit = vblock; unit < total_tiles; unit += vgrid, tile_coord_advance(tc, tstep)) {
+      int k_begin, k_end;
+      k_range(tc.s, k_begin, k_end);
+      const int n_base = tc.nt * BLOCK_N + crank * (BLOCK_N / CL);  // a pair: my half of the weight tile
+      const int w0 = (tc.wi * mw + cw) * p.tw;
+      const int h0 = (tc.hi * mh + ch) * p.th;
+      const int n0 = (tc.ni * mn + cn) * p.tn;
+      int tap = k_begin / p.k_chunks;
+      int kc = k_begin - tap * p.k_chunks;
+      int c_off = p.tap_coff[tap] + kc * BLOCK_K, cw0 = w0 + p.tap_dw[tap], cph = p.tap_ph[tap], ch0 = h0 + p.tap_dh[tap];
+      for (int it = k_begin; it < k_end; ++it) {
+        const long long tw = dbg ? clock64() : 0;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (dbg) t_empty += clock64() - tw;
+        // a pair accounts both CTAs' boxes on the leader's barrier
+        if (CL == 1 || crank == 0) mbar_expect_tx_elect(full_bar(stage), CL * (A_STAGE_BYTES + B_STAGE_BYTES));
+        const uint32_t fb = lead_full0 + 8u * stage;
+        tma_load_5d_elect<CL == 2>(sA + stage * A_STAGE_BYTES, &tmA, fb, c_off, cw0, cph, ch0, n0);
+        tma_load_3d_elect<CL == 2>(sB + stage * B_STAGE_BYTES, &tmB, fb, kc * BLOCK_K, n_base, tap);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        c_off += BLOCK_K;
+        if (++kc == p.k_chunks && it + 1 < k_end) {
+          kc = 0;
+          ++tap;
+          c_off = p.tap_coff[tap]; cw0 = w0 + p.tap_dw[tap]; cph = p.tap_ph[tap]; ch0 = h0 + p.tap_dh[tap];
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (dbg && lane == 0) g_gemm_dbg[3] = t_empty;
+  } else if (warp == 1 && (CL == 1 || crank == 0)) {
+    // ================= MMA issuer (pair: the leader CTA only) =================
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CL, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int ti = 0;
-    int s_idx = static_cast<int>(blockIdx.x % split_k);
-    const int s_step = static_cast<int>(gridDim.x % split_k);
+    int s_idx = vblock % split_k;
+    const int s_step = vgrid % split_k;
     const bool dbg = p.debug != 0 && blockIdx.x == 0;
     long long t_all = dbg ? clock64() : 0, t_full = 0, t_tmem = 0, n_it = 0;
-    for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++ti) {
+    for (int unit = vblock; unit < total_tiles; unit += vgrid, ++ti) {
       const int buf = ti & 1;
       int k_begin, k_end;
       k_range(s_idx, k_begin, k_end);
@@ -231,10 +272,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the 16-B-unit start address field
-            umma_bf16_ss_elect(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > k_begin || k > 0) ? 1u : 0u);
+            if (CL == 2) umma_bf16_ss_pair_elect(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > k_begin || k > 0) ? 1u : 0u);
+            else umma_bf16_ss_elect(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > k_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit_elect(empty_bar(stage));  // smem slot free once these MMAs retire
-          if (it == k_end - 1) umma_commit_elect(tmem_full_bar(buf));
+          // smem slot free once these MMAs retire; accumulator complete after the last k step (both CTAs of a pair)
+          if (CL == 2) {
+            umma_commit_pair_elect(empty_bar(stage), static_cast<uint16_t>(3));
+            if (it == k_end - 1) umma_commit_pair_elect(tmem_full_bar(buf), static_cast<uint16_t>(3));
+          } else {
+            umma_commit_elect(empty_bar(stage));
+            if (it == k_end - 1) umma_commit_elect(tmem_full_bar(buf));
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -245,7 +293,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       g_gemm_dbg[2] = t_tmem;
       g_gemm_dbg[4] = n_it;
     }
-  } else {
+  } else if (warp >= 2) {
     // ================= Epilogue (warps 2..9) =================
     // Two warp-sets of 4 warps (one warp per TMEM lane quarter). A warp-set handles every other 32-column chunk of a
     // tile (alternating per tile for balance) and owns two 16 KB shared-memory slots.  Per chunk:
@@ -268,6 +316,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t slot_base = smem_base + PIPE_BYTES;
     uint8_t* slot_gen_base = smem_gen + PIPE_BYTES;
     auto res_full_bar = [&](int s) { return sBar + 8u * (2 * STAGES + 4 + s); };
+    // "accumulator drained" goes to the CTA that issues the MMAs
+    const uint32_t lead_tmem_empty0 = CL == 2 ? map_to_cta(tmem_empty_bar(0), 0) : tmem_empty_bar(0);
+    auto tmem_empty_arrive = [&](int b) {
+      if (CL == 2) mbar_arrive_cluster(lead_tmem_empty0 + 8u * b);
+      else mbar_arrive(tmem_empty_bar(b));
+    };
     const float* __restrict__ rowbias = p.rowbias;
     bf16* __restrict__ out_bf16 = p.out_bf16;
 
@@ -276,12 +330,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto chunk_valid = [&](int n_tile, int c) { return c < nchunks && n_tile * tile_out_cols + c * chunk_cols < out_cols_total; };
 
     // ---- prefetch iterator (elected thread): walks the chunks this warp-set will consume, in order ----
-    int pf_ti = 0, pf_tile = blockIdx.x, pf_c = ws & 1, pf_seq = 0;
-    TileCoord pf_tc = tile_coord_from_unit(blockIdx.x, tstep);
+    int pf_ti = 0, pf_tile = vblock, pf_c = ws & 1, pf_seq = 0;
+    TileCoord pf_tc = tile_coord_from_unit(vblock, tstep);
     auto pf_issue_next = [&]() {
       // find the next valid chunk at or after (pf_ti, pf_c)
       while (pf_tile < total_tiles) {
-        const int n_tile = pf_tc.nt, w0 = pf_tc.wi * p.tw, h0 = pf_tc.hi * p.th, n0 = pf_tc.ni * p.tn;
+        const int n_tile = pf_tc.nt, w0 = (pf_tc.wi * mw + cw) * p.tw, h0 = (pf_tc.hi * mh + ch) * p.th,
+                  n0 = (pf_tc.ni * mn + cn) * p.tn;
         if (!tile_is_vt(n_tile) && chunk_valid(n_tile, pf_c)) {
           const int slot = ws * 2 + (pf_seq & 1);
           if (p.has_res) {
@@ -297,7 +352,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         // advance to the next tile
         ++pf_ti;
-        pf_tile += gridDim.x;
+        pf_tile += vgrid;
         tile_coord_advance(pf_tc, tstep);
         pf_c = (ws + pf_ti) & 1;
       }
@@ -313,10 +368,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int wl = row % p.tw;
     const int hl = (row / p.tw) % p.th;
     const int nl = row / (p.tw * p.th);
-    TileCoord tc = tile_coord_from_unit(blockIdx.x, tstep);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, tile_coord_advance(tc, tstep)) {
+    TileCoord tc = tile_coord_from_unit(vblock, tstep);
+    for (int tile = vblock; tile < total_tiles; tile += vgrid, ++ti, tile_coord_advance(tc, tstep)) {
       const int buf = ti & 1;
-      const int n_tile = tc.nt, w0 = tc.wi * p.tw, h0 = tc.hi * p.th, n0 = tc.ni * p.tn;
+      const int n_tile = tc.nt, w0 = (tc.wi * mw + cw) * p.tw, h0 = (tc.hi * mh + ch) * p.th,
+                n0 = (tc.ni * mn + cn) * p.tn;
       const int n_base = n_tile * BLOCK_N;
       const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
       const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
@@ -331,7 +387,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // V^T scatter: out_vt[b][c][token]; lanes are consecutive tokens -> 64-B contiguous per column
         int last_c = -1;
         for (int c = c_first; c < nchunks; c += 2) last_c = c;
-        if (last_c < 0 && lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        if (last_c < 0 && lane == 0) tmem_empty_arrive(buf);
 #pragma unroll 1
         for (int c = c_first; c <= last_c; c += 2) {
           uint32_t v[32];
@@ -340,7 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c == last_c) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+            if (lane == 0) tmem_empty_arrive(buf);
           }
           if (my_valid) {
             const long long tokens = static_cast<long long>(p.Ho) * p.Wo;
@@ -356,7 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       int last_c = -1;
       for (int c = c_first; chunk_valid(n_tile, c); c += 2) last_c = c;
-      if (last_c < 0 && lane == 0) mbar_arrive(tmem_empty_bar(buf));
+      if (last_c < 0 && lane == 0) tmem_empty_arrive(buf);
 #pragma unroll 1
       for (int c = c_first; c <= last_c; c += 2, ++seq) {
         const int slot = ws * 2 + (seq & 1);
@@ -372,7 +428,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c == last_c) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+            if (lane == 0) tmem_empty_arrive(buf);
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -392,7 +448,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c == last_c) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+            if (lane == 0) tmem_empty_arrive(buf);
           }
           const int col = n_base + c * 32;
 #pragma unroll
@@ -493,28 +549,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CL == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while the pair's MMAs / signals may still touch it
+  if (warp == 1) {
+    if (CL == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CL>
 constexpr size_t smem_bytes_for() {
-  return 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + EPI_STAGING_BYTES + 8 * (2 * STAGES + 6 + NUM_SLOTS);
+  return 1024 + STAGES * (A_STAGE_BYTES + (BLOCK_N / CL) * BLOCK_K * 2) + EPI_STAGING_BYTES + 8 * (2 * STAGES + 6 + NUM_SLOTS);
 }
 
-template <int BLOCK_N, int STAGES>
-int launch_t(const GemmPlan& plan, cudaStream_t stream) {
+template <int BLOCK_N, int STAGES, int CL>
+int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
-  constexpr size_t smem = smem_bytes_for<BLOCK_N, STAGES>();
+  constexpr size_t smem = smem_bytes_for<BLOCK_N, STAGES, CL>();
   if (!attr_set) {
-    PBE_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
+    PBE_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, CL>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  conv_gemm_kernel<BLOCK_N, STAGES><<<plan.grid, NUM_THREADS, smem, stream>>>(plan.tmA, plan.tmB, plan.tmR, plan.tmO32,
-                                                                              plan.tmO16, plan.p);
-  PBE_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = plan.grid;
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (CL > 1) {
+    // persistent clusters are statically scheduled: never launch more than can be co-resident (GPCs with an odd number
+    // of free SMs cannot host a last 2-CTA cluster)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      PBE_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, conv_gemm_kernel<BLOCK_N, STAGES, CL>, &cfg));
+      if (getenv("PBE_GEMM_DEBUG")) fprintf(stderr, "[pbe] conv_gemm<%d,%d> max active %d-CTA clusters: %d\n", BLOCK_N, STAGES, CL, max_clusters);
+      PBE_REQUIRE(max_clusters > 0, "no co-resident cluster fits");
+    }
+    cfg.gridDim.x = std::min<unsigned>(cfg.gridDim.x, static_cast<unsigned>(max_clusters * CL));
+  }
+  PBE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, STAGES, CL>, plan.tmA, plan.tmB, plan.tmR,
+                                    plan.tmO32, plan.tmO16, plan.p));
   return 0;
+}
+template <int BLOCK_N, int STAGES, int STAGES_PAIR>
+int launch_t(const GemmPlan& plan, cudaStream_t stream) {
+  return plan.cluster == 2 ? launch_tc<BLOCK_N, STAGES_PAIR, 2>(plan, stream) : launch_tc<BLOCK_N, STAGES, 1>(plan, stream);
 }
 
 int num_sms() {
@@ -699,8 +785,22 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   plan->block_n = bn;
   p.n_tiles = (d.Cout + bn - 1) / bn;
   {
+    // pair neighbouring m tiles into 2-CTA clusters that share the weight tile (first tile dimension with an even count)
+    static const bool cluster_on = [] { const char* e = getenv("PBE_GEMM_CLUSTER"); return e == nullptr || atoi(e) != 0; }();
+    p.pair_dim = -1;
+    // pairs pay off when the main loop dominates (long K: 3x3 convs, ff.out); the short-K GEMMs are epilogue-bound and
+    // measured ~15 % slower with the two epilogues coupled through one MMA issuer
+    const int pair_min_k = [] { const char* e = getenv("PBE_GEMM_PAIR_MIN_K"); return e ? atoi(e) : 12; }();
+    if (cluster_on && p.num_taps * p.k_chunks >= pair_min_k * p.split_k) {
+      if (p.tiles_w % 2 == 0) p.pair_dim = 0;
+      else if (p.tiles_h % 2 == 0) p.pair_dim = 1;
+      else if (p.tiles_n % 2 == 0) p.pair_dim = 2;
+    }
+    plan->cluster = p.pair_dim >= 0 ? 2 : 1;
     const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.split_k;
-    plan->grid = dim3(std::min(total, num_sms()), 1, 1);
+    int grid = std::min(total, num_sms());
+    if (plan->cluster == 2) grid &= ~1;
+    plan->grid = dim3(grid, 1, 1);
   }
 
   // A: 5-D view (c, w, phase, h, n)
@@ -773,7 +873,8 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     const uint64_t dims[3] = {static_cast<uint64_t>(d.C), static_cast<uint64_t>(d.Cout),
                               static_cast<uint64_t>(p.num_taps)};
     const uint64_t strides[2] = {static_cast<uint64_t>(d.C) * 2, static_cast<uint64_t>(d.C) * d.Cout * 2};
-    const uint32_t box[3] = {64u, static_cast<uint32_t>(bn), 1u};
+    // CTA pair: each CTA loads its half of the n tile
+    const uint32_t box[3] = {64u, static_cast<uint32_t>(bn / plan->cluster), 1u};
     int rc = make_tmap_bf16(&plan->tmB, d.wt, 3, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -795,11 +896,12 @@ int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream) {
 
 static int launch_main(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.block_n) {
-    case 32: return launch_t<32, 6>(plan, stream);
-    case 64: return launch_t<64, 6>(plan, stream);
-    case 128: return launch_t<128, 4>(plan, stream);
-    case 160: return launch_t<160, 4>(plan, stream);
-    case 256: return launch_t<256, 3>(plan, stream);
+    // stages: single CTA / CTA pair (half weight tile per CTA)
+    case 32: return launch_t<32, 6, 8>(plan, stream);
+    case 64: return launch_t<64, 6, 8>(plan, stream);
+    case 128: return launch_t<128, 4, 6>(plan, stream);
+    case 160: return launch_t<160, 4, 6>(plan, stream);
+    case 256: return launch_t<256, 3, 5>(plan, stream);
     default: set_error("launch_gemm_plan: bad block_n"); return -1;
   }
 }

@@ -58,6 +58,7 @@ struct ConvGemmParams {
   int n_tiles;             // ceil(n_total / BLOCK_N)
   int has_res, has_o32, has_o16;  // which epilogue tensor maps are live
   int debug;                      // 1: CTA 0 records wait-time counters (PBE_GEMM_DEBUG)
+  int pair_dim;                   // 2-CTA clusters: tile dimension (0 w, 1 h, 2 n) whose neighbours form a cluster; -1 none
   int split_k;                    // >1: K range split over work units, partial sums to a workspace
   float* stats_out;               // optional [M/32][n_total][2] per-32-row (sum, sumsq) of the fp32 output (GroupNorm)
   int8_t tap_dw[9], tap_dh[9], tap_ph[9];
@@ -91,6 +92,7 @@ struct GemmPlan {
   CUtensorMap tmR, tmO32, tmO16;  // residual (fp32 load), fp32 output store, bf16 output store (epilogue TMA)
   ConvGemmParams p;
   int block_n;
+  int cluster;  // CTAs per cluster (1 or 2)
   dim3 grid;
   size_t smem;
 };
