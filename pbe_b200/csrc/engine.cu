@@ -432,8 +432,9 @@ int Engine::build(Prepared& P, bool dry) {
     a.partial = static_cast<float*>(SA(static_cast<size_t>(gn_workspace_floats(a.Nb, a.HW, a.C0 + a.C1)) * sizeof(float)));
     const double n = static_cast<double>(a.Nb) * a.HW * (a.C0 + a.C1);
     const bool fused_stats = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
-    add_op_meta(name, fused_stats ? 2 : 3, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
-                n * ((fused_stats ? 4.0 : 8.0) + 2.0 + (a.raw ? 2.0 : 0.0)));
+    const int launches = gn_num_launches(a);
+    add_op_meta(name, launches, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
+                n * ((launches == 3 ? 8.0 : 4.0) + 2.0 + (a.raw ? 2.0 : 0.0)));
   };
 
   P.x_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.in_channels * H0 * W0 * sizeof(float)));

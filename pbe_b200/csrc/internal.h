@@ -164,6 +164,7 @@ struct GroupNormArgs {
 };
 int gn_num_slabs(int HW);
 int gn_workspace_floats(int Nb, int HW, int C);
+int gn_num_launches(const GroupNormArgs& a);  // kernels launch_groupnorm will launch for these arguments
 int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream);
 
 // LayerNorm over the last dim of fp32 [M, C] -> bf16 [M, C]

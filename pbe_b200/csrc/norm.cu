@@ -9,6 +9,8 @@
 // the concat is never materialised in fp32, only the normalised bf16 operand is.
 #include "internal.h"
 
+#include <algorithm>
+
 namespace pbe {
 
 namespace {
@@ -197,57 +199,143 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const fl
   }
 }
 
-// pure streaming pass: four float4 of x per thread, all loads issued before the first use
-__device__ __forceinline__ void gn_apply_one(const float4 v, const float4 ab01, const float4 ab23, int silu,
-                                             bf16* __restrict__ y, bf16* __restrict__ raw, long long off) {
-  float o0 = fmaf(v.x, ab01.x, ab01.y), o1 = fmaf(v.y, ab01.z, ab01.w);
-  float o2 = fmaf(v.z, ab23.x, ab23.y), o3 = fmaf(v.w, ab23.z, ab23.w);
-  if (silu) {
-    o0 = o0 / (1.0f + __expf(-o0)); o1 = o1 / (1.0f + __expf(-o1));
-    o2 = o2 / (1.0f + __expf(-o2)); o3 = o3 / (1.0f + __expf(-o3));
-  }
-  uint2 pk;
-  pk.x = pack2(o0, o1);
-  pk.y = pack2(o2, o3);
-  *reinterpret_cast<uint2*>(y + off) = pk;
-  if (raw != nullptr) {
-    uint2 rk;
-    rk.x = pack2(v.x, v.y);
-    rk.y = pack2(v.z, v.w);
-    *reinterpret_cast<uint2*>(raw + off) = rk;
-  }
-}
+// Streaming pass y = silu(x * a + b) (+ raw bf16 copy).  grid (pixel blocks, Nb); a thread owns ONE float4 channel
+// column of one sample (its scale / shift are loaded once, no index arithmetic per element) and walks GN_UNROLL pixels
+// with every load issued before the first use.  (The first version recomputed pixel / sample / channel with two 64-bit
+// divisions per float4 and re-read the scale / shift table per element: 2.2-3.4 TB/s.)
+constexpr int GN_UNROLL = 8;
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x0, int C0,
-                                                              const float* __restrict__ x1, int C1, int HW,
-                                                              long long total_vec, const float2* __restrict__ ab,
-                                                              int silu, bf16* __restrict__ y, bf16* __restrict__ raw) {
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
+                                                        int C1, int HW, int rows_par, const float2* __restrict__ ab,
+                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw) {
   const int C = C0 + C1;
-  const int vec_per_pix = C / 4;
-  const long long base = static_cast<long long>(blockIdx.x) * (GN_THREADS * 4) + threadIdx.x;
-  float4 v[4], a01[4], a23[4];
-  long long off[4];
+  const int vpp = C / 4;
+  const int t = threadIdx.x;
+  const int prow = t / vpp;          // blockDim.x == vpp * rows_par
+  const int c = (t - prow * vpp) * 4;
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * (rows_par * GN_UNROLL) + prow;
+  const float* __restrict__ src;
+  int ld;
+  if (c < C0) { src = x0 + static_cast<long long>(b) * HW * C0 + c; ld = C0; }
+  else { src = x1 + static_cast<long long>(b) * HW * C1 + (c - C0); ld = C1; }
+  const float4 s01 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c));
+  const float4 s23 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
+  const long long obase = static_cast<long long>(b) * HW * C + c;
+  float4 v[GN_UNROLL];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const long long idx = base + u * GN_THREADS;
-    off[u] = -1;
-    if (idx < total_vec) {
-      const long long gp = idx / vec_per_pix;
-      const int c = static_cast<int>(idx - gp * vec_per_pix) * 4;
-      const int b = static_cast<int>(gp / HW);
-      v[u] = ld4(x0, C0, x1, C1, gp, c);
-      a01[u] = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c));
-      a23[u] = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
-      off[u] = gp * C + c;
+  for (int u = 0; u < GN_UNROLL; ++u) {
+    const int pix = p_begin + u * rows_par;
+    if (pix < HW) v[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(pix) * ld));
+  }
+#pragma unroll
+  for (int u = 0; u < GN_UNROLL; ++u) {
+    const int pix = p_begin + u * rows_par;
+    if (pix < HW) {
+      float o0 = fmaf(v[u].x, s01.x, s01.y), o1 = fmaf(v[u].y, s01.z, s01.w);
+      float o2 = fmaf(v[u].z, s23.x, s23.y), o3 = fmaf(v[u].w, s23.z, s23.w);
+      if (silu) { o0 = silu_fast(o0); o1 = silu_fast(o1); o2 = silu_fast(o2); o3 = silu_fast(o3); }
+      const long long off = obase + static_cast<long long>(pix) * C;
+      *reinterpret_cast<uint2*>(y + off) = make_uint2(pack2(o0, o1), pack2(o2, o3));
+      if (raw != nullptr) *reinterpret_cast<uint2*>(raw + off) = make_uint2(pack2(v[u].x, v[u].y), pack2(v[u].z, v[u].w));
     }
   }
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-    if (off[u] >= 0) gn_apply_one(v[u], a01[u], a23[u], silu, y, raw, off[u]);
 }
 
-// One warp per row; row held in registers (C <= 1280).
+// Low-resolution GroupNorm in ONE kernel: grid (32 groups, Nb); the (sample, group) slice (HW pixels x C/32 channels,
+// <= 80 KB of fp32) is staged in shared memory, so x is read once from HBM, statistics are an exact two-pass
+// (mean, then centred sum of squares; fixed-order reductions) and the normalised bf16 operand is written straight
+// from shared memory.  Replaces the stats -> finalize -> apply chain for the 8x8 / 16x16 levels, where three launches
+// over a few MB were pure latency.
+constexpr int GNS_THREADS = 512;
+__device__ __forceinline__ double block_sum_double(double v, double* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[w] = v;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int i = 0; i < GNS_THREADS / 32; ++i) tot += s_red[i];
+  return tot;
+}
+__global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __restrict__ x0, int C0,
+                                                               const float* __restrict__ x1, int C1, int HW, int rows_par,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps, int silu,
+                                                               bf16* __restrict__ y, bf16* __restrict__ raw) {
+  extern __shared__ float2 s_x[];  // [HW][cpg / 2]
+  __shared__ double s_red[GNS_THREADS / 32];
+  const int C = C0 + C1;
+  const int cpg = C / 32;
+  const int hv = cpg / 2;  // float2 per pixel of this group (cpg is even; a float2 never straddles the concat seam)
+  const int g = blockIdx.x, b = blockIdx.y;
+  // a thread owns one channel pair and walks pixels prow, prow + rows_par, ... (threads >= hv * rows_par idle)
+  const int prow = threadIdx.x / hv;
+  const int cv = threadIdx.x - prow * hv;
+  const bool active = prow < rows_par;
+  const int c = g * cpg + cv * 2;
+  const float* __restrict__ src;
+  int ld;
+  if (c < C0) { src = x0 + static_cast<long long>(b) * HW * C0 + c; ld = C0; }
+  else { src = x1 + static_cast<long long>(b) * HW * C1 + (c - C0); ld = C1; }
+  float ps = 0.0f;
+  if (active) {
+    int pix = prow;
+    for (; pix + 3 * rows_par < HW; pix += 4 * rows_par) {
+      const float2 v0 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix) * ld));
+      const float2 v1 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix + rows_par) * ld));
+      const float2 v2 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix + 2 * rows_par) * ld));
+      const float2 v3 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix + 3 * rows_par) * ld));
+      s_x[pix * hv + cv] = v0;
+      s_x[(pix + rows_par) * hv + cv] = v1;
+      s_x[(pix + 2 * rows_par) * hv + cv] = v2;
+      s_x[(pix + 3 * rows_par) * hv + cv] = v3;
+      ps += ((v0.x + v0.y) + (v1.x + v1.y)) + ((v2.x + v2.y) + (v3.x + v3.y));
+    }
+    for (; pix < HW; pix += rows_par) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix) * ld));
+      s_x[pix * hv + cv] = v;
+      ps += v.x + v.y;
+    }
+  }
+  const double cnt = static_cast<double>(HW) * cpg;
+  const float mean = static_cast<float>(block_sum_double(static_cast<double>(ps), s_red) / cnt);
+  // each thread re-reads exactly the elements it wrote: no barrier needed between the passes
+  float pq = 0.0f;
+  if (active)
+    for (int pix = prow; pix < HW; pix += rows_par) {
+      const float2 v = s_x[pix * hv + cv];
+      const float dx = v.x - mean, dy = v.y - mean;
+      pq = fmaf(dx, dx, fmaf(dy, dy, pq));
+    }
+  const double var = block_sum_double(static_cast<double>(pq), s_red) / cnt;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  if (active) {
+    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c));
+    const float2 be = __ldg(reinterpret_cast<const float2*>(beta + c));
+    const float a0 = ga.x * rstd, a1 = ga.y * rstd;
+    const float b0 = be.x - mean * a0, b1 = be.y - mean * a1;
+    bf16* __restrict__ yo = y + static_cast<long long>(b) * HW * C + c;
+    bf16* __restrict__ ro = raw != nullptr ? raw + static_cast<long long>(b) * HW * C + c : nullptr;
+#pragma unroll 4
+    for (int pix = prow; pix < HW; pix += rows_par) {
+      const float2 v = s_x[pix * hv + cv];
+      float o0 = fmaf(v.x, a0, b0), o1 = fmaf(v.y, a1, b1);
+      if (silu) { o0 = silu_fast(o0); o1 = silu_fast(o1); }
+      *reinterpret_cast<uint32_t*>(yo + static_cast<long long>(pix) * C) = pack2(o0, o1);
+      if (ro != nullptr) *reinterpret_cast<uint32_t*>(ro + static_cast<long long>(pix) * C) = pack2(v.x, v.y);
+    }
+  }
+}
+
 constexpr int LN_MAX_VEC = 10;
+// One warp per row; row held in registers (C <= 1280).  NV = float4 per lane: instantiated for the widths the U-Net
+// uses so the 320-wide rows of the 64x64 level do not carry the 1280-wide register footprint (occupancy = bytes in
+// flight for this pure streaming pass).
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, int M,
                                                         int C, float eps) {
@@ -256,22 +344,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (row >= M) return;
   const int nvec = C / 4;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
-  float4 v[LN_MAX_VEC];
+  float4 v[NV];
   float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int k = lane + i * 32;
-    if (k < nvec) {
-      v[i] = xr[k];
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+    if (k < nvec) v[i] = __ldg(xr + k);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int k = lane + i * 32;
+    if (k < nvec) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / C;
   float sq = 0.0f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int k = lane + i * 32;
     if (k < nvec) {
       const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
@@ -285,16 +375,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float4* br = reinterpret_cast<const float4*>(beta);
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(row) * C);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int k = lane + i * 32;
     if (k < nvec) {
-      const float4 g = gr[k], bb = br[k];
-      __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
-      __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      yr[k] = pk;
+      const float4 g = __ldg(gr + k), bb = __ldg(br + k);
+      yr[k] = make_uint2(pack2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y),
+                         pack2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w));
     }
   }
 }
@@ -312,14 +398,36 @@ int gn_workspace_floats(int Nb, int HW, int C) {
   return Nb * gn_num_slabs(HW) * 64 + Nb * C * 2 + 64;
 }
 
+int gn_num_launches(const GroupNormArgs& a) {
+  const int C = a.C0 + a.C1;
+  const bool fused = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
+  if (fused) return 2;
+  return static_cast<size_t>(a.HW) * (C / 32) * sizeof(float) <= 96 * 1024 ? 1 : 3;
+}
+
 int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   const int C = a.C0 + a.C1;
   PBE_REQUIRE(C % 64 == 0 && C <= GN_MAX_C, "GroupNorm channels must be a multiple of 64, <= 2560");
   PBE_REQUIRE(a.C0 % 4 == 0 && a.C1 % 4 == 0, "GroupNorm concat halves must be multiples of 4 channels");
+  const bool fused = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
+  const size_t small_smem = static_cast<size_t>(a.HW) * (C / 32) * sizeof(float);
+  if (!fused && small_smem <= 96 * 1024) {
+    // low-resolution levels: one kernel, the (sample, group) slice staged in shared memory
+    static bool attr_set = false;
+    if (!attr_set) {
+      PBE_CHECK_CUDA(cudaFuncSetAttribute(gn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    const int hv = C / 64;
+    const int rows_par = std::min(GNS_THREADS / hv, a.HW);
+    gn_small_kernel<<<dim3(32, a.Nb), GNS_THREADS, small_smem, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, a.gamma,
+                                                                        a.beta, a.eps, a.silu, a.y, a.raw);
+    PBE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int slabs = gn_num_slabs(a.HW);
   float* partial = a.partial;
   float2* ab = reinterpret_cast<float2*>(a.partial + ((static_cast<size_t>(a.Nb) * slabs * 64 + 3) & ~static_cast<size_t>(3)));
-  const bool fused = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
   if (fused) {
     gn_finalize_fused_kernel<<<dim3(32, a.Nb), GNF_THREADS, 0, stream>>>(a.stats0, a.C0, a.stats1, a.C1, a.HW, a.gamma,
                                                                         a.beta, a.eps, ab);
@@ -330,11 +438,11 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
     gn_finalize_kernel<<<a.Nb, GN_THREADS, 0, stream>>>(partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab);
     PBE_CHECK_CUDA(cudaGetLastError());
   }
-  const long long total_vec = static_cast<long long>(a.Nb) * a.HW * (C / 4);
-  long long blocks = (total_vec + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
-  if (blocks < 1) blocks = 1;
-  gn_apply_kernel<<<static_cast<unsigned>(blocks), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, total_vec, ab,
-                                                                         a.silu, a.y, a.raw);
+  const int vpp = C / 4;
+  const int rows_par = vpp >= 256 ? 1 : 256 / vpp;
+  const int pix_per_block = rows_par * GN_UNROLL;
+  gn_apply_kernel<<<dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb), vpp * rows_par, 0, stream>>>(
+      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -342,7 +450,10 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
 int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16* y, int M, int C, float eps,
                      cudaStream_t stream) {
   PBE_REQUIRE(C % 4 == 0 && C / 4 <= 32 * LN_MAX_VEC, "LayerNorm width must be a multiple of 4, <= 1280");
-  layernorm_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+  const int nv = (C / 4 + 31) / 32;
+  if (nv <= 3) layernorm_kernel<3><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+  else if (nv <= 5) layernorm_kernel<5><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+  else layernorm_kernel<LN_MAX_VEC><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
