@@ -287,7 +287,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 // P·V products; K/V tiles are loaded once for both query tiles.
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 64 + 2 * 256;   // 2 MMA(+TMA) warps, 2 warpgroups x 8 softmax warps (18 warps: 112 regs/thread)
+constexpr int ATT2_THREADS = 64 + 2 * 256 + 32;   // 2 MMA warps, 2 warpgroups x 8 softmax warps, 1 TMA warp (19 warps: 104 regs)
+constexpr int ATT2_KV_STAGES = 2;
 
 // 128-key tiles, 256 queries per CTA, SIXTEEN softmax warps: every query row is shared by two threads (64 keys each),
 // so each scheduler always has four softmax warps to pick from.  Findings that shaped this (clock64 traces, ncu):
@@ -296,20 +297,27 @@ constexpr int ATT2_THREADS = 64 + 2 * 256;   // 2 MMA(+TMA) warps, 2 warpgroups 
 //    reference maximum only moves when exceeded by 2^8);
 //  * one MMA-issuing warp per warpgroup (mbarrier round trips serialise otherwise);
 //  * exponentials are computed in place first, sums / bf16 packing / stores afterwards.
-// warps: 0, 1 MMA issue for warpgroup 0, 1 (warp 0 also drives the K/V TMA ring) | 2..9 softmax wg 0 | 10..17 softmax wg 1
+//  * S(j+1) = Q K^T is issued as soon as the softmax warps have READ S(j) for the last time (s_free), not when P(j) is
+//    published: the tensor-core round trip overlaps the exponentials of tile j instead of idling the warpgroup;
+//  * P is double-buffered in shared memory (per-buffer pv_done barriers): the exponentials of tile j never wait for
+//    P.V(j-1), only for P.V(j-2), which has long retired -- the softmax warps of BOTH warpgroups stay runnable;
+//  * the K/V ring has its own warp, so neither MMA warp ever blocks on the other warpgroup's P.V.
+// warps: 0, 1 MMA issue for warpgroup 0, 1 | 2..9 softmax wg 0 | 10..17 softmax wg 1 | 18 Q / K / V TMA
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_att2[];   // 1024-B aligned base (128B-swizzle atoms), no padding budget
+  uint8_t* smem_raw = smem_att2;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();
+  uint8_t* smem_gen = smem_raw;
   constexpr int V_STAGE_BYTES = 2 * 64 * 128;  // two 64-key chunks of up to 64 rows
   const int v_chunk_bytes = p.dv * 128;
   const uint32_t sQ = smem_base;                          // 2 query tiles
-  const uint32_t sK = sQ + 2 * CHUNK_BYTES;               // 2 stages
-  const uint32_t sV = sK + 2 * CHUNK_BYTES;               // 2 stages
-  const uint32_t sP = sV + 2 * V_STAGE_BYTES;             // 2 warpgroups x 2 chunks
-  const uint32_t sX = sP + 4 * CHUNK_BYTES;               // row-max / row-sum exchange: [2 wg][2 halves][128] floats
+  const uint32_t sK = sQ + 2 * CHUNK_BYTES;               // ATT2_KV_STAGES stages
+  const uint32_t sV = sK + ATT2_KV_STAGES * CHUNK_BYTES;  // ATT2_KV_STAGES stages
+  const uint32_t sP = sV + ATT2_KV_STAGES * V_STAGE_BYTES;  // [2 warpgroups][2 buffers][2 chunks]
+  const uint32_t sX = sP + 8 * CHUNK_BYTES;               // row-max / row-sum exchange: [2 wg][2 halves][128] floats
   const uint32_t sBar = sX + 2 * 2 * 128 * 4;
   uint8_t* bar_gen = smem_gen + (sBar - smem_base);
   uint8_t* p_gen = smem_gen + (sP - smem_base);
@@ -319,9 +327,10 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   auto kv_empty = [&](int s) { return sBar + 8u * (3 + s); };
   auto s_full = [&](int g) { return sBar + 8u * (5 + g); };
   auto p_full = [&](int g) { return sBar + 8u * (7 + g); };
-  auto pv_done = [&](int g) { return sBar + 8u * (9 + g); };
-  const uint32_t tmem_ptr_addr = sBar + 8u * 11;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 11);
+  auto pv_done = [&](int g, int buf) { return sBar + 8u * (9 + g * 2 + buf); };  // P.V of the tiles using P buffer `buf`
+  auto s_free = [&](int g) { return sBar + 8u * (13 + g); };
+  const uint32_t tmem_ptr_addr = sBar + 8u * 15;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 15);
 
   const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
@@ -334,12 +343,16 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ATT2_KV_STAGES; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 2);   // one tcgen05.commit arrival per MMA warp
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(p_full(s), 8);
-      mbar_init(pv_done(s), 1);
+      mbar_init(pv_done(s, 0), 1);
+      mbar_init(pv_done(s, 1), 1);
+      mbar_init(s_free(s), 8);
     }
     fence_barrier_init();
   }
@@ -361,59 +374,52 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const uint32_t tmem_S = tmem_base + g * 128;
     const uint32_t tmem_O = tmem_base + 256 + g * 64;
     auto issue_qk = [&](int j) {
-      const uint64_t kdesc = umma_desc_sw128(sK + (j & 1) * CHUNK_BYTES);
+      const uint64_t kdesc = umma_desc_sw128(sK + (j % ATT2_KV_STAGES) * CHUNK_BYTES);
       for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16_ss_elect(tmem_S, qdesc + 2u * ks, kdesc + 2u * ks, idesc_qk, ks > 0 ? 1u : 0u);
       umma_commit_elect(s_full(g));
     };
-    // K/V TMA ring (2 stages), driven by MMA warp 0: tile t goes to stage t & 1 once P·V of tile t-2 (both
-    // warpgroups) has released it
-    auto load_kv = [&](int t) {
-      if (lane == 0) {
-        const int st = t & 1;
-        mbar_expect_tx(kv_full(st), CHUNK_BYTES + 2 * v_chunk_bytes);
-        tma_load_4d(sK + st * CHUNK_BYTES, &tmQK, kv_full(st), 0, p.heads + head, t * KT, b);
-        for (int jj = 0; jj < 2; ++jj)
-          tma_load_3d(sV + st * V_STAGE_BYTES + jj * v_chunk_bytes, &tmV, kv_full(st), t * KT + jj * 64, head * p.d, b);
-      }
-      __syncwarp();
-    };
-    if (g == 0) {
-      if (lane == 0) {
-        mbar_expect_tx(q_full, 2 * CHUNK_BYTES);
-        tma_load_4d(sQ, &tmQK, q_full, 0, head, q0, b);
-        tma_load_4d(sQ + CHUNK_BYTES, &tmQK, q_full, 0, head, q0 + QT, b);
-      }
-      __syncwarp();
-      load_kv(0);
-      if (T > 1) load_kv(1);
-    }
     mbar_wait(q_full, 0);
     mbar_wait(kv_full(0), 0);
     tc_fence_after();
     issue_qk(0);
+    int st = 0, st_next = 1;            // stage of tile j / j + 1
+    uint32_t ph_next = 0;               // kv_full parity of tile j + 1
     for (int j = 0; j < T; ++j) {
-      const int st = j & 1;
-      mbar_wait(p_full(g), j & 1);   // P(j) published => S(j) fully read
       if (j + 1 < T) {
-        mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1);
+        mbar_wait(s_free(g), j & 1);    // every softmax warp has read S(j) for the last time
+        mbar_wait(kv_full(st_next), ph_next);
         tc_fence_after();
         issue_qk(j + 1);
       }
+      mbar_wait(p_full(g), j & 1);      // P(j) is in shared memory
       tc_fence_after();
       {
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
-          const uint64_t pdesc = umma_desc_sw128(sP + (g * 2 + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
+          const uint64_t pdesc = umma_desc_sw128(sP + ((g * 2 + (j & 1)) * 2 + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
           const uint64_t vdesc = umma_desc_sw128(sV + st * V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
           umma_bf16_ss_elect(tmem_O, pdesc, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit_elect(pv_done(g));
+        umma_commit_elect(pv_done(g, j & 1));
         umma_commit_elect(kv_empty(st));
       }
-      if (g == 0 && j + 2 < T) {
-        mbar_wait(kv_empty(st), (j >> 1) & 1);   // P·V(j) of both warpgroups has retired
-        load_kv(j + 2);
-      }
+      st = st_next;
+      if (++st_next == ATT2_KV_STAGES) { st_next = 0; ph_next ^= 1u; }
+    }
+  } else if (warp == 18) {
+    // ================= Q / K / V loads (uniform code, elected issue) =================
+    mbar_expect_tx_elect(q_full, 2 * CHUNK_BYTES);
+    tma_load_4d_elect(sQ, &tmQK, q_full, 0, head, q0, b);
+    tma_load_4d_elect(sQ + CHUNK_BYTES, &tmQK, q_full, 0, head, q0 + QT, b);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int t = 0; t < T; ++t) {
+      if (t >= ATT2_KV_STAGES) mbar_wait(kv_empty(st), ph ^ 1u);   // P.V of the tile that used this stage has retired
+      mbar_expect_tx_elect(kv_full(st), CHUNK_BYTES + 2 * v_chunk_bytes);
+      tma_load_4d_elect(sK + st * CHUNK_BYTES, &tmQK, kv_full(st), 0, p.heads + head, t * KT, b);
+      tma_load_3d_elect<false>(sV + st * V_STAGE_BYTES, &tmV, kv_full(st), t * KT, head * p.d, b);
+      tma_load_3d_elect<false>(sV + st * V_STAGE_BYTES + v_chunk_bytes, &tmV, kv_full(st), t * KT + 64, head * p.d, b);
+      if (++st == ATT2_KV_STAGES) { st = 0; ph ^= 1u; }
     }
   } else {
     const int sw = warp - 2;            // 0..15
@@ -424,7 +430,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tmem_S = tmem_base + g * 128 + sub * 64;
     const uint32_t tmem_O = tmem_base + 256 + g * 64;
-    uint8_t* prow = p_gen + (g * 2 + sub) * CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    uint8_t* prow0 = p_gen + (g * 4 + sub) * CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128;  // P buffer 0
     float* xmine = x_gen + (g * 2 + sub) * 128 + row;
     float* xpeer = x_gen + (g * 2 + (sub ^ 1)) * 128 + row;
     const int bar_id = 1 + g;
@@ -469,7 +475,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         alpha = ex2((m_run - m_new) * sl2);  // first tile: ex2(-inf) = 0
         m_run = m_new;
         if (j > 0 && sub == 0) {
-          mbar_wait(pv_done(g), (j - 1) & 1);
+          mbar_wait(pv_done(g, (j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
           for (int c = 0; c < p.dv; c += 16) {
             uint32_t o[16];
@@ -483,8 +489,9 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         }
       }
       const float mneg = -m_run * sl2;
-      // P is single-buffered: P·V of tile j-1 must have read it (issued right after P(j-1) was published)
-      if (j > 0) mbar_wait(pv_done(g), (j - 1) & 1);
+      // P buffer j & 1 was last read by P.V of tile j-2
+      if (j > 1) mbar_wait(pv_done(g, j & 1), ((j >> 1) & 1) ^ 1u);
+      uint8_t* prow = prow0 + (j & 1) * (2 * CHUNK_BYTES);
       // pass 2: exponentials, partial row sum, bf16 P -> shared memory (chunk `sub`, K-major, 128B swizzle)
       float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
 #pragma unroll
@@ -492,6 +499,11 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         uint32_t v[32];
         tmem_ld_x32(tmem_S + lane_off + h * 32, v);
         tmem_ld_wait();
+        if (h == 1) {  // last read of S(j): the tensor core may start S(j+1) while the exponentials run
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free(g));
+        }
         if (MASKED) {
           const int kvalid = p.N - j * KT - sub * 64 - h * 32;
 #pragma unroll
@@ -530,7 +542,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     *xmine = l_run;
     named_bar_sync(bar_id, 256);
     const float l_tot = l_run + *xpeer;
-    mbar_wait(pv_done(g), (T - 1) & 1);
+    mbar_wait(pv_done(g, (T - 1) & 1), ((T - 1) >> 1) & 1);
     tc_fence_after();
     if (sub == 0) {
       const float inv_l = 1.0f / l_tot;
@@ -562,7 +574,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr size_t ATT2_SMEM = 1024 + 2 * CHUNK_BYTES + 2 * CHUNK_BYTES + 2 * (2 * 64 * 128) + 4 * CHUNK_BYTES + 2048 + 8 * 16;
+constexpr size_t ATT2_SMEM = 2 * CHUNK_BYTES + ATT2_KV_STAGES * CHUNK_BYTES + ATT2_KV_STAGES * (2 * 64 * 128) +
+                             8 * CHUNK_BYTES + 2048 + 8 * 16;
 
 int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;

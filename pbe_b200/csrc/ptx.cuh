@@ -291,6 +291,16 @@ __device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMa
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];\n\t}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // Broadcast lane 0's value: tells the compiler the result is warp-uniform.
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
