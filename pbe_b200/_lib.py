@@ -5,7 +5,10 @@ import ctypes
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpbe_b200.so"
+import os
+
+# PBE_B200_LIB: development override (A/B of two builds of the same library in one GPU session)
+_LIB_PATH = Path(os.environ.get("PBE_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libpbe_b200.so")
 _lib = None
 
 

@@ -431,7 +431,6 @@ int Engine::build(Prepared& P, bool dry) {
   auto add_gn = [&](const std::string& name, GroupNormArgs a) {
     a.partial = static_cast<float*>(SA(static_cast<size_t>(gn_workspace_floats(a.Nb, a.HW, a.C0 + a.C1)) * sizeof(float)));
     const double n = static_cast<double>(a.Nb) * a.HW * (a.C0 + a.C1);
-    const bool fused_stats = a.stats0 != nullptr && (a.C1 == 0 || a.stats1 != nullptr) && a.HW % 32 == 0;
     const int launches = gn_num_launches(a);
     add_op_meta(name, launches, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
                 n * ((launches == 3 ? 8.0 : 4.0) + 2.0 + (a.raw ? 2.0 : 0.0)));
