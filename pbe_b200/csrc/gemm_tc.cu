@@ -42,38 +42,51 @@ constexpr int EPI_STAGING_BYTES = NUM_SLOTS * SLOT_BYTES;
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-// exact-erf GELU (torch.nn.functional.gelu default): erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
-// the bf16 resolution of the stored result): 1 MUFU.RCP + 1 MUFU.EX2 + a handful of FMAs instead of libdevice erff
-// (rcp.approx / ex2.approx: <= 2 ulp each).  See geglu2() below.
+// exact-erf GELU (torch.nn.functional.gelu default) for the GEGLU epilogue, division free:
+//   erf(|g| / sqrt2) = 1 - 2^u(t),  t = min(|g|, 4 sqrt2),  u = t (c1 + t (c2 + t (c3 + t (c4 + t c5))))
+// u is a weighted-minimax fit of log2(erfc(t / sqrt2)) (fit script: tools/fit_erf.py; max |erf error| 6.7e-7, max GELU
+// error 1.3e-6 absolute -- bf16 stores the result with 2^-9 relative precision).  One MUFU.EX2 per output instead of the
+// RCP + EX2 of Abramowitz-Stegun 7.1.26: the epilogue of the short-K GEGLU GEMMs was bound by the MUFU pipe.
 
 // ---- packed fp32x2 arithmetic (FFMA2 on sm_100): two GEGLU outputs per instruction stream ----
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// (a0, a1) * gelu_erf((g0, g1)) with the same Abramowitz-Stegun 7.1.26 erf as gelu_erf(), two lanes per FFMA2.
-// The GEGLU epilogue is ALU-issue bound (K = C is short, 64 GELUs per thread per tile): ~11 issue slots per output
-// instead of ~20.
-__device__ __forceinline__ f32x2 geglu2(f32x2 a, f32x2 g) {
-  const f32x2 az = g & 0x7fffffff7fffffffull;                                   // |g|
-  const f32x2 z = mul2(az, pk2(0.70710678118654752440f, 0.70710678118654752440f));
-  const f32x2 d = fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.0f, 1.0f));
-  float d0, d1;
-  upk2(d, d0, d1);
-  const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
-  // -poly(t): constants negated so that erf_abs = fma(-poly * t, e, 1)
-  f32x2 np = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));
-  np = fma2(np, t, pk2(-1.421413741f, -1.421413741f));
-  np = fma2(np, t, pk2(0.284496736f, 0.284496736f));
-  np = fma2(np, t, pk2(-0.254829592f, -0.254829592f));
-  np = mul2(np, t);
-  const f32x2 arg = mul2(mul2(z, z), pk2(-1.4426950408889634f, -1.4426950408889634f));
-  float x0, x1;
-  upk2(arg, x0, x1);
-  const f32x2 e = pk2(ex2_approx(x0), ex2_approx(x1));
-  const f32x2 erf_abs = fma2(np, e, pk2(1.0f, 1.0f));                            // >= 0
-  const f32x2 erfv = erf_abs | (g & 0x8000000080000000ull);                      // copysign(erf_abs, g)
-  const f32x2 h = fma2(erfv, pk2(0.5f, 0.5f), pk2(0.5f, 0.5f));                  // 0.5 (1 + erf)
-  return mul2(a, mul2(g, h));
+// NP output pairs at once, stage by stage: a[i] <- a[i] * gelu_erf(g[i])
+template <int NP>
+__device__ __forceinline__ void geglu_block(f32x2* a, const f32x2* g) {
+  f32x2 t[NP], u[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float g0, g1;
+    upk2(g[i], g0, g1);
+    t[i] = pk2(fminf(fabsf(g0), 5.65685425f), fminf(fabsf(g1), 5.65685425f));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) u[i] = fma2(t[i], pk2(-5.204507615e-04f, -5.204507615e-04f), pk2(7.397474721e-03f, 7.397474721e-03f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) u[i] = fma2(u[i], t[i], pk2(-5.256118253e-02f, -5.256118253e-02f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) u[i] = fma2(u[i], t[i], pk2(-4.592547119e-01f, -4.592547119e-01f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) u[i] = fma2(u[i], t[i], pk2(-1.151091337e+00f, -1.151091337e+00f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) u[i] = mul2(u[i], t[i]);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float u0, u1;
+    upk2(u[i], u0, u1);
+    u[i] = pk2(ex2_approx(u0), ex2_approx(u1));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float e0, e1, g0, g1;
+    upk2(u[i], e0, e1);
+    upk2(g[i], g0, g1);
+    const f32x2 hs = pk2(copysignf(fmaf(e0, -0.5f, 0.5f), g0), copysignf(fmaf(e1, -0.5f, 0.5f), g1));
+    u[i] = add2(hs, pk2(0.5f, 0.5f));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) a[i] = mul2(a[i], mul2(g[i], u[i]));
 }
 
 // Work-unit coordinates (split slice, n tile, w / h / batch tile) advanced incrementally: unit += gridDim.x is a
@@ -357,13 +370,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pf_c = (ws + pf_ti) & 1;
       }
     };
-    if (elected) {
+    if (elected && p.has_res) {
       pf_issue_next();
       pf_issue_next();
     }
+    const bool store_warp = (ew & 3) == 0;
 
     int ti = 0;
     int seq = 0;  // chunks consumed by this warp-set
+    // debug counters of CTA 0, epilogue warp 3 (not the electing warp): total, waiting for an accumulator, slot, barrier
+    const bool edbg = p.debug != 0 && blockIdx.x == 0 && warp == 3 && lane == 0;
+    long long e_all = edbg ? clock64() : 0, e_full = 0, e_slot = 0, e_bar = 0;
     // position of my accumulator row inside a tile: constant over all tiles
     const int wl = row % p.tw;
     const int hl = (row / p.tw) % p.th;
@@ -378,7 +395,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
       const long long my_m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
 
+      long long te = edbg ? clock64() : 0;
       mbar_wait(tmem_full_bar(buf), (ti >> 1) & 1);
+      if (edbg) e_full += clock64() - te;
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
       const int c_first = (ws + ti) & 1;
@@ -424,22 +443,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t va[32], vg[32];
           tmem_ld_x32(taddr + c * 32, va);
           tmem_ld_x32(taddr + HALF + c * 32, vg);
+          // this chunk's 32 value + 32 gate biases: one coalesced load per lane, broadcast through a per-warp scratch in
+          // the unused upper half of the slot (bf16-only epilogues stage 8 KB of the 16 KB).  Sixteen float4 __ldg's
+          // inside the GELU math stalled every group of four outputs on a global-load round trip.
+          float* bscr = reinterpret_cast<float*>(slot_gen + 8192 + (ew & 3) * 256);
+          {
+            const float b_val = __ldg(p.bias + n_base + c * 32 + lane);
+            const float b_gate = __ldg(p.bias + n_base + HALF + c * 32 + lane);
+            __syncwarp();   // previous chunk's reads of the scratch are done
+            bscr[lane] = b_val;
+            bscr[32 + lane] = b_gate;
+            __syncwarp();
+          }
           tmem_ld_wait();
           if (c == last_c) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) tmem_empty_arrive(buf);
           }
+          // eight output pairs per block, evaluated stage by stage: every dependent step of the GELU polynomial has
+          // seven independent neighbours to hide its latency behind (two warps per scheduler cannot)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c * 32 + j));
-            const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + HALF + c * 32 + j));
-            const f32x2 a01 = add2(pk2(__uint_as_float(va[j + 0]), __uint_as_float(va[j + 1])), pk2(ba.x, ba.y));
-            const f32x2 a23 = add2(pk2(__uint_as_float(va[j + 2]), __uint_as_float(va[j + 3])), pk2(ba.z, ba.w));
-            const f32x2 g01 = add2(pk2(__uint_as_float(vg[j + 0]), __uint_as_float(vg[j + 1])), pk2(bg.x, bg.y));
-            const f32x2 g23 = add2(pk2(__uint_as_float(vg[j + 2]), __uint_as_float(vg[j + 3])), pk2(bg.z, bg.w));
-            upk2(geglu2(a01, g01), o[j + 0], o[j + 1]);
-            upk2(geglu2(a23, g23), o[j + 2], o[j + 3]);
+          for (int j0 = 0; j0 < 32; j0 += 16) {
+            f32x2 av[8], gv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 ba = *reinterpret_cast<const float4*>(bscr + j0 + 4 * i);
+              const float4 bg = *reinterpret_cast<const float4*>(bscr + 32 + j0 + 4 * i);
+              const int j = j0 + 4 * i;
+              av[2 * i] = add2(pk2(__uint_as_float(va[j + 0]), __uint_as_float(va[j + 1])), pk2(ba.x, ba.y));
+              av[2 * i + 1] = add2(pk2(__uint_as_float(va[j + 2]), __uint_as_float(va[j + 3])), pk2(ba.z, ba.w));
+              gv[2 * i] = add2(pk2(__uint_as_float(vg[j + 0]), __uint_as_float(vg[j + 1])), pk2(bg.x, bg.y));
+              gv[2 * i + 1] = add2(pk2(__uint_as_float(vg[j + 2]), __uint_as_float(vg[j + 3])), pk2(bg.z, bg.w));
+            }
+            geglu_block<8>(av, gv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) upk2(av[i], o[j0 + 2 * i], o[j0 + 2 * i + 1]);
           }
         } else {
           uint32_t v[32];
@@ -466,7 +505,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // the slot is ours once the residual prefetch (or the plain arrive that stands in for it) has landed
-        mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
+        if (edbg) te = clock64();
+        // Without a residual nothing is prefetched into the slot: it is free once the store issued from it two
+        // chunks ago has read it, which the storing warp checks before it joins the previous chunk's barrier (below).
+        if (p.has_res) mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
+        if (edbg) e_slot += clock64() - te;
         uint8_t* my_row128 = slot_gen + row * 128;
         if (p.has_res) {
 #pragma unroll
@@ -533,18 +576,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         fence_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (elected) {
-          const int ocol = n_tile * tile_out_cols + c * chunk_cols;
-          if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
-          else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
-          tma_store_commit();
-          tma_store_wait_read0();  // slot may be overwritten again
-          pf_issue_next();         // residual prefetch (or hand-back) for the chunk two ahead, same slot
+        const int ocol = n_tile * tile_out_cols + c * chunk_cols;
+        if (edbg) te = clock64();
+        if (p.has_res) {
+          named_bar_sync(bar_id, 128);
+          if (elected) {
+            if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
+            else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
+            tma_store_commit();
+            tma_store_wait_read0();  // slot may be overwritten again
+            pf_issue_next();         // residual prefetch for the chunk two ahead, into this slot
+          }
+        } else {
+          // The storing warp runs warp-uniform code (elected lane issues).  Before the barrier it makes sure the store
+          // of the PREVIOUS chunk (issued a whole chunk ago, from the other slot) has read its slot: passing the
+          // barrier then tells all four warps that the other slot may be overwritten -- no mbarrier round trip, no
+          // stall on the store just issued, no single-lane code between two barriers.
+          if (store_warp) tma_store_wait_read0();
+          named_bar_sync(bar_id, 128);
+          if (edbg) e_bar += clock64() - te;
+          if (store_warp) {
+            if (p.has_o32) tma_store_4d_commit_elect(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
+            else tma_store_4d_commit_elect(&tmO16, slot_addr, ocol, w0, h0, n0);
+          }
         }
       }
     }
-    if (elected) tma_store_wait_all();
+    if (edbg) {
+      g_gemm_dbg[5] = clock64() - e_all;
+      g_gemm_dbg[6] = e_full;
+      g_gemm_dbg[7] = (e_slot << 32) | (e_bar & 0xffffffffll);
+    }
+    if (store_warp) tma_store_wait_all();
   }
 
   tc_fence_before();

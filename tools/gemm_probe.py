@@ -35,6 +35,8 @@ def case(name, Nb, H, W, C, k, Cout, mode=0, residual=False, rowbias=False, f32=
         lib.pbe_debug_gemm_counters(c)
         if c[0] > 0:
             extra = f"  | CTA0 MMA warp: {c[0]} cyc, wait TMA {100*c[1]/c[0]:.0f}%, wait TMEM {100*c[2]/c[0]:.0f}%, {c[4]} k-iters, {c[0]/max(c[4],1):.0f} cyc/iter"
+            if c[5] > 0:
+                extra += f" | epi warp: {c[5]} cyc, wait acc {100*c[6]/c[5]:.0f}%, wait slot {100*(c[7]>>32)/c[5]:.0f}%, barrier {100*(c[7]&0xffffffff)/c[5]:.0f}%"
     print(f"{name:28s} {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TF/s{extra}", flush=True)
 
 which = sys.argv[1:] or ["proj_out", "geglu", "conv2", "conv1", "ffout", "lowres"]
