@@ -127,6 +127,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="edit requests per GPU per step (CFG doubles it)")
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--sampler-steps", type=int, default=50)
+    ap.add_argument("--sampler", default="plms", choices=["plms", "ddim"],
+                    help="plms (BASELINE configs 1-3, 5) or ddim (config 4: DDIM-20 latency)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-op breakdown of one U-Net call to this JSON")
     args = ap.parse_args()
@@ -148,7 +150,7 @@ def main():
 
     from oracle import sampler_ref as S, unet_ref as U   # synthetic weights / requests only (not timed, not the product)
     from pbe_b200.diffusion import LatentDiffusion
-    from pbe_b200.samplers import PLMSSampler
+    from pbe_b200.samplers import DDIMSampler, PLMSSampler
 
     cfg = U.V1_CFG
     sd = U.make_state_dict(cfg, 321)
@@ -160,7 +162,11 @@ def main():
     req = S.synthetic_request(B, hw, hw, seed=321 + rank)
     pin = {k: v.contiguous().pin_memory() for k, v in req.items()}
     d = {k: v.to(dev) for k, v in req.items()}
-    sampler = PLMSSampler(model)
+    sampler = PLMSSampler(model) if args.sampler == "plms" else DDIMSampler(model)
+    calls = Sn + 1 if args.sampler == "plms" else Sn   # PLMS evaluates the first step twice (plms.py:230-235)
+    flops_per_eval = F64_MIN * (hw * hw) / 4096.0 if hw == 64 else None   # SURVEY 8(d) gives F only for 64 and 96
+    if hw == 96:
+        flops_per_eval = 2079.9e9
     unet = model.model.diffusion_model
 
     def sample_device():
@@ -247,7 +253,7 @@ def main():
     imgs = world * B * args.steps
     value = imgs / (total_ms / 1e3)
     e2e_value = imgs / (e2e_ms / 1e3)
-    launches = UNET_CALLS * (unet.launches_per_forward() + 2) + 1
+    launches = calls * (unet.launches_per_forward() + 2) + 1
     gemm = fam.get("conv_gemm", dict(ms=1.0, flops=0.0, launches=1))
     gemm_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     cpu_baseline = None
@@ -261,8 +267,8 @@ def main():
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: v1.yaml U-Net (859.5M params, seeded random weights), batch {B} "
-                               f"per GPU (CFG batch {Bc}), {hw}x{hw} latent ({hw*8}x{hw*8} image), PLMS {Sn} steps "
-                               f"({UNET_CALLS} U-Net calls), guidance scale 5",
+                               f"per GPU (CFG batch {Bc}), {hw}x{hw} latent ({hw*8}x{hw*8} image), {args.sampler.upper()} {Sn} steps "
+                               f"({calls} U-Net calls), guidance scale 5",
                    "global_batch": world * B, "parallelism": f"dp{world} (independent requests, no collective)",
                    "l2": "working set per step (1.7 GB bf16 weights + >1 GB activations per U-Net call) exceeds the "
                          "126 MB L2; no explicit flush"},
@@ -270,8 +276,8 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches * args.steps,
         "unet_step_ms": {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
-                         "cfg_batch": Bc, "floor_ms_at_sustained_peak": Bc * F64_MIN / (peaks["tf_sustained"] * 1e12) * 1e3},
-        "tensor_utilisation_whole_job": {"achieved_tflops": world * B * args.steps * 2 * UNET_CALLS * F64_MIN / (total_ms / 1e3) / 1e12 / world,
+                         "cfg_batch": Bc, "floor_ms_at_sustained_peak": (Bc * flops_per_eval / (peaks["tf_sustained"] * 1e12) * 1e3) if flops_per_eval else None},
+        "tensor_utilisation_whole_job": {"achieved_tflops": (B * args.steps * 2 * calls * flops_per_eval / (total_ms / 1e3) / 1e12) if flops_per_eval else None,
                                          "peak_tflops_sustained": peaks["tf_sustained"], "peak_source": peaks["src"]},
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM conv / linear, tcgen05)",
                      "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",

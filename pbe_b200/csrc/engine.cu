@@ -344,7 +344,7 @@ int Engine::finalize() {
     modules_.push_back({Module::OUT, static_cast<int>(convs_.size()) - 1, false, false});
   }
   emb_total_ = static_cast<int>(emb_b.size());
-  if ((rc = upload_f32(emb_w, &emb_w_))) return rc;
+  if ((rc = upload_bf16(emb_w, &emb_w_))) return rc;
   if ((rc = upload_f32(emb_b, &emb_b_))) return rc;
 
   {
@@ -448,16 +448,24 @@ int Engine::build(Prepared& P, bool dry) {
   float* emb_all = static_cast<float*>(PA(static_cast<size_t>(Bc) * emb_total_ * sizeof(float)));
   {
     const int64_t* tp = P.t_stage;
-    float *w0 = te_w0_, *b0 = te_b0_, *w1 = te_w1_, *b1 = te_b1_, *ew = emb_w_, *eb = emb_b_;
-    const int et = emb_total_;
+    float *w0 = te_w0_, *b0 = te_b0_, *w1 = te_w1_, *b1 = te_b1_;
+    bf16* emb_silu16 = static_cast<bf16*>(PA(static_cast<size_t>(Bc) * ted * sizeof(bf16)));
     add_op("timestep_embedding", 1, [=](cudaStream_t s) { return launch_timestep_embedding(tp, t_emb, Bc, mc, s); });
     add_op("time_embed.0+silu", 1,
            [=](cudaStream_t s) { return launch_small_linear(t_emb, w0, b0, t_hid, Bc, mc, ted, 0, 1, s); });
     add_op("time_embed.2", 1,
            [=](cudaStream_t s) { return launch_small_linear(t_hid, w1, b1, emb, Bc, ted, ted, 0, 0, s, emb_silu); });
-    // every ResBlock's emb_layers = Linear(SiLU(emb)) (openaimodel.py:218-224): SiLU once, all 22 Linears in one launch
-    add_op("emb_layers(all)", 1,
-           [=](cudaStream_t s) { return launch_small_linear(emb_silu, ew, eb, emb_all, Bc, ted, et, 0, 0, s); });
+    // every ResBlock's emb_layers = Linear(SiLU(emb)) (openaimodel.py:218-224): SiLU once, all 22 Linears as ONE
+    // [Bc, 1280] x [1280, 20160] GEMM on the tensor cores (a 52 MB bf16 weight stream; as batched fp32 GEMVs it was
+    // latency bound at 185 us per call)
+    add_op("emb_silu.bf16", 1,
+           [=](cudaStream_t s) { return launch_cast_bf16(emb_silu, emb_silu16, static_cast<size_t>(Bc) * ted, s); });
+    {
+      ConvGemmDesc d{};
+      d.act = emb_silu16; d.Nb = Bc; d.H = 1; d.W = 1; d.C = ted; d.ksize = 1; d.stride = 1;
+      d.wt = emb_w_; d.Cout = emb_total_; d.mode = EPI_STD; d.bias = emb_b_; d.out_f32 = emb_all;
+      add_gemm("emb_layers(all)", d);
+    }
   }
 
   struct Act {

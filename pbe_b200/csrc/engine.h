@@ -126,7 +126,8 @@ class Engine {
   std::vector<ConvW> convs_;  // conv_in, downsample, upsample, out convs
   NormW out_norm_;
   float *te_w0_ = nullptr, *te_b0_ = nullptr, *te_w1_ = nullptr, *te_b1_ = nullptr;  // time_embed
-  float *emb_w_ = nullptr, *emb_b_ = nullptr;  // all ResBlock emb_layers concatenated [emb_total, 4*mc]
+  bf16* emb_w_ = nullptr;   // all ResBlock emb_layers concatenated [emb_total, 4*mc] (one GEMM per U-Net call)
+  float* emb_b_ = nullptr;
   int emb_total_ = 0;
   int ctx_total_ = 0;  // sum of C over SpatialTransformers
 
