@@ -28,6 +28,7 @@ os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "WARN")   # keep std
 import torch
 
 F64_MIN = 771.3e9   # algorithmic FLOPs per sample-eval at 64x64 with the dead cross-attention work elided
+NCU_TRAFFIC_CONV1 = 43869440 + 36049152   # dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_conv1_pair_summary.txt)
 UNET_CALLS = 51     # PLMS-50: the first step evaluates twice (plms.py:230-235)
 
 
@@ -281,7 +282,10 @@ def main():
                                          "peak_tflops_sustained": peaks["tf_sustained"], "peak_source": peaks["src"]},
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM conv / linear, tcgen05)",
                      "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tf / peaks["tf_sustained"], "traffic": None,
+                     "frac": gemm_tf / peaks["tf_sustained"], "traffic": NCU_TRAFFIC_CONV1,
+                     "traffic_note": "DRAM read+write bytes of ONE representative launch (64x64 320->320 3x3 conv, CFG batch "
+                                     "16; algorithmic 127.7 MB, fp32 output still in L2 at kernel end) from ncu --set full: "
+                                     "profiles/r01_ncu_conv1_pair_summary.txt; achieved/peak aggregate all launches",
                      "how": f"sum of algorithmic FLOPs of the {gemm['launches']} conv_gemm launches of one U-Net call "
                             f"(CFG batch {Bc}) / sum of their CUDA-event durations (eager pass after the timed region); "
                             f"peak = {peaks['src']} sustained bf16",
