@@ -118,6 +118,37 @@ int pbe_op_info(pbe_handle h, int i, const char** name, const char** family, dou
 /* number of kernels one pbe_unet_forward launches for the current shape (0 before the first forward). */
 int pbe_launches_per_forward(pbe_handle h);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * VAE decode (first "next" row of SURVEY.md 8f): AutoencoderKL.decode = Decoder(post_quant_conv(z)),
+ * ldm/models/autoencoder.py:66-69 + ldm/modules/diffusionmodules/model.py:474-580, reached from
+ * LatentDiffusion.decode_first_stage (ldm/models/diffusion/latent_diffusion.py:444-508) after the sampling loop.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct pbe_vae_config {
+  int32_t embed_dim;      /* 4  (configs/v1.yaml:51) */
+  int32_t z_channels;     /* 4 */
+  int32_t ch;             /* 128, multiple of 64 */
+  int32_t out_ch;         /* 3 */
+  int32_t num_levels;     /* len(ch_mult) */
+  int32_t ch_mult[8];     /* 1,2,4,4 */
+  int32_t num_res_blocks; /* 2 (the decoder runs num_res_blocks + 1 blocks per level) */
+} pbe_vae_config;
+
+typedef struct pbe_vae* pbe_vae_handle;
+
+int pbe_vae_create(const pbe_vae_config* cfg, pbe_vae_handle* out);
+void pbe_vae_destroy(pbe_vae_handle h);
+/* name = reference state-dict key relative to the autoencoder ("decoder.conv_in.weight", "post_quant_conv.bias", ...,
+ * i.e. the part after "first_stage_model."); host fp32 data; encoder / loss keys may simply not be loaded. */
+int pbe_vae_load_weight(pbe_vae_handle h, const char* name, const float* host_data, const int64_t* shape, int rank);
+int pbe_vae_finalize_weights(pbe_vae_handle h);
+/* out[B,out_ch,fH,fW] = decode(z[B,embed_dim,H,W]) (fp32 NCHW, device), f = 2^(num_levels-1); H*W % 64 == 0. */
+int pbe_vae_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream);
+/* Measurement aid, as pbe_profile_forward / pbe_op_info. */
+int pbe_vae_profile_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream, float* ms_out,
+                           int max_ops);
+int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops);
+int pbe_vae_launches_per_decode(pbe_vae_handle h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,3 +95,27 @@ def reference_sampler(kind: str, model):
             setattr(self, name, attr)
 
     return CpuSafe(model)
+
+
+def build_reference_vae_decode(cfg, sd):
+    """decode(z) built from the reference's own modules: Decoder (ldm/modules/diffusionmodules/model.py:474) after a
+    post_quant_conv torch.nn.Conv2d, exactly as AutoencoderKL.decode composes them (autoencoder.py:37,66-69).
+    (ldm.models.autoencoder itself does not import here: it needs pytorch_lightning.)"""
+    _install_stubs()
+    import contextlib, io
+    from ldm.modules.diffusionmodules.model import Decoder
+    with contextlib.redirect_stdout(io.StringIO()):
+        dec = Decoder(ch=cfg["ch"], out_ch=cfg["out_ch"], ch_mult=tuple(cfg["ch_mult"]), num_res_blocks=cfg["num_res_blocks"],
+                      attn_resolutions=[], dropout=0.0, in_channels=3, resolution=256, z_channels=cfg["z_channels"])
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    pq = torch.nn.Conv2d(cfg["embed_dim"], cfg["z_channels"], 1)
+    pq.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]}, strict=True)
+    dec.eval()
+
+    def decode(z):
+        with torch.no_grad():
+            return dec(pq(z))
+
+    decode.state_dict_keys = sorted(["decoder." + k for k in dec.state_dict().keys()] +
+                                    ["post_quant_conv.weight", "post_quant_conv.bias"])
+    return decode

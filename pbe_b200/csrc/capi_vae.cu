@@ -1,0 +1,68 @@
+// C-ABI of the VAE decoder (include/pbe_b200.h).  Nothing throws across the boundary.
+#include "vae.h"
+
+#include <new>
+
+using namespace pbe;
+
+struct pbe_vae {
+  VaeDecoder* d;
+};
+
+extern "C" {
+
+int pbe_vae_create(const pbe_vae_config* cfg, pbe_vae_handle* out) {
+  if (cfg == nullptr || out == nullptr) { set_error("pbe_vae_create: null argument"); return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("pbe_vae_create: no CUDA device (this library has no CPU fallback)");
+    return -2;
+  }
+  try {
+    pbe_vae* h = new pbe_vae;
+    h->d = new VaeDecoder(*cfg);
+    *out = h;
+  } catch (const std::exception& ex) {
+    set_error(std::string("pbe_vae_create: ") + ex.what());
+    return -1;
+  }
+  return 0;
+}
+
+void pbe_vae_destroy(pbe_vae_handle h) {
+  if (h == nullptr) return;
+  delete h->d;
+  delete h;
+}
+
+#define PBE_VAE_GUARD(stmt)                                      \
+  if (h == nullptr) { set_error("null handle"); return -1; }     \
+  try { return (stmt); }                                         \
+  catch (const std::exception& ex) { set_error(ex.what()); return -1; }
+
+int pbe_vae_load_weight(pbe_vae_handle h, const char* name, const float* host_data, const int64_t* shape, int rank) {
+  PBE_VAE_GUARD(h->d->load_weight(name, host_data, shape, rank));
+}
+int pbe_vae_finalize_weights(pbe_vae_handle h) { PBE_VAE_GUARD(h->d->finalize()); }
+int pbe_vae_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream) {
+  PBE_VAE_GUARD(h->d->decode(z, out, B, H, W, static_cast<cudaStream_t>(stream)));
+}
+int pbe_vae_profile_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream, float* ms_out,
+                           int max_ops) {
+  PBE_VAE_GUARD(h->d->profile_decode(z, out, B, H, W, static_cast<cudaStream_t>(stream), ms_out, max_ops));
+}
+int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops) {
+  if (h == nullptr || h->d->current() == nullptr) { set_error("no prepared shape"); return -1; }
+  const VaePrepared* P = h->d->current();
+  if (i < 0 || i >= static_cast<int>(P->ops.size())) { set_error("op index out of range"); return -1; }
+  if (name) *name = P->op_names[i].c_str();
+  if (family) *family = P->op_family[i].c_str();
+  if (flops) *flops = P->op_flops[i];
+  return 0;
+}
+int pbe_vae_launches_per_decode(pbe_vae_handle h) {
+  if (h == nullptr || h->d->current() == nullptr) return 0;
+  return h->d->current()->launches;
+}
+
+}  // extern "C"

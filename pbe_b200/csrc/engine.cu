@@ -38,10 +38,13 @@ Prepared::~Prepared() {
 Engine::~Engine() {
   prepared_.clear();
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
+}
+
+WeightLoader::~WeightLoader() {
   for (void* p : dev_allocs_) cudaFree(p);
 }
 
-int Engine::load_weight(const char* name, const float* host, const int64_t* shape, int rank) {
+int WeightLoader::load_weight(const char* name, const float* host, const int64_t* shape, int rank) {
   PBE_REQUIRE(!finalized_, "weights already finalized");
   HostTensor t;
   size_t n = 1;
@@ -54,12 +57,12 @@ int Engine::load_weight(const char* name, const float* host, const int64_t* shap
   return 0;
 }
 
-const HostTensor* Engine::find(const std::string& name) {
+const HostTensor* WeightLoader::find(const std::string& name) {
   auto it = host_.find(name);
   return it == host_.end() ? nullptr : &it->second;
 }
 
-int Engine::get(const std::string& name, const HostTensor** out) {
+int WeightLoader::get(const std::string& name, const HostTensor** out) {
   *out = find(name);
   if (*out == nullptr) {
     set_error("missing weight: " + name);
@@ -68,7 +71,7 @@ int Engine::get(const std::string& name, const HostTensor** out) {
   return 0;
 }
 
-int Engine::upload_f32(const std::vector<float>& v, float** dst) {
+int WeightLoader::upload_f32(const std::vector<float>& v, float** dst) {
   void* p = nullptr;
   PBE_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(float)));
   dev_allocs_.push_back(p);
@@ -77,7 +80,7 @@ int Engine::upload_f32(const std::vector<float>& v, float** dst) {
   return 0;
 }
 
-int Engine::upload_bf16(const std::vector<float>& v, bf16** dst) {
+int WeightLoader::upload_bf16(const std::vector<float>& v, bf16** dst) {
   std::vector<uint16_t> h(v.size());
   for (size_t i = 0; i < v.size(); ++i) h[i] = f32_to_bf16_rn(v[i]);
   void* p = nullptr;
@@ -89,7 +92,7 @@ int Engine::upload_bf16(const std::vector<float>& v, bf16** dst) {
 }
 
 // conv / linear weight `prefix.weight` ([O,I,k,k] or [O,I]) (+ `prefix.bias`) -> [k*k][O][I_pad] bf16
-int Engine::make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad) {
+int WeightLoader::make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad, int cout_pad) {
   const HostTensor* W;
   int rc = get(prefix + ".weight", &W);
   if (rc) return rc;
@@ -100,27 +103,30 @@ int Engine::make_conv(const std::string& prefix, int k, int cin, int cout, ConvW
               std::to_string(expect));
     return -4;
   }
-  std::vector<float> packed(static_cast<size_t>(k) * k * cout * cin_pad, 0.0f);
+  if (cout_pad == 0) cout_pad = cout;   // zero output rows (e.g. a 3-channel conv_out run as 4 columns)
+  std::vector<float> packed(static_cast<size_t>(k) * k * cout_pad * cin_pad, 0.0f);
   for (int o = 0; o < cout; ++o)
     for (int i = 0; i < cin; ++i)
       for (int t = 0; t < k * k; ++t)
-        packed[(static_cast<size_t>(t) * cout + o) * cin_pad + i] = W->data[(static_cast<size_t>(o) * cin + i) * k * k + t];
+        packed[(static_cast<size_t>(t) * cout_pad + o) * cin_pad + i] = W->data[(static_cast<size_t>(o) * cin + i) * k * k + t];
   rc = upload_bf16(packed, &w->w);
   if (rc) return rc;
-  w->cin = cin; w->cin_pad = cin_pad; w->cout = cout; w->k = k;
+  w->cin = cin; w->cin_pad = cin_pad; w->cout = cout_pad; w->k = k;
   const HostTensor* B = find(prefix + ".bias");
   if (B) {
     if (static_cast<int>(B->data.size()) != cout) {
       set_error("bias " + prefix + ".bias has wrong size");
       return -4;
     }
-    rc = upload_f32(B->data, &w->b);
+    std::vector<float> bp(B->data);
+    bp.resize(cout_pad, 0.0f);
+    rc = upload_f32(bp, &w->b);
     if (rc) return rc;
   }
   return 0;
 }
 
-int Engine::make_norm(const std::string& prefix, int c, NormW* n) {
+int WeightLoader::make_norm(const std::string& prefix, int c, NormW* n) {
   const HostTensor *G, *B;
   int rc = get(prefix + ".weight", &G);
   if (rc) return rc;

@@ -88,11 +88,29 @@ struct Prepared {
   ~Prepared();
 };
 
-class Engine {
+// Host-side weight staging shared by the U-Net engine and the VAE decoder: tensors arrive by reference state-dict name,
+// are repacked at finalize() and uploaded once.
+class WeightLoader {
+ public:
+  int load_weight(const char* name, const float* host, const int64_t* shape, int rank);
+
+ protected:
+  ~WeightLoader();
+  const HostTensor* find(const std::string& name);
+  int get(const std::string& name, const HostTensor** out);
+  int make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad = 0, int cout_pad = 0);
+  int make_norm(const std::string& prefix, int c, NormW* n);
+  int upload_f32(const std::vector<float>& v, float** dst);
+  int upload_bf16(const std::vector<float>& v, bf16** dst);
+  std::unordered_map<std::string, HostTensor> host_;
+  bool finalized_ = false;
+  std::vector<void*> dev_allocs_;
+};
+
+class Engine : public WeightLoader {
  public:
   explicit Engine(const pbe_config& cfg) : cfg_(cfg) {}
   ~Engine();
-  int load_weight(const char* name, const float* host, const int64_t* shape, int rank);
   int finalize();
   int set_context(const float* ctx_dev, int Bc, cudaStream_t stream);
   int forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream);
@@ -107,17 +125,8 @@ class Engine {
  private:
   int prepare(int Bc, int H, int W);
   int build(Prepared& P, bool dry);
-  const HostTensor* find(const std::string& name);
-  int get(const std::string& name, const HostTensor** out);
-  int make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad = 0);
-  int make_norm(const std::string& prefix, int c, NormW* n);
-  int upload_f32(const std::vector<float>& v, float** dst);
-  int upload_bf16(const std::vector<float>& v, bf16** dst);
 
   pbe_config cfg_;
-  std::unordered_map<std::string, HostTensor> host_;
-  bool finalized_ = false;
-  std::vector<void*> dev_allocs_;
 
   // network description
   std::vector<Module> modules_;

@@ -422,6 +422,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long tok = static_cast<long long>(oh) * p.Wo + ow;
             const int vC = p.n_total - p.qk_cols;
             bf16* dst = p.out_vt + (static_cast<long long>(on) * vC + (n_base + c * 32 - p.qk_cols)) * tokens + tok;
+            if (p.bias != nullptr) {   // v projection with a bias (VAE attention; the U-Net's to_v has none)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n_base + c * 32 + j));
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[j * tokens] = __float2bfloat16(__uint_as_float(v[j]));
           }
@@ -869,10 +873,12 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   // A: 5-D view (c, w, phase, h, n)
   {
     const uint64_t C = d.C, W = d.W, H = d.H, N = d.Nb;
+    const uint64_t L = d.act_ld ? d.act_ld : d.C;   // pixel pitch (a column slice of a wider tensor)
+    PBE_REQUIRE(L >= C && L % 8 == 0 && (d.act_ld == 0 || d.stride == 1), "act_ld: >= C, multiple of 8, stride-1 only");
     uint64_t dims[5], strides[4];
     if (d.stride == 1) {
       dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
-      strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = W * C * 2; strides[3] = H * W * C * 2;
+      strides[0] = L * 2; strides[1] = W * L * 2; strides[2] = W * L * 2; strides[3] = H * W * L * 2;
     } else {
       dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
       strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
@@ -935,7 +941,9 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(d.C), static_cast<uint64_t>(d.Cout),
                               static_cast<uint64_t>(p.num_taps)};
-    const uint64_t strides[2] = {static_cast<uint64_t>(d.C) * 2, static_cast<uint64_t>(d.C) * d.Cout * 2};
+    const uint64_t wl = d.wt_ld ? d.wt_ld : d.C;
+    PBE_REQUIRE(wl >= static_cast<uint64_t>(d.C) && wl % 8 == 0 && (d.wt_ld == 0 || d.ksize == 1), "wt_ld: >= C, multiple of 8, 1x1 only");
+    const uint64_t strides[2] = {wl * 2, wl * d.Cout * 2};
     // CTA pair: each CTA loads its half of the n tile
     const uint32_t box[3] = {64u, static_cast<uint32_t>(bn / plan->cluster), 1u};
     int rc = make_tmap_bf16(&plan->tmB, d.wt, 3, dims, strides, box, true);

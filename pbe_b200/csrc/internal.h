@@ -118,6 +118,8 @@ struct ConvGemmDesc {
   int block_n;  // 0 -> auto
   float* splitk_ws;        // optional workspace enabling split-K (size from gemm_splitk_ws_bytes)
   float* stats_out;        // optional fused GroupNorm statistics of out_f32 (see gemm_can_fuse_stats)
+  int act_ld;              // elements between consecutive pixels of `act` (0 -> C): an operand that is a column slice
+  int wt_ld;               // elements between consecutive output rows of `wt` (0 -> C; ksize 1 only)
 };
 // Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
 int gemm_read_debug_counters(long long* out8);
@@ -173,6 +175,10 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
 
 // nearest 2x upsample, fp32 NHWC [Nb,H,W,C] -> bf16 NHWC [Nb,2H,2W,C]
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
+// VAE decode helpers: post_quant_conv fused with the NCHW -> NHWC bf16 pack; row softmax fp32 -> bf16
+int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16* y, int Nb, int Cin, int Cz, int H, int W,
+                          int Cpad, cudaStream_t stream);
+int launch_softmax_rows(const float* S, bf16* P, long long rows, int N, float scale, cudaStream_t stream);
 // fp32 -> bf16 cast of a flat buffer
 int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
 

@@ -164,6 +164,85 @@ __global__ void add_rowvec_kernel(const float* __restrict__ a, const float* __re
   y[idx] = a[idx % N] + v[idx];
 }
 
+// ---- VAE decode helpers (AutoencoderKL.decode, ldm/models/autoencoder.py:66-69; AttnBlock model.py:152-182) ----
+// post_quant_conv (1x1, embed_dim -> z_channels, fp32) fused with the NCHW -> NHWC bf16 pack (channels padded with zeros)
+__global__ void vae_pack_input_kernel(const float* __restrict__ z, const float* __restrict__ Wp, const float* __restrict__ bp,
+                                      bf16* __restrict__ y, int Nb, int Cin, int Cz, int HW, int Cpad) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Nb) * HW) return;
+  const int n = static_cast<int>(idx / HW);
+  const int pix = static_cast<int>(idx % HW);
+  float zin[8];
+  for (int i = 0; i < Cin; ++i) zin[i] = z[(static_cast<long long>(n) * Cin + i) * HW + pix];
+  bf16* dst = y + idx * Cpad;
+  for (int o = 0; o < Cpad; ++o) {
+    float v = 0.0f;
+    if (o < Cz) {
+      v = bp[o];
+      for (int i = 0; i < Cin; ++i) v += Wp[o * Cin + i] * zin[i];
+    }
+    dst[o] = __float2bfloat16(v);
+  }
+}
+
+// P[r][:] = softmax(S[r][:] * scale), fp32 in, bf16 out; one 256-thread block per row, the row lives in registers
+constexpr int SM_MAXV = 16;   // float4 per thread -> rows of up to 16384
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int N,
+                                                           float scale_log2) {
+  __shared__ float s_red[8];
+  const long long row = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(S + row * N);
+  const int nv = N / 4;
+  float4 v[SM_MAXV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SM_MAXV; ++i) {
+    const int k = threadIdx.x + i * 256;
+    if (k < nv) {
+      v[i] = src[k];
+      mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+  }
+  auto block_reduce = [&](float val, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, val, o);
+      val = is_max ? fmaxf(val, other) : val + other;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = val;
+    __syncthreads();
+    float r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, s_red[i]) : r + s_red[i];
+    return r;
+  };
+  mx = block_reduce(mx, true);
+  const float off = -mx * scale_log2;
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < SM_MAXV; ++i) {
+    const int k = threadIdx.x + i * 256;
+    if (k < nv) {
+      v[i].x = exp2f(fmaf(v[i].x, scale_log2, off)); v[i].y = exp2f(fmaf(v[i].y, scale_log2, off));
+      v[i].z = exp2f(fmaf(v[i].z, scale_log2, off)); v[i].w = exp2f(fmaf(v[i].w, scale_log2, off));
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  sum = block_reduce(sum, false);
+  const float inv = 1.0f / sum;
+  uint2* dst = reinterpret_cast<uint2*>(P + row * N);
+#pragma unroll
+  for (int i = 0; i < SM_MAXV; ++i) {
+    const int k = threadIdx.x + i * 256;
+    if (k < nv) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
+      dst[k] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
 }  // namespace
 
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream) {
@@ -201,6 +280,22 @@ int launch_small_linear(const float* x, const float* W, const float* bias, float
                         int post_silu, cudaStream_t stream, float* y_silu) {
   PBE_REQUIRE(K % 4 == 0, "small_linear K % 4");
   small_linear_kernel<<<(O + 8 * SL_OW - 1) / (8 * SL_OW), 256, 0, stream>>>(x, W, bias, y, y_silu, B, K, O, pre_silu, post_silu);
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16* y, int Nb, int Cin, int Cz, int H, int W,
+                          int Cpad, cudaStream_t stream) {
+  PBE_REQUIRE(Cin <= 8 && Cz <= Cpad, "vae_pack_input: embed_dim <= 8");
+  const long long total = static_cast<long long>(Nb) * H * W;
+  vae_pack_input_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(z, Wp, bp, y, Nb, Cin, Cz, H * W, Cpad);
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_softmax_rows(const float* S, bf16* P, long long rows, int N, float scale, cudaStream_t stream) {
+  PBE_REQUIRE(N % 4 == 0 && N <= 4 * 256 * SM_MAXV, "softmax_rows: row length % 4 == 0, <= 16384");
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(S, P, N, scale * 1.4426950408889634f);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -3,6 +3,7 @@
 Run in the authoring container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py small      # seconds..a minute
     python tests/golden/make_golden.py v1         # one full-size U-Net call (~10 s) + PLMS-50 C1 trajectory (~10 min)
+    python tests/golden/make_golden.py vae        # VAE decode: small config + the v1.yaml decoder on a 16x16 latent
 
 Inputs and weights are regenerated from seeds (oracle.unet_ref.make_state_dict, oracle.sampler_ref.synthetic_request),
 so only outputs are stored.  Every file is written as float32 .npy; golden_index.json records shapes, seeds and sha256.
@@ -13,7 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import unet_ref as U, sampler_ref as S, reference_bridge as R
+from oracle import unet_ref as U, sampler_ref as S, reference_bridge as R, vae_ref as V
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 INDEX = os.path.join(OUT, "golden_index.json")
@@ -90,6 +91,19 @@ def main(which):
         save("v1_plms50_final", out, dict(cfg="V1_CFG", S=50, scale=5.0, B=1, hw=64, unet_calls=model.calls,
                                           cpu_seconds=time.time() - t0, cpu_threads=torch.get_num_threads(),
                                           source="reference PLMSSampler.sample (BASELINE config C1)"), index)
+    elif which == "vae":
+        for tag, cfg, B, hw in (("small", V.SMALL_VAE_CFG, 2, 16), ("v1", V.V1_VAE_CFG, 1, 16)):
+            sd = V.make_state_dict(cfg, 321)
+            dec = R.build_reference_vae_decode(cfg, sd)
+            if tag == "v1":
+                index["vae_state_dict_keys"] = dict(keys=dec.state_dict_keys, n=len(dec.state_dict_keys))
+            z = V.synthetic_latents(B, hw, hw, seed=321)
+            t0 = time.time()
+            img = dec(z)
+            print(tag, "vae decode", time.time() - t0, "s", flush=True)
+            save(f"{tag}_vae_decode", img, dict(cfg=("SMALL_VAE_CFG" if tag == "small" else "V1_VAE_CFG"), weight_seed=321,
+                                                latent_seed=321, B=B, hw=hw,
+                                                source="reference Decoder(post_quant_conv(z)) fp32 CPU"), index)
     json.dump(index, open(INDEX, "w"), indent=1, sort_keys=True)
 
 

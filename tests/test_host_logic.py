@@ -137,3 +137,28 @@ def _gloo_worker(rank, world, out_dir):
     assert all(float(full[i, 0, 0, 0]) == float(i) for i in range(7))
     open(os.path.join(out_dir, f"r{rank}.txt"), "w").write(" ".join(str(i) for i in (mine if rank == 0 else mine)))
     dist.destroy_process_group()
+
+
+def test_vae_state_dict_keys_and_no_cpu_fallback(golden_dir):
+    """pbe_b200.AutoencoderKL carries the reference's decoder keys (a checkpoint's first_stage_model.* entries load with
+    strict=False) and refuses to decode without a CUDA device."""
+    import json
+    import os
+    import pytest
+    import torch
+    from pbe_b200.vae import AutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    m = AutoencoderKL(ddconfig=dd, embed_dim=4, lossconfig=dict(target="torch.nn.Identity"), monitor="val/rec_loss")
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    assert sorted(m.state_dict().keys()) == idx["vae_state_dict_keys"]["keys"]
+    sd = {"first_stage_model." + k: torch.zeros_like(v) for k, v in m.state_dict().items()}
+    sd["first_stage_model.encoder.conv_in.weight"] = torch.zeros(128, 3, 3, 3)     # encoder half: ignored
+    host = torch.nn.Module()
+    host.first_stage_model = m
+    missing, unexpected = host.load_state_dict(sd, strict=False)
+    assert not missing and unexpected == ["first_stage_model.encoder.conv_in.weight"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.decode(torch.zeros(1, 4, 8, 8))
+    with pytest.raises(NotImplementedError):
+        AutoencoderKL(ddconfig=dict(dd, attn_resolutions=[16]), embed_dim=4)

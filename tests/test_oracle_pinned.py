@@ -101,3 +101,36 @@ def test_oracle_bit_equals_live_reference(small):
                             test_model_kwargs=dict(images_inpaint=req["z_inpaint"], images_mask=req["mask"]))
     out = S.plms_sample(S.OracleModel(sd, cfg), 4, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"])
     assert torch.equal(out, out_ref)
+
+
+# ---- VAE decode: oracle/vae_ref.py ------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["small", "v1"])
+def test_vae_oracle_matches_reference_golden(golden_dir, tag):
+    """oracle.vae_ref.decode == the reference Decoder(post_quant_conv(z)) golden (same seeds), bit for bit on CPU fp32."""
+    from oracle import vae_ref as V
+    g, meta = _golden(golden_dir, f"{tag}_vae_decode")
+    cfg = V.SMALL_VAE_CFG if tag == "small" else V.V1_VAE_CFG
+    sd = V.make_state_dict(cfg, meta["weight_seed"])
+    z = V.synthetic_latents(meta["B"], meta["hw"], meta["hw"], seed=meta["latent_seed"])
+    with torch.no_grad():
+        img = V.decode(sd, cfg, z)
+    assert img.shape == g.shape
+    assert (img - g).abs().max().item() <= 2e-5 * g.abs().max().item()
+
+
+def test_vae_state_dict_keys_match_reference(golden_dir):
+    from oracle import vae_ref as V
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    assert sorted(V.param_shapes(V.V1_VAE_CFG).keys()) == idx["vae_state_dict_keys"]["keys"]
+
+
+def test_vae_oracle_bit_equals_live_reference():
+    if not R.available():
+        pytest.skip("/root/reference not mounted")
+    from oracle import vae_ref as V
+    cfg = V.SMALL_VAE_CFG
+    sd = V.make_state_dict(cfg, 11)
+    dec = R.build_reference_vae_decode(cfg, sd)
+    z = V.synthetic_latents(2, 8, 16, seed=5)
+    with torch.no_grad():
+        assert torch.equal(dec(z), V.decode(sd, cfg, z))
