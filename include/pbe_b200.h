@@ -33,6 +33,11 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
                      int Cout, int mode, const float* bias, const float* rowbias, const float* residual,
                      float* out_f32, void* out_bf16, void* out_vt, int qk_cols, int block_n, void* stream);
 
+/* Test / measurement aid: while dev_buffer != NULL, pbe_op_conv_gemm (mode 0, fp32 output) also writes the GroupNorm
+ * statistics the engine fuses into producing GEMMs: [M/32][Cout][2] = (sum, sum of squares) of out_f32 over each run of
+ * 32 consecutive output rows. Errors if the geometry cannot fuse them (split-K grids, ragged tiles). */
+void pbe_debug_set_gemm_stats_out(float* dev_buffer);
+
 /* Debug aid (env PBE_GEMM_DEBUG=1): wait-time counters of CTA 0 of the last conv_gemm launch: [0] MMA-warp cycles,
  * [1] cycles waiting for TMA stages, [2] cycles waiting for a free TMEM buffer, [4] K iterations. Host array of 8. */
 int pbe_debug_gemm_counters(long long* out8);

@@ -54,6 +54,7 @@ _OPTIONAL_SIGS: dict = {
     "pbe_op_self_attention": (c_int, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "pbe_debug_set_attention_trace": (None, [_p]),
     "pbe_debug_gemm_counters": (c_int, [_p]),
+    "pbe_debug_set_gemm_stats_out": (None, [_p]),
     "pbe_op_groupnorm": (c_int, [_p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p]),
     "pbe_op_groupnorm_workspace_bytes": (c_int64, [_i, _i]),
     "pbe_op_layernorm": (c_int, [_p, _p, _p, _p, _i, _i, _f, _p]),

@@ -9,6 +9,8 @@ extern "C" {
 
 const char* pbe_last_error(void) { return get_error(); }
 
+static float* g_stats_out = nullptr;
+
 int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksize, int stride, const void* wt_bf16,
                      int Cout, int mode, const float* bias, const float* rowbias, const float* residual,
                      float* out_f32, void* out_bf16, void* out_vt, int qk_cols, int block_n, void* stream) {
@@ -39,11 +41,18 @@ int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksiz
     }
     d.splitk_ws = need ? ws : nullptr;
   }
+  if (g_stats_out != nullptr) {   // pbe_debug_set_gemm_stats_out: fused GroupNorm statistics of out_f32
+    d.splitk_ws = nullptr;
+    if (!gemm_can_fuse_stats(d) || out_f32 == nullptr) { set_error("fused statistics not available for this GEMM"); return -3; }
+    d.stats_out = g_stats_out;
+  }
   GemmPlan plan;
   int rc = build_gemm_plan(d, &plan);
   if (rc) return rc;
   return launch_gemm_plan(plan, static_cast<cudaStream_t>(stream));
 }
+
+void pbe_debug_set_gemm_stats_out(float* dev_buffer) { g_stats_out = dev_buffer; }
 
 }  // extern "C"
 

@@ -535,14 +535,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long m_first = __shfl_sync(0xffffffffu, my_m, 0);
             const int col = n_base + c * 32 + lane;
             if (vmask != 0u && col < p.n_total) {
-              float sm = 0.0f, sq = 0.0f;
-              const uint8_t* wrow = slot_gen + (q * 32) * 128;
-#pragma unroll 8
-              for (int r = 0; r < 32; ++r) {
-                const float x = *reinterpret_cast<const float*>(wrow + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-                if ((vmask >> r) & 1u) { sm += x; sq = fmaf(x, x, sq); }
+              // shared-space loads and branch-free accumulation into four independent chains (the first version --
+              // generic loads plus a divergent `if` per row -- cost an S2UR, a BSSY/BSYNC pair and a branch per
+              // element and doubled the epilogue time of every GEMM that carried statistics)
+              float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+              const uint32_t wrow = slot_addr + (q * 32) * 128 + ((lane & 3) << 2);
+              const int l2 = lane >> 2;
+#pragma unroll
+              for (int r = 0; r < 32; r += 4) {
+                float x0 = lds_f32(wrow + (r + 0) * 128 + ((l2 ^ ((r + 0) & 7)) << 4));
+                float x1 = lds_f32(wrow + (r + 1) * 128 + ((l2 ^ ((r + 1) & 7)) << 4));
+                float x2 = lds_f32(wrow + (r + 2) * 128 + ((l2 ^ ((r + 2) & 7)) << 4));
+                float x3 = lds_f32(wrow + (r + 3) * 128 + ((l2 ^ ((r + 3) & 7)) << 4));
+                if (vmask != 0xffffffffu) {   // warp-uniform: only ragged tiles pay for the selects
+                  x0 = ((vmask >> (r + 0)) & 1u) ? x0 : 0.0f; x1 = ((vmask >> (r + 1)) & 1u) ? x1 : 0.0f;
+                  x2 = ((vmask >> (r + 2)) & 1u) ? x2 : 0.0f; x3 = ((vmask >> (r + 3)) & 1u) ? x3 : 0.0f;
+                }
+                s0 += x0; q0 = fmaf(x0, x0, q0); s1 += x1; q1 = fmaf(x1, x1, q1);
+                s2 += x2; q2 = fmaf(x2, x2, q2); s3 += x3; q3 = fmaf(x3, x3, q3);
               }
-              *reinterpret_cast<float2*>(p.stats_out + ((m_first >> 5) * p.n_total + col) * 2) = make_float2(sm, sq);
+              *reinterpret_cast<float2*>(p.stats_out + ((m_first >> 5) * p.n_total + col) * 2) =
+                  make_float2((s0 + s1) + (s2 + s3), (q0 + q1) + (q2 + q3));
             }
           }
           if (p.has_o16 && my_valid) {  // rare side copy (feeds a stride-2 conv): direct 64-B row store

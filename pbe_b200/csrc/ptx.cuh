@@ -313,6 +313,11 @@ __device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {   // explicit shared-space load (no generic-address conversion)
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 // Broadcast lane 0's value: tells the compiler the result is warp-uniform.
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

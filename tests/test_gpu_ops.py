@@ -82,6 +82,33 @@ def test_conv_gemm_matches_conv2d(lib, case):
     assert _rel(outb, ref) < 5e-3                     # bf16 rounding of the output
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 3, 320, True), (2, 32, 32, 128, 1, 160, False), (3, 16, 16, 64, 3, 128, True)])
+def test_gemm_fused_groupnorm_statistics(lib, case):
+    """The epilogue's fused GroupNorm statistics: (sum, sum of squares) of the fp32 output over each run of 32 rows."""
+    Nb, H, W, C, k, Cout, use_res = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(77 + sum(case[:6]))
+    x = torch.randn(Nb, H, W, C, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Cout, C, k, k, generator=g) / math.sqrt(C * k * k)).to(dev).bfloat16()
+    wt = w.permute(2, 3, 0, 1).contiguous().view(k * k, Cout, C)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    res = torch.randn(Nb, H, W, Cout, generator=g).to(dev) if use_res else None
+    out = torch.zeros((Nb, H, W, Cout), device=dev)
+    M = Nb * H * W
+    stats = torch.full((M // 32, Cout, 2), float("nan"), device=dev)
+    lib.pbe_debug_set_gemm_stats_out(stats.data_ptr())
+    try:
+        rc = lib.pbe_op_conv_gemm(x.data_ptr(), Nb, H, W, C, k, 1, wt.data_ptr(), Cout, 0, _p(bias), None, _p(res),
+                                  out.data_ptr(), None, None, 0, 0, _stream())
+    finally:
+        lib.pbe_debug_set_gemm_stats_out(None)
+    assert rc == 0, _err(lib)
+    torch.cuda.synchronize()
+    o = out.view(M // 32, 32, Cout).double()
+    assert torch.allclose(stats[..., 0].double(), o.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[..., 1].double(), (o * o).sum(1), rtol=1e-5, atol=1e-3)
+
+
 def test_gemm_geglu_epilogue(lib):
     """GEGLU: value * gelu_erf(gate), ldm/modules/attention.py:43-45, with the per-tile interleaved weight layout."""
     dev = torch.device("cuda:0")

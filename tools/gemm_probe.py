@@ -17,6 +17,12 @@ def case(name, Nb, H, W, C, k, Cout, mode=0, residual=False, rowbias=False, f32=
     of = torch.empty(Nb, H, W, ncol, device=dev) if f32 else None
     ob = torch.empty(Nb, H, W, ncol, device=dev, dtype=torch.bfloat16) if (b16 or mode == 1) else None
     p = _lib.ptr
+    if os.environ.get("PBE_PROBE_STATS") and mode == 0 and f32:
+        stats = torch.zeros(Nb * H * W // 32 * Cout * 2 + 64, device=dev)
+        lib.pbe_debug_set_gemm_stats_out(p(stats))
+        name += " +stats"
+    else:
+        lib.pbe_debug_set_gemm_stats_out(None)
     for _ in range(iters):
         rc = lib.pbe_op_conv_gemm(p(x), Nb, H, W, C, k, 1, p(w), Cout, mode, p(bias), p(rb), p(res), p(of), p(ob), None, 0, bn, st)
         assert rc == 0, lib.pbe_last_error()
