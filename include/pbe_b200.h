@@ -136,21 +136,28 @@ typedef struct pbe_vae_config {
   int32_t num_levels;     /* len(ch_mult) */
   int32_t ch_mult[8];     /* 1,2,4,4 */
   int32_t num_res_blocks; /* 2 (the decoder runs num_res_blocks + 1 blocks per level) */
+  int32_t in_channels;    /* 3  (encoder input; double_z = true: the encoder emits 2 * z_channels moment channels) */
 } pbe_vae_config;
 
 typedef struct pbe_vae* pbe_vae_handle;
 
 int pbe_vae_create(const pbe_vae_config* cfg, pbe_vae_handle* out);
 void pbe_vae_destroy(pbe_vae_handle h);
-/* name = reference state-dict key relative to the autoencoder ("decoder.conv_in.weight", "post_quant_conv.bias", ...,
- * i.e. the part after "first_stage_model."); host fp32 data; encoder / loss keys may simply not be loaded. */
+/* name = reference state-dict key relative to the autoencoder ("decoder.conv_in.weight", "post_quant_conv.bias",
+ * "encoder.down.0.block.0.norm1.weight", "quant_conv.weight", ..., i.e. the part after "first_stage_model."); host fp32
+ * data. Either half may be left out: pbe_vae_finalize_weights prepares the halves that are complete, and the entry
+ * point of a missing half fails. */
 int pbe_vae_load_weight(pbe_vae_handle h, const char* name, const float* host_data, const int64_t* shape, int rank);
 int pbe_vae_finalize_weights(pbe_vae_handle h);
 /* out[B,out_ch,fH,fW] = decode(z[B,embed_dim,H,W]) (fp32 NCHW, device), f = 2^(num_levels-1); H*W % 64 == 0. */
 int pbe_vae_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream);
-/* Measurement aid, as pbe_profile_forward / pbe_op_info. */
-int pbe_vae_profile_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream, float* ms_out,
-                           int max_ops);
+/* moments[B, 2*embed_dim, H/f, W/f] = quant_conv(Encoder(x[B,in_channels,H,W])) (fp32 NCHW, device):
+ * AutoencoderKL.encode, autoencoder.py:56-64, before DiagonalGaussianDistribution (mean | logvar along dim 1);
+ * reached from LatentDiffusion.encode_first_stage (latent_diffusion.py:571-610). H, W multiples of 8f. */
+int pbe_vae_encode(pbe_vae_handle h, const float* x, float* moments, int B, int H, int W, void* stream);
+/* Measurement aid, as pbe_profile_forward / pbe_op_info (encode = 0: decode, 1: encode). */
+int pbe_vae_profile(pbe_vae_handle h, int encode, const float* in, float* out, int B, int H, int W, void* stream,
+                    float* ms_out, int max_ops);
 int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops);
 int pbe_vae_launches_per_decode(pbe_vae_handle h);
 

@@ -119,3 +119,26 @@ def build_reference_vae_decode(cfg, sd):
     decode.state_dict_keys = sorted(["decoder." + k for k in dec.state_dict().keys()] +
                                     ["post_quant_conv.weight", "post_quant_conv.bias"])
     return decode
+
+
+def build_reference_vae_encode(cfg, sd):
+    """moments(x) built from the reference's own modules: quant_conv(Encoder(x)) as AutoencoderKL.encode composes them
+    (autoencoder.py:36,56-61; Encoder: ldm/modules/diffusionmodules/model.py:370)."""
+    _install_stubs()
+    import contextlib, io
+    from ldm.modules.diffusionmodules.model import Encoder
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = Encoder(ch=cfg["ch"], out_ch=cfg["out_ch"], ch_mult=tuple(cfg["ch_mult"]), num_res_blocks=cfg["num_res_blocks"],
+                      attn_resolutions=[], dropout=0.0, in_channels=cfg["in_channels"], resolution=256,
+                      z_channels=cfg["z_channels"], double_z=True)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    qc = torch.nn.Conv2d(2 * cfg["z_channels"], 2 * cfg["embed_dim"], 1)
+    qc.load_state_dict({"weight": sd["quant_conv.weight"], "bias": sd["quant_conv.bias"]}, strict=True)
+    enc.eval()
+
+    def encode(x):
+        with torch.no_grad():
+            return qc(enc(x))
+
+    encode.state_dict_keys = sorted(["encoder." + k for k in enc.state_dict().keys()] + ["quant_conv.weight", "quant_conv.bias"])
+    return encode

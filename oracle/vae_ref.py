@@ -15,10 +15,10 @@ import torch
 import torch.nn.functional as F
 
 V1_VAE_CFG = dict(  # configs/v1.yaml:48-67
-    embed_dim=4, z_channels=4, ch=128, out_ch=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2)
+    embed_dim=4, z_channels=4, ch=128, out_ch=3, in_channels=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2)
 
 SMALL_VAE_CFG = dict(  # same topology (three levels), narrower: CPU-fast parity config
-    embed_dim=4, z_channels=4, ch=64, out_ch=3, ch_mult=(1, 2, 2), num_res_blocks=1)
+    embed_dim=4, z_channels=4, ch=64, out_ch=3, in_channels=3, ch_mult=(1, 2, 2), num_res_blocks=1)
 
 
 def param_shapes(cfg) -> Dict[str, tuple]:
@@ -57,6 +57,24 @@ def param_shapes(cfg) -> Dict[str, tuple]:
             conv(f"decoder.up.{lvl}.upsample.conv", block_in, block_in, 3)
     norm("decoder.norm_out", block_in)
     conv("decoder.conv_out", cfg["out_ch"], block_in, 3)
+    # quant_conv (autoencoder.py:36) + Encoder.__init__ (model.py:370-438), double_z=True
+    conv("encoder.conv_in", ch, cfg["in_channels"], 3)
+    block_in = ch
+    for lvl in range(L):
+        block_out = ch * mult[lvl]
+        for i in range(cfg["num_res_blocks"]):
+            res(f"encoder.down.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != L - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    res("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", 2 * cfg["z_channels"], block_in, 3)
+    conv("quant_conv", 2 * cfg["embed_dim"], 2 * cfg["z_channels"], 1)
     return s
 
 
@@ -137,6 +155,34 @@ def decode(sd: Dict[str, torch.Tensor], cfg, z: torch.Tensor, taps: dict | None 
             taps[f"up{lvl}"] = h
     h = _swish(_norm(sd, "decoder.norm_out", h))
     return _conv(sd, "decoder.conv_out", h, 1)
+
+
+def encode_moments(sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.encode up to the posterior parameters (autoencoder.py:56-61): quant_conv(Encoder.forward(x)),
+    model.py:440-471.  x: [B, in_channels, H, W] -> moments [B, 2*embed_dim, H/f, W/f] (mean | logvar)."""
+    L = len(cfg["ch_mult"])
+    h = _conv(sd, "encoder.conv_in", x, 1)
+    for lvl in range(L):
+        for i in range(cfg["num_res_blocks"]):
+            h = resnet_block(sd, f"encoder.down.{lvl}.block.{i}", h)
+        if lvl != L - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)      # Downsample.forward, model.py:73-77
+            h = F.conv2d(h, sd[f"encoder.down.{lvl}.downsample.conv.weight"], sd[f"encoder.down.{lvl}.downsample.conv.bias"],
+                         stride=2, padding=0)
+    h = resnet_block(sd, "encoder.mid.block_1", h)
+    h = attn_block(sd, "encoder.mid.attn_1", h)
+    h = resnet_block(sd, "encoder.mid.block_2", h)
+    h = _swish(_norm(sd, "encoder.norm_out", h))
+    h = _conv(sd, "encoder.conv_out", h, 1)
+    return _conv(sd, "quant_conv", h, 0)
+
+
+def synthetic_images(B: int, H: int, W: int, seed: int = 321) -> torch.Tensor:
+    """Images in [-1, 1] as encode_first_stage sees them (smooth + noise, so that the statistics are image-like)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    low = F.interpolate(torch.randn(B, 3, max(H // 16, 1), max(W // 16, 1), generator=g), size=(H, W), mode="bilinear",
+                        align_corners=False)
+    return (0.6 * low + 0.15 * torch.randn(B, 3, H, W, generator=g)).clamp(-1, 1)
 
 
 def synthetic_latents(B: int, h: int, w: int, seed: int = 321) -> torch.Tensor:

@@ -76,7 +76,8 @@ _OPTIONAL_SIGS: dict = {
     "pbe_vae_load_weight": (c_int, [_p, c_char_p, _p, _p, _i]),
     "pbe_vae_finalize_weights": (c_int, [_p]),
     "pbe_vae_decode": (c_int, [_p, _p, _p, _i, _i, _i, _p]),
-    "pbe_vae_profile_decode": (c_int, [_p, _p, _p, _i, _i, _i, _p, _p, _i]),
+    "pbe_vae_encode": (c_int, [_p, _p, _p, _i, _i, _i, _p]),
+    "pbe_vae_profile": (c_int, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i]),
     "pbe_vae_op_info": (c_int, [_p, _i, _p, _p, _p]),
     "pbe_vae_launches_per_decode": (c_int, [_p]),
 }

@@ -6,7 +6,7 @@
 using namespace pbe;
 
 struct pbe_vae {
-  VaeDecoder* d;
+  VaeModel* d;
 };
 
 extern "C" {
@@ -20,7 +20,7 @@ int pbe_vae_create(const pbe_vae_config* cfg, pbe_vae_handle* out) {
   }
   try {
     pbe_vae* h = new pbe_vae;
-    h->d = new VaeDecoder(*cfg);
+    h->d = new VaeModel(*cfg);
     *out = h;
   } catch (const std::exception& ex) {
     set_error(std::string("pbe_vae_create: ") + ex.what());
@@ -47,9 +47,12 @@ int pbe_vae_finalize_weights(pbe_vae_handle h) { PBE_VAE_GUARD(h->d->finalize())
 int pbe_vae_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream) {
   PBE_VAE_GUARD(h->d->decode(z, out, B, H, W, static_cast<cudaStream_t>(stream)));
 }
-int pbe_vae_profile_decode(pbe_vae_handle h, const float* z, float* out, int B, int H, int W, void* stream, float* ms_out,
-                           int max_ops) {
-  PBE_VAE_GUARD(h->d->profile_decode(z, out, B, H, W, static_cast<cudaStream_t>(stream), ms_out, max_ops));
+int pbe_vae_encode(pbe_vae_handle h, const float* x, float* moments, int B, int H, int W, void* stream) {
+  PBE_VAE_GUARD(h->d->encode(x, moments, B, H, W, static_cast<cudaStream_t>(stream)));
+}
+int pbe_vae_profile(pbe_vae_handle h, int encode, const float* in, float* out, int B, int H, int W, void* stream,
+                    float* ms_out, int max_ops) {
+  PBE_VAE_GUARD(h->d->profile(encode, in, out, B, H, W, static_cast<cudaStream_t>(stream), ms_out, max_ops));
 }
 int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops) {
   if (h == nullptr || h->d->current() == nullptr) { set_error("no prepared shape"); return -1; }

@@ -830,6 +830,12 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
         p.tap_dh[t] = static_cast<int8_t>(kh - 1);
         p.tap_ph[t] = 0;
         p.tap_coff[t] = 0;
+      } else if (d.pad_end) {
+        // padding (0,1,0,1): input col = 2*ow + kw: kw=0 -> parity 0 ; kw=1 -> parity 1 ; kw=2 -> parity 0, shift +1
+        p.tap_dw[t] = static_cast<int8_t>(kw == 2 ? 1 : 0);
+        p.tap_coff[t] = (kw == 1) ? d.C : 0;
+        p.tap_dh[t] = static_cast<int8_t>(kh == 2 ? 1 : 0);
+        p.tap_ph[t] = static_cast<int8_t>(kh == 1 ? 1 : 0);
       } else {
         // input col = 2*ow + kw - 1: kw=0 -> parity 1, shift -1 ; kw=1 -> parity 0 ; kw=2 -> parity 1, shift 0
         p.tap_dw[t] = static_cast<int8_t>(kw == 0 ? -1 : 0);

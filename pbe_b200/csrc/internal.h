@@ -120,6 +120,8 @@ struct ConvGemmDesc {
   float* stats_out;        // optional fused GroupNorm statistics of out_f32 (see gemm_can_fuse_stats)
   int act_ld;              // elements between consecutive pixels of `act` (0 -> C): an operand that is a column slice
   int wt_ld;               // elements between consecutive output rows of `wt` (0 -> C; ksize 1 only)
+  int pad_end;             // stride-2 3x3 only: 1 = zero padding (0,1,0,1) as the VAE Downsample (model.py:74-76)
+                           // instead of the symmetric padding 1 of the U-Net Downsample
 };
 // Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
 int gemm_read_debug_counters(long long* out8);
@@ -175,6 +177,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
 
 // nearest 2x upsample, fp32 NHWC [Nb,H,W,C] -> bf16 NHWC [Nb,2H,2W,C]
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
+// VAE encode tail: quant_conv (1x1, fp32) fused with the NHWC -> NCHW unpack of the moments
+int launch_vae_unpack_moments(const float* y, const float* Wq, const float* bq, float* out, int Nb, int Cin, int Cout,
+                              int H, int W, int ld, cudaStream_t stream);
 // VAE decode helpers: post_quant_conv fused with the NCHW -> NHWC bf16 pack; row softmax fp32 -> bf16
 int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16* y, int Nb, int Cin, int Cz, int H, int W,
                           int Cpad, cudaStream_t stream);

@@ -185,6 +185,23 @@ __global__ void vae_pack_input_kernel(const float* __restrict__ z, const float* 
   }
 }
 
+// quant_conv (1x1, Cin -> Cout, fp32; autoencoder.py:36,60) fused with the NHWC -> NCHW unpack of the encoder output
+__global__ void vae_unpack_moments_kernel(const float* __restrict__ y, const float* __restrict__ Wq,
+                                          const float* __restrict__ bq, float* __restrict__ out, int Nb, int Cin, int Cout,
+                                          int HW, int ld) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Nb) * HW) return;
+  const int n = static_cast<int>(idx / HW);
+  const int pix = static_cast<int>(idx % HW);
+  float hin[16];
+  for (int i = 0; i < Cin; ++i) hin[i] = y[idx * ld + i];
+  for (int o = 0; o < Cout; ++o) {
+    float v = bq[o];
+    for (int i = 0; i < Cin; ++i) v += Wq[o * Cin + i] * hin[i];
+    out[(static_cast<long long>(n) * Cout + o) * HW + pix] = v;
+  }
+}
+
 // P[r][:] = softmax(S[r][:] * scale), fp32 in, bf16 out; one 256-thread block per row, the row lives in registers
 constexpr int SM_MAXV = 16;   // float4 per thread -> rows of up to 16384
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int N,
@@ -289,6 +306,16 @@ int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16
   PBE_REQUIRE(Cin <= 8 && Cz <= Cpad, "vae_pack_input: embed_dim <= 8");
   const long long total = static_cast<long long>(Nb) * H * W;
   vae_pack_input_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(z, Wp, bp, y, Nb, Cin, Cz, H * W, Cpad);
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_vae_unpack_moments(const float* y, const float* Wq, const float* bq, float* out, int Nb, int Cin, int Cout,
+                              int H, int W, int ld, cudaStream_t stream) {
+  PBE_REQUIRE(Cin <= 16, "vae_unpack_moments: at most 16 moment channels");
+  const long long total = static_cast<long long>(Nb) * H * W;
+  vae_unpack_moments_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(y, Wq, bq, out, Nb, Cin, Cout,
+                                                                                         H * W, ld);
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -95,8 +95,16 @@ def main(which):
         for tag, cfg, B, hw in (("small", V.SMALL_VAE_CFG, 2, 16), ("v1", V.V1_VAE_CFG, 1, 16)):
             sd = V.make_state_dict(cfg, 321)
             dec = R.build_reference_vae_decode(cfg, sd)
+            enc = R.build_reference_vae_encode(cfg, sd)
             if tag == "v1":
-                index["vae_state_dict_keys"] = dict(keys=dec.state_dict_keys, n=len(dec.state_dict_keys))
+                keys = sorted(dec.state_dict_keys + enc.state_dict_keys)
+                index["vae_state_dict_keys"] = dict(keys=keys, n=len(keys))
+            f = 2 ** (len(cfg["ch_mult"]) - 1)
+            x = V.synthetic_images(B, 16 * f, 16 * f, seed=321)
+            mom = enc(x)
+            save(f"{tag}_vae_encode_moments", mom, dict(cfg=("SMALL_VAE_CFG" if tag == "small" else "V1_VAE_CFG"), weight_seed=321,
+                                                        image_seed=321, B=B, hw=16 * f,
+                                                        source="reference quant_conv(Encoder(x)) fp32 CPU"), index)
             z = V.synthetic_latents(B, hw, hw, seed=321)
             t0 = time.time()
             img = dec(z)

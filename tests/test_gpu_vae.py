@@ -44,7 +44,7 @@ def _make_vae(cfg, sd, dev):
     dd = dict(double_z=True, z_channels=cfg["z_channels"], resolution=256, in_channels=3, out_ch=cfg["out_ch"], ch=cfg["ch"],
               ch_mult=list(cfg["ch_mult"]), num_res_blocks=cfg["num_res_blocks"], attn_resolutions=[], dropout=0.0)
     m = AutoencoderKL(ddconfig=dd, embed_dim=cfg["embed_dim"])
-    missing, unexpected = m.load_state_dict(sd, strict=True)
+    m.load_state_dict(sd, strict=True)
     return m.to(dev).eval()
 
 
@@ -92,3 +92,59 @@ def test_decode_first_stage_uses_the_vae(dev):
     a = ld.decode_first_stage(z * ld.scale_factor)
     b = vae.decode(z)
     assert _rel(a, b) < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["small", "v1"])
+def test_vae_encode_vs_reference_golden(dev, golden_dir, tag):
+    from oracle import vae_ref as V
+    g, meta = _golden(golden_dir, f"{tag}_vae_encode_moments")
+    cfg = V.SMALL_VAE_CFG if tag == "small" else V.V1_VAE_CFG
+    vae = _make_vae(cfg, V.make_state_dict(cfg, meta["weight_seed"]), dev)
+    x = V.synthetic_images(meta["B"], meta["hw"], meta["hw"], seed=meta["image_seed"])
+    post = vae.encode(x.to(dev))
+    mom = post.parameters.cpu()
+    assert mom.shape == g.shape and torch.isfinite(mom).all()
+    print(f"{tag} VAE encode: rel-L2 = {_rel(mom, g):.3e}, PSNR = {_psnr(mom, g):.1f} dB")
+    assert _rel(mom, g) <= 1e-2 and _psnr(mom, g) >= 40.0
+    # DiagonalGaussianDistribution semantics (distributions.py:24-41)
+    mean, logvar = torch.chunk(post.parameters, 2, dim=1)
+    assert torch.equal(post.mode(), mean) and torch.equal(post.logvar, logvar.clamp(-30.0, 20.0))
+    torch.manual_seed(0)
+    s1 = post.sample()
+    torch.manual_seed(0)
+    noise = torch.randn(mean.shape).to(dev)
+    assert torch.equal(s1, mean + post.std * noise)
+
+
+def test_vae_encode_512_vs_oracle_on_gpu(dev):
+    """The real geometry (512x512 image -> 64x64 latent, asymmetric-padding stride-2 convs, 4096-token mid attention)."""
+    from oracle import vae_ref as V
+    cfg = V.V1_VAE_CFG
+    sd = V.make_state_dict(cfg, 321)
+    vae = _make_vae(cfg, sd, dev)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    for B, H, W in ((2, 512, 512), (1, 256, 384)):
+        x = V.synthetic_images(B, H, W, seed=B * 10 + H).to(dev)
+        mom = vae.encode(x).parameters
+        with torch.no_grad():
+            ref = torch.cat([V.encode_moments(sd_dev, cfg, x[i:i + 1]) for i in range(B)])
+        print(f"v1 VAE encode B={B} {H}x{W}: rel-L2 = {_rel(mom, ref):.3e}, PSNR = {_psnr(mom, ref):.1f} dB")
+        assert mom.shape == (B, 8, H // 8, W // 8)
+        assert _rel(mom, ref) <= 1e-2 and _psnr(mom, ref) >= 40.0
+
+
+def test_vae_round_trip_first_stage(dev):
+    """encode_first_stage -> get_first_stage_encoding -> decode_first_stage through LatentDiffusion (latent_diffusion.py
+    :571-610, :444-508): shapes, scale factor and the posterior plumbing."""
+    from oracle import unet_ref as U, vae_ref as V
+    from pbe_b200.diffusion import LatentDiffusion
+    cfg = V.SMALL_VAE_CFG
+    ld = LatentDiffusion(unet_config=dict(params=dict(U.SMALL_CFG)))
+    ld.first_stage_model = _make_vae(cfg, V.make_state_dict(cfg, 3), dev)
+    x = V.synthetic_images(2, 64, 64, seed=4).to(dev)
+    post = ld.encode_first_stage(x)
+    z = ld.get_first_stage_encoding(post)
+    assert z.shape == (2, 4, 16, 16)
+    assert torch.allclose(ld.get_first_stage_encoding(post.mode()), ld.scale_factor * post.mean)
+    img = ld.decode_first_stage(z)
+    assert img.shape == x.shape and torch.isfinite(img).all()

@@ -140,8 +140,8 @@ def _gloo_worker(rank, world, out_dir):
 
 
 def test_vae_state_dict_keys_and_no_cpu_fallback(golden_dir):
-    """pbe_b200.AutoencoderKL carries the reference's decoder keys (a checkpoint's first_stage_model.* entries load with
-    strict=False) and refuses to decode without a CUDA device."""
+    """pbe_b200.AutoencoderKL carries the reference's encoder / decoder keys (a checkpoint's first_stage_model.* entries
+    load with strict=False) and refuses to encode / decode without a CUDA device."""
     import json
     import os
     import pytest
@@ -153,12 +153,14 @@ def test_vae_state_dict_keys_and_no_cpu_fallback(golden_dir):
     idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
     assert sorted(m.state_dict().keys()) == idx["vae_state_dict_keys"]["keys"]
     sd = {"first_stage_model." + k: torch.zeros_like(v) for k, v in m.state_dict().items()}
-    sd["first_stage_model.encoder.conv_in.weight"] = torch.zeros(128, 3, 3, 3)     # encoder half: ignored
+    sd["first_stage_model.loss.logvar"] = torch.zeros(())     # training-only entries of a checkpoint: ignored
     host = torch.nn.Module()
     host.first_stage_model = m
     missing, unexpected = host.load_state_dict(sd, strict=False)
-    assert not missing and unexpected == ["first_stage_model.encoder.conv_in.weight"]
+    assert not missing and unexpected == ["first_stage_model.loss.logvar"]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.decode(torch.zeros(1, 4, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.encode(torch.zeros(1, 3, 64, 64))
     with pytest.raises(NotImplementedError):
         AutoencoderKL(ddconfig=dict(dd, attn_resolutions=[16]), embed_dim=4)

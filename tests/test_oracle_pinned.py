@@ -134,3 +134,29 @@ def test_vae_oracle_bit_equals_live_reference():
     z = V.synthetic_latents(2, 8, 16, seed=5)
     with torch.no_grad():
         assert torch.equal(dec(z), V.decode(sd, cfg, z))
+
+
+@pytest.mark.parametrize("tag", ["small", "v1"])
+def test_vae_encode_oracle_matches_reference_golden(golden_dir, tag):
+    """oracle.vae_ref.encode_moments == the reference quant_conv(Encoder(x)) golden (same seeds) on CPU fp32."""
+    from oracle import vae_ref as V
+    g, meta = _golden(golden_dir, f"{tag}_vae_encode_moments")
+    cfg = V.SMALL_VAE_CFG if tag == "small" else V.V1_VAE_CFG
+    sd = V.make_state_dict(cfg, meta["weight_seed"])
+    x = V.synthetic_images(meta["B"], meta["hw"], meta["hw"], seed=meta["image_seed"])
+    with torch.no_grad():
+        mom = V.encode_moments(sd, cfg, x)
+    assert mom.shape == g.shape
+    assert (mom - g).abs().max().item() <= 2e-5 * g.abs().max().item()
+
+
+def test_vae_encode_oracle_bit_equals_live_reference():
+    if not R.available():
+        pytest.skip("/root/reference not mounted")
+    from oracle import vae_ref as V
+    cfg = V.SMALL_VAE_CFG
+    sd = V.make_state_dict(cfg, 11)
+    enc = R.build_reference_vae_encode(cfg, sd)
+    x = V.synthetic_images(2, 32, 48, seed=5)
+    with torch.no_grad():
+        assert torch.equal(enc(x), V.encode_moments(sd, cfg, x))
