@@ -46,6 +46,7 @@ template <int DK_CHUNKS, int KV_STAGES>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                   const __grid_constant__ AttnParams p) {
+  griddep_launch_dependents();   // PDL (ptx.cuh): successor may be scheduled; griddep_wait() after the prologue
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -102,6 +103,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
+  griddep_wait();   // PDL: the prologue above overlapped the previous kernel; no dependent global access before this
   const uint32_t tmem_O = tmem_base + 256;
 
   if (warp == 0) {
@@ -306,6 +308,7 @@ constexpr int ATT2_KV_STAGES = 2;
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ AttnParams p) {
+  griddep_launch_dependents();   // PDL (ptx.cuh): successor may be scheduled; griddep_wait() after the prologue
   extern __shared__ __align__(1024) uint8_t smem_att2[];   // 1024-B aligned base (128B-swizzle atoms), no padding budget
   uint8_t* smem_raw = smem_att2;
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -364,6 +367,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
+  griddep_wait();   // PDL: the prologue above overlapped the previous kernel; no dependent global access before this
 
   if (warp <= 1) {
     // ================= MMA issue for warpgroup g (uniform code, elect.sync issues) =================
@@ -596,7 +600,7 @@ int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   p.exp_mode = 0;
   p.wg_skew = 0;
   dim3 grid((plan.N + 2 * QT - 1) / (2 * QT), plan.heads, plan.B);
-  flash_attn2_kernel<<<grid, ATT2_THREADS, ATT2_SMEM, stream>>>(plan.tmQ, plan.tmV, p);
+  PBE_CHECK_CUDA(launch_k(flash_attn2_kernel, dim3(grid), dim3(ATT2_THREADS), ATT2_SMEM, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -627,7 +631,7 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   p.dbg = nullptr;
   p.exp_mode = 0;
   p.wg_skew = 0;
-  flash_attn_kernel<DK_CHUNKS, KV_STAGES><<<plan.grid, ATT_THREADS, smem, stream>>>(plan.tmQ, plan.tmV, p);
+  PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

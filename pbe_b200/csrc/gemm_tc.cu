@@ -140,6 +140,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 
+  griddep_launch_dependents();   // PDL: the next kernel may be scheduled behind this one; see griddep_wait below
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -212,6 +213,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+  // nothing below may touch global memory before the previous kernel has completed and flushed
+  griddep_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -656,13 +660,15 @@ int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (CL > 1) {
     // persistent clusters are statically scheduled: never launch more than can be co-resident (GPCs with an odd number
     // of free SMs cannot host a last 2-CTA cluster)
@@ -714,6 +720,7 @@ void pick_tile(int Wo, int Ho, int Nb, int* tw, int* th, int* tn) {
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitKReduce r) {
+  griddep_enter();
   const long long n4 = r.M * (r.N / 4);
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n4) return;
@@ -978,7 +985,7 @@ int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream) {
   if (rc) return rc;
   if (plan.red.S > 1) {
     const long long n4 = plan.red.M * (plan.red.N / 4);
-    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(plan.red);
+    PBE_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, stream, plan.red));
     PBE_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

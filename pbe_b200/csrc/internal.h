@@ -97,6 +97,25 @@ struct GemmPlan {
   size_t smem;
 };
 
+// Kernel launch, optionally (PBE_PDL=1) with programmatic dependent launch: consecutive kernels of a stream (and of
+// the captured CUDA graph) then overlap the successor's prologue with the predecessor's tail; every kernel of this
+// library calls griddep_wait() (ptx.cuh) before it touches memory its predecessor may still be writing.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct ConvGemmDesc {
   const bf16* act;  // NHWC activations [Nb, H, W, C]
   int Nb, H, W, C;  // input geometry (C % 64 == 0)

@@ -1,12 +1,14 @@
 // Layout / elementwise helpers and the small CUDA-core dense layers of the timestep-embedding path.
 // All are HBM- or latency-bound; none is GEMM-shaped enough for the tensor cores (M = batch rows only).
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace pbe {
 
 namespace {
 
 __global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict__ y, int Nb, int H, int W, int C) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   // one thread per input float4
   const long long total = static_cast<long long>(Nb) * H * W * (C / 4);
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -34,6 +36,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict_
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -48,6 +51,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__
 // thread per (n, pixel): gathers Cin channel planes (coalesced across threads), writes Cpad bf16 contiguous
 __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ y, int Nb, int Cin, int HW,
                                   int Cpad) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Nb) * HW) return;
   const int n = static_cast<int>(idx / HW);
@@ -73,6 +77,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict_
 
 __global__ void unpack_output_kernel(const float* __restrict__ y, float* __restrict__ out, int Nb, int Cout, int HW,
                                      int ld) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Nb) * HW) return;
   const int n = static_cast<int>(idx / HW);
@@ -92,6 +97,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            const float* __restrict__ bias, float* __restrict__ y,
                                                            float* __restrict__ y_silu, int B, int K, int O,
                                                            int pre_silu, int post_silu) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int o0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SL_OW;
   const int lane = threadIdx.x & 31;
   if (o0 >= O) return;
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 
 // reference: timestep_embedding, ldm/modules/diffusionmodules/util.py:151-171  (cos || sin, fp32)
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int B, int dim) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= B * half) return;
@@ -159,6 +166,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
 
 __global__ void add_rowvec_kernel(const float* __restrict__ a, const float* __restrict__ v, float* __restrict__ y,
                                   int B, int N) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * N) return;
   y[idx] = a[idx % N] + v[idx];
@@ -168,6 +176,7 @@ __global__ void add_rowvec_kernel(const float* __restrict__ a, const float* __re
 // post_quant_conv (1x1, embed_dim -> z_channels, fp32) fused with the NCHW -> NHWC bf16 pack (channels padded with zeros)
 __global__ void vae_pack_input_kernel(const float* __restrict__ z, const float* __restrict__ Wp, const float* __restrict__ bp,
                                       bf16* __restrict__ y, int Nb, int Cin, int Cz, int HW, int Cpad) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Nb) * HW) return;
   const int n = static_cast<int>(idx / HW);
@@ -189,6 +198,7 @@ __global__ void vae_pack_input_kernel(const float* __restrict__ z, const float* 
 __global__ void vae_unpack_moments_kernel(const float* __restrict__ y, const float* __restrict__ Wq,
                                           const float* __restrict__ bq, float* __restrict__ out, int Nb, int Cin, int Cout,
                                           int HW, int ld) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Nb) * HW) return;
   const int n = static_cast<int>(idx / HW);
@@ -206,6 +216,7 @@ __global__ void vae_unpack_moments_kernel(const float* __restrict__ y, const flo
 constexpr int SM_MAXV = 16;   // float4 per thread -> rows of up to 16384
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int N,
                                                            float scale_log2) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   __shared__ float s_red[8];
   const long long row = blockIdx.x;
   const float4* src = reinterpret_cast<const float4*>(S + row * N);
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream) {
   PBE_REQUIRE(C % 4 == 0, "upsample channels % 4");
   const long long total = static_cast<long long>(Nb) * H * W * (C / 4);
-  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, y, Nb, H, W, C);
+  PBE_CHECK_CUDA(launch_k(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, y, Nb, H, W, C));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -273,7 +284,7 @@ int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C,
 int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
   PBE_REQUIRE(n % 4 == 0, "cast length % 4");
   const size_t n4 = n / 4;
-  cast_bf16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(x, y, n4);
+  PBE_CHECK_CUDA(launch_k(cast_bf16_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, stream, x, y, n4));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -281,14 +292,14 @@ int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
 int launch_pack_input(const float* x, bf16* y, int Nb, int Cin, int H, int W, int Cpad, cudaStream_t stream) {
   PBE_REQUIRE(Cpad % 8 == 0 && Cpad >= Cin, "padded channel count");
   const long long total = static_cast<long long>(Nb) * H * W;
-  pack_input_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(x, y, Nb, Cin, H * W, Cpad);
+  PBE_CHECK_CUDA(launch_k(pack_input_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, x, y, Nb, Cin, H * W, Cpad));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, int W, int ld, cudaStream_t stream) {
   const long long total = static_cast<long long>(Nb) * H * W;
-  unpack_output_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(y, out, Nb, Cout, H * W, ld);
+  PBE_CHECK_CUDA(launch_k(unpack_output_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, y, out, Nb, Cout, H * W, ld));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -296,7 +307,7 @@ int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, in
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
                         int post_silu, cudaStream_t stream, float* y_silu) {
   PBE_REQUIRE(K % 4 == 0, "small_linear K % 4");
-  small_linear_kernel<<<(O + 8 * SL_OW - 1) / (8 * SL_OW), 256, 0, stream>>>(x, W, bias, y, y_silu, B, K, O, pre_silu, post_silu);
+  PBE_CHECK_CUDA(launch_k(small_linear_kernel, dim3((O + 8 * SL_OW - 1) / (8 * SL_OW)), dim3(256), 0, stream, x, W, bias, y, y_silu, B, K, O, pre_silu, post_silu));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -305,7 +316,7 @@ int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16
                           int Cpad, cudaStream_t stream) {
   PBE_REQUIRE(Cin <= 8 && Cz <= Cpad, "vae_pack_input: embed_dim <= 8");
   const long long total = static_cast<long long>(Nb) * H * W;
-  vae_pack_input_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(z, Wp, bp, y, Nb, Cin, Cz, H * W, Cpad);
+  PBE_CHECK_CUDA(launch_k(vae_pack_input_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, z, Wp, bp, y, Nb, Cin, Cz, H * W, Cpad));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -314,28 +325,28 @@ int launch_vae_unpack_moments(const float* y, const float* Wq, const float* bq, 
                               int H, int W, int ld, cudaStream_t stream) {
   PBE_REQUIRE(Cin <= 16, "vae_unpack_moments: at most 16 moment channels");
   const long long total = static_cast<long long>(Nb) * H * W;
-  vae_unpack_moments_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(y, Wq, bq, out, Nb, Cin, Cout,
-                                                                                         H * W, ld);
+  PBE_CHECK_CUDA(launch_k(vae_unpack_moments_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, y, Wq, bq, out, Nb, Cin, Cout,
+                                                                                         H * W, ld));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_softmax_rows(const float* S, bf16* P, long long rows, int N, float scale, cudaStream_t stream) {
   PBE_REQUIRE(N % 4 == 0 && N <= 4 * 256 * SM_MAXV, "softmax_rows: row length % 4 == 0, <= 16384");
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(S, P, N, scale * 1.4426950408889634f);
+  PBE_CHECK_CUDA(launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, S, P, N, scale * 1.4426950408889634f));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_timestep_embedding(const int64_t* t, float* out, int B, int dim, cudaStream_t stream) {
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, out, B, dim);
+  PBE_CHECK_CUDA(launch_k(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, stream, t, out, B, dim));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_add_rowvec(const float* a, const float* v, float* y, int B, int N, cudaStream_t stream) {
-  add_rowvec_kernel<<<(B * N + 255) / 256, 256, 0, stream>>>(a, v, y, B, N);
+  PBE_CHECK_CUDA(launch_k(add_rowvec_kernel, dim3((B * N + 255) / 256), dim3(256), 0, stream, a, v, y, B, N));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

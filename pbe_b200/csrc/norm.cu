@@ -8,6 +8,7 @@
 // The GroupNorm input may be the channel concat of two tensors (th.cat([h, hs.pop()], 1), openaimodel.py:883):
 // the concat is never materialised in fp32, only the normalised bf16 operand is.
 #include "internal.h"
+#include "ptx.cuh"
 
 #include <algorithm>
 
@@ -37,6 +38,7 @@ __device__ __forceinline__ float4 ld4(const float* __restrict__ x0, int C0, cons
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x0, int C0,
                                                               const float* __restrict__ x1, int C1, int HW, int slabs,
                                                               float* __restrict__ partial) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   __shared__ float s_sum[GN_MAX_C];
   __shared__ float s_sq[GN_MAX_C];
   const int C = C0 + C1;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_kernel(const float* __
                                                                  int C, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps,
                                                                  float2* __restrict__ ab) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
   if (threadIdx.x < 32) {
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const fl
                                                                         const float* __restrict__ gamma,
                                                                         const float* __restrict__ beta, float eps,
                                                                         float2* __restrict__ ab) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   __shared__ double s_a[GNF_THREADS], s_q[GNF_THREADS];
   __shared__ float s_mean, s_rstd;
   const int C = C0 + C1;
@@ -209,6 +213,7 @@ __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f 
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
                                                         int C1, int HW, int rows_par, const float2* __restrict__ ab,
                                                         int silu, bf16* __restrict__ y, bf16* __restrict__ raw) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int C = C0 + C1;
   const int vpp = C / 4;
   const int t = threadIdx.x;
@@ -266,6 +271,7 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, int silu,
                                                                bf16* __restrict__ y, bf16* __restrict__ raw) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   extern __shared__ float2 s_x[];  // [HW][cpg / 2]
   __shared__ double s_red[GNS_THREADS / 32];
   const int C = C0 + C1;
@@ -339,6 +345,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, int M,
                                                         int C, float eps) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -420,8 +427,8 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
     }
     const int hv = C / 64;
     const int rows_par = std::min(GNS_THREADS / hv, a.HW);
-    gn_small_kernel<<<dim3(32, a.Nb), GNS_THREADS, small_smem, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, a.gamma,
-                                                                        a.beta, a.eps, a.silu, a.y, a.raw);
+    PBE_CHECK_CUDA(launch_k(gn_small_kernel, dim3(dim3(32, a.Nb)), dim3(GNS_THREADS), small_smem, stream, a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, a.gamma,
+                                                                        a.beta, a.eps, a.silu, a.y, a.raw));
     PBE_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -429,20 +436,20 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   float* partial = a.partial;
   float2* ab = reinterpret_cast<float2*>(a.partial + ((static_cast<size_t>(a.Nb) * slabs * 64 + 3) & ~static_cast<size_t>(3)));
   if (fused) {
-    gn_finalize_fused_kernel<<<dim3(32, a.Nb), GNF_THREADS, 0, stream>>>(a.stats0, a.C0, a.stats1, a.C1, a.HW, a.gamma,
-                                                                        a.beta, a.eps, ab);
+    PBE_CHECK_CUDA(launch_k(gn_finalize_fused_kernel, dim3(dim3(32, a.Nb)), dim3(GNF_THREADS), 0, stream, a.stats0, a.C0, a.stats1, a.C1, a.HW, a.gamma,
+                                                                        a.beta, a.eps, ab));
     PBE_CHECK_CUDA(cudaGetLastError());
   } else {
-    gn_stats_kernel<<<dim3(slabs, a.Nb), GN_THREADS, 0, stream>>>(a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial);
+    PBE_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(dim3(slabs, a.Nb)), dim3(GN_THREADS), 0, stream, a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial));
     PBE_CHECK_CUDA(cudaGetLastError());
-    gn_finalize_kernel<<<a.Nb, GN_THREADS, 0, stream>>>(partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab);
+    PBE_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(a.Nb), dim3(GN_THREADS), 0, stream, partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab));
     PBE_CHECK_CUDA(cudaGetLastError());
   }
   const int vpp = C / 4;
   const int rows_par = vpp >= 256 ? 1 : 256 / vpp;
   const int pix_per_block = rows_par * GN_UNROLL;
-  gn_apply_kernel<<<dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb), vpp * rows_par, 0, stream>>>(
-      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw);
+  PBE_CHECK_CUDA(launch_k(gn_apply_kernel, dim3(dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb)), dim3(vpp * rows_par), 0, stream, 
+      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -451,9 +458,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
                      cudaStream_t stream) {
   PBE_REQUIRE(C % 4 == 0 && C / 4 <= 32 * LN_MAX_VEC, "LayerNorm width must be a multiple of 4, <= 1280");
   const int nv = (C / 4 + 31) / 32;
-  if (nv <= 3) layernorm_kernel<3><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
-  else if (nv <= 5) layernorm_kernel<5><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
-  else layernorm_kernel<LN_MAX_VEC><<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
+  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
+  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

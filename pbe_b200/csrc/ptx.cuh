@@ -318,6 +318,13 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {   // explicit shared-
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
   return v;
 }
+// ---- programmatic dependent launch: every kernel lets its successor's CTAs be scheduled as soon as all of its own
+// CTAs have started (the successor's prologue -- barrier init, TMEM allocation, tensor-map prefetch -- then overlaps this
+// kernel's tail), and waits here until its predecessor has completed and flushed before touching dependent memory.
+// Both are no-ops for launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_enter() { griddep_launch_dependents(); griddep_wait(); }
 // Broadcast lane 0's value: tells the compiler the result is warp-uniform.
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

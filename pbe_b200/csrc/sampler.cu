@@ -6,6 +6,7 @@
 // (ldm/models/diffusion/ddim.py:209-242).  Every op uses the round-to-nearest intrinsics so nvcc cannot contract
 // a*b+c into an FMA: PyTorch eager rounds after each op, and the parity test is bit-exact.
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace pbe {
 
@@ -49,6 +50,7 @@ __device__ __forceinline__ float step_one(float eu, float ec, float h1, float h2
 }
 
 __global__ void __launch_bounds__(256) sampler_step_kernel(SamplerStepArgs a, Coef k) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t n4 = a.n / 4;
   if (i >= n4) return;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(SamplerStepArgs a, Co
 __global__ void build_unet_input_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                         const float* __restrict__ mask, float* __restrict__ out, int B, int HW,
                                         int dup) {
+  griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per = static_cast<long long>(9) * HW;
   if (idx >= static_cast<long long>(B) * per) return;
@@ -106,7 +109,7 @@ int launch_sampler_step(const SamplerStepArgs& a, cudaStream_t stream) {
   volatile float inner = one_minus - sig2;
   k.dir_coef = sqrtf(inner);
   const size_t n4 = a.n / 4;
-  sampler_step_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(a, k);
+  PBE_CHECK_CUDA(launch_k(sampler_step_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, stream, a, k));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -114,7 +117,7 @@ int launch_sampler_step(const SamplerStepArgs& a, cudaStream_t stream) {
 int launch_build_unet_input(const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup,
                             cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * 9 * HW;
-  build_unet_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, z, mask, out, B, HW, dup);
+  PBE_CHECK_CUDA(launch_k(build_unet_input_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, z, mask, out, B, HW, dup));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
