@@ -259,9 +259,9 @@ def main():
     gemm_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        per_call, threads = cpu_reference_call_seconds(n_calls=2)
+        per_call, threads = cpu_reference_call_seconds(n_calls=5)
         cpu_baseline = {"value": 1.0 / (UNET_CALLS * per_call), "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": f"median of 2 CFG U-Net calls (batch 2, 64x64 latent) of the fp32 oracle port x "
+                        "sample": f"median of 5 CFG U-Net calls (batch 2, 64x64 latent) of the fp32 oracle port x "
                                   f"{UNET_CALLS} calls per image (extrapolated); {per_call:.2f} s per call"}
     line = {
         "metric": "images_per_sec_512px_plms50_cfg", "value": value, "unit": "images/s", "n_gpus": world,
