@@ -158,6 +158,10 @@ int pbe_vae_encode(pbe_vae_handle h, const float* x, float* moments, int B, int 
 /* Measurement aid, as pbe_profile_forward / pbe_op_info (encode = 0: decode, 1: encode). */
 int pbe_vae_profile(pbe_vae_handle h, int encode, const float* in, float* out, int B, int H, int W, void* stream,
                     float* ms_out, int max_ops);
+/* Post-processing of decoded images, scripts/inference.py:346-348,379-380 (second "next" row, device part):
+ * out_u8[b,h,w,c] = (uint8) (255 * clamp((img[b,c,h,w] + 1) / 2, 0, 1)), fp32 NCHW -> uint8 NHWC, same fp32 rounding
+ * and truncation as the reference's clamp -> numpy -> astype(uint8) sequence. */
+int pbe_postprocess_u8(const float* img, uint8_t* out_u8, int B, int C, int H, int W, void* stream);
 int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops);
 int pbe_vae_launches_per_decode(pbe_vae_handle h);
 

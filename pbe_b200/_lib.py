@@ -80,6 +80,7 @@ _OPTIONAL_SIGS: dict = {
     "pbe_vae_profile": (c_int, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i]),
     "pbe_vae_op_info": (c_int, [_p, _i, _p, _p, _p]),
     "pbe_vae_launches_per_decode": (c_int, [_p]),
+    "pbe_postprocess_u8": (c_int, [_p, _p, _i, _i, _i, _i, _p]),
 }
 
 

@@ -63,6 +63,10 @@ int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** fam
   if (flops) *flops = P->op_flops[i];
   return 0;
 }
+int pbe_postprocess_u8(const float* img, uint8_t* out, int B, int C, int H, int W, void* stream) {
+  if (img == nullptr || out == nullptr) { set_error("pbe_postprocess_u8: null argument"); return -1; }
+  return launch_postprocess_u8(img, out, B, C, H, W, static_cast<cudaStream_t>(stream));
+}
 int pbe_vae_launches_per_decode(pbe_vae_handle h) {
   if (h == nullptr || h->d->current() == nullptr) return 0;
   return h->d->current()->launches;

@@ -196,6 +196,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
 
 // nearest 2x upsample, fp32 NHWC [Nb,H,W,C] -> bf16 NHWC [Nb,2H,2W,C]
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
+// images fp32 NCHW in [-1, 1] -> uint8 NHWC (clamp((x+1)/2) * 255, truncated)
+int launch_postprocess_u8(const float* x, uint8_t* out, int Nb, int C, int H, int W, cudaStream_t stream);
 // VAE encode tail: quant_conv (1x1, fp32) fused with the NHWC -> NCHW unpack of the moments
 int launch_vae_unpack_moments(const float* y, const float* Wq, const float* bq, float* out, int Nb, int Cin, int Cout,
                               int H, int W, int ld, cudaStream_t stream);

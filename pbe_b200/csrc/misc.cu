@@ -212,6 +212,21 @@ __global__ void vae_unpack_moments_kernel(const float* __restrict__ y, const flo
   }
 }
 
+// Post-processing of decoded images (scripts/inference.py:346-348,379-380): u8[b,h,w,c] = trunc(255 * clamp((x+1)/2, 0, 1))
+// from fp32 NCHW in one pass (the reference does clamp on the device, permute + scale + astype(uint8) in numpy).
+__global__ void postprocess_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int Nb, int C, int HW) {
+  griddep_enter();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Nb) * HW) return;
+  const int n = static_cast<int>(idx / HW);
+  const int pix = static_cast<int>(idx % HW);
+  for (int c = 0; c < C; ++c) {
+    float v = __fdiv_rn(__fadd_rn(x[(static_cast<long long>(n) * C + c) * HW + pix], 1.0f), 2.0f);
+    v = fminf(fmaxf(v, 0.0f), 1.0f);
+    out[idx * C + c] = static_cast<uint8_t>(__fmul_rn(255.0f, v));
+  }
+}
+
 // P[r][:] = softmax(S[r][:] * scale), fp32 in, bf16 out; one 256-thread block per row, the row lives in registers
 constexpr int SM_MAXV = 16;   // float4 per thread -> rows of up to 16384
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int N,
@@ -328,6 +343,13 @@ int launch_vae_unpack_moments(const float* y, const float* Wq, const float* bq, 
   PBE_CHECK_CUDA(launch_k(vae_unpack_moments_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, y, Wq, bq, out, Nb, Cin, Cout,
                                                                                          H * W, ld));
   PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_postprocess_u8(const float* x, uint8_t* out, int Nb, int C, int H, int W, cudaStream_t stream) {
+  const long long total = static_cast<long long>(Nb) * H * W;
+  PBE_CHECK_CUDA(launch_k(postprocess_u8_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x,
+                          out, Nb, C, H * W));
   return 0;
 }
 

@@ -244,6 +244,17 @@ class AutoencoderKL(nn.Module):
             _lib.check(_lib.load().pbe_vae_decode(self._engine, zz.data_ptr(), out.data_ptr(), B, h, w, st), "pbe_vae_decode")
         return out.to(z.dtype)
 
+    def decode_to_uint8(self, z: torch.Tensor) -> torch.Tensor:
+        """decode(z) followed by the scripts' post-processing (scripts/inference.py:346-348,379-380) on the device:
+        uint8 [B, H, W, 3] = trunc(255 * clamp((img + 1) / 2, 0, 1)), ready for PIL / PNG encoding on the host."""
+        img = self.decode(z).to(torch.float32).contiguous()
+        B, C, H, W = img.shape
+        out = torch.empty((B, H, W, C), device=img.device, dtype=torch.uint8)
+        st = torch.cuda.current_stream(img.device).cuda_stream
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.load().pbe_postprocess_u8(img.data_ptr(), out.data_ptr(), B, C, H, W, st), "pbe_postprocess_u8")
+        return out
+
     def encode(self, x: torch.Tensor) -> DiagonalGaussianDistribution:
         """posterior = DiagonalGaussianDistribution(quant_conv(Encoder(x))) (autoencoder.py:56-64).
         x: [B, in_channels, H, W] CUDA, H and W multiples of 8 * 2^(levels-1)."""

@@ -148,3 +148,19 @@ def test_vae_round_trip_first_stage(dev):
     assert torch.allclose(ld.get_first_stage_encoding(post.mode()), ld.scale_factor * post.mean)
     img = ld.decode_first_stage(z)
     assert img.shape == x.shape and torch.isfinite(img).all()
+
+
+def test_decode_to_uint8_matches_reference_postprocessing(dev):
+    """scripts/inference.py:346-348,379-380: clamp((x+1)/2, 0, 1) -> HWC -> 255 * x -> astype(uint8), bit for bit."""
+    import numpy as np
+    from oracle import vae_ref as V
+    cfg = V.SMALL_VAE_CFG
+    vae = _make_vae(cfg, V.make_state_dict(cfg, 3), dev)
+    z = V.synthetic_latents(2, 16, 16, seed=2).to(dev) * 2.0       # large enough to exercise both clamps
+    u8 = vae.decode_to_uint8(z)
+    x = vae.decode(z)
+    x = torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0).cpu().permute(0, 2, 3, 1).numpy()
+    ref = (255. * x).astype(np.uint8)
+    assert u8.shape == (2, 64, 64, 3) and u8.dtype == torch.uint8
+    assert (ref == 0).any() and (ref == 255).any()
+    assert np.array_equal(u8.cpu().numpy(), ref)
