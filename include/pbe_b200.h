@@ -47,10 +47,6 @@ int pbe_debug_gemm_counters(long long* out8);
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
                           void* stream);
 
-/* Debug aid: device buffer (>= 8 * ceil(N/128) int64) that receives clock64 stamps of one softmax warp per key tile
- * on the next pbe_op_self_attention calls (NULL disables). */
-void pbe_debug_set_attention_trace(void* dev_buffer);
-
 /* GroupNorm(32 groups)(+SiLU) of the channel-concat of x0 [Nb,HW,C0] and x1 [Nb,HW,C1] (fp32 NHWC; x1 may be NULL)
  * -> y_bf16 [Nb,HW,C0+C1] (+ optional raw bf16 copy). Replaces GroupNorm32/Normalize (+SiLU, + th.cat):
  * ldm/modules/diffusionmodules/util.py:199-216, ldm/modules/attention.py:77-78, openaimodel.py:883.

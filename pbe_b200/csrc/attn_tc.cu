@@ -31,9 +31,6 @@ struct AttnParams {
   int N, heads, d, dv, ksteps, C;
   float scale_log2;
   bf16* out;
-  int exp_mode;    // 0 normal; 1 = experiment: skip MUFU (p = 1)
-  int wg_skew;     // cycles warpgroup 1 starts after warpgroup 0 (flash_attn4)
-  long long* dbg;  // optional: per-tile clock64 stamps of CTA (0,0,0), softmax warp 2 lane 0 (tools/attn_probe.py)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -596,9 +593,6 @@ int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   p.C = plan.heads * plan.d;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
-  p.dbg = plan.dbg;
-  p.exp_mode = 0;
-  p.wg_skew = 0;
   dim3 grid((plan.N + 2 * QT - 1) / (2 * QT), plan.heads, plan.B);
   PBE_CHECK_CUDA(launch_k(flash_attn2_kernel, dim3(grid), dim3(ATT2_THREADS), ATT2_SMEM, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
@@ -628,9 +622,6 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   p.C = plan.heads * plan.d;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
-  p.dbg = nullptr;
-  p.exp_mode = 0;
-  p.wg_skew = 0;
   PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -645,7 +636,6 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
   plan->B = B; plan->N = N; plan->heads = heads; plan->d = d;
   plan->scale_log2 = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(d)));
   plan->out = out;
-  plan->dbg = nullptr;
   plan->grid = dim3((N + QT - 1) / QT, heads, B);
   const int dv = (d + 15) / 16 * 16;
   {

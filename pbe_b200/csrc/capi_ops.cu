@@ -59,8 +59,6 @@ void pbe_debug_set_gemm_stats_out(float* dev_buffer) { g_stats_out = dev_buffer;
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" {
 
-static long long* g_attn_dbg = nullptr;
-
 int pbe_debug_gemm_counters(long long* out8) { return gemm_read_debug_counters(out8); }
 
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
@@ -69,11 +67,9 @@ int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf
   int rc = build_attn_plan(static_cast<const bf16*>(qk_bf16), static_cast<const bf16*>(vt_bf16),
                            static_cast<bf16*>(out_bf16), B, N, heads, d, &plan);
   if (rc) return rc;
-  plan.dbg = g_attn_dbg;
   return launch_attn_plan(plan, static_cast<cudaStream_t>(stream));
 }
 
-void pbe_debug_set_attention_trace(void* dev_buffer) { g_attn_dbg = static_cast<long long*>(dev_buffer); }
 
 int64_t pbe_op_groupnorm_workspace_bytes(int Nb, int HW) {
   return static_cast<int64_t>(gn_workspace_floats(Nb, HW, 2560)) * sizeof(float);

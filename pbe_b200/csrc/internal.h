@@ -161,7 +161,6 @@ struct AttnPlan {
   int B, N, heads, d;
   float scale_log2;
   bf16* out;
-  long long* dbg;
   dim3 grid;
   size_t smem;
 };
