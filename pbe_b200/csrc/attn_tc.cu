@@ -5,10 +5,12 @@
 // Replaces CrossAttention.forward with context=None (ldm/modules/attention.py:207-230), where the reference builds
 // sim[(B*8), N, N] in fp32 (1 GB per layer at N=4096, B=2).
 //
-// One CTA = one (sample, head, 128-query tile).  warp 0: TMA producer; warp 1: MMA issuer; warps 2..5: softmax
-// (one query row per thread).  S = Q K^T lands in a double-buffered 128x128 fp32 TMEM tile, the softmax warps read it
-// with tcgen05.ld, keep running max / sum in registers, write P (bf16) into 128B-swizzled shared memory, and the MMA
-// warp accumulates O += P V into a third TMEM region.  Q and K come from the fused projection output [B, N, 2C];
+// flash_attn_kernel (head dims > 64, short sequences): one CTA = one (sample, head, 128-query tile).  warp 0: TMA
+// producer; warp 1: MMA issuer; warps 2..5: softmax (one query row per thread).  S = Q K^T lands in a double-buffered
+// 128x128 fp32 TMEM tile, the softmax warps read it with tcgen05.ld, keep running max / sum in registers, write P
+// (bf16) into 128B-swizzled shared memory, and the MMA warp accumulates O += P V into a third TMEM region.
+// flash_attn2_kernel (head dims <= 64, the 64x64-latent level): 256 queries per CTA, 19 warps -- see its comment.
+// Q and K come from the fused projection output [B, N, 2C];
 // V arrives transposed ([B, C, N], written by the projection GEMM's epilogue) so both MMAs take K-major operands.
 // Head dims that are not a multiple of 64 (40, 80, 160) rely on TMA out-of-bounds zero fill.
 #include "internal.h"

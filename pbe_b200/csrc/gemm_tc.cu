@@ -8,9 +8,10 @@
 //   the same memory (phase = input row parity, channel offset = input column parity).
 // * W tiles come from the repacked weights [tap][Cout][Cin] (bf16) through a 3-D map.
 // * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
-// * warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 = epilogue
-//   (tcgen05.ld -> registers -> smem transpose -> coalesced global I/O with bias / per-sample bias / residual,
-//   GEGLU gate, or the Q|K / V^T split store).
+// * Persistent kernel, one CTA per SM (CTA pairs / cta_group::2 for long-K GEMMs): warp 0 = TMA producer, warp 1 = MMA
+//   issuer + TMEM owner (two accumulator buffers), warps 2..9 = epilogue (tcgen05.ld -> registers -> shared-memory
+//   slot -> TMA store, with bias / per-sample bias / TMA-prefetched residual, fused GroupNorm statistics, the GEGLU
+//   gate, or the Q|K / V^T split store).  See the comment on conv_gemm_kernel and DESIGN.md 3.1.
 //
 // Replaces (reference, PyTorch library calls): conv2d in ResBlock/Downsample/Upsample
 // (ldm/modules/diffusionmodules/openaimodel.py:107-119,150-160,201-241), 1x1 proj_in/proj_out and all Linear layers of
