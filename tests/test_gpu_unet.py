@@ -12,6 +12,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 EPS_REL_L2 = 1e-2          # BASELINE.json tolerance, judged on the real v1.yaml width
 # The 5x narrower CI network (64..256 channels, head dims 8..32) averages bf16 rounding noise over far fewer terms:
 # an IDEAL bf16-operand / fp32-accumulate pipeline (oracle/bf16_emul.py) already sits at 1.15e-2 there.  The narrow
@@ -262,3 +264,39 @@ def test_v1_batch8_and_96_vs_oracle_on_gpu(v1, dev):
         ref = torch.cat([U.unet_forward(sd_dev, cfg, x[i:i + 2], t[i:i + 2], c[i:i + 2]) for i in range(0, Bc, 2)])
         print(f"v1 Bc={Bc} hw={hw}: rel-L2(cuda, fp32 oracle on GPU) = {_rel(eps, ref):.3e}")
         assert _rel(eps, ref) <= EPS_REL_L2, (Bc, hw, _rel(eps, ref))
+
+
+def test_programmatic_dependent_launch_option_is_bit_identical(small, dev, tmp_path):
+    """PBE_PDL=1 (optional programmatic dependent launch of every kernel, graph replay included) must not change a
+    single bit: every kernel waits on its predecessor (griddepcontrol.wait) before touching dependent memory."""
+    import subprocess
+    import sys
+    cfg, sd, req, model = small
+    x_in, c_in = _cfg_inputs(req, 2)
+    t = torch.full((4,), 501, dtype=torch.int64)
+    eps = model.apply_model(x_in.to(dev), t.to(dev), c_in.to(dev))
+    eps2 = model.apply_model(x_in.to(dev), t.to(dev), c_in.to(dev))      # second call = graph replay
+    assert torch.equal(eps, eps2)
+    out = tmp_path / "eps_pdl.pt"
+    code = f"""
+import sys, torch
+sys.path.insert(0, {str(ROOT)!r})
+from oracle import sampler_ref as S, unet_ref as U
+from pbe_b200.diffusion import LatentDiffusion
+cfg = U.SMALL_CFG
+sd = U.make_state_dict(cfg, 321)
+req = S.synthetic_request(2, 32, 32, seed=321)
+m = LatentDiffusion(unet_config=dict(params=dict(cfg)))
+m.load_state_dict({{"model.diffusion_model." + k: v for k, v in sd.items()}}, strict=False)
+m = m.to("cuda:0").eval()
+x9 = torch.cat((req["x_T"], req["z_inpaint"], req["mask"]), 1)
+x_in = torch.cat([x9] * 2).cuda(); c_in = torch.cat((req["uc"].expand(2, 1, 768), req["c"])).cuda()
+t = torch.full((4,), 501, dtype=torch.int64).cuda()
+e1 = m.apply_model(x_in, t, c_in); e2 = m.apply_model(x_in, t, c_in)
+assert torch.equal(e1, e2)
+torch.save(e2.cpu(), {str(out)!r})
+"""
+    env = dict(os.environ, PBE_PDL="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert torch.equal(torch.load(out), eps.cpu())
