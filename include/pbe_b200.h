@@ -27,7 +27,8 @@ const char* pbe_last_error(void);
  *   act_bf16 : NHWC bf16 [Nb,H,W,C], C % 64 == 0        wt_bf16 : [ksize*ksize][Cout][C] bf16
  *   mode 0 (STD)  : out = acc + bias[n] + rowbias[b,n] + residual[m,n]  -> out_f32 and/or out_bf16 (row-major [M,Cout])
  *   mode 1 (GEGLU): out_bf16[m, j] = (acc_a+b_a) * gelu_erf(acc_g+b_g); weight rows interleaved per 256-col tile
- *   mode 2 (QKV)  : cols < qk_cols -> out_bf16 [M, qk_cols]; cols >= qk_cols -> out_vt [Nb][Cout-qk_cols][H*W]
+ *   mode 2 (QKV)  : cols < qk_cols -> out_bf16 [M, qk_cols]; cols >= qk_cols -> out_vt [Nb][Cout-qk_cols][pitch],
+ *                   pitch = H*W rounded up to a multiple of 8 (rows start 16-byte aligned; pad columns are not written)
  */
 int pbe_op_conv_gemm(const void* act_bf16, int Nb, int H, int W, int C, int ksize, int stride, const void* wt_bf16,
                      int Cout, int mode, const float* bias, const float* rowbias, const float* residual,
@@ -43,7 +44,8 @@ void pbe_debug_set_gemm_stats_out(float* dev_buffer);
 int pbe_debug_gemm_counters(long long* out8);
 
 /* Flash self-attention on tcgen05. Replaces CrossAttention.forward with context=None, ldm/modules/attention.py:207-230.
- *   qk_bf16 [B,N,2C] (Q | K), vt_bf16 [B,C,N], out_bf16 [B,N,C]; C = heads*d, scale = d^-1/2. */
+ *   qk_bf16 [B,N,2C] (Q | K), vt_bf16 [B,C,pitch] with pitch = N rounded up to a multiple of 8, out_bf16 [B,N,C];
+ *   C = heads*d, scale = d^-1/2. */
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
                           void* stream);
 

@@ -633,7 +633,6 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 
 int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan) {
   PBE_REQUIRE(d % 8 == 0 && d <= 160, "head dim must be a multiple of 8, <= 160");
-  PBE_REQUIRE(N % 8 == 0, "token count must be a multiple of 8");
   const int C = heads * d;
   plan->B = B; plan->N = N; plan->heads = heads; plan->d = d;
   plan->scale_log2 = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(d)));
@@ -654,9 +653,10 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
     if (rc) return rc;
   }
   {
-    // V^T: (N, C, B) over [B, C, N]
+    // V^T: (N, C, B) over [B, C, vt_pitch(N)]
+    const uint64_t Np = static_cast<uint64_t>(vt_pitch(N));
     const uint64_t dims[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(C), static_cast<uint64_t>(B)};
-    const uint64_t strides[2] = {static_cast<uint64_t>(N) * 2, static_cast<uint64_t>(C) * N * 2};
+    const uint64_t strides[2] = {Np * 2, static_cast<uint64_t>(C) * Np * 2};
     const uint32_t box[3] = {64u, static_cast<uint32_t>(dv), 1u};
     int rc = make_tmap_bf16(&plan->tmV, vt, 3, dims, strides, box, true);
     if (rc) return rc;

@@ -606,7 +606,7 @@ int Engine::build(Prepared& P, bool dry) {
                       "layernorm", 0.0, static_cast<double>(M) * C * 6.0);
         }
         bf16* qk = static_cast<bf16*>(SA(M * 2 * C * sizeof(bf16)));
-        bf16* vt = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        bf16* vt = static_cast<bf16*>(SA(static_cast<size_t>(Bc) * C * vt_pitch(N) * sizeof(bf16)));   // [Bc][C][pitch]
         {
           ConvGemmDesc d{};
           d.act = n1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;

@@ -423,7 +423,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) tmem_empty_arrive(buf);
           }
           if (my_valid) {
-            const long long tokens = static_cast<long long>(p.Ho) * p.Wo;
+            const long long tokens = (static_cast<long long>(p.Ho) * p.Wo + 7) & ~7ll;   // row pitch: vt_pitch(), internal.h
             const long long tok = static_cast<long long>(oh) * p.Wo + ow;
             const int vC = p.n_total - p.qk_cols;
             bf16* dst = p.out_vt + (static_cast<long long>(on) * vC + (n_base + c * 32 - p.qk_cols)) * tokens + tok;

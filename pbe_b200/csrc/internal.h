@@ -164,6 +164,9 @@ struct AttnPlan {
   dim3 grid;
   size_t smem;
 };
+// Row pitch (elements) of the transposed V buffer [B][C][vt_pitch(N)]: token counts that are not multiples of 8 are padded
+// so that every row starts 16-byte aligned (TMA global stride requirement); the pad columns are never read.
+inline int vt_pitch(int N) { return (N + 7) & ~7; }
 int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan);
 int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream);
 

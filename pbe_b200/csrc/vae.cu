@@ -335,7 +335,7 @@ int VaeModel::build(VaePrepared& P, bool dry, int enc) {
     g.y = a; g.stats0 = h.has_stats ? h.stats : nullptr;
     add_gn(tag + ".norm", g);
     bf16* qk = static_cast<bf16*>(SA(M * 2 * C * sizeof(bf16)));
-    bf16* vt = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+    bf16* vt = static_cast<bf16*>(SA(M * C * sizeof(bf16)));   // [B][C][N]: N % 64 == 0 here, so vt_pitch(N) == N
     {
       ConvGemmDesc d{};
       d.act = a; d.Nb = B; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;

@@ -155,7 +155,7 @@ def test_gemm_qkv_split_store(lib):
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,N,heads,d", [(2, 4096, 8, 40), (2, 1024, 8, 80), (2, 256, 8, 160), (2, 64, 8, 160),
                                          (1, 16, 8, 8), (1, 1024, 8, 16), (1, 200, 8, 32), (1, 2304, 8, 80),
-                                         (1, 144, 8, 160)])
+                                         (1, 144, 8, 160), (2, 180, 8, 160), (1, 45, 8, 160), (2, 1035, 8, 40)])
 def test_self_attention_matches_softmax_reference(lib, B, N, heads, d):
     """softmax(q k^T d^-1/2) v, ldm/modules/attention.py:217-229."""
     dev = torch.device("cuda:0")
@@ -165,7 +165,9 @@ def test_self_attention_matches_softmax_reference(lib, B, N, heads, d):
     k = torch.randn(B, N, C, generator=g).to(dev).bfloat16()
     v = torch.randn(B, N, C, generator=g).to(dev).bfloat16()
     qk = torch.cat((q, k), dim=-1).contiguous()
-    vt = v.transpose(1, 2).contiguous()
+    Np = (N + 7) // 8 * 8                       # V^T rows are pitched to a multiple of 8 tokens (pad never read)
+    vt = torch.full((B, C, Np), float("nan"), device=dev, dtype=torch.bfloat16)
+    vt[:, :, :N] = v.transpose(1, 2)
     out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
     rc = lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, _stream())
     assert rc == 0, _err(lib)

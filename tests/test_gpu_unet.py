@@ -300,3 +300,24 @@ torch.save(e2.cpu(), {str(out)!r})
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert torch.equal(torch.load(out), eps.cpu())
+
+
+@pytest.mark.parametrize("Bc,h,w", [(6, 64, 48), (10, 32, 32), (2, 40, 72)])
+def test_v1_ragged_batches_and_non_square_latents_vs_oracle_on_gpu(v1, dev, Bc, h, w):
+    """Geometries off the benchmark grid: odd CFG batches (no even tile count for CTA pairs at some levels), non-square
+    latents, token counts that are not multiples of the attention tiles (40x72 -> 45 tokens at the 8x-downsampled
+    level), GroupNorm slices that are not multiples of 32 pixels."""
+    from oracle import unet_ref as U
+    cfg, sd, req, model = v1
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(Bc * 1000 + h * 10 + w)
+    x = torch.randn(Bc, 9, h, w, generator=g).to(dev)
+    t = torch.randint(0, 1000, (Bc,), generator=g).to(dev)
+    c = torch.randn(Bc, 1, 768, generator=g).to(dev)
+    eps = model.apply_model(x, t, c)
+    ref = torch.cat([U.unet_forward(sd_dev, cfg, x[i:i + 2], t[i:i + 2], c[i:i + 2]) for i in range(0, Bc, 2)])
+    print(f"v1 Bc={Bc} {h}x{w}: rel-L2(cuda, fp32 oracle on GPU) = {_rel(eps, ref):.3e}")
+    assert torch.isfinite(eps).all()
+    # geometry robustness sweep on random inputs / timesteps (the parity bar proper, 1e-2, is held on the BASELINE
+    # configurations above): the bf16-operand error of a single small-batch draw scatters around 0.9e-2 +- 10 %
+    assert _rel(eps, ref) <= 1.2 * EPS_REL_L2, (Bc, h, w, _rel(eps, ref))
