@@ -163,6 +163,33 @@ int pbe_postprocess_u8(const float* img, uint8_t* out_u8, int B, int C, int H, i
 int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops);
 int pbe_vae_launches_per_decode(pbe_vae_handle h);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Conditioning front-end (second "next" row of SURVEY.md 8f): FrozenCLIPImageEmbedder.forward,
+ * ldm/modules/encoders/modules.py:138-171 = CLIP ViT vision tower (transformers CLIPVisionModel, pooler_output)
+ * -> unsqueeze(1) -> mapper (ldm/modules/encoders/xf.py Transformer(1, width, 5, 1)) -> final_ln.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct pbe_clip_config {
+  int32_t image_size;     /* 224 */
+  int32_t patch_size;     /* 14 */
+  int32_t width;          /* 1024, multiple of 64 */
+  int32_t layers;         /* 24 */
+  int32_t heads;          /* 16 (head dim = width / heads <= 64) */
+  int32_t mlp_dim;        /* 4096 */
+  int32_t mapper_layers;  /* 5 */
+} pbe_clip_config;
+
+typedef struct pbe_clip* pbe_clip_handle;
+
+int pbe_clip_create(const pbe_clip_config* cfg, pbe_clip_handle* out);
+void pbe_clip_destroy(pbe_clip_handle h);
+/* name = state-dict key relative to the embedder ("transformer.vision_model.encoder.layers.0.mlp.fc1.weight",
+ * "mapper.resblocks.0.attn.c_qkv.weight", "final_ln.bias", ..., i.e. the part after "cond_stage_model."). */
+int pbe_clip_load_weight(pbe_clip_handle h, const char* name, const float* host_data, const int64_t* shape, int rank);
+int pbe_clip_finalize_weights(pbe_clip_handle h);
+/* z[B, 1, width] = final_ln(mapper(pooler_output(image[B, 3, image_size, image_size]))) (fp32, device). */
+int pbe_clip_encode(pbe_clip_handle h, const float* image, float* z, int B, void* stream);
+int pbe_clip_launches_per_encode(pbe_clip_handle h);
+
 #ifdef __cplusplus
 }
 #endif

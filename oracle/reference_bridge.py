@@ -142,3 +142,32 @@ def build_reference_vae_encode(cfg, sd):
 
     encode.state_dict_keys = sorted(["encoder." + k for k in enc.state_dict().keys()] + ["quant_conv.weight", "quant_conv.bias"])
     return encode
+
+
+def build_reference_clip_embedder(cfg, sd):
+    """encode(image) composed exactly as FrozenCLIPImageEmbedder.forward (modules.py:160-166) from the LIVE third-party
+    tower (transformers.CLIPVisionModel with the given architecture, random-init then loaded from `sd`) and the
+    reference's own xf.Transformer / xf.LayerNorm (ldm/modules/encoders/xf.py)."""
+    _install_stubs()
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from ldm.modules.encoders.xf import LayerNorm, Transformer
+    vc = CLIPVisionConfig(hidden_size=cfg["width"], intermediate_size=cfg["mlp_dim"], num_hidden_layers=cfg["layers"],
+                          num_attention_heads=cfg["heads"], image_size=cfg["image_size"], patch_size=cfg["patch_size"])
+    tower = CLIPVisionModel(vc).eval()
+    tsd = {k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}
+    missing, unexpected = tower.load_state_dict(tsd, strict=False)
+    assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
+    mp = Transformer(1, cfg["width"], cfg["mapper_layers"], 1).eval()
+    mp.load_state_dict({k[len("mapper."):]: v for k, v in sd.items() if k.startswith("mapper.")}, strict=True)
+    ln = LayerNorm(cfg["width"])
+    ln.load_state_dict({"weight": sd["final_ln.weight"], "bias": sd["final_ln.bias"]})
+
+    def encode(image):
+        with torch.no_grad():
+            z = tower(pixel_values=image).pooler_output.unsqueeze(1)
+            return ln(mp(z))
+
+    keys = ["transformer." + k for k in tower.state_dict().keys() if "position_ids" not in k]
+    keys += ["mapper." + k for k in mp.state_dict().keys()] + ["final_ln.weight", "final_ln.bias"]
+    encode.state_dict_keys = sorted(keys)
+    return encode

@@ -1,0 +1,283 @@
+// Conditioning front-end engine implementation.  See clip.h.
+#include "clip.h"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace pbe {
+
+// fp32 upload of a named tensor, optionally only rows [row0, row0 + rows) of a [*, cols] matrix / vector
+int ClipEncoder::upload_named(const std::string& name, size_t expect, float** dst, size_t row0, size_t rows, size_t cols) {
+  const HostTensor* T;
+  int rc = get(name, &T);
+  if (rc) return rc;
+  if (T->data.size() != expect) {
+    set_error("weight " + name + " has " + std::to_string(T->data.size()) + " elements, expected " + std::to_string(expect));
+    return -4;
+  }
+  if (rows == 0) return upload_f32(T->data, dst);
+  std::vector<float> part(T->data.begin() + row0 * cols, T->data.begin() + (row0 + rows) * cols);
+  return upload_f32(part, dst);
+}
+
+int ClipEncoder::finalize() {
+  PBE_REQUIRE(!finalized_, "weights already finalized");
+  const int C = cfg_.width, p = cfg_.patch_size, S = cfg_.image_size;
+  PBE_REQUIRE(C % 64 == 0 && cfg_.heads > 0 && C % cfg_.heads == 0 && C / cfg_.heads <= 64 && (C / cfg_.heads) % 8 == 0 &&
+                  S % p == 0 && cfg_.mlp_dim % 64 == 0 && cfg_.layers >= 1 && cfg_.mapper_layers >= 0,
+              "unsupported CLIP vision configuration");
+  const int P = (S / p) * (S / p);
+  const std::string vm = "transformer.vision_model.";
+  int rc;
+  {
+    // patch_embedding: Conv2d(3, C, p, stride=p, bias=False) -> [C][Kpad] bf16 rows in (c, kh, kw) order
+    const HostTensor* W;
+    if ((rc = get(vm + "embeddings.patch_embedding.weight", &W))) return rc;
+    const int K = 3 * p * p;
+    PBE_REQUIRE(W->data.size() == static_cast<size_t>(C) * K, "patch_embedding.weight has the wrong shape");
+    kpad_ = (K + 63) / 64 * 64;
+    std::vector<float> packed(static_cast<size_t>(C) * kpad_, 0.0f);
+    for (int o = 0; o < C; ++o)
+      std::copy(W->data.begin() + static_cast<size_t>(o) * K, W->data.begin() + static_cast<size_t>(o + 1) * K,
+                packed.begin() + static_cast<size_t>(o) * kpad_);
+    if ((rc = upload_bf16(packed, &patch_w_))) return rc;
+  }
+  if ((rc = upload_named(vm + "embeddings.class_embedding", C, &cls_))) return rc;
+  if ((rc = upload_named(vm + "embeddings.position_embedding.weight", static_cast<size_t>(P + 1) * C, &pos_))) return rc;
+  if ((rc = make_norm(vm + "pre_layrnorm", C, &pre_ln_))) return rc;
+  if ((rc = make_norm(vm + "post_layernorm", C, &post_ln_))) return rc;
+  layers_.resize(cfg_.layers);
+  for (int i = 0; i < cfg_.layers; ++i) {
+    ClipLayerW& L = layers_[i];
+    const std::string lp = vm + "encoder.layers." + std::to_string(i) + ".";
+    if ((rc = make_norm(lp + "layer_norm1", C, &L.ln1))) return rc;
+    if ((rc = make_norm(lp + "layer_norm2", C, &L.ln2))) return rc;
+    std::vector<float> w(static_cast<size_t>(3) * C * C), b(static_cast<size_t>(3) * C);
+    const char* names[3] = {"q_proj", "k_proj", "v_proj"};
+    for (int j = 0; j < 3; ++j) {
+      const HostTensor *Wj, *Bj;
+      if ((rc = get(lp + "self_attn." + names[j] + ".weight", &Wj))) return rc;
+      if ((rc = get(lp + "self_attn." + names[j] + ".bias", &Bj))) return rc;
+      PBE_REQUIRE(Wj->data.size() == static_cast<size_t>(C) * C && Bj->data.size() == static_cast<size_t>(C),
+                  "self_attn projection has the wrong shape");
+      std::copy(Wj->data.begin(), Wj->data.end(), w.begin() + static_cast<size_t>(j) * C * C);
+      std::copy(Bj->data.begin(), Bj->data.end(), b.begin() + static_cast<size_t>(j) * C);
+    }
+    if ((rc = upload_bf16(w, &L.qkv.w))) return rc;
+    if ((rc = upload_f32(b, &L.qkv.b))) return rc;
+    L.qkv.cin = L.qkv.cin_pad = C; L.qkv.cout = 3 * C; L.qkv.k = 1;
+    if ((rc = make_linear(lp + "self_attn.out_proj", C, C, &L.out_proj))) return rc;
+    if ((rc = make_linear(lp + "mlp.fc1", C, cfg_.mlp_dim, &L.fc1))) return rc;
+    if ((rc = make_linear(lp + "mlp.fc2", cfg_.mlp_dim, C, &L.fc2))) return rc;
+  }
+  mapper_.resize(cfg_.mapper_layers);
+  for (int j = 0; j < cfg_.mapper_layers; ++j) {
+    ClipMapW& M = mapper_[j];
+    const std::string mp = "mapper.resblocks." + std::to_string(j) + ".";
+    const size_t c = static_cast<size_t>(C);
+    if ((rc = make_norm(mp + "ln_1", C, &M.ln1))) return rc;
+    if ((rc = make_norm(mp + "ln_2", C, &M.ln2))) return rc;
+    if ((rc = upload_named(mp + "attn.c_qkv.weight", 3 * c * c, &M.wv, 2 * c, c, c))) return rc;
+    if ((rc = upload_named(mp + "attn.c_qkv.bias", 3 * c, &M.bv, 2 * c, c, 1))) return rc;
+    if ((rc = upload_named(mp + "attn.c_proj.weight", c * c, &M.wproj))) return rc;
+    if ((rc = upload_named(mp + "attn.c_proj.bias", c, &M.bproj))) return rc;
+    if ((rc = upload_named(mp + "mlp.c_fc.weight", 4 * c * c, &M.wfc))) return rc;
+    if ((rc = upload_named(mp + "mlp.c_fc.bias", 4 * c, &M.bfc))) return rc;
+    if ((rc = upload_named(mp + "mlp.c_proj.weight", 4 * c * c, &M.wfc2))) return rc;
+    if ((rc = upload_named(mp + "mlp.c_proj.bias", c, &M.bfc2))) return rc;
+  }
+  if ((rc = make_norm("final_ln", C, &final_ln_))) return rc;
+  finalized_ = true;
+  host_.clear();
+  return 0;
+}
+
+int ClipEncoder::prepare(int B) {
+  auto it = prepared_.find(B);
+  if (it != prepared_.end()) { cur_ = it->second.get(); return 0; }
+  PBE_REQUIRE(finalized_, "pbe_clip_finalize_weights has not been called");
+  PBE_REQUIRE(B >= 1 && B <= 4096, "batch out of range");
+  auto P = std::make_unique<ClipPrepared>();
+  P->B = B;
+  int rc = build(*P, true);
+  if (rc) return rc;
+  P->persist.cap_ = P->persist.high() + 4096;
+  void* p = nullptr;
+  PBE_CHECK_CUDA(cudaMalloc(&p, P->persist.cap_));
+  P->persist.base_ = static_cast<char*>(p);
+  PBE_CHECK_CUDA(cudaMemset(p, 0, P->persist.cap_));
+  rc = build(*P, false);
+  if (rc) return rc;
+  cur_ = P.get();
+  prepared_[B] = std::move(P);
+  return 0;
+}
+
+int ClipEncoder::build(ClipPrepared& P, bool dry) {
+  const int B = P.B, C = cfg_.width, S = cfg_.image_size, p = cfg_.patch_size, F = cfg_.mlp_dim;
+  const int Pn = (S / p) * (S / p), N = Pn + 1, M = B * N, heads = cfg_.heads, d = C / heads;
+  const float eps = 1e-5f;   // CLIPVisionConfig.layer_norm_eps; nn.LayerNorm default in xf.py
+  P.persist.reset(dry);
+  auto PA = [&](size_t bytes) { return P.persist.alloc(bytes); };
+  int launches = 0, err = 0;
+  P.ops.clear(); P.op_names.clear();
+  auto add_op = [&](const std::string& name, int nlaunch, std::function<int(cudaStream_t)> fn) {
+    if (!dry) { P.ops.push_back(std::move(fn)); P.op_names.push_back(name); }
+    launches += nlaunch;
+  };
+  auto add_gemm = [&](const std::string& name, ConvGemmDesc dsc) {
+    const size_t ws_bytes = gemm_splitk_ws_bytes(dsc);
+    dsc.splitk_ws = ws_bytes ? static_cast<float*>(PA(ws_bytes)) : nullptr;
+    if (dry) { launches += ws_bytes ? 2 : 1; return; }
+    auto plan = std::make_shared<GemmPlan>();
+    int rc = build_gemm_plan(dsc, plan.get());
+    if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + name + "]"; }
+    add_op(name, ws_bytes ? 2 : 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); });
+  };
+  // every linear layer sees the tokens as one flat row range: [1, 1, rows, channels]
+  auto linear = [&](const bf16* act, int rows, int cin, const ConvW& w) {
+    ConvGemmDesc dsc{};
+    dsc.act = act; dsc.Nb = 1; dsc.H = 1; dsc.W = rows; dsc.C = cin; dsc.ksize = 1; dsc.stride = 1;
+    dsc.wt = w.w; dsc.Cout = w.cout; dsc.mode = EPI_STD; dsc.bias = w.b;
+    return dsc;
+  };
+
+  P.img_stage = static_cast<float*>(PA(static_cast<size_t>(B) * 3 * S * S * sizeof(float)));
+  P.z_stage = static_cast<float*>(PA(static_cast<size_t>(B) * C * sizeof(float)));
+  bf16* patches = static_cast<bf16*>(PA(static_cast<size_t>(B) * Pn * kpad_ * sizeof(bf16)));
+  float* patch_emb = static_cast<float*>(PA(static_cast<size_t>(B) * Pn * C * sizeof(float)));
+  float* tokens = static_cast<float*>(PA(static_cast<size_t>(M) * C * sizeof(float)));
+  float* hbuf[2] = {static_cast<float*>(PA(static_cast<size_t>(M) * C * sizeof(float))),
+                    static_cast<float*>(PA(static_cast<size_t>(M) * C * sizeof(float)))};
+  bf16* a16 = static_cast<bf16*>(PA(static_cast<size_t>(M) * C * sizeof(bf16)));
+  bf16* qk = static_cast<bf16*>(PA(static_cast<size_t>(M) * 2 * C * sizeof(bf16)));
+  bf16* vt = static_cast<bf16*>(PA(static_cast<size_t>(B) * C * vt_pitch(N) * sizeof(bf16)));
+  bf16* ao = static_cast<bf16*>(PA(static_cast<size_t>(M) * C * sizeof(bf16)));
+  bf16* mlp = static_cast<bf16*>(PA(static_cast<size_t>(M) * F * sizeof(bf16)));
+
+  // ---- embeddings (CLIPVisionEmbeddings.forward) + pre_layrnorm ----
+  {
+    const float* img = P.img_stage;
+    const int kp = kpad_;
+    add_op("pack_patches", 1, [=](cudaStream_t s) { return launch_clip_pack_patches(img, patches, B, S, S, p, kp, s); });
+    ConvW pw; pw.w = patch_w_; pw.b = nullptr; pw.cout = C;
+    ConvGemmDesc dsc = linear(patches, B * Pn, kpad_, pw);
+    dsc.c_real = 3 * p * p; dsc.out_f32 = patch_emb;
+    add_gemm("patch_embedding", dsc);
+    const float *cls = cls_, *pos = pos_;
+    add_op("embed", 1, [=](cudaStream_t s) { return launch_clip_embed(patch_emb, cls, pos, tokens, B, Pn, C, s); });
+    const float *g = pre_ln_.g, *b = pre_ln_.b;
+    float* h0 = hbuf[0];
+    add_op("pre_layrnorm", 1, [=](cudaStream_t s) { return launch_layernorm(tokens, g, b, nullptr, M, C, eps, s, h0); });
+  }
+  // ---- encoder layers (CLIPEncoderLayer.forward): h += attn(LN1(h)); h += mlp(LN2(h)) ----
+  int cur = 0;
+  for (int i = 0; i < cfg_.layers; ++i) {
+    const ClipLayerW& L = layers_[i];
+    const std::string tag = "layer" + std::to_string(i);
+    float* h = hbuf[cur];
+    float* h2 = hbuf[cur ^ 1];
+    {
+      const float *g = L.ln1.g, *b = L.ln1.b;
+      add_op(tag + ".ln1", 1, [=](cudaStream_t s) { return launch_layernorm(h, g, b, a16, M, C, eps, s); });
+    }
+    {
+      ConvGemmDesc dsc = linear(a16, M, C, L.qkv);
+      dsc.mode = EPI_QKV; dsc.out_bf16 = qk; dsc.ld_out = 2 * C; dsc.out_vt = vt; dsc.qk_cols = 2 * C; dsc.vt_tokens = N;
+      add_gemm(tag + ".qkv", dsc);
+    }
+    {
+      auto plan = std::make_shared<AttnPlan>();
+      if (!dry) {
+        int rc = build_attn_plan(qk, vt, ao, B, N, heads, d, plan.get());
+        if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + tag + ".attn]"; }
+      }
+      add_op(tag + ".attn", 1, [plan](cudaStream_t s) { return launch_attn_plan(*plan, s); });
+    }
+    {
+      ConvGemmDesc dsc = linear(ao, M, C, L.out_proj);
+      dsc.residual = h; dsc.out_f32 = h2;
+      add_gemm(tag + ".out_proj", dsc);
+    }
+    {
+      const float *g = L.ln2.g, *b = L.ln2.b;
+      add_op(tag + ".ln2", 1, [=](cudaStream_t s) { return launch_layernorm(h2, g, b, a16, M, C, eps, s); });
+    }
+    {
+      ConvGemmDesc dsc = linear(a16, M, C, L.fc1);
+      dsc.epi_act = 1; dsc.out_bf16 = mlp;   // quick_gelu (CLIPVisionConfig.hidden_act)
+      add_gemm(tag + ".fc1", dsc);
+    }
+    {
+      ConvGemmDesc dsc = linear(mlp, M, F, L.fc2);
+      dsc.residual = h2; dsc.out_f32 = h;
+      add_gemm(tag + ".fc2", dsc);
+    }
+    // h (hbuf[cur]) holds the layer output again
+  }
+  // ---- pooler_output = post_layernorm(last_hidden_state[:, 0]) ----
+  float* x = static_cast<float*>(PA(static_cast<size_t>(B) * C * sizeof(float)));
+  {
+    const float* h = hbuf[cur];
+    const float *g = post_ln_.g, *b = post_ln_.b;
+    const long long ld = static_cast<long long>(N) * C;
+    add_op("post_layernorm(cls)", 1, [=](cudaStream_t s) { return launch_layernorm(h, g, b, nullptr, B, C, eps, s, x, ld); });
+  }
+  // ---- mapper: 5 x ResidualAttentionBlock on one token (xf.py:86-104), fp32 GEMVs ----
+  float* n32 = static_cast<float*>(PA(static_cast<size_t>(B) * C * sizeof(float)));
+  float* v32 = static_cast<float*>(PA(static_cast<size_t>(B) * C * sizeof(float)));
+  float* x2 = static_cast<float*>(PA(static_cast<size_t>(B) * C * sizeof(float)));
+  float* f32 = static_cast<float*>(PA(static_cast<size_t>(B) * 4 * C * sizeof(float)));
+  float* xa = x;
+  float* xb = x2;
+  for (int j = 0; j < cfg_.mapper_layers; ++j) {
+    const ClipMapW& Mw = mapper_[j];
+    const std::string tag = "mapper" + std::to_string(j);
+    {
+      const float *g = Mw.ln1.g, *b = Mw.ln1.b;
+      float* xin = xa;
+      add_op(tag + ".ln_1", 1, [=](cudaStream_t s) { return launch_layernorm(xin, g, b, nullptr, B, C, eps, s, n32); });
+      const float *wv = Mw.wv, *bv = Mw.bv, *wp = Mw.wproj, *bp = Mw.bproj;
+      add_op(tag + ".attn.v", 1, [=](cudaStream_t s) { return launch_small_linear(n32, wv, bv, v32, B, C, C, 0, 0, s); });
+      float* xout = xb;
+      add_op(tag + ".attn.c_proj+res", 1,
+             [=](cudaStream_t s) { return launch_small_linear(v32, wp, bp, xout, B, C, C, 0, 0, s, nullptr, xin); });
+    }
+    {
+      const float *g = Mw.ln2.g, *b = Mw.ln2.b;
+      float* xin = xb;
+      add_op(tag + ".ln_2", 1, [=](cudaStream_t s) { return launch_layernorm(xin, g, b, nullptr, B, C, eps, s, n32); });
+      const float *wf = Mw.wfc, *bf = Mw.bfc, *wf2 = Mw.wfc2, *bf2 = Mw.bfc2;
+      add_op(tag + ".mlp.c_fc+gelu", 1, [=](cudaStream_t s) { return launch_small_linear(n32, wf, bf, f32, B, C, 4 * C, 0, 2, s); });
+      float* xout = xa;
+      add_op(tag + ".mlp.c_proj+res", 1,
+             [=](cudaStream_t s) { return launch_small_linear(f32, wf2, bf2, xout, B, 4 * C, C, 0, 0, s, nullptr, xin); });
+    }
+  }
+  {
+    const float *g = final_ln_.g, *b = final_ln_.b;
+    float* xin = xa;
+    float* z = P.z_stage;
+    add_op("final_ln", 1, [=](cudaStream_t s) { return launch_layernorm(xin, g, b, nullptr, B, C, eps, s, z); });
+  }
+  P.launches = launches;
+  return err;
+}
+
+int ClipEncoder::encode(const float* image, float* z, int B, cudaStream_t stream) {
+  int rc = prepare(B);
+  if (rc) return rc;
+  ClipPrepared& P = *cur_;
+  const int S = cfg_.image_size;
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.img_stage, image, static_cast<size_t>(B) * 3 * S * S * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 stream));
+  for (size_t i = 0; i < P.ops.size(); ++i) {
+    rc = P.ops[i](stream);
+    if (rc) { last_error = std::string(get_error()) + " [" + P.op_names[i] + "]"; set_error(last_error); return rc; }
+  }
+  PBE_CHECK_CUDA(cudaMemcpyAsync(z, P.z_stage, static_cast<size_t>(B) * cfg_.width * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+}  // namespace pbe

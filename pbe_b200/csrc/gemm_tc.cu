@@ -423,10 +423,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) tmem_empty_arrive(buf);
           }
           if (my_valid) {
-            const long long tokens = (static_cast<long long>(p.Ho) * p.Wo + 7) & ~7ll;   // row pitch: vt_pitch(), internal.h
-            const long long tok = static_cast<long long>(oh) * p.Wo + ow;
+            // sample / token of my row: (n, h*W + w), or -- flat [1,1,M,C] activations -- (m / vt_tokens, m % vt_tokens)
+            const long long ntok = p.vt_tokens ? p.vt_tokens : static_cast<long long>(p.Ho) * p.Wo;
+            const long long tokens = (ntok + 7) & ~7ll;   // row pitch: vt_pitch(), internal.h
+            const long long smp = p.vt_tokens ? my_m / ntok : on;
+            const long long tok = p.vt_tokens ? my_m - smp * ntok : static_cast<long long>(oh) * p.Wo + ow;
             const int vC = p.n_total - p.qk_cols;
-            bf16* dst = p.out_vt + (static_cast<long long>(on) * vC + (n_base + c * 32 - p.qk_cols)) * tokens + tok;
+            bf16* dst = p.out_vt + (smp * vC + (n_base + c * 32 - p.qk_cols)) * tokens + tok;
             if (p.bias != nullptr) {   // v projection with a bias (VAE attention; the U-Net's to_v has none)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n_base + c * 32 + j));
@@ -511,6 +514,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             o[j + 1] = __uint_as_float(v[j + 1]) + a.y;
             o[j + 2] = __uint_as_float(v[j + 2]) + a.z;
             o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
+          }
+          if (p.act == 1) {   // quick_gelu (CLIP MLP): x * sigmoid(1.702 x)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __fdividef(o[j], 1.0f + __expf(-1.702f * o[j]));
           }
         }
         // the slot is ours once the residual prefetch (or the plain arrive that stands in for it) has landed
@@ -773,7 +780,7 @@ int gemm_read_debug_counters(long long* out8) {
 }
 
 int gemm_split_k(const ConvGemmDesc& d) {
-  if (d.mode != EPI_STD || d.Cout % 4 != 0) return 1;
+  if (d.mode != EPI_STD || d.Cout % 4 != 0 || d.epi_act != 0) return 1;   // the reduce kernel applies no activation
   int tw, th, tn;
   const int Wo = d.W / d.stride, Ho = d.H / d.stride;
   pick_tile(Wo, Ho, d.Nb, &tw, &th, &tn);
@@ -861,6 +868,9 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.out_bf16 = d.out_bf16;
   p.out_vt = d.out_vt;
   p.qk_cols = d.qk_cols;
+  p.vt_tokens = d.vt_tokens;
+  p.act = d.epi_act;
+  PBE_REQUIRE(d.epi_act == 0 || d.mode == EPI_STD, "activation epilogue needs mode STD");
   p.ld_out = d.ld_out ? d.ld_out : (d.mode == EPI_GEGLU ? d.Cout / 2 : d.Cout);
 
   const int bn = auto_block_n(d);

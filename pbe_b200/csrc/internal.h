@@ -75,6 +75,8 @@ struct ConvGemmParams {
   // EPI_QKV: columns [0, qk_cols) go to out_bf16 (ld_out), columns >= qk_cols go transposed to out_vt[b][c][token]
   bf16* out_vt;
   int qk_cols;
+  int vt_tokens;          // EPI_QKV: tokens per sample of the V^T store when the activation is one flat row range (0: H*W)
+  int act;                // EPI_STD: 0 none, 1 quick_gelu x * sigmoid(1.702 x) (CLIP MLP), applied after the biases
 };
 
 // Deterministic split-K: slice s of the K range writes its partial tile to ws[s]; a second small kernel sums the
@@ -139,6 +141,8 @@ struct ConvGemmDesc {
   float* stats_out;        // optional fused GroupNorm statistics of out_f32 (see gemm_can_fuse_stats)
   int act_ld;              // elements between consecutive pixels of `act` (0 -> C): an operand that is a column slice
   int wt_ld;               // elements between consecutive output rows of `wt` (0 -> C; ksize 1 only)
+  int vt_tokens;           // EPI_QKV over a flat [1,1,M,C] activation: tokens per sample (0: H*W and sample = n)
+  int epi_act;             // EPI_STD: 0 none, 1 quick_gelu (applied after bias / rowbias, before the residual)
   int pad_end;             // stride-2 3x3 only: 1 = zero padding (0,1,0,1) as the VAE Downsample (model.py:74-76)
                            // instead of the symmetric padding 1 of the U-Net Downsample
 };
@@ -193,8 +197,9 @@ int gn_num_launches(const GroupNormArgs& a);  // kernels launch_groupnorm will l
 int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream);
 
 // LayerNorm over the last dim of fp32 [M, C] -> bf16 [M, C]
+// y (bf16) and / or y32 (fp32), row r of x at x + r * ld_x (ld_x = 0: contiguous rows of C)
 int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16* y, int M, int C, float eps,
-                     cudaStream_t stream);
+                     cudaStream_t stream, float* y32 = nullptr, long long ld_x = 0);
 
 // nearest 2x upsample, fp32 NHWC [Nb,H,W,C] -> bf16 NHWC [Nb,2H,2W,C]
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
@@ -218,8 +223,14 @@ int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, in
 // Small dense layers on CUDA cores (M = batch rows only): y[b, o] = act_in(x[b, :]) . W[o, :] + bias[o]
 // pre_silu applies SiLU to x on load. W is fp32 [O, K] row-major.
 // y_silu (optional) additionally receives silu(y) so consumers that all start with SiLU apply it once.
+// post_act: 0 none, 1 SiLU, 2 GELU (erf); residual (optional, [B, O]) is added after the activation
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
-                        int post_silu, cudaStream_t stream, float* y_silu = nullptr);
+                        int post_act, cudaStream_t stream, float* y_silu = nullptr, const float* residual = nullptr);
+// CLIP ViT front-end helpers (transformers CLIPVisionEmbeddings): patches [B,3,H,W] fp32 -> [B*P, Kpad] bf16 rows in
+// (c, kh, kw) order; tokens[b,0] = class + pos[0], tokens[b,1+p] = patch_embed[b,p] + pos[1+p]
+int launch_clip_pack_patches(const float* img, bf16* out, int B, int H, int W, int patch, int Kpad, cudaStream_t stream);
+int launch_clip_embed(const float* patch_emb, const float* cls, const float* pos, float* tokens, int B, int P, int C,
+                      cudaStream_t stream);
 // sinusoidal timestep embedding [B, dim] (cos || sin), reference util.py:151-171
 int launch_timestep_embedding(const int64_t* t, float* out, int B, int dim, cudaStream_t stream);
 // y[b, n] = a[n] + v[b, n]

@@ -96,7 +96,7 @@ constexpr int SL_OW = 4, SL_RB = 16;
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ y,
                                                            float* __restrict__ y_silu, int B, int K, int O,
-                                                           int pre_silu, int post_silu) {
+                                                           int pre_silu, int post_act, const float* __restrict__ residual) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int o0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SL_OW;
   const int lane = threadIdx.x & 31;
@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
       const int j = n / SL_RB, i = n % SL_RB;
       if (o0 + j < O && b0 + i < B) {
         float v = acc[e] + (bias ? bias[o0 + j] : 0.0f);
-        if (post_silu) v = silu_f(v);
+        if (post_act == 1) v = silu_f(v);
+        else if (post_act == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // nn.GELU() (erf)
+        if (residual != nullptr) v += residual[static_cast<long long>(b0 + i) * O + o0 + j];
         y[static_cast<long long>(b0 + i) * O + o0 + j] = v;
         if (y_silu) y_silu[static_cast<long long>(b0 + i) * O + o0 + j] = silu_f(v);
       }
@@ -225,6 +227,42 @@ __global__ void postprocess_u8_kernel(const float* __restrict__ x, uint8_t* __re
     v = fminf(fmaxf(v, 0.0f), 1.0f);
     out[idx * C + c] = static_cast<uint8_t>(__fmul_rn(255.0f, v));
   }
+}
+
+// CLIP ViT patch embedding input (transformers CLIPVisionEmbeddings.patch_embedding: Conv2d(3, C, patch, stride=patch,
+// bias=False)): one row per patch, columns in the conv weight's (c, kh, kw) order, zero padded to Kpad
+__global__ void clip_pack_patches_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W, int patch,
+                                         int Kpad) {
+  griddep_enter();
+  const int pw = W / patch, ph = H / patch;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * ph * pw * Kpad;
+  if (idx >= total) return;
+  const int k = static_cast<int>(idx % Kpad);
+  const long long row = idx / Kpad;
+  const int px = static_cast<int>(row % pw);
+  const int py = static_cast<int>((row / pw) % ph);
+  const int b = static_cast<int>(row / (static_cast<long long>(pw) * ph));
+  float v = 0.0f;
+  if (k < 3 * patch * patch) {
+    const int c = k / (patch * patch), r = k % (patch * patch), kh = r / patch, kw = r % patch;
+    v = img[((static_cast<long long>(b) * 3 + c) * H + py * patch + kh) * W + px * patch + kw];
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+// tokens[b, 0] = class_embedding + pos[0]; tokens[b, 1 + p] = patch_emb[b, p] + pos[1 + p]  (CLIPVisionEmbeddings.forward)
+__global__ void clip_embed_kernel(const float* __restrict__ patch_emb, const float* __restrict__ cls,
+                                  const float* __restrict__ pos, float* __restrict__ tokens, int B, int P, int C) {
+  griddep_enter();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * (P + 1) * C;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const int t = static_cast<int>((idx / C) % (P + 1));
+  const int b = static_cast<int>(idx / (static_cast<long long>(C) * (P + 1)));
+  const float base = t == 0 ? cls[c] : patch_emb[(static_cast<long long>(b) * P + (t - 1)) * C + c];
+  tokens[idx] = base + pos[static_cast<long long>(t) * C + c];
 }
 
 // P[r][:] = softmax(S[r][:] * scale), fp32 in, bf16 out; one 256-thread block per row, the row lives in registers
@@ -320,9 +358,9 @@ int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, in
 }
 
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
-                        int post_silu, cudaStream_t stream, float* y_silu) {
+                        int post_act, cudaStream_t stream, float* y_silu, const float* residual) {
   PBE_REQUIRE(K % 4 == 0, "small_linear K % 4");
-  PBE_CHECK_CUDA(launch_k(small_linear_kernel, dim3((O + 8 * SL_OW - 1) / (8 * SL_OW)), dim3(256), 0, stream, x, W, bias, y, y_silu, B, K, O, pre_silu, post_silu));
+  PBE_CHECK_CUDA(launch_k(small_linear_kernel, dim3((O + 8 * SL_OW - 1) / (8 * SL_OW)), dim3(256), 0, stream, x, W, bias, y, y_silu, B, K, O, pre_silu, post_act, residual));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -350,6 +388,22 @@ int launch_postprocess_u8(const float* x, uint8_t* out, int Nb, int C, int H, in
   const long long total = static_cast<long long>(Nb) * H * W;
   PBE_CHECK_CUDA(launch_k(postprocess_u8_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x,
                           out, Nb, C, H * W));
+  return 0;
+}
+
+int launch_clip_pack_patches(const float* img, bf16* out, int B, int H, int W, int patch, int Kpad, cudaStream_t stream) {
+  PBE_REQUIRE(H % patch == 0 && W % patch == 0 && Kpad >= 3 * patch * patch, "clip_pack_patches: image / patch geometry");
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * Kpad;
+  PBE_CHECK_CUDA(launch_k(clip_pack_patches_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, img,
+                          out, B, H, W, patch, Kpad));
+  return 0;
+}
+
+int launch_clip_embed(const float* patch_emb, const float* cls, const float* pos, float* tokens, int B, int P, int C,
+                      cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (P + 1) * C;
+  PBE_CHECK_CUDA(launch_k(clip_embed_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, patch_emb,
+                          cls, pos, tokens, B, P, C));
   return 0;
 }
 

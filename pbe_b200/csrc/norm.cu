@@ -344,13 +344,13 @@ constexpr int LN_MAX_VEC = 10;
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, int M,
-                                                        int C, float eps) {
+                                                        int C, float eps, float* __restrict__ y32, long long ld_x) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int nvec = C / 4;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ld_x);
   float4 v[NV];
   float sum = 0.0f;
 #pragma unroll
@@ -386,8 +386,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const int k = lane + i * 32;
     if (k < nvec) {
       const float4 g = __ldg(gr + k), bb = __ldg(br + k);
-      yr[k] = make_uint2(pack2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y),
-                         pack2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w));
+      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                                   (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+      if (y != nullptr) yr[k] = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+      if (y32 != nullptr) reinterpret_cast<float4*>(y32 + static_cast<long long>(row) * C)[k] = o;
     }
   }
 }
@@ -455,12 +457,14 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16* y, int M, int C, float eps,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float* y32, long long ld_x) {
+  if (ld_x == 0) ld_x = C;
+  PBE_REQUIRE(ld_x % 4 == 0 && (y != nullptr || y32 != nullptr), "LayerNorm: row stride % 4, at least one output");
   PBE_REQUIRE(C % 4 == 0 && C / 4 <= 32 * LN_MAX_VEC, "LayerNorm width must be a multiple of 4, <= 1280");
   const int nv = (C / 4 + 31) / 32;
-  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
-  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
-  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
+  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x));
+  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x));
+  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,7 @@ Run in the authoring container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py small      # seconds..a minute
     python tests/golden/make_golden.py v1         # one full-size U-Net call (~10 s) + PLMS-50 C1 trajectory (~10 min)
     python tests/golden/make_golden.py vae        # VAE decode: small config + the v1.yaml decoder on a 16x16 latent
+    python tests/golden/make_golden.py clip       # conditioning front-end: live transformers CLIPVisionModel + reference mapper
 
 Inputs and weights are regenerated from seeds (oracle.unet_ref.make_state_dict, oracle.sampler_ref.synthetic_request),
 so only outputs are stored.  Every file is written as float32 .npy; golden_index.json records shapes, seeds and sha256.
@@ -14,7 +15,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import unet_ref as U, sampler_ref as S, reference_bridge as R, vae_ref as V
+from oracle import unet_ref as U, sampler_ref as S, reference_bridge as R, vae_ref as V, clip_ref as K
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 INDEX = os.path.join(OUT, "golden_index.json")
@@ -112,6 +113,21 @@ def main(which):
             save(f"{tag}_vae_decode", img, dict(cfg=("SMALL_VAE_CFG" if tag == "small" else "V1_VAE_CFG"), weight_seed=321,
                                                 latent_seed=321, B=B, hw=hw,
                                                 source="reference Decoder(post_quant_conv(z)) fp32 CPU"), index)
+    elif which == "clip":
+        for tag, cfg, B in (("small", K.SMALL_CLIP_CFG, 2), ("v1", K.V1_CLIP_CFG, 1)):
+            sd = K.make_state_dict(cfg, 321)
+            enc = R.build_reference_clip_embedder(cfg, sd)
+            if tag == "v1":
+                index["clip_state_dict_keys"] = dict(keys=enc.state_dict_keys, n=len(enc.state_dict_keys))
+            x = K.synthetic_exemplars(B, cfg["image_size"], seed=321)
+            t0 = time.time()
+            z = enc(x)
+            print(tag, "clip encode", time.time() - t0, "s", flush=True)
+            import transformers
+            save(f"{tag}_clip_embed", z, dict(cfg=("SMALL_CLIP_CFG" if tag == "small" else "V1_CLIP_CFG"), weight_seed=321,
+                                              image_seed=321, B=B, transformers=transformers.__version__,
+                                              source="transformers CLIPVisionModel.pooler_output -> reference xf mapper -> "
+                                                     "final_ln, fp32 CPU"), index)
     json.dump(index, open(INDEX, "w"), indent=1, sort_keys=True)
 
 

@@ -155,7 +155,8 @@ def test_gemm_qkv_split_store(lib):
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,N,heads,d", [(2, 4096, 8, 40), (2, 1024, 8, 80), (2, 256, 8, 160), (2, 64, 8, 160),
                                          (1, 16, 8, 8), (1, 1024, 8, 16), (1, 200, 8, 32), (1, 2304, 8, 80),
-                                         (1, 144, 8, 160), (2, 180, 8, 160), (1, 45, 8, 160), (2, 1035, 8, 40)])
+                                         (1, 144, 8, 160), (2, 180, 8, 160), (1, 45, 8, 160), (2, 1035, 8, 40),
+                                         (2, 257, 16, 64), (1, 26, 2, 64)])
 def test_self_attention_matches_softmax_reference(lib, B, N, heads, d):
     """softmax(q k^T d^-1/2) v, ldm/modules/attention.py:217-229."""
     dev = torch.device("cuda:0")

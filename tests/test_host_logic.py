@@ -164,3 +164,18 @@ def test_vae_state_dict_keys_and_no_cpu_fallback(golden_dir):
         m.encode(torch.zeros(1, 3, 64, 64))
     with pytest.raises(NotImplementedError):
         AutoencoderKL(ddconfig=dict(dd, attn_resolutions=[16]), embed_dim=4)
+
+
+def test_clip_embedder_state_dict_keys_and_no_cpu_fallback(golden_dir):
+    import json
+    import os
+    import pytest
+    import torch
+    from pbe_b200.clip import FrozenCLIPImageEmbedder
+    m = FrozenCLIPImageEmbedder()
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    assert sorted(m.state_dict().keys()) == idx["clip_state_dict_keys"]["keys"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 200, 224))

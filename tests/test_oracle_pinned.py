@@ -160,3 +160,38 @@ def test_vae_encode_oracle_bit_equals_live_reference():
     x = V.synthetic_images(2, 32, 48, seed=5)
     with torch.no_grad():
         assert torch.equal(enc(x), V.encode_moments(sd, cfg, x))
+
+
+# ---- conditioning front-end: oracle/clip_ref.py ------------------------------------------------
+@pytest.mark.parametrize("tag", ["small", "v1"])
+def test_clip_oracle_matches_reference_golden(golden_dir, tag):
+    """oracle.clip_ref.encode == live transformers CLIPVisionModel -> reference xf mapper -> final_ln golden."""
+    from oracle import clip_ref as K
+    g, meta = _golden(golden_dir, f"{tag}_clip_embed")
+    cfg = K.SMALL_CLIP_CFG if tag == "small" else K.V1_CLIP_CFG
+    sd = K.make_state_dict(cfg, meta["weight_seed"])
+    x = K.synthetic_exemplars(meta["B"], cfg["image_size"], seed=meta["image_seed"])
+    with torch.no_grad():
+        z = K.encode(sd, cfg, x)
+    assert z.shape == g.shape
+    assert (z - g).abs().max().item() <= 1e-4 * g.abs().max().item()
+
+
+def test_clip_state_dict_keys_match_reference(golden_dir):
+    from oracle import clip_ref as K
+    idx = json.load(open(os.path.join(golden_dir, "golden_index.json")))
+    assert sorted(K.param_shapes(K.V1_CLIP_CFG).keys()) == idx["clip_state_dict_keys"]["keys"]
+
+
+def test_clip_oracle_matches_live_reference():
+    if not R.available():
+        pytest.skip("/root/reference not mounted")
+    pytest.importorskip("transformers")
+    from oracle import clip_ref as K
+    cfg = K.SMALL_CLIP_CFG
+    sd = K.make_state_dict(cfg, 11)
+    enc = R.build_reference_clip_embedder(cfg, sd)
+    x = K.synthetic_exemplars(3, cfg["image_size"], seed=5)
+    with torch.no_grad():
+        a, b = enc(x), K.encode(sd, cfg, x)
+    assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
