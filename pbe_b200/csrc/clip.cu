@@ -2,6 +2,8 @@
 #include "clip.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -272,9 +274,26 @@ int ClipEncoder::encode(const float* image, float* z, int B, cudaStream_t stream
   const int S = cfg_.image_size;
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.img_stage, image, static_cast<size_t>(B) * 3 * S * S * sizeof(float), cudaMemcpyDeviceToDevice,
                                  stream));
+  static const bool trace = getenv("PBE_CLIP_TRACE") != nullptr;   // debug aid: per-op device times on stderr
+  std::vector<cudaEvent_t> ev;
+  if (trace) {
+    ev.resize(P.ops.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], stream);
+  }
   for (size_t i = 0; i < P.ops.size(); ++i) {
     rc = P.ops[i](stream);
     if (rc) { last_error = std::string(get_error()) + " [" + P.op_names[i] + "]"; set_error(last_error); return rc; }
+    if (trace) cudaEventRecord(ev[i + 1], stream);
+  }
+  if (trace) {
+    cudaStreamSynchronize(stream);
+    for (size_t i = 0; i < P.ops.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      if (i < 12 || i + 24 >= P.ops.size()) fprintf(stderr, "[pbe clip] %-28s %8.1f us\n", P.op_names[i].c_str(), ms * 1e3f);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
   }
   PBE_CHECK_CUDA(cudaMemcpyAsync(z, P.z_stage, static_cast<size_t>(B) * cfg_.width * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   return 0;

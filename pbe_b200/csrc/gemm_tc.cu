@@ -708,23 +708,21 @@ int num_sms() {
   return n;
 }
 
+// 128-row tile = tn samples x th rows x tw pixels (powers of two): the shape that covers the output with the fewest tiles;
+// ties go to the widest, then the tallest tile (longest contiguous runs for TMA).  (The first version minimised the
+// padding of W and H one after the other and ignored Nb: a flat [1, 1, 257, C] activation got 1-pixel x 128-sample tiles,
+// 257 of them with one valid row each.)
 void pick_tile(int Wo, int Ho, int Nb, int* tw, int* th, int* tn) {
-  auto best = [](int extent, int budget) {
-    int best_t = 1;
-    long best_pad = -1;
-    for (int t = 1; t <= budget; t *= 2) {
-      long padded = static_cast<long>((extent + t - 1) / t) * t;
-      if (best_pad < 0 || padded < best_pad || (padded == best_pad && t > best_t)) {
-        best_pad = padded;
-        best_t = t;
+  long best_cost = -1;
+  for (int w = 128; w >= 1; w >>= 1)
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      const int n = 128 / (w * h);
+      const long cost = static_cast<long>((Wo + w - 1) / w) * ((Ho + h - 1) / h) * ((Nb + n - 1) / n);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        *tw = w; *th = h; *tn = n;
       }
     }
-    return best_t;
-  };
-  *tw = best(Wo, 128);
-  *th = best(Ho, 128 / *tw);
-  *tn = 128 / (*tw * *th);
-  (void)Nb;
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitKReduce r) {

@@ -53,3 +53,8 @@ if "conv1" in which: case("conv1 64^2 320->320 +rb", 16, 64, 64, 320, 3, 320, ro
 if "ffout" in which: case("ff.out 64^2 1280->320 +res", 16, 64, 64, 1280, 1, 320, residual=True, f32=False, b16=True)
 if "lowres" in which: case("conv 8^2 1280->1280 +res", 16, 8, 8, 1280, 3, 1280, residual=True)
 if "nores" in which: case("proj 64^2 320->320 no res", 16, 64, 64, 320, 1, 320)
+if "clip" in which:
+    case("clip fc1 M=257 1024->4096", 1, 1, 257, 1024, 1, 4096, f32=False, b16=True)
+    case("clip fc2 M=257 4096->1024 +res", 1, 1, 257, 4096, 1, 1024, residual=True)
+    case("clip fc1 M=2056 1024->4096", 1, 1, 2056, 1024, 1, 4096, f32=False, b16=True)
+    case("same as [8,1,257]", 8, 1, 257, 1024, 1, 4096, f32=False, b16=True)
