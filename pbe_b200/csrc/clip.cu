@@ -275,6 +275,13 @@ int ClipEncoder::encode(const float* image, float* z, int B, cudaStream_t stream
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.img_stage, image, static_cast<size_t>(B) * 3 * S * S * sizeof(float), cudaMemcpyDeviceToDevice,
                                  stream));
   static const bool trace = getenv("PBE_CLIP_TRACE") != nullptr;   // debug aid: per-op device times on stderr
+  if (!trace) {   // product path: CUDA-graph replay of the launch plan (252 short kernels at B = 1 are launch-bound)
+    rc = run_op_list(P.ops, P.op_names, stream, true, &P.graph, &cap_stream_);
+    if (rc) { last_error = get_error(); return rc; }
+    PBE_CHECK_CUDA(cudaMemcpyAsync(z, P.z_stage, static_cast<size_t>(B) * cfg_.width * sizeof(float), cudaMemcpyDeviceToDevice,
+                                   stream));
+    return 0;
+  }
   std::vector<cudaEvent_t> ev;
   if (trace) {
     ev.resize(P.ops.size() + 1);

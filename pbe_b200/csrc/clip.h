@@ -31,13 +31,20 @@ struct ClipPrepared {
   float* img_stage = nullptr;  // [B, 3, S, S]
   float* z_stage = nullptr;    // [B, C]
   int launches = 0;
-  ~ClipPrepared() { if (persist.base_) cudaFree(persist.base_); }
+  cudaGraphExec_t graph = nullptr;
+  ~ClipPrepared() {
+    if (graph) cudaGraphExecDestroy(graph);
+    if (persist.base_) cudaFree(persist.base_);
+  }
 };
 
 class ClipEncoder : public WeightLoader {
  public:
   explicit ClipEncoder(const pbe_clip_config& cfg) : cfg_(cfg) {}
-  ~ClipEncoder() { prepared_.clear(); }
+  ~ClipEncoder() {
+    prepared_.clear();
+    if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  }
   int finalize();
   int encode(const float* image, float* z, int B, cudaStream_t stream);
   int launches() const { return cur_ ? cur_->launches : 0; }
@@ -58,6 +65,7 @@ class ClipEncoder : public WeightLoader {
   std::vector<ClipMapW> mapper_;
   std::map<int, std::unique_ptr<ClipPrepared>> prepared_;
   ClipPrepared* cur_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr;
 };
 
 }  // namespace pbe

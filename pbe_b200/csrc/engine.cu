@@ -797,6 +797,44 @@ int Engine::profile_forward(const float* x, const int64_t* t, float* eps, int Bc
   return static_cast<int>(n);
 }
 
+int run_op_list(const std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<std::string>& names,
+                cudaStream_t stream, bool use_graph, cudaGraphExec_t* graph, cudaStream_t* cap_stream) {
+  int rc;
+  if (!use_graph) {
+    for (size_t i = 0; i < ops.size(); ++i) {
+      rc = ops[i](stream);
+      if (rc) { set_error(std::string(get_error()) + " [" + names[i] + "]"); return rc; }
+    }
+    return 0;
+  }
+  if (*graph == nullptr) {
+    // warm every kernel once eagerly (sets function attributes outside capture), then capture
+    for (size_t i = 0; i < ops.size(); ++i) {
+      rc = ops[i](stream);
+      if (rc) { set_error(std::string(get_error()) + " [" + names[i] + "]"); return rc; }
+    }
+    PBE_CHECK_CUDA(cudaStreamSynchronize(stream));
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
+    // the instantiated graph is then launched on the caller's stream.
+    if (*cap_stream == nullptr) PBE_CHECK_CUDA(cudaStreamCreateWithFlags(cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    PBE_CHECK_CUDA(cudaStreamBeginCapture(*cap_stream, cudaStreamCaptureModeThreadLocal));
+    for (size_t i = 0; i < ops.size(); ++i) {
+      rc = ops[i](*cap_stream);
+      if (rc) {
+        cudaStreamEndCapture(*cap_stream, &g);
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+    }
+    PBE_CHECK_CUDA(cudaStreamEndCapture(*cap_stream, &g));
+    PBE_CHECK_CUDA(cudaGraphInstantiate(graph, g, 0));
+    cudaGraphDestroy(g);
+  }
+  PBE_CHECK_CUDA(cudaGraphLaunch(*graph, stream));
+  return 0;
+}
+
 int Engine::forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream) {
   int rc = prepare(Bc, H, W);
   if (rc) return rc;
@@ -806,38 +844,8 @@ int Engine::forward(const float* x, const int64_t* t, float* eps, int Bc, int H,
                                  cudaMemcpyDeviceToDevice, stream));
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage, t, static_cast<size_t>(Bc) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
                                  stream));
-  if (use_graph) {
-    if (P.graph == nullptr) {
-      // warm every kernel once eagerly (sets function attributes outside capture), then capture
-      for (size_t i = 0; i < P.ops.size(); ++i) {
-        rc = P.ops[i](stream);
-        if (rc) { set_error(std::string(get_error()) + " [" + P.op_names[i] + "]"); return rc; }
-      }
-      PBE_CHECK_CUDA(cudaStreamSynchronize(stream));
-      // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
-      // the instantiated graph is then launched on the caller's stream.
-      if (cap_stream_ == nullptr) PBE_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
-      cudaGraph_t g = nullptr;
-      PBE_CHECK_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
-      for (size_t i = 0; i < P.ops.size(); ++i) {
-        rc = P.ops[i](cap_stream_);
-        if (rc) {
-          cudaStreamEndCapture(cap_stream_, &g);
-          if (g) cudaGraphDestroy(g);
-          return rc;
-        }
-      }
-      PBE_CHECK_CUDA(cudaStreamEndCapture(cap_stream_, &g));
-      PBE_CHECK_CUDA(cudaGraphInstantiate(&P.graph, g, 0));
-      cudaGraphDestroy(g);
-    }
-    PBE_CHECK_CUDA(cudaGraphLaunch(P.graph, stream));
-  } else {
-    for (size_t i = 0; i < P.ops.size(); ++i) {
-      rc = P.ops[i](stream);
-      if (rc) { set_error(std::string(get_error()) + " [" + P.op_names[i] + "]"); return rc; }
-    }
-  }
+  rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_);
+  if (rc) return rc;
   PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
                                  cudaMemcpyDeviceToDevice, stream));
   return 0;

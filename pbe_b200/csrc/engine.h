@@ -88,6 +88,12 @@ struct Prepared {
   ~Prepared();
 };
 
+// Runs a launch plan: the first call runs every op eagerly once (function attributes are set outside capture), captures
+// the list on a private stream and instantiates a CUDA graph; every call then replays the graph on the caller's stream.
+// With use_graph = false the ops are simply launched one by one.
+int run_op_list(const std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<std::string>& names,
+                cudaStream_t stream, bool use_graph, cudaGraphExec_t* graph, cudaStream_t* cap_stream);
+
 // Host-side weight staging shared by the U-Net engine and the VAE decoder: tensors arrive by reference state-dict name,
 // are repacked at finalize() and uploaded once.
 class WeightLoader {

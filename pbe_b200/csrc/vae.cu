@@ -12,6 +12,7 @@
 namespace pbe {
 
 VaePrepared::~VaePrepared() {
+  if (graph) cudaGraphExecDestroy(graph);
   if (persist.base_) cudaFree(persist.base_);
   if (scratch.base_) cudaFree(scratch.base_);
 }
@@ -515,7 +516,13 @@ int VaeModel::run(VaePrepared& P, const float* in, size_t in_bytes, float* out, 
     for (auto& e : ev) PBE_CHECK_CUDA(cudaEventCreate(&e));
   }
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.z_stage, in, in_bytes, cudaMemcpyDeviceToDevice, stream));
-  if (ms != nullptr) PBE_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+  if (ms == nullptr) {   // product path: CUDA-graph replay of the launch plan
+    int rc = run_op_list(P.ops, P.op_names, stream, true, &P.graph, &cap_stream_);
+    if (rc) { last_error = get_error(); return rc; }
+    PBE_CHECK_CUDA(cudaMemcpyAsync(out, P.out_stage, out_bytes, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  }
+  PBE_CHECK_CUDA(cudaEventRecord(ev[0], stream));
   for (int i = 0; i < n; ++i) {
     int rc = P.ops[i](stream);
     if (rc) { last_error = std::string(get_error()) + " [" + P.op_names[i] + "]"; set_error(last_error); return rc; }

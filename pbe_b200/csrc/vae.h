@@ -29,13 +29,17 @@ struct VaePrepared {
   float* z_stage = nullptr;    // input staging: latents [B, embed_dim, H, W] (decode) or images [B, in_ch, H, W] (encode)
   float* out_stage = nullptr;  // output staging: images [B, out_ch, fH, fW] (decode) or moments [B, 2*embed, H/f, W/f]
   int launches = 0;
+  cudaGraphExec_t graph = nullptr;
   ~VaePrepared();
 };
 
 class VaeModel : public WeightLoader {
  public:
   explicit VaeModel(const pbe_vae_config& cfg) : cfg_(cfg) {}
-  ~VaeModel() { prepared_.clear(); }
+  ~VaeModel() {
+    prepared_.clear();
+    if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  }
   // Repacks whichever halves have been loaded (decoder.* + post_quant_conv.*, encoder.* + quant_conv.*).
   int finalize();
   // z [B, embed_dim, H, W] fp32 NCHW (device) -> out [B, out_ch, f*H, f*W] fp32 NCHW (device), f = 2^(levels-1)
@@ -76,6 +80,7 @@ class VaeModel : public WeightLoader {
   NormW e_norm_out_;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<VaePrepared>> prepared_;
   VaePrepared* cur_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr;
 };
 
 }  // namespace pbe
