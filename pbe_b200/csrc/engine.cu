@@ -844,7 +844,10 @@ int Engine::forward(const float* x, const int64_t* t, float* eps, int Bc, int H,
                                  cudaMemcpyDeviceToDevice, stream));
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage, t, static_cast<size_t>(Bc) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
                                  stream));
+  // latency-bound small batches gain from programmatic dependent launch, throughput batches lose (tmap.cu: pdl_enabled)
+  pdl_set_scope(Bc <= 4 ? 1 : 0);
   rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_);
+  pdl_set_scope(-1);
   if (rc) return rc;
   PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
                                  cudaMemcpyDeviceToDevice, stream));

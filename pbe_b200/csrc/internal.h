@@ -99,10 +99,11 @@ struct GemmPlan {
   size_t smem;
 };
 
-// Kernel launch, optionally (PBE_PDL=1) with programmatic dependent launch: consecutive kernels of a stream (and of
+// Kernel launch, optionally (small-batch U-Net plans, or PBE_PDL=1) with programmatic dependent launch: consecutive kernels of a stream (and of
 // the captured CUDA graph) then overlap the successor's prologue with the predecessor's tail; every kernel of this
 // library calls griddep_wait() (ptx.cuh) before it touches memory its predecessor may still be writing.
 bool pdl_enabled();
+void pdl_set_scope(int v);   // 1 / 0: the launches (and graph captures) that follow on this thread use / do not use PDL; -1: default
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

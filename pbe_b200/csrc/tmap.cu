@@ -70,11 +70,18 @@ int make_tmap(CUtensorMap* out, const void* base, bool is_f32, int rank, const u
   return 0;
 }
 
+namespace {
+thread_local int g_pdl_scope = -1;   // -1: no preference from the engine that is building / capturing a launch plan
+}
+void pdl_set_scope(int v) { g_pdl_scope = v; }
+
 bool pdl_enabled() {
-  // Off by default: measured on B200 inside the captured graph, PDL gives +1.7 % at CFG batch 2 (4.20 -> 4.13 ms per
-  // U-Net call) but -1.5 % at CFG batch 16 (17.25 -> 17.60 ms); PBE_PDL=1 turns it on.
-  static const bool on = [] { const char* e = getenv("PBE_PDL"); return e != nullptr && atoi(e) != 0; }();
-  return on;
+  // Measured on B200 inside the captured graph: PDL gives +1.7 % at CFG batch 2 (4.20 -> 4.13 ms per U-Net call) but
+  // -1.5 % at CFG batch 16 (17.25 -> 17.60 ms).  So the U-Net engine asks for it (pdl_set_scope) only while it captures
+  // small-batch plans; PBE_PDL=0 / 1 overrides everything.
+  static const int env = [] { const char* e = getenv("PBE_PDL"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
+  if (env >= 0) return env == 1;
+  return g_pdl_scope == 1;
 }
 
 }  // namespace pbe
