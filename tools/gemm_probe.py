@@ -58,3 +58,7 @@ if "clip" in which:
     case("clip fc2 M=257 4096->1024 +res", 1, 1, 257, 4096, 1, 1024, residual=True)
     case("clip fc1 M=2056 1024->4096", 1, 1, 2056, 1024, 1, 4096, f32=False, b16=True)
     case("same as [8,1,257]", 8, 1, 257, 1024, 1, 4096, f32=False, b16=True)
+if "vae" in which:
+    case("vae L0 conv1 512^2 128->128", 8, 512, 512, 128, 3, 128)
+    case("vae L0 conv2 512^2 128->128 +res", 8, 512, 512, 128, 3, 128, residual=True)
+    case("vae L1 conv 256^2 256->256 +res", 8, 256, 256, 256, 3, 256, residual=True)
