@@ -148,6 +148,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        # the synthetic weights are generated on the host by every rank: share the cores instead of oversubscribing them
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
 
     from oracle import sampler_ref as S, unet_ref as U   # synthetic weights / requests only (not timed, not the product)
     from pbe_b200.diffusion import LatentDiffusion
