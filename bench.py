@@ -260,7 +260,7 @@ def main():
     gemm = fam.get("conv_gemm", dict(ms=1.0, flops=0.0, launches=1))
     gemm_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
         per_call, threads = cpu_reference_call_seconds(n_calls=5)
         cpu_baseline = {"value": 1.0 / (UNET_CALLS * per_call), "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": f"median of 5 CFG U-Net calls (batch 2, 64x64 latent) of the fp32 oracle port x "
