@@ -110,6 +110,13 @@ int pbe_finalize_weights(pbe_handle h);
 int pbe_set_context(pbe_handle h, const float* ctx, int Bc, void* stream);
 /* eps[Bc,out_ch,H,W] = UNet(x[Bc,in_ch,H,W] fp32 NCHW, t[Bc] int64, context set by pbe_set_context). */
 int pbe_unet_forward(pbe_handle h, const float* x, const int64_t* t, float* eps, int Bc, int H, int W, void* stream);
+/* The classifier-free-guidance evaluation of p_sample_plms / p_sample_ddim (plms.py:185-188, ddim.py:200-212):
+ *   e_t_uncond, e_t = apply_model(cat([x] * 2), cat([t] * 2), cat([uc, c])).chunk(2)
+ * with x [B,in_ch,H,W] and t [B] given ONCE: eps[2B,out_ch,H,W] holds the unconditional half then the conditional half;
+ * the context set by pbe_set_context must have 2B rows (uc rows first).  The two halves differ only where the context
+ * enters, so the layers before the first cross-attention are evaluated once for the B shared samples; the result is
+ * bit-identical to pbe_unet_forward on the duplicated batch. */
+int pbe_unet_forward_cfg_pair(pbe_handle h, const float* x, const int64_t* t, float* eps, int B, int H, int W, void* stream);
 /* 1 = replay a captured CUDA graph per forward (default), 0 = launch kernels one by one. */
 int pbe_set_use_graph(pbe_handle h, int enable);
 /* Measurement aid: one eager forward with a CUDA-event pair around every op of the launch plan. Fills ms_out[i]

@@ -66,6 +66,7 @@ _OPTIONAL_SIGS: dict = {
     "pbe_finalize_weights": (c_int, [_p]),
     "pbe_set_context": (c_int, [_p, _p, _i, _p]),
     "pbe_unet_forward": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "pbe_unet_forward_cfg_pair": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "pbe_set_use_graph": (c_int, [_p, _i]),
     "pbe_launches_per_forward": (c_int, [_p]),
     "pbe_profile_forward": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i]),

@@ -50,6 +50,9 @@ int pbe_set_context(pbe_handle h, const float* ctx, int Bc, void* stream) {
 int pbe_unet_forward(pbe_handle h, const float* x, const int64_t* t, float* eps, int Bc, int H, int W, void* stream) {
   PBE_GUARD(h->e->forward(x, t, eps, Bc, H, W, static_cast<cudaStream_t>(stream)));
 }
+int pbe_unet_forward_cfg_pair(pbe_handle h, const float* x, const int64_t* t, float* eps, int B, int H, int W, void* stream) {
+  PBE_GUARD(h->e->forward_pair(x, t, eps, B, H, W, static_cast<cudaStream_t>(stream)));
+}
 int pbe_set_use_graph(pbe_handle h, int enable) {
   if (h == nullptr) { set_error("null handle"); return -1; }
   h->e->use_graph = enable != 0;

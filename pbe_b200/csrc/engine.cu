@@ -389,7 +389,12 @@ int Engine::set_context(const float* ctx_dev, int Bc, cudaStream_t stream) {
 }
 
 int Engine::build(Prepared& P, bool dry) {
-  const int Bc = P.Bc, H0 = P.H, W0 = P.W;
+  const int BcFull = P.Bc, H0 = P.H, W0 = P.W;
+  // CFG pair plan: ops are emitted for the B = Bc/2 shared samples until the context enters (first SpatialTransformer's
+  // attn1.to_out), then for all Bc samples; `Bc` is the batch of the ops currently being emitted.
+  const bool pair = P.pair;
+  bool diverged = !pair;
+  int Bc = pair ? BcFull / 2 : BcFull;
   const int mc = cfg_.model_channels, ted = 4 * mc;
   P.persist.reset(dry);
   P.scratch.reset(dry);
@@ -417,6 +422,7 @@ int Engine::build(Prepared& P, bool dry) {
   };
   int err = 0;
   auto add_gemm = [&](const std::string& name, ConvGemmDesc d) {
+    if (!diverged) d.split_batch = 2 * d.Nb;   // CFG-pair prefix: same split-K decision (summation order) as the full batch
     const size_t ws_bytes = d.stats_out ? 0 : gemm_splitk_ws_bytes(d);
     d.splitk_ws = ws_bytes ? static_cast<float*>(SA(ws_bytes)) : nullptr;
     if (dry) { launches += ws_bytes ? 2 : 1; return; }
@@ -442,33 +448,33 @@ int Engine::build(Prepared& P, bool dry) {
                 n * ((launches == 3 ? 8.0 : 4.0) + 2.0 + (a.raw ? 2.0 : 0.0)));
   };
 
-  P.x_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.in_channels * H0 * W0 * sizeof(float)));
-  P.t_stage = static_cast<int64_t*>(PA(static_cast<size_t>(Bc) * sizeof(int64_t)));
-  P.eps_stage = static_cast<float*>(PA(static_cast<size_t>(Bc) * cfg_.out_channels * H0 * W0 * sizeof(float)));
+  P.x_stage = static_cast<float*>(PA(static_cast<size_t>(BcFull) * cfg_.in_channels * H0 * W0 * sizeof(float)));
+  P.t_stage = static_cast<int64_t*>(PA(static_cast<size_t>(BcFull) * sizeof(int64_t)));
+  P.eps_stage = static_cast<float*>(PA(static_cast<size_t>(BcFull) * cfg_.out_channels * H0 * W0 * sizeof(float)));
 
   // ---- timestep embedding path (K8) ----
-  float* t_emb = static_cast<float*>(PA(static_cast<size_t>(Bc) * mc * sizeof(float)));
-  float* t_hid = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
-  float* emb = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
-  float* emb_silu = static_cast<float*>(PA(static_cast<size_t>(Bc) * ted * sizeof(float)));
-  float* emb_all = static_cast<float*>(PA(static_cast<size_t>(Bc) * emb_total_ * sizeof(float)));
+  float* t_emb = static_cast<float*>(PA(static_cast<size_t>(BcFull) * mc * sizeof(float)));
+  float* t_hid = static_cast<float*>(PA(static_cast<size_t>(BcFull) * ted * sizeof(float)));
+  float* emb = static_cast<float*>(PA(static_cast<size_t>(BcFull) * ted * sizeof(float)));
+  float* emb_silu = static_cast<float*>(PA(static_cast<size_t>(BcFull) * ted * sizeof(float)));
+  float* emb_all = static_cast<float*>(PA(static_cast<size_t>(BcFull) * emb_total_ * sizeof(float)));
   {
     const int64_t* tp = P.t_stage;
     float *w0 = te_w0_, *b0 = te_b0_, *w1 = te_w1_, *b1 = te_b1_;
-    bf16* emb_silu16 = static_cast<bf16*>(PA(static_cast<size_t>(Bc) * ted * sizeof(bf16)));
-    add_op("timestep_embedding", 1, [=](cudaStream_t s) { return launch_timestep_embedding(tp, t_emb, Bc, mc, s); });
+    bf16* emb_silu16 = static_cast<bf16*>(PA(static_cast<size_t>(BcFull) * ted * sizeof(bf16)));
+    add_op("timestep_embedding", 1, [=](cudaStream_t s) { return launch_timestep_embedding(tp, t_emb, BcFull, mc, s); });
     add_op("time_embed.0+silu", 1,
-           [=](cudaStream_t s) { return launch_small_linear(t_emb, w0, b0, t_hid, Bc, mc, ted, 0, 1, s); });
+           [=](cudaStream_t s) { return launch_small_linear(t_emb, w0, b0, t_hid, BcFull, mc, ted, 0, 1, s); });
     add_op("time_embed.2", 1,
-           [=](cudaStream_t s) { return launch_small_linear(t_hid, w1, b1, emb, Bc, ted, ted, 0, 0, s, emb_silu); });
+           [=](cudaStream_t s) { return launch_small_linear(t_hid, w1, b1, emb, BcFull, ted, ted, 0, 0, s, emb_silu); });
     // every ResBlock's emb_layers = Linear(SiLU(emb)) (openaimodel.py:218-224): SiLU once, all 22 Linears as ONE
-    // [Bc, 1280] x [1280, 20160] GEMM on the tensor cores (a 52 MB bf16 weight stream; as batched fp32 GEMVs it was
+    // [BcFull, 1280] x [1280, 20160] GEMM on the tensor cores (a 52 MB bf16 weight stream; as batched fp32 GEMVs it was
     // latency bound at 185 us per call)
     add_op("emb_silu.bf16", 1,
-           [=](cudaStream_t s) { return launch_cast_bf16(emb_silu, emb_silu16, static_cast<size_t>(Bc) * ted, s); });
+           [=](cudaStream_t s) { return launch_cast_bf16(emb_silu, emb_silu16, static_cast<size_t>(BcFull) * ted, s); });
     {
       ConvGemmDesc d{};
-      d.act = emb_silu16; d.Nb = Bc; d.H = 1; d.W = 1; d.C = ted; d.ksize = 1; d.stride = 1;
+      d.act = emb_silu16; d.Nb = BcFull; d.H = 1; d.W = 1; d.C = ted; d.ksize = 1; d.stride = 1;
       d.wt = emb_w_; d.Cout = emb_total_; d.mode = EPI_STD; d.bias = emb_b_; d.out_f32 = emb_all;
       add_gemm("emb_layers(all)", d);
     }
@@ -485,9 +491,10 @@ int Engine::build(Prepared& P, bool dry) {
   // Attach fused GroupNorm statistics to a GEMM whose fp32 output `o` is normalised by the next op.
   auto want_stats = [&](ConvGemmDesc& d, Act& o, bool persistent) {
     d.splitk_ws = nullptr;
+    if (!diverged) d.split_batch = 2 * d.Nb;   // as in add_gemm: decide like the full CFG batch would
     if (!gemm_can_fuse_stats(d)) return;
     const size_t rows = static_cast<size_t>(d.Nb) * (d.H / d.stride) * (d.W / d.stride);
-    const size_t bytes = rows / 32 * d.Cout * 2 * sizeof(float);
+    const size_t bytes = rows / 32 * d.Cout * 2 * sizeof(float) * (diverged ? 1 : 2);   // prefix tensors are duplicated later
     o.stats = static_cast<float*>(persistent ? PA(bytes) : SA(bytes));
     o.has_stats = true;
     d.stats_out = o.stats;
@@ -509,7 +516,7 @@ int Engine::build(Prepared& P, bool dry) {
         const float* xs = P.x_stage;
         const int cin = cfg_.in_channels;
         add_op(tag + ".pack_input", 1, [=](cudaStream_t s) { return launch_pack_input(xs, xin, Bc, cin, H0, W0, 64, s); });
-        Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, H0, W0};
+        Act o{static_cast<float*>(PA(M * (diverged ? 1 : 2) * c.cout * sizeof(float))), nullptr, c.cout, H0, W0};
         ConvGemmDesc d{};
         d.act = xin; d.Nb = Bc; d.H = H0; d.W = W0; d.C = 64; d.c_real = cin; d.ksize = 3; d.stride = 1;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
@@ -567,8 +574,8 @@ int Engine::build(Prepared& P, bool dry) {
           add_gemm(tag + ".skip", d);
           resid = sk;
         }
-        Act o{static_cast<float*>(PA(M * r.cout * sizeof(float))), nullptr, r.cout, h.H, h.W};
-        if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * r.cout * sizeof(bf16))); o.has16 = true; }
+        Act o{static_cast<float*>(PA(M * (diverged ? 1 : 2) * r.cout * sizeof(float))), nullptr, r.cout, h.H, h.W};
+        if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * (diverged ? 1 : 2) * r.cout * sizeof(bf16))); o.has16 = true; }
         {
           ConvGemmDesc d{};
           d.act = a2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = r.cout; d.ksize = 3; d.stride = 1;
@@ -583,7 +590,7 @@ int Engine::build(Prepared& P, bool dry) {
       case Module::ST: {
         const STW& s = st_[m.idx];
         const int C = s.c, N = h.H * h.W;
-        const size_t M = static_cast<size_t>(Bc) * N;
+        size_t M = static_cast<size_t>(Bc) * N;
         if (C != h.C) { err = -5; last_error = "channel mismatch at " + tag; return err; }
         bf16* a = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
         GroupNormArgs g{};
@@ -625,15 +632,51 @@ int Engine::build(Prepared& P, bool dry) {
         } else {
           launches += 1;
         }
-        float* t1 = static_cast<float*>(SA(M * C * sizeof(float)));
-        {
-          // x1 = to_out(attn) + b + x ; x2 = x1 + to_out2(to_v2(ctx))  (single-key cross-attention, folded)
+        float* t1 = static_cast<float*>(SA(M * (diverged ? 1 : 2) * C * sizeof(float)));
+        for (int half = 0; half < (diverged ? 1 : 2); ++half) {
+          // x1 = to_out(attn) + b + x ; x2 = x1 + to_out2(to_v2(ctx))  (single-key cross-attention, folded).
+          // CFG pair plan: this is where the context enters -- the shared activations feed one GEMM per half, each
+          // with its own rows of the per-sample context bias, writing its half of the full batch.
           ConvGemmDesc d{};
           d.act = ao; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.to_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.to_out.b;
-          d.rowbias = ctx_vecs_ + static_cast<size_t>(MAX_BC) * s.ctx_vec_off; d.rowbias_ld = C;
-          d.residual = t0; d.out_f32 = t1;
-          add_gemm(tag + ".attn1.to_out+attn2", d);
+          d.rowbias = ctx_vecs_ + static_cast<size_t>(MAX_BC) * s.ctx_vec_off + static_cast<size_t>(half) * Bc * C;
+          d.rowbias_ld = C;
+          d.residual = t0; d.out_f32 = t1 + static_cast<size_t>(half) * M * C;
+          add_gemm(tag + (half ? ".attn1.to_out+attn2[cond]" : ".attn1.to_out+attn2"), d);
+        }
+        if (!diverged) {
+          // from here on the two halves differ: duplicate the shared block outputs that later ops read per sample
+          // (the skip tensors pushed so far and this transformer's input, the residual of proj_out)
+          std::vector<Act*> dup;
+          for (Act& a0 : hs) dup.push_back(&a0);
+          dup.push_back(&h);
+          for (Act* a0 : dup) {
+            const size_t elems = static_cast<size_t>(Bc) * a0->H * a0->W * a0->C;
+            float* f = a0->f32;
+            add_op(tag + ".dup_f32", 0, [=](cudaStream_t st) {
+              PBE_CHECK_CUDA(cudaMemcpyAsync(f + elems, f, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+              return 0;
+            });
+            if (a0->has_stats) {
+              const size_t sel = static_cast<size_t>(Bc) * a0->H * a0->W / 32 * a0->C * 2;
+              float* sp = a0->stats;
+              add_op(tag + ".dup_stats", 0, [=](cudaStream_t st) {
+                PBE_CHECK_CUDA(cudaMemcpyAsync(sp + sel, sp, sel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                return 0;
+              });
+            }
+            if (a0->has16) {
+              bf16* bp = a0->b16;
+              add_op(tag + ".dup_b16", 0, [=](cudaStream_t st) {
+                PBE_CHECK_CUDA(cudaMemcpyAsync(bp + elems, bp, elems * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+                return 0;
+              });
+            }
+          }
+          diverged = true;
+          Bc = BcFull;
+          M = static_cast<size_t>(Bc) * N;
         }
         bf16* n3 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
         {
@@ -739,20 +782,25 @@ int Engine::build(Prepared& P, bool dry) {
   return 0;
 }
 
-int Engine::prepare(int Bc, int H, int W) {
+bool Engine::pair_plan_possible() const {
+  return modules_.size() > 2 && modules_[0].kind == Module::CONV_IN && modules_[1].kind == Module::RES &&
+         modules_[2].kind == Module::ST && !modules_[1].pop_skip;
+}
+
+int Engine::prepare(int Bc, int H, int W, bool pair) {
   PBE_REQUIRE(finalized_, "weights not finalized");
   PBE_REQUIRE(Bc >= 1 && Bc <= MAX_BC, "batch out of range");
   int down = 1;
   for (int i = 1; i < cfg_.num_levels; ++i) down *= 2;
   PBE_REQUIRE(H % down == 0 && W % down == 0, "latent size must be divisible by 2^(levels-1)");
-  auto key = std::make_tuple(Bc, H, W);
+  auto key = std::make_tuple(Bc, H, W, pair ? 1 : 0);
   auto it = prepared_.find(key);
   if (it != prepared_.end()) {
     cur_ = it->second.get();
     return 0;
   }
   auto P = std::make_unique<Prepared>();
-  P->Bc = Bc; P->H = H; P->W = W;
+  P->Bc = Bc; P->H = H; P->W = W; P->pair = pair;
   int rc = build(*P, true);
   if (rc) { set_error(last_error); return rc; }
   const size_t pbytes = P->persist.high() + 4096, sbytes = P->scratch.high() + 4096;
@@ -832,6 +880,28 @@ int run_op_list(const std::vector<std::function<int(cudaStream_t)>>& ops, const 
     cudaGraphDestroy(g);
   }
   PBE_CHECK_CUDA(cudaGraphLaunch(*graph, stream));
+  return 0;
+}
+
+int Engine::forward_pair(const float* x, const int64_t* t, float* eps, int B, int H, int W, cudaStream_t stream) {
+  const int Bc = 2 * B;
+  const bool pair = pair_plan_possible();
+  int rc = prepare(Bc, H, W, pair);
+  if (rc) return rc;
+  Prepared& P = *cur_;
+  PBE_REQUIRE(ctx_Bc_ == Bc, "set_context must be called with 2 * B rows (unconditional, then conditional) before forward_pair");
+  const size_t xb = static_cast<size_t>(B) * cfg_.in_channels * H * W * sizeof(float);
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.x_stage, x, xb, cudaMemcpyDeviceToDevice, stream));
+  if (!pair)   // no shared-prefix plan for this architecture: run the ordinary plan on the duplicated batch
+    PBE_CHECK_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(P.x_stage) + xb, x, xb, cudaMemcpyDeviceToDevice, stream));
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage, t, static_cast<size_t>(B) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+  PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage + B, t, static_cast<size_t>(B) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+  pdl_set_scope(Bc <= 4 ? 1 : 0);
+  rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_);
+  pdl_set_scope(-1);
+  if (rc) return rc;
+  PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, stream));
   return 0;
 }
 

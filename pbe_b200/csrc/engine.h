@@ -74,6 +74,7 @@ class Arena {
 
 struct Prepared {
   int Bc = 0, H = 0, W = 0;
+  bool pair = false;   // CFG pair plan: samples [0, Bc/2) and [Bc/2, Bc) share x and t (see Engine::forward_pair)
   Arena persist, scratch;
   std::vector<std::function<int(cudaStream_t)>> ops;
   std::vector<std::string> op_names;
@@ -120,6 +121,13 @@ class Engine : public WeightLoader {
   int finalize();
   int set_context(const float* ctx_dev, int Bc, cudaStream_t stream);
   int forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream);
+  // Classifier-free-guidance pair (plms.py:185-188: x_in = cat([x] * 2), t_in = cat([t] * 2), c_in = cat([uc, c])): the two
+  // halves of the batch differ only in the context, and the context first enters at the first SpatialTransformer's
+  // attn1.to_out (+ folded cross-attention).  Everything before that point -- conv_in, the first ResBlock, the first
+  // transformer's norm / proj_in / LayerNorm / qkv / self-attention -- is computed ONCE for the B shared samples;
+  // results are bit-identical to forward() on the duplicated batch.  x [B, in_ch, H, W], t [B] -> eps [2B, out_ch, H, W];
+  // set_context must have been called with 2B rows (unconditional rows first).
+  int forward_pair(const float* x, const int64_t* t, float* eps, int B, int H, int W, cudaStream_t stream);
   int launches_per_forward() const { return cur_ ? cur_->launches : 0; }
   // Eager forward with a CUDA event pair around every op; fills ms[i] for op i (returns number of ops, <0 on error).
   int profile_forward(const float* x, const int64_t* t, float* eps, int Bc, int H, int W, cudaStream_t stream,
@@ -129,7 +137,8 @@ class Engine : public WeightLoader {
   std::string last_error;
 
  private:
-  int prepare(int Bc, int H, int W);
+  int prepare(int Bc, int H, int W, bool pair = false);
+  bool pair_plan_possible() const;
   int build(Prepared& P, bool dry);
 
   pbe_config cfg_;
@@ -151,7 +160,7 @@ class Engine : public WeightLoader {
   float* ctx_tmp_ = nullptr;
   int ctx_Bc_ = 0;
 
-  std::map<std::tuple<int, int, int>, std::unique_ptr<Prepared>> prepared_;
+  std::map<std::tuple<int, int, int, int>, std::unique_ptr<Prepared>> prepared_;
   Prepared* cur_ = nullptr;
   cudaStream_t cap_stream_ = nullptr;
 };

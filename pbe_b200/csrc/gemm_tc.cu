@@ -781,9 +781,10 @@ int gemm_split_k(const ConvGemmDesc& d) {
   if (d.mode != EPI_STD || d.Cout % 4 != 0 || d.epi_act != 0) return 1;   // the reduce kernel applies no activation
   int tw, th, tn;
   const int Wo = d.W / d.stride, Ho = d.H / d.stride;
-  pick_tile(Wo, Ho, d.Nb, &tw, &th, &tn);
+  const int nb = d.split_batch ? d.split_batch : d.Nb;
+  pick_tile(Wo, Ho, nb, &tw, &th, &tn);
   const int bn = auto_block_n(d);
-  const int tiles = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((d.Nb + tn - 1) / tn) * ((d.Cout + bn - 1) / bn);
+  const int tiles = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((nb + tn - 1) / tn) * ((d.Cout + bn - 1) / bn);
   const int k_iters = d.ksize * d.ksize * (d.C / 64);
   const int sms = num_sms();
   if (tiles * 2 > sms) return 1;

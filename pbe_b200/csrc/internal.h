@@ -144,6 +144,8 @@ struct ConvGemmDesc {
   int wt_ld;               // elements between consecutive output rows of `wt` (0 -> C; ksize 1 only)
   int vt_tokens;           // EPI_QKV over a flat [1,1,M,C] activation: tokens per sample (0: H*W and sample = n)
   int epi_act;             // EPI_STD: 0 none, 1 quick_gelu (applied after bias / rowbias, before the residual)
+  int split_batch;         // batch the split-K heuristic should assume (0 -> Nb): a CFG-pair prefix GEMM over B samples
+                           // must accumulate in the same order as the same layer over the full 2B batch
   int pad_end;             // stride-2 3x3 only: 1 = zero padding (0,1,0,1) as the VAE Downsample (model.py:74-76)
                            // instead of the symmetric padding 1 of the U-Net Downsample
 };

@@ -121,8 +121,11 @@ class _SamplerBase:
             raise RuntimeError("pbe_b200 samplers run on CUDA (sm_100a) only: no CPU fallback exists")
 
     def _model_eps(self, unet, x9_in, t_in, c_in, eps_out):
-        """U-Net evaluation on the (possibly CFG-doubled) batch."""
+        """U-Net evaluation on the (possibly CFG-doubled) batch.  On the fast path under CFG the input holds the B shared
+        samples once (see _build_input / _dup) and the engine evaluates the pair (UNetModel.run_cfg_pair)."""
         if unet is not None:
+            if eps_out.shape[0] == 2 * x9_in.shape[0]:
+                return unet.run_cfg_pair(x9_in, t_in[:x9_in.shape[0]], out=eps_out)
             return unet.run(x9_in, t_in, out=eps_out)
         return self.model.apply_model(x9_in, t_in, c_in).to(torch.float32).contiguous()
 
@@ -229,7 +232,8 @@ class PLMSSampler(_SamplerBase):
         _, C, H, W = img.shape
         if unet is not None:
             unet.set_context(c_in)
-        x9 = torch.empty((dup * b, C + z_inp.shape[1] + m_inp.shape[1], H, W), device=device, dtype=torch.float32)
+        in_dup = 1 if unet is not None else dup     # the engine takes the CFG pair's shared input once
+        x9 = torch.empty((in_dup * b, C + z_inp.shape[1] + m_inp.shape[1], H, W), device=device, dtype=torch.float32)
         eps_buf = torch.empty((dup * b, C, H, W), device=device, dtype=torch.float32)
         ts_dev = torch.as_tensor(np.ascontiguousarray(time_range), device=device, dtype=torch.int64)
         ts_all = ts_dev[:, None].expand(total_steps, dup * b).contiguous()   # one row per step, no per-step H2D
@@ -242,7 +246,7 @@ class PLMSSampler(_SamplerBase):
                 ts = ts_all[i, :b]
                 img_orig = self.model.q_sample(x0, ts)
                 img = (img_orig * mask + (1 - mask) * img).contiguous()
-            self._build_input(img, z_inp, m_inp, x9, dup)
+            self._build_input(img, z_inp, m_inp, x9, in_dup)
             eps = self._model_eps(unet, x9, ts_all[i], c_in, eps_buf)
             x_prev = torch.empty_like(img)
             pred_x0 = torch.empty_like(img)
@@ -250,7 +254,7 @@ class PLMSSampler(_SamplerBase):
             if len(old_eps) == 0:
                 # Pseudo Improved Euler (plms.py:230-235): provisional x_prev from e_t, second U-Net call at t_next
                 self._step_kernel(eps, b, cfg, unconditional_guidance_scale, 0, [], img, index, None, e_t, x_prev, None)
-                self._build_input(x_prev, z_inp, m_inp, x9, dup)
+                self._build_input(x_prev, z_inp, m_inp, x9, in_dup)
                 eps2 = self._model_eps(unet, x9, ts_all[min(i + 1, total_steps - 1)], c_in, eps_buf)
                 self._step_kernel(eps2, b, cfg, unconditional_guidance_scale, 4, [e_t], img, index, None, None,
                                   x_prev, pred_x0)
@@ -326,7 +330,8 @@ class DDIMSampler(_SamplerBase):
         _, C, H, W = img.shape
         if unet is not None:
             unet.set_context(c_in)
-        x9 = torch.empty((dup * b, C + z_inp.shape[1] + m_inp.shape[1], H, W), device=device, dtype=torch.float32)
+        in_dup = 1 if unet is not None else dup     # the engine takes the CFG pair's shared input once
+        x9 = torch.empty((in_dup * b, C + z_inp.shape[1] + m_inp.shape[1], H, W), device=device, dtype=torch.float32)
         eps_buf = torch.empty((dup * b, C, H, W), device=device, dtype=torch.float32)
         ts_dev = torch.as_tensor(np.ascontiguousarray(time_range), device=device, dtype=torch.int64)
         ts_all = ts_dev[:, None].expand(total_steps, dup * b).contiguous()
@@ -337,7 +342,7 @@ class DDIMSampler(_SamplerBase):
                 assert x0 is not None
                 img_orig = self.model.q_sample(x0, ts_all[i, :b])
                 img = (img_orig * mask + (1. - mask) * img).contiguous()
-            self._build_input(img, z_inp, m_inp, x9, dup)
+            self._build_input(img, z_inp, m_inp, x9, in_dup)
             eps = self._model_eps(unet, x9, ts_all[i], c_in, eps_buf)
             noise = None
             if self._coef["sigma"][index] != 0.0:

@@ -242,6 +242,27 @@ class UNetModel(nn.Module):
                                                     st), "pbe_unet_forward")
         return out
 
+    def run_cfg_pair(self, x: torch.Tensor, timesteps: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The CFG evaluation ``apply_model(cat([x]*2), cat([t]*2), cat([uc, c]))`` (plms.py:185-188) with x [B, in_ch, H, W]
+        and t [B] given once; the context (2B rows, unconditional first) comes from :meth:`set_context`.  Returns
+        eps [2B, out_ch, H, W], bit-identical to :meth:`run` on the duplicated batch: the layers in front of the first
+        cross-attention are evaluated once for the B shared samples (``pbe_unet_forward_cfg_pair``)."""
+        self._ensure_engine(x.device)
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected x of shape [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        x = x.detach().to(torch.float32).contiguous()
+        t = timesteps.detach().to(device=x.device, dtype=torch.int64).contiguous()
+        if t.shape[0] != x.shape[0]:
+            raise ValueError("timesteps batch != x batch")
+        B, _, H, W = x.shape
+        if out is None:
+            out = torch.empty((2 * B, self.out_channels, H, W), device=x.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pbe_unet_forward_cfg_pair(self._engine, x.data_ptr(), t.data_ptr(), out.data_ptr(), B,
+                                                             H, W, st), "pbe_unet_forward_cfg_pair")
+        return out
+
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """Same contract as the reference ``UNetModel.forward`` (openaimodel.py:852-889)."""
         if y is not None:

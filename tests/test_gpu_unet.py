@@ -321,3 +321,25 @@ def test_v1_ragged_batches_and_non_square_latents_vs_oracle_on_gpu(v1, dev, Bc, 
     # geometry robustness sweep on random inputs / timesteps (the parity bar proper, 1e-2, is held on the BASELINE
     # configurations above): the bf16-operand error of a single small-batch draw scatters around 0.9e-2 +- 10 %
     assert _rel(eps, ref) <= 1.2 * EPS_REL_L2, (Bc, h, w, _rel(eps, ref))
+
+
+@pytest.mark.parametrize("which", ["small", "v1"])
+def test_cfg_pair_plan_is_bit_identical_to_the_duplicated_batch(which, small, v1, dev):
+    """pbe_unet_forward_cfg_pair (layers in front of the first cross-attention evaluated once for the shared half of
+    the CFG batch) == pbe_unet_forward on cat([x]*2), cat([t]*2) with the same cat([uc, c]) context, bit for bit."""
+    cfg, sd, req, model = small if which == "small" else v1
+    unet = model.model.diffusion_model
+    B = req["x_T"].shape[0]
+    x9 = torch.cat((req["x_T"], req["z_inpaint"], req["mask"]), 1).to(dev)
+    c_in = torch.cat((req["uc"].expand(B, 1, 768), req["c"])).to(dev)
+    for tval in (981, 401):
+        t = torch.full((B,), tval, dtype=torch.int64, device=dev)
+        unet.set_context(c_in)
+        ref = unet.run(torch.cat([x9] * 2), torch.cat([t] * 2)).clone()
+        out = unet.run_cfg_pair(x9, t)
+        out2 = unet.run_cfg_pair(x9, t)          # graph replay
+        assert out.shape == ref.shape
+        assert torch.equal(out, ref), (which, tval, (out - ref).abs().max().item())
+        assert torch.equal(out2, ref)
+    # the two halves really differ (the context matters) and the plan launches fewer kernels' worth of work
+    assert not torch.equal(ref[:B], ref[B:])
