@@ -28,6 +28,10 @@ os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "WARN")   # keep std
 import torch
 
 F64_MIN = 771.3e9   # algorithmic FLOPs per sample-eval at 64x64 with the dead cross-attention work elided
+# FLOPs the CFG-pair plan does NOT execute, per sample-eval at 64x64: the layers in front of the first cross-attention
+# run once per (uncond, cond) pair -- conv_in 0.212 + first ResBlock 15.099 + proj_in 0.839 + qkv 2.517 + self-attention
+# 21.475 = 40.142 GFLOP per pair, i.e. half of that per sample-eval.  Only executed work is claimed below.
+F64_PAIR_SHARED = 40.142e9 / 2
 NCU_TRAFFIC_CONV1 = 43869440 + 36049152   # dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_conv1_pair_summary.txt)
 UNET_CALLS = 51     # PLMS-50: the first step evaluates twice (plms.py:230-235)
 
@@ -280,7 +284,10 @@ def main():
         "gpu_launches": launches * args.steps,
         "unet_step_ms": {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                          "cfg_batch": Bc, "floor_ms_at_sustained_peak": (Bc * flops_per_eval / (peaks["tf_sustained"] * 1e12) * 1e3) if flops_per_eval else None},
-        "tensor_utilisation_whole_job": {"achieved_tflops": (B * args.steps * 2 * calls * flops_per_eval / (total_ms / 1e3) / 1e12) if flops_per_eval else None,
+        "tensor_utilisation_whole_job": {"achieved_tflops": (B * args.steps * 2 * calls * (flops_per_eval - (F64_PAIR_SHARED if hw == 64 else 0.0))
+                                                             / (total_ms / 1e3) / 1e12) if flops_per_eval else None,
+                                         "note": "executed FLOPs only: the CFG-pair plan evaluates the layers in front of the "
+                                                 "first cross-attention once per (uncond, cond) pair",
                                          "peak_tflops_sustained": peaks["tf_sustained"], "peak_source": peaks["src"]},
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM conv / linear, tcgen05)",
                      "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
