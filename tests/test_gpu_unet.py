@@ -343,3 +343,24 @@ def test_cfg_pair_plan_is_bit_identical_to_the_duplicated_batch(which, small, v1
         assert torch.equal(out2, ref)
     # the two halves really differ (the context matters) and the plan launches fewer kernels' worth of work
     assert not torch.equal(ref[:B], ref[B:])
+
+
+def test_cfg_pair_entry_falls_back_when_no_attention_at_the_first_level(dev):
+    """With attention_resolutions that skip the first level the context enters later than the shared-prefix plan
+    handles: pbe_unet_forward_cfg_pair then runs the ordinary plan on the duplicated batch — same bits, vs the oracle too."""
+    from oracle import sampler_ref as S, unet_ref as U
+    cfg = dict(U.SMALL_CFG, attention_resolutions=(2, 4))
+    sd = U.make_state_dict(cfg, 5)
+    model = _make_model(cfg, sd, dev)
+    unet = model.model.diffusion_model
+    req = S.synthetic_request(2, 32, 32, seed=9)
+    x9 = torch.cat((req["x_T"], req["z_inpaint"], req["mask"]), 1).to(dev)
+    c_in = torch.cat((req["uc"].expand(2, 1, 768), req["c"])).to(dev)
+    t = torch.full((2,), 301, dtype=torch.int64, device=dev)
+    unet.set_context(c_in)
+    ref = unet.run(torch.cat([x9] * 2), torch.cat([t] * 2)).clone()
+    out = unet.run_cfg_pair(x9, t)
+    assert torch.equal(out, ref)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    orc = U.unet_forward(sd_dev, cfg, torch.cat([x9] * 2), torch.cat([t] * 2), c_in)
+    assert _rel(out, orc) <= SMALL_EPS_REL_L2
