@@ -33,6 +33,7 @@ struct AttnParams {
   int N, heads, d, dv, ksteps, C;
   float scale_log2;
   bf16* out;
+  int two_pass;   // flash_attn2_kernel: 1 = exact running maximum in every tile (PBE_ATTN_TWO_PASS=1), 0 = single-pass tiles
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -286,10 +287,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 // One CTA = one (sample, head, 256-query pair of tiles).  Softmax is MUFU(ex2)-bound at d = 40, so the point is to keep
 // two softmax warps resident per scheduler: warpgroup A works on S_A(j) while the tensor core produces S_B(j) and the
 // P·V products; K/V tiles are loaded once for both query tiles.
-// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) -- P (bf16 pairs) is the A
+// operand of P.V read straight from tensor memory: tcgen05.mma costs exactly its shared-memory operand bytes / 128 B/clk
+// (micro-benchmark, profiles/README.md), and with P staged in shared memory the tensor core's operand reads (1088 clk per
+// 256 x 128 tile pair), the softmax warps' P stores (512 clk) and the K/V TMA writes (224 clk) kept the shared-memory /
+// MIO path busier than the MUFU pipe they were queued behind (ncu: MUFU.EX2 stalled on mio_throttle, XU 61 %).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ATT2_THREADS = 64 + 2 * 256 + 32;   // 2 MMA warps, 2 warpgroups x 8 softmax warps, 1 TMA warp (19 warps: 104 regs)
-constexpr int ATT2_KV_STAGES = 2;
+constexpr int ATT2_KV_STAGES = 3;
+constexpr float ATT2_BIAS = 64.0f;    // single-pass tiles: exponentials are kept 2^-64 below the reference maximum
 
 // 128-key tiles, 256 queries per CTA, SIXTEEN softmax warps: every query row is shared by two threads (64 keys each),
 // so each scheduler always has four softmax warps to pick from.  Findings that shaped this (clock64 traces, ncu):
@@ -300,8 +306,8 @@ constexpr int ATT2_KV_STAGES = 2;
 //  * exponentials are computed in place first, sums / bf16 packing / stores afterwards.
 //  * S(j+1) = Q K^T is issued as soon as the softmax warps have READ S(j) for the last time (s_free), not when P(j) is
 //    published: the tensor-core round trip overlaps the exponentials of tile j instead of idling the warpgroup;
-//  * P is double-buffered in shared memory (per-buffer pv_done barriers): the exponentials of tile j never wait for
-//    P.V(j-1), only for P.V(j-2), which has long retired -- the softmax warps of BOTH warpgroups stay runnable;
+//  * P lives in tensor memory, one buffer per warpgroup: the first P store of tile j waits for P.V(j-1), which was
+//    issued a whole half-tile of exponentials earlier;
 //  * the K/V ring has its own warp, so neither MMA warp ever blocks on the other warpgroup's P.V.
 // warps: 0, 1 MMA issue for warpgroup 0, 1 | 2..9 softmax wg 0 | 10..17 softmax wg 1 | 18 Q / K / V TMA
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
@@ -318,21 +324,20 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const uint32_t sQ = smem_base;                          // 2 query tiles
   const uint32_t sK = sQ + 2 * CHUNK_BYTES;               // ATT2_KV_STAGES stages
   const uint32_t sV = sK + ATT2_KV_STAGES * CHUNK_BYTES;  // ATT2_KV_STAGES stages
-  const uint32_t sP = sV + ATT2_KV_STAGES * V_STAGE_BYTES;  // [2 warpgroups][2 buffers][2 chunks]
-  const uint32_t sX = sP + 8 * CHUNK_BYTES;               // row-max / row-sum exchange: [2 wg][2 halves][128] floats
+  const uint32_t sX = sV + ATT2_KV_STAGES * V_STAGE_BYTES;  // row-max / row-sum exchange: [2 wg][2 halves][128] floats
   const uint32_t sBar = sX + 2 * 2 * 128 * 4;
   uint8_t* bar_gen = smem_gen + (sBar - smem_base);
-  uint8_t* p_gen = smem_gen + (sP - smem_base);
   float* x_gen = reinterpret_cast<float*>(smem_gen + (sX - smem_base));
+  constexpr int ST = ATT2_KV_STAGES;
   const uint32_t q_full = sBar;
   auto kv_full = [&](int s) { return sBar + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return sBar + 8u * (3 + s); };
-  auto s_full = [&](int g) { return sBar + 8u * (5 + g); };
-  auto p_full = [&](int g) { return sBar + 8u * (7 + g); };
-  auto pv_done = [&](int g, int buf) { return sBar + 8u * (9 + g * 2 + buf); };  // P.V of the tiles using P buffer `buf`
-  auto s_free = [&](int g) { return sBar + 8u * (13 + g); };
-  const uint32_t tmem_ptr_addr = sBar + 8u * 15;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 15);
+  auto kv_empty = [&](int s) { return sBar + 8u * (1 + ST + s); };
+  auto s_full = [&](int g) { return sBar + 8u * (1 + 2 * ST + g); };
+  auto p_full = [&](int g) { return sBar + 8u * (3 + 2 * ST + g); };
+  auto pv_done = [&](int g, int par) { return sBar + 8u * (5 + 2 * ST + g * 2 + par); };  // P.V of the even / odd tiles
+  auto s_free = [&](int g) { return sBar + 8u * (9 + 2 * ST + g); };
+  const uint32_t tmem_ptr_addr = sBar + 8u * (11 + 2 * ST);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (11 + 2 * ST));
 
   const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
@@ -376,6 +381,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const uint64_t qdesc = umma_desc_sw128(sQ + g * CHUNK_BYTES);
     const uint32_t tmem_S = tmem_base + g * 128;
     const uint32_t tmem_O = tmem_base + 256 + g * 64;
+    const uint32_t tmem_P = tmem_base + 384 + g * 64;
     auto issue_qk = [&](int j) {
       const uint64_t kdesc = umma_desc_sw128(sK + (j % ATT2_KV_STAGES) * CHUNK_BYTES);
       for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16_ss_elect(tmem_S, qdesc + 2u * ks, kdesc + 2u * ks, idesc_qk, ks > 0 ? 1u : 0u);
@@ -394,14 +400,13 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         tc_fence_after();
         issue_qk(j + 1);
       }
-      mbar_wait(p_full(g), j & 1);      // P(j) is in shared memory
+      mbar_wait(p_full(g), j & 1);      // P(j) is in tensor memory
       tc_fence_after();
       {
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
-          const uint64_t pdesc = umma_desc_sw128(sP + ((g * 2 + (j & 1)) * 2 + (ks >> 2)) * CHUNK_BYTES) + 2u * (ks & 3);
           const uint64_t vdesc = umma_desc_sw128(sV + st * V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
-          umma_bf16_ss_elect(tmem_O, pdesc, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16_ts_elect(tmem_O, tmem_P + 8u * ks, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit_elect(pv_done(g, j & 1));
         umma_commit_elect(kv_empty(st));
@@ -433,13 +438,21 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tmem_S = tmem_base + g * 128 + sub * 64;
     const uint32_t tmem_O = tmem_base + 256 + g * 64;
-    uint8_t* prow0 = p_gen + (g * 4 + sub) * CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128;  // P buffer 0
+    const uint32_t tmem_P = tmem_base + 384 + g * 64 + sub * 32;   // my 64 keys of the row = 32 columns of bf16 pairs
+    // bf16 P -> tensor memory (A operand of P.V): 32 exponentials -> 16 columns
+    auto store_p = [&](const uint32_t (&v)[32], int h) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      tmem_st_x16(tmem_P + lane_off + h * 16, pk);
+    };
     float* xmine = x_gen + (g * 2 + sub) * 128 + row;
     float* xpeer = x_gen + (g * 2 + (sub ^ 1)) * 128 + row;
     const int bar_id = 1 + g;
     float m_run = -INFINITY;   // reference maximum used by the exponentials (lazy)
     float l_run = 0.0f;        // partial row sum over this thread's columns
     const float sl2 = p.scale_log2;
+    const float bias = p.two_pass ? 0.0f : ATT2_BIAS;
 
     auto tile = [&](int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
@@ -491,11 +504,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           tmem_st_wait();
         }
       }
-      const float mneg = -m_run * sl2;
-      // P buffer j & 1 was last read by P.V of tile j-2
-      if (j > 1) mbar_wait(pv_done(g, j & 1), ((j >> 1) & 1) ^ 1u);
-      uint8_t* prow = prow0 + (j & 1) * (2 * CHUNK_BYTES);
-      // pass 2: exponentials, partial row sum, bf16 P -> shared memory (chunk `sub`, K-major, 128B swizzle)
+      const float mneg = fmaf(-m_run, sl2, -bias);
+      // pass 2: exponentials, partial row sum, bf16 P -> tensor memory
       float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -521,24 +531,132 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           sum1 += __uint_as_float(v[c + 1]) + __uint_as_float(v[c + 5]);
           sum2 += __uint_as_float(v[c + 2]) + __uint_as_float(v[c + 6]);
           sum3 += __uint_as_float(v[c + 3]) + __uint_as_float(v[c + 7]);
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
-          pk.y = pack_bf16x2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-          pk.z = pack_bf16x2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
-          pk.w = pack_bf16x2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
-          const int u = (h * 32 + c) >> 3;
-          *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = pk;
         }
+        if (h == 0 && j > 0) {   // P is single-buffered: P.V(j-1) must have read it
+          mbar_wait(pv_done(g, (j - 1) & 1), ((j - 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        store_p(v, h);
       }
       l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
-      fence_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(g));
+    };
+    // ---- single-pass tiles (every tile but the first) ----
+    // The exponentials of tile j do not need the maximum of tile j: any reference works as long as nothing overflows, and
+    // the softmax warps are bound by their instruction count (ncu: 6.5 issued instructions per exponential in the two-pass
+    // loop -- at the MUFU rate of one warp-instruction per 8 clk and four warps per scheduler that is 82 % of all issue
+    // slots).  Tile 0 takes the exact row maximum (two passes, above).  Later tiles read S ONCE and spend ~2.5 math
+    // instructions per exponential: FFMA2 (two logits), MUFU.EX2, FADD2 (two sums), F2FP (two bf16) -- and no maximum at all:
+    //  * the row sum of a tile bounds its maximum: max <= log2(sum) <= max + 7.  The sum is needed anyway, so the reference
+    //    follows  ref(tile) + ATT2_BIAS + log2(row sum of the tile)  and only moves when that exceeds it by 2^8.
+    //  * exchange: a row is shared by two threads (64 keys each).  At the start of tile j a thread publishes the bf16-rounded
+    //    sum over ITS columns of tile j-1 and reads its partner's sum of tile j-2; both add the same two rounded numbers, so
+    //    both take the same decision.  Ordering comes from the S hand-off that already exists: a partner's slot of tile j-2
+    //    was written before it arrived on s_free(j-1), which precedes S(j) and so my s_full(j) wait; the slot is rewritten
+    //    (tile j) only after s_full(j+1), i.e. after my s_free(j) arrive, which follows my read.
+    //  * range: values are kept ATT2_BIAS powers of two below 1 (the common factor cancels in O / l): a logit may exceed every
+    //    key of the tiles up to j-2 by (127 + ATT2_BIAS) / log2(e) = 132 nats before fp32 overflows (the output row is then
+    //    NaN, not silently wrong; fp32 softmax is a one-hot long before that), and terms 2^-55 below the maximum still count.
+    //    PBE_ATTN_TWO_PASS=1 selects the exact running maximum for every tile.
+    //  * both halves of S(j) are loaded before the first exponential, so the tensor core gets s_free(j) -- and produces
+    //    S(j+1) -- a whole tile of exponentials ahead of its use.
+    float mrs = 0.0f;                    // reference maximum in log2 units
+    float sm1 = 0.0f, sm2 = 0.0f;        // bf16-rounded sums over my columns of tiles j-1 and j-2 ...
+    float rf1 = 0.0f, rf2 = 0.0f;        // ... and the references those tiles were computed against
+    // [2 wg][2 slots][2 halves][128] bf16: a warpgroup's slots alias ITS OWN 1 KB of xmine / xpeer (tile 0, final row sums),
+    // whose uses are ordered against the slots by the warpgroup's own barriers -- the two warpgroups run unsynchronised
+    uint16_t* xs16 = reinterpret_cast<uint16_t*>(x_gen);
+    const f32x2 sl2_2 = pk2(sl2, sl2);
+    auto tile1p = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      mbar_wait(s_full(g), j & 1);
+      tc_fence_after();
+      float alpha = 1.0f;
+      if (j >= 2) {
+        xs16[((g * 2 + ((j - 1) & 1)) * 2 + sub) * 128 + row] = __bfloat16_as_ushort(__float2bfloat16_rn(sm1));
+        if (j >= 3) {
+          const float peer = __bfloat162float(__ushort_as_bfloat16(xs16[((g * 2 + (j & 1)) * 2 + (sub ^ 1)) * 128 + row]));
+          const float est = rf2 + ATT2_BIAS + __log2f(sm2 + peer);   // >= the row maximum of tile j-2, by at most 7
+          if (__any_sync(0xffffffffu, est - mrs > 8.0f)) {
+            const float m_new = fmaxf(mrs, est);
+            alpha = ex2(mrs - m_new);
+            mrs = m_new;
+            if (sub == 0) {
+              mbar_wait(pv_done(g, (j - 1) & 1), ((j - 1) >> 1) & 1);
+              tc_fence_after();
+              for (int c = 0; c < p.dv; c += 16) {
+                uint32_t o[16];
+                tmem_ld_x16(tmem_O + lane_off + c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_x16(tmem_O + lane_off + c, o);
+              }
+              tmem_st_wait();
+            }
+          }
+        }
+      }
+      const float mneg = -mrs - ATT2_BIAS;
+      const f32x2 mneg_2 = pk2(mneg, mneg);
+      f32x2 acc0 = pk2(0.0f, 0.0f), acc1 = acc0;
+      auto half = [&](uint32_t (&v)[32], int h) {
+        if (MASKED) {
+          const int kvalid = p.N - j * KT - sub * 64 - h * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= kvalid) v[i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0, x1;
+          upk2(fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2_2, mneg_2), x0, x1);
+          v[i] = __float_as_uint(ex2(x0));
+          v[i + 1] = __float_as_uint(ex2(x1));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          acc0 = add2(acc0, pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          acc1 = add2(acc1, pk2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        }
+        if (h == 0) {   // P is single-buffered: P.V(j-1) must have read it (j >= 1 here)
+          mbar_wait(pv_done(g, (j - 1) & 1), ((j - 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        store_p(v, h);
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld_x32x2_wait(tmem_S + lane_off, tmem_S + lane_off + 32, va, vb);
+      tc_fence_before();                         // last read of S(j): the tensor core may start S(j+1)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(g));
+      half(va, 0);
+      half(vb, 1);
+      float t0, t1, t2, t3;
+      upk2(acc0, t0, t1);
+      upk2(acc1, t2, t3);
+      const float tsum = (t0 + t1) + (t2 + t3);
+      l_run = l_run * alpha + tsum;
+      sm2 = sm1; rf2 = rf1;
+      sm1 = __bfloat162float(__float2bfloat16_rn(tsum)); rf1 = mrs;
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(g));
     };
     const int T_full = p.N / KT;
-    for (int j = 0; j < T_full; ++j) tile(j, std::false_type{});
-    if (T_full < T) tile(T_full, std::true_type{});
+    if (p.two_pass) {
+      for (int j = 0; j < T_full; ++j) tile(j, std::false_type{});
+      if (T_full < T) tile(T_full, std::true_type{});
+    } else {
+      tile(0, std::false_type{});          // N > 128 here: the first tile is always full
+      mrs = m_run * sl2;
+      for (int j = 1; j < T_full; ++j) tile1p(j, std::false_type{});
+      if (T_full < T) tile1p(T_full, std::true_type{});
+    }
 
     // combine the two partial row sums, then the `sub == 0` thread of each row writes O / l
     named_bar_sync(bar_id, 256);   // all reads of the max-exchange slots are done
@@ -578,7 +696,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 }
 
 constexpr size_t ATT2_SMEM = 2 * CHUNK_BYTES + ATT2_KV_STAGES * CHUNK_BYTES + ATT2_KV_STAGES * (2 * 64 * 128) +
-                             8 * CHUNK_BYTES + 2048 + 8 * 16;
+                             2048 + 8 * (12 + 2 * ATT2_KV_STAGES);
 
 int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
@@ -595,6 +713,8 @@ int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   p.C = plan.heads * plan.d;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
+  static const int two_pass = [] { const char* e = getenv("PBE_ATTN_TWO_PASS"); return (e && atoi(e) != 0) ? 1 : 0; }();
+  p.two_pass = two_pass;
   dim3 grid((plan.N + 2 * QT - 1) / (2 * QT), plan.heads, plan.B);
   PBE_CHECK_CUDA(launch_k(flash_attn2_kernel, dim3(grid), dim3(ATT2_THREADS), ATT2_SMEM, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
@@ -624,6 +744,7 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   p.C = plan.heads * plan.d;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
+  p.two_pass = 1;
   PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -183,6 +183,47 @@ def test_self_attention_matches_softmax_reference(lib, B, N, heads, d):
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("N,d,heads,drift", [(4096, 40, 8, 12.0), (4096, 40, 8, 45.0), (1035, 40, 8, 40.0),
+                                             (257, 64, 16, 30.0), (2048, 64, 4, -50.0), (4096, 40, 8, 3.0),
+                                             (4096, 40, 8, 1.0), (1035, 40, 8, 1.5), (2048, 64, 4, 2.0)])
+def test_self_attention_drifting_maximum(lib, N, d, heads, drift):
+    """The single-pass tiles of flash_attn2_kernel take their reference maximum two key tiles late: logits that climb
+    (or fall) by `drift` nats per 128 keys exercise the stale reference, the lazy rescale of O (small drifts: the old
+    contributions still matter after a rescale, so a wrong rescale factor shows) and the headroom
+    (ATT2_BIAS) without reaching the documented saturation bound (a logit 111 nats above every key of the tiles up to
+    j-2, i.e. a sustained climb of > 55 nats per 128 keys).  Same softmax as attention.py:217-229."""
+    dev = torch.device("cuda:0")
+    B = 1
+    g = torch.Generator().manual_seed(7 + N + d)
+    C = heads * d
+    q = torch.randn(B, N, heads, d, generator=g)
+    k = torch.randn(B, N, heads, d, generator=g) * 0.5
+    # one direction per head carries a ramp over the key index: q.k * d^-1/2 gains `drift` nats per 128 keys
+    u = torch.nn.functional.normalize(torch.randn(heads, d, generator=g), dim=-1)
+    q = q - (q * u).sum(-1, keepdim=True) * u + 4.0 * u           # every query has component 4 along u
+    ramp = torch.arange(N, dtype=torch.float32) / 128.0 * drift * math.sqrt(d) / 4.0
+    k = k - (k * u).sum(-1, keepdim=True) * u + ramp.view(1, N, 1, 1) * u
+    q = q.reshape(B, N, C).to(dev).bfloat16()
+    k = k.reshape(B, N, C).to(dev).bfloat16()
+    v = torch.randn(B, N, C, generator=g).to(dev).bfloat16()
+    qk = torch.cat((q, k), dim=-1).contiguous()
+    Np = (N + 7) // 8 * 8
+    vt = torch.zeros(B, C, Np, device=dev, dtype=torch.bfloat16)
+    vt[:, :, :N] = v.transpose(1, 2)
+    out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
+    rc = lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, _stream())
+    assert rc == 0, _err(lib)
+    torch.cuda.synchronize()
+
+    def split(t):
+        return t.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+
+    sim = torch.einsum("bhid,bhjd->bhij", split(q), split(k)) * d ** -0.5
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), split(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Nb,HW,C0,C1,eps,silu", [(2, 4096, 320, 0, 1e-5, 1), (2, 1024, 640, 320, 1e-5, 1),
                                                   (2, 256, 1280, 640, 1e-5, 1), (3, 64, 1280, 1280, 1e-5, 1),
