@@ -42,6 +42,20 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// O[lane, 0:dv) *= alpha in tensor memory.  Deliberately NOT inlined: it runs in the rare "reference moved" branch of the
+// softmax loops, and as a call its register needs (and the spills around it) stay inside that branch.
+__device__ __noinline__ void rescale_o_rows(uint32_t taddr, int dv, float alpha) {
+  for (int c = 0; c < dv; c += 16) {
+    uint32_t o[16];
+    tmem_ld_x16(taddr + c, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st_x16(taddr + c, o);
+  }
+  tmem_st_wait();
+}
+
 template <int DK_CHUNKS, int KV_STAGES>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
@@ -493,15 +507,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         if (j > 0 && sub == 0) {
           mbar_wait(pv_done(g, (j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
-          for (int c = 0; c < p.dv; c += 16) {
-            uint32_t o[16];
-            tmem_ld_x16(tmem_O + lane_off + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(tmem_O + lane_off + c, o);
-          }
-          tmem_st_wait();
+          rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
         }
       }
       const float mneg = fmaf(-m_run, sl2, -bias);
@@ -568,17 +574,25 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     float rf1 = 0.0f, rf2 = 0.0f;        // ... and the references those tiles were computed against
     // [2 wg][2 slots][2 halves][128] bf16: a warpgroup's slots alias ITS OWN 1 KB of xmine / xpeer (tile 0, final row sums),
     // whose uses are ordered against the slots by the warpgroup's own barriers -- the two warpgroups run unsynchronised
-    uint16_t* xs16 = reinterpret_cast<uint16_t*>(x_gen);
+    const uint32_t xs_mine = sX + (((g * 2 + 0) * 2 + sub) * 128 + row) * 2;        // slot s: + s * 512 bytes
+    const uint32_t xs_peer = sX + (((g * 2 + 0) * 2 + (sub ^ 1)) * 128 + row) * 2;
     const f32x2 sl2_2 = pk2(sl2, sl2);
     auto tile1p = [&](int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       mbar_wait(s_full(g), j & 1);
       tc_fence_after();
+      uint32_t va[32], vb[32];
+      tmem_ld_x32(tmem_S + lane_off, va);        // in flight during the exchange below
+      tmem_ld_x32(tmem_S + lane_off + 32, vb);
       float alpha = 1.0f;
       if (j >= 2) {
-        xs16[((g * 2 + ((j - 1) & 1)) * 2 + sub) * 128 + row] = __bfloat16_as_ushort(__float2bfloat16_rn(sm1));
+        // sm1 is already bf16-rounded: its upper half is the bf16 pattern (shared-space accesses: no generic address math)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(xs_mine + (((j - 1) & 1) << 9)),
+                     "h"(static_cast<unsigned short>(__float_as_uint(sm1) >> 16)) : "memory");
         if (j >= 3) {
-          const float peer = __bfloat162float(__ushort_as_bfloat16(xs16[((g * 2 + (j & 1)) * 2 + (sub ^ 1)) * 128 + row]));
+          unsigned short peer_bits;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(peer_bits) : "r"(xs_peer + ((j & 1) << 9)) : "memory");
+          const float peer = __uint_as_float(static_cast<uint32_t>(peer_bits) << 16);
           const float est = rf2 + ATT2_BIAS + __log2f(sm2 + peer);   // >= the row maximum of tile j-2, by at most 7
           if (__any_sync(0xffffffffu, est - mrs > 8.0f)) {
             const float m_new = fmaxf(mrs, est);
@@ -587,15 +601,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
             if (sub == 0) {
               mbar_wait(pv_done(g, (j - 1) & 1), ((j - 1) >> 1) & 1);
               tc_fence_after();
-              for (int c = 0; c < p.dv; c += 16) {
-                uint32_t o[16];
-                tmem_ld_x16(tmem_O + lane_off + c, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st_x16(tmem_O + lane_off + c, o);
-              }
-              tmem_st_wait();
+              rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
             }
           }
         }
@@ -628,8 +634,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         }
         store_p(v, h);
       };
-      uint32_t va[32], vb[32];
-      tmem_ld_x32x2_wait(tmem_S + lane_off, tmem_S + lane_off + 32, va, vb);
+      tmem_ld_wait_x32x2(va, vb);
       tc_fence_before();                         // last read of S(j): the tensor core may start S(j+1)
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(g));
