@@ -7,8 +7,9 @@
 //
 // flash_attn_kernel (head dims > 64, short sequences): one CTA = one (sample, head, 128-query tile).  warp 0: TMA
 // producer; warp 1: MMA issuer; warps 2..5: softmax (one query row per thread).  S = Q K^T lands in a double-buffered
-// 128x128 fp32 TMEM tile, the softmax warps read it with tcgen05.ld, keep running max / sum in registers, write P
-// (bf16) into 128B-swizzled shared memory, and the MMA warp accumulates O += P V into a third TMEM region.
+// 128x128 fp32 TMEM tile, the softmax warps read it with tcgen05.ld, keep the reference maximum / row sum in registers,
+// write P (bf16 pairs) into a fourth TMEM region, and the MMA warp accumulates O += P V (A operand from tensor memory)
+// into a third.  TMEM: S0 [0,128) S1 [128,256) O [256, 256+dv <= 416) P [448,512).
 // flash_attn2_kernel (head dims <= 64, the 64x64-latent level): 256 queries per CTA, 19 warps -- see its comment.
 // Q and K come from the fused projection output [B, N, 2C];
 // V arrives transposed ([B, C, N], written by the projection GEMM's epilogue) so both MMAs take K-major operands.
@@ -28,6 +29,7 @@ constexpr int ATT_THREADS = 192;
 constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 128;   // keys per tile
 constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr float ATT2_BIAS = 64.0f;      // single-pass tiles: exponentials are kept 2^-64 below the reference maximum
 
 struct AttnParams {
   int N, heads, d, dv, ksteps, C;
@@ -69,10 +71,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   const uint32_t sQ = smem_base;
   const uint32_t sK = sQ + DK_CHUNKS * CHUNK_BYTES;                     // KV_STAGES x DK_CHUNKS chunks
   const uint32_t sV = sK + KV_STAGES * DK_CHUNKS * CHUNK_BYTES;         // KV_STAGES x 2 chunks of (dv x 64)
-  const uint32_t sP = sV + KV_STAGES * 2 * 160 * 128;                   // 2 chunks of (128 x 64); V region sized for dv<=160
-  const uint32_t sBar = sP + 2 * CHUNK_BYTES;
+  const uint32_t sBar = sV + KV_STAGES * 2 * 160 * 128;                 // V region sized for dv <= 160
   uint8_t* bar_gen = smem_gen + (sBar - smem_base);
-  uint8_t* p_gen = smem_gen + (sP - smem_base);
 
   const uint32_t q_full = sBar;
   auto k_full = [&](int s) { return sBar + 8u * (1 + s); };
@@ -169,9 +169,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       {
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
-          const uint64_t adesc = umma_desc_sw128(sP + (ks >> 2) * CHUNK_BYTES) + 2u * (ks & 3);
           const uint64_t bdesc = umma_desc_sw128(sV + st * 2 * 160 * 128 + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
-          umma_bf16_ss_elect(tmem_O, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16_ts_elect(tmem_O, tmem_base + 448 + 8u * ks, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit_elect(kv_empty(st));
         umma_commit_elect(pv_done);
@@ -181,12 +180,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     }
   } else {
     // ================= softmax / correction / output (warps 2..5) =================
+    // One query row per thread, all 128 logits of the tile in registers.  As in flash_attn2_kernel (see there): the exact
+    // row maximum is taken for tile 0 only; later tiles use a reference that follows  ref + ATT2_BIAS + log2(row sum)  of
+    // the previous tile (an upper bound of its maximum, by at most 7) and only moves when that exceeds it by 2^8 -- no
+    // maximum pass, O is rescaled (and the tensor core waited for) only then; FFMA2 / FADD2 packed math; bf16 P goes to
+    // tensor memory and is the A operand of P.V (no shared-memory round trip).
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_run = -INFINITY;  // running max of raw scores
+    const uint32_t tmem_P = tmem_base + 448;
+    float mrs = 0.0f;         // reference maximum, log2 units
     float l_run = 0.0f;
+    float sm1 = 0.0f, rf1 = 0.0f;   // row sum of the previous tile and the reference it was computed against
     const float sl2 = p.scale_log2;
+    const f32x2 sl2_2 = pk2(sl2, sl2);
 
     for (int j = 0; j < T; ++j) {
       const int sb = j & 1;
@@ -206,60 +213,63 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       if (lane == 0) mbar_arrive(s_free(sb));
 
       const int kvalid = p.N - j * KT;  // keys valid in this tile
-      float mx = m_run;
-      if (kvalid >= KT) {
+      if (kvalid < KT) {
 #pragma unroll
-        for (int i = 0; i < KT; ++i) mx = fmaxf(mx, s[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < KT; ++i) {
+        for (int i = 0; i < KT; ++i)
           if (i >= kvalid) s[i] = -INFINITY;
-          mx = fmaxf(mx, s[i]);
+      }
+      float alpha = 1.0f;
+      if (j == 0) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < KT; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+          mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+        }
+        mrs = fmaxf(mx0, mx1) * sl2;
+      } else {
+        const float est = rf1 + ATT2_BIAS + __log2f(sm1);
+        if (__any_sync(0xffffffffu, est - mrs > 8.0f)) {
+          const float m_new = fmaxf(mrs, est);
+          alpha = ex2(mrs - m_new);
+          mrs = m_new;
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
         }
       }
-      const float alpha = ex2((m_run - mx) * sl2);  // first tile: ex2(-inf) = 0
-      const float mneg = -mx * sl2;
-      float sum = 0.0f;
+      const float mneg = -mrs - ATT2_BIAS;
+      const f32x2 mneg_2 = pk2(mneg, mneg);
+      f32x2 acc0 = pk2(0.0f, 0.0f), acc1 = acc0;
 #pragma unroll
-      for (int i = 0; i < KT; ++i) {
-        s[i] = ex2(fmaf(s[i], sl2, mneg));
-        sum += s[i];
+      for (int i = 0; i < KT; i += 4) {
+        float x0, x1, x2, x3;
+        upk2(fma2(pk2(s[i], s[i + 1]), sl2_2, mneg_2), x0, x1);
+        upk2(fma2(pk2(s[i + 2], s[i + 3]), sl2_2, mneg_2), x2, x3);
+        s[i] = ex2(x0); s[i + 1] = ex2(x1); s[i + 2] = ex2(x2); s[i + 3] = ex2(x3);
+        acc0 = add2(acc0, pk2(s[i], s[i + 1]));
+        acc1 = add2(acc1, pk2(s[i + 2], s[i + 3]));
       }
-      l_run = l_run * alpha + sum;
-      m_run = mx;
+      float t0, t1, t2, t3;
+      upk2(acc0, t0, t1);
+      upk2(acc1, t2, t3);
+      const float tsum = (t0 + t1) + (t2 + t3);
+      l_run = l_run * alpha + tsum;
+      sm1 = tsum;
+      rf1 = mrs;
 
-      if (j > 0) {
-        // previous PV must have landed before O is rescaled and before P is overwritten
+      if (j > 0) {   // P is single-buffered: P.V(j-1) must have read it
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          for (int c = 0; c < p.dv; c += 16) {
-            uint32_t o[16];
-            tmem_ld_x16(tmem_O + lane_off + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(tmem_O + lane_off + c, o);
-          }
-          tmem_st_wait();
-        }
       }
-      // P -> shared memory, K-major, 128B swizzle (16-byte unit index XOR row%8)
-      {
-        uint8_t* prow = p_gen + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-        for (int c = 0; c < KT; c += 8) {
-          uint4 pk;
-          pk.x = pack_bf16x2(s[c + 0], s[c + 1]);
-          pk.y = pack_bf16x2(s[c + 2], s[c + 3]);
-          pk.z = pack_bf16x2(s[c + 4], s[c + 5]);
-          pk.w = pack_bf16x2(s[c + 6], s[c + 7]);
-          const int chunk = c >> 6;
-          const int u = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((u ^ (row & 7)) << 4)) = pk;
-        }
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[c + 2 * i], s[c + 2 * i + 1]);
+        tmem_st_x16(tmem_P + lane_off + (c >> 1), pk);
       }
-      fence_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -309,7 +319,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ATT2_THREADS = 64 + 2 * 256 + 32;   // 2 MMA warps, 2 warpgroups x 8 softmax warps, 1 TMA warp (19 warps: 104 regs)
 constexpr int ATT2_KV_STAGES = 3;
-constexpr float ATT2_BIAS = 64.0f;    // single-pass tiles: exponentials are kept 2^-64 below the reference maximum
 
 // 128-key tiles, 256 queries per CTA, SIXTEEN softmax warps: every query row is shared by two threads (64 keys each),
 // so each scheduler always has four softmax warps to pick from.  Findings that shaped this (clock64 traces, ncu):
@@ -729,7 +738,7 @@ int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
 template <int DK_CHUNKS, int KV_STAGES>
 constexpr size_t attn_smem_bytes() {
   return 1024 + DK_CHUNKS * CHUNK_BYTES + KV_STAGES * DK_CHUNKS * CHUNK_BYTES + KV_STAGES * 2 * 160 * 128 +
-         2 * CHUNK_BYTES + 8 * (8 + 3 * KV_STAGES);
+         8 * (8 + 3 * KV_STAGES);
 }
 
 template <int DK_CHUNKS, int KV_STAGES>

@@ -185,9 +185,12 @@ def test_self_attention_matches_softmax_reference(lib, B, N, heads, d):
 
 @pytest.mark.parametrize("N,d,heads,drift", [(4096, 40, 8, 12.0), (4096, 40, 8, 45.0), (1035, 40, 8, 40.0),
                                              (257, 64, 16, 30.0), (2048, 64, 4, -50.0), (4096, 40, 8, 3.0),
-                                             (4096, 40, 8, 1.0), (1035, 40, 8, 1.5), (2048, 64, 4, 2.0)])
+                                             (4096, 40, 8, 1.0), (1035, 40, 8, 1.5), (2048, 64, 4, 2.0),
+                                             (1024, 80, 8, 2.0), (1024, 80, 8, 30.0), (2304, 80, 8, -40.0),
+                                             (256, 160, 8, 3.0), (576, 160, 8, 25.0), (1024, 16, 8, 4.0)])
 def test_self_attention_drifting_maximum(lib, N, d, heads, drift):
-    """The single-pass tiles of flash_attn2_kernel take their reference maximum two key tiles late: logits that climb
+    """The single-pass tiles of flash_attn2_kernel (d <= 64) take their reference maximum two key tiles late, those of
+    flash_attn_kernel (d = 80, 160) one tile late: logits that climb
     (or fall) by `drift` nats per 128 keys exercise the stale reference, the lazy rescale of O (small drifts: the old
     contributions still matter after a rescale, so a wrong rescale factor shows) and the headroom
     (ATT2_BIAS) without reaching the documented saturation bound (a logit 111 nats above every key of the tiles up to

@@ -7,7 +7,7 @@ lib = _lib.load()
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-N, heads, d = 4096, 8, 40
+N, heads, d = (int(a) for a in sys.argv[2:5]) if len(sys.argv) > 4 else (4096, 8, 40)
 C = heads * d
 qk = torch.randn(B, N, 2 * C, device=dev).bfloat16()
 vt = torch.randn(B, C, N, device=dev).bfloat16()
