@@ -317,7 +317,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 // 256 x 128 tile pair), the softmax warps' P stores (512 clk) and the K/V TMA writes (224 clk) kept the shared-memory /
 // MIO path busier than the MUFU pipe they were queued behind (ncu: MUFU.EX2 stalled on mio_throttle, XU 61 %).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int ATT2_THREADS = 64 + 2 * 256 + 32;   // 2 MMA warps, 2 warpgroups x 8 softmax warps, 1 TMA warp (19 warps: 104 regs)
+// warps 0..15 softmax (two warpgroups of eight), 16 / 17 MMA issue, 18 Q / K / V TMA, 19 idle: the service warps form a
+// hardware warpgroup of their own, give most of their registers back (setmaxnreg.dec) and the softmax warps take them
+// (setmaxnreg.inc): at the 96 registers the launch grants 20 warps, the softmax loop (64 logits of S live per thread) spilled
+// its loop state and recomputed its addresses every tile -- 40 % of its instructions (ncu, profiles/r01_ncu_attn2_v5).
+constexpr int ATT2_THREADS = 640;
+constexpr int ATT2_SOFTMAX_REGS = 104, ATT2_SERVICE_REGS = 32;
 constexpr int ATT2_KV_STAGES = 3;
 
 // 128-key tiles, 256 queries per CTA, SIXTEEN softmax warps: every query row is shared by two threads (64 keys each),
@@ -332,7 +337,7 @@ constexpr int ATT2_KV_STAGES = 3;
 //  * P lives in tensor memory, one buffer per warpgroup: the first P store of tile j waits for P.V(j-1), which was
 //    issued a whole half-tile of exponentials earlier;
 //  * the K/V ring has its own warp, so neither MMA warp ever blocks on the other warpgroup's P.V.
-// warps: 0, 1 MMA issue for warpgroup 0, 1 | 2..9 softmax wg 0 | 10..17 softmax wg 1 | 18 Q / K / V TMA
+// warps: 0..7 softmax wg 0 | 8..15 softmax wg 1 | 16, 17 MMA issue for wg 0, 1 | 18 Q / K / V TMA | 19 idle
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ AttnParams p) {
@@ -369,7 +374,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const int b = blockIdx.z;
   const int T = (p.N + KT - 1) / KT;
 
-  if (warp == 1 && lane == 0) {
+  if (warp == 17 && lane == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
@@ -386,7 +391,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 16) {
     tmem_alloc(tmem_ptr_addr, 512);
     tmem_relinquish();
   }
@@ -396,9 +401,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
   griddep_wait();   // PDL: the prologue above overlapped the previous kernel; no dependent global access before this
 
-  if (warp <= 1) {
+  // setmaxnreg sits at the top of each role's branch (ptxas bounds the code it dominates); all four warps of the service
+  // warpgroup execute the .dec
+  if (warp == 16 || warp == 17) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
     // ================= MMA issue for warpgroup g (uniform code, elect.sync issues) =================
-    const int g = warp;
+    const int g = warp - 16;
     const uint32_t idesc_qk = umma_idesc_bf16(128, KT);
     const uint32_t idesc_pv = umma_idesc_bf16(128, p.dv);
     const uint64_t qdesc = umma_desc_sw128(sQ + g * CHUNK_BYTES);
@@ -437,7 +445,10 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       st = st_next;
       if (++st_next == ATT2_KV_STAGES) { st_next = 0; ph_next ^= 1u; }
     }
+  } else if (warp == 19) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
   } else if (warp == 18) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
     // ================= Q / K / V loads (uniform code, elected issue) =================
     mbar_expect_tx_elect(q_full, 2 * CHUNK_BYTES);
     tma_load_4d_elect(sQ, &tmQK, q_full, 0, head, q0, b);
@@ -453,7 +464,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       if (++st == ATT2_KV_STAGES) { st = 0; ph ^= 1u; }
     }
   } else {
-    const int sw = warp - 2;            // 0..15
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT2_SOFTMAX_REGS));
+    const int sw = warp;                // 0..15
     const int g = sw >> 3;              // warpgroup = query tile
     const int sub = (sw >> 2) & 1;      // which 64-key half of the row this thread owns
     const int q = warp & 3;             // TMEM lane quarter
@@ -706,7 +718,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 constexpr size_t ATT2_SMEM = 2 * CHUNK_BYTES + ATT2_KV_STAGES * CHUNK_BYTES + ATT2_KV_STAGES * (2 * 64 * 128) +
