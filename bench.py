@@ -23,7 +23,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "WARN")
+# stdout carries exactly ONE line, the JSON result: libraries write to file descriptor 1 behind Python's back (NCCL prints
+# "NCCL version ..." there at WARN level when the first communicator is created), so fd 1 is pointed at stderr for the
+# whole run and the JSON line goes to a private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import torch
 
@@ -102,6 +114,16 @@ def cpu_reference_call_seconds(n_calls=1, threads=None):
     return statistics.median(times), threads
 
 
+def workload_string(args) -> str:
+    """config.workload, shared by both arms (BASELINE configs[1] with the default flags)."""
+    B, hw, Sn = args.batch, args.latent, args.sampler_steps
+    calls = Sn + 1 if args.sampler == "plms" else Sn
+    name = "BASELINE configs[1]: " if (B, hw, Sn, args.sampler) == (8, 64, 50, "plms") else ""
+    return (f"{name}v1.yaml U-Net (859.5M params, seeded random weights), batch {B} per GPU (CFG batch {2 * B}), "
+            f"{hw}x{hw} latent ({hw * 8}x{hw * 8} image), {args.sampler.upper()} {Sn} steps ({calls} U-Net calls), "
+            f"guidance scale 5")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -112,15 +134,18 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "images_per_sec_512px_plms50_cfg", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_call * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "v1.yaml U-Net, 512x512 (64x64 latent), PLMS-50 + CFG scale 5; reference algorithm "
-                               "(oracle port of ldm UNetModel.forward) on host CPU cores"},
+        "config": {"workload": workload_string(args),
+                   "global_batch": args.gpus * args.batch,
+                   "reference_sample": "each step times ONE CFG U-Net call of one image (batch 2) of the reference algorithm "
+                                       "(fp32 oracle port of ldm UNetModel.forward) on all host cores; value = 1 / "
+                                       f"({UNET_CALLS} calls x median call time); ms_per_step is that call time"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"median of {max(1, total)} CFG U-Net call(s) (batch 2, 64x64 latent) x {UNET_CALLS} "
                                    f"calls per image (extrapolated); {per_call:.2f} s per call"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -273,9 +298,7 @@ def main():
         "metric": "images_per_sec_512px_plms50_cfg", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: v1.yaml U-Net (859.5M params, seeded random weights), batch {B} "
-                               f"per GPU (CFG batch {Bc}), {hw}x{hw} latent ({hw*8}x{hw*8} image), {args.sampler.upper()} {Sn} steps "
-                               f"({calls} U-Net calls), guidance scale 5",
+        "config": {"workload": workload_string(args),
                    "global_batch": world * B, "parallelism": f"dp{world} (independent requests, no collective)",
                    "l2": "working set per step (1.7 GB bf16 weights + >1 GB activations per U-Net call) exceeds the "
                          "126 MB L2; no explicit flush"},
@@ -303,7 +326,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "clocks": clk,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
