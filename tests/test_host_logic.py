@@ -179,3 +179,24 @@ def test_clip_embedder_state_dict_keys_and_no_cpu_fallback(golden_dir):
         m(torch.zeros(1, 3, 224, 224))
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 200, 224))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """The measurement contract: `bench.py --impl reference` times the reference algorithm (the oracle port -- one of the
+    places allowed to execute oracle/) on the host cores and prints exactly ONE line on stdout, a JSON object carrying the
+    base keys, the arm's own cpu_baseline and an e2e block with zero copy bytes; everything else goes to stderr."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "images_per_sec_512px_plms50_cfg" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["config"]["workload"].startswith("BASELINE configs[1]") and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
