@@ -167,6 +167,21 @@ int pbe_vae_profile(pbe_vae_handle h, int encode, const float* in, float* out, i
  * out_u8[b,h,w,c] = (uint8) (255 * clamp((img[b,c,h,w] + 1) / 2, 0, 1)), fp32 NCHW -> uint8 NHWC, same fp32 rounding
  * and truncation as the reference's clamp -> numpy -> astype(uint8) sequence. */
 int pbe_postprocess_u8(const float* img, uint8_t* out_u8, int B, int C, int H, int W, void* stream);
+/* Pre-processing of an edit request (third "next" row of SURVEY.md 8f, device part); all buffers on the device, uint8 images
+ * in the HWC layout PIL / numpy hand over, fp32 outputs NCHW.  Bit-identical to the reference's fp32 op sequences.
+ *  - pbe_normalize_u8: torchvision ToTensor + Normalize(mean, std) as built by get_tensor() / get_tensor_clip()
+ *    (scripts/inference.py:106-124, ldm/data/test_bench_dataset.py:37-61): out[b,c,h,w] = (u8[b,h,w,c]/255 - mean[c]) / std[c];
+ *    mean3 / std3 are HOST arrays of three floats.
+ *  - pbe_prepare_inpaint_u8: mask = 1 - m/255, thresholded to {0, 1} at 0.5 when binarize != 0 (scripts/inference.py:311-317;
+ *    binarize = 0 is ldm/data/test_bench_dataset.py:89-92), image = get_tensor()(img), inpaint = image * mask (:318, :98).
+ *    image_out [B,3,H,W] and mask_out [B,1,H,W] may be NULL; inpaint_out [B,3,H,W] is required.
+ *  - pbe_resize_bilinear: torchvision Resize([h, w]) of a float tensor [NC,H,W] -> [NC,h,w] (scripts/inference.py:332, the
+ *    latent-resolution mask) = F.interpolate(bilinear, align_corners=False); antialias = 0 is the reference's pinned
+ *    torchvision 0.12 behaviour for tensors, antialias = 1 the default of torchvision >= 0.17. */
+int pbe_normalize_u8(const uint8_t* img_u8, float* out, int B, int H, int W, const float* mean3, const float* std3, void* stream);
+int pbe_prepare_inpaint_u8(const uint8_t* img_u8, const uint8_t* mask_u8, int B, int H, int W, int binarize, float* image_out,
+                           float* mask_out, float* inpaint_out, void* stream);
+int pbe_resize_bilinear(const float* in, float* out, int NC, int H, int W, int h, int w, int antialias, void* stream);
 int pbe_vae_op_info(pbe_vae_handle h, int i, const char** name, const char** family, double* flops);
 int pbe_vae_launches_per_decode(pbe_vae_handle h);
 

@@ -81,6 +81,9 @@ _OPTIONAL_SIGS: dict = {
     "pbe_vae_op_info": (c_int, [_p, _i, _p, _p, _p]),
     "pbe_vae_launches_per_decode": (c_int, [_p]),
     "pbe_postprocess_u8": (c_int, [_p, _p, _i, _i, _i, _i, _p]),
+    "pbe_normalize_u8": (c_int, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "pbe_prepare_inpaint_u8": (c_int, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "pbe_resize_bilinear": (c_int, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pbe_clip_create": (c_int, [_p, _p]),
     "pbe_clip_destroy": (None, [_p]),
     "pbe_clip_load_weight": (c_int, [_p, c_char_p, _p, _p, _i]),

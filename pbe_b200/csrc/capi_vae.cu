@@ -67,6 +67,24 @@ int pbe_postprocess_u8(const float* img, uint8_t* out, int B, int C, int H, int 
   if (img == nullptr || out == nullptr) { set_error("pbe_postprocess_u8: null argument"); return -1; }
   return launch_postprocess_u8(img, out, B, C, H, W, static_cast<cudaStream_t>(stream));
 }
+int pbe_normalize_u8(const uint8_t* img_u8, float* out, int B, int H, int W, const float* mean3, const float* std3, void* stream) {
+  if (img_u8 == nullptr || out == nullptr || mean3 == nullptr || std3 == nullptr) { set_error("pbe_normalize_u8: null argument"); return -1; }
+  if (B <= 0 || H <= 0 || W <= 0) { set_error("pbe_normalize_u8: empty geometry"); return -1; }
+  for (int c = 0; c < 3; ++c)
+    if (std3[c] == 0.0f) { set_error("pbe_normalize_u8: std evaluated to zero, leading to division by zero"); return -1; }
+  return launch_normalize_u8(img_u8, out, B, H, W, mean3, std3, static_cast<cudaStream_t>(stream));
+}
+int pbe_prepare_inpaint_u8(const uint8_t* img_u8, const uint8_t* mask_u8, int B, int H, int W, int binarize, float* image_out,
+                           float* mask_out, float* inpaint_out, void* stream) {
+  if (img_u8 == nullptr || mask_u8 == nullptr || inpaint_out == nullptr) { set_error("pbe_prepare_inpaint_u8: null argument"); return -1; }
+  if (B <= 0 || H <= 0 || W <= 0) { set_error("pbe_prepare_inpaint_u8: empty geometry"); return -1; }
+  return launch_prepare_inpaint_u8(img_u8, mask_u8, image_out, mask_out, inpaint_out, B, H, W, binarize,
+                                   static_cast<cudaStream_t>(stream));
+}
+int pbe_resize_bilinear(const float* in, float* out, int NC, int H, int W, int h, int w, int antialias, void* stream) {
+  if (in == nullptr || out == nullptr) { set_error("pbe_resize_bilinear: null argument"); return -1; }
+  return launch_resize_bilinear(in, out, NC, H, W, h, w, antialias, static_cast<cudaStream_t>(stream));
+}
 int pbe_vae_launches_per_decode(pbe_vae_handle h) {
   if (h == nullptr || h->d->current() == nullptr) return 0;
   return h->d->current()->launches;

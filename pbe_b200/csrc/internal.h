@@ -208,6 +208,11 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
 // images fp32 NCHW in [-1, 1] -> uint8 NHWC (clamp((x+1)/2) * 255, truncated)
 int launch_postprocess_u8(const float* x, uint8_t* out, int Nb, int C, int H, int W, cudaStream_t stream);
+int launch_normalize_u8(const uint8_t* in, float* out, int Nb, int H, int W, const float* mean, const float* stdv,
+                        cudaStream_t stream);
+int launch_prepare_inpaint_u8(const uint8_t* img, const uint8_t* mask, float* image_out, float* mask_out, float* inpaint_out,
+                              int Nb, int H, int W, int binarize, cudaStream_t stream);
+int launch_resize_bilinear(const float* in, float* out, int NC, int H, int W, int h, int w, int antialias, cudaStream_t stream);
 // VAE encode tail: quant_conv (1x1, fp32) fused with the NHWC -> NCHW unpack of the moments
 int launch_vae_unpack_moments(const float* y, const float* Wq, const float* bq, float* out, int Nb, int Cin, int Cout,
                               int H, int W, int ld, cudaStream_t stream);

@@ -229,6 +229,113 @@ __global__ void postprocess_u8_kernel(const float* __restrict__ x, uint8_t* __re
   }
 }
 
+// ---- pre-processing of an edit request (third "next" row, device part) ----
+// ToTensor + Normalize (scripts/inference.py:106-124 get_tensor / get_tensor_clip; ldm/data/test_bench_dataset.py:37-61):
+// out[b,c,h,w] = (u8[b,h,w,c] / 255 - mean[c]) / std[c], the reference's fp32 op sequence (true divisions, no FMA).
+struct Norm3 { float mean[3], std[3]; };
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int Nb, int HW, Norm3 nm) {
+  griddep_enter();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Nb) * HW) return;
+  const int n = static_cast<int>(idx / HW);
+  const int pix = static_cast<int>(idx % HW);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fdiv_rn(static_cast<float>(in[idx * 3 + c]), 255.0f);
+    out[(static_cast<long long>(n) * 3 + c) * HW + pix] = __fdiv_rn(__fsub_rn(v, nm.mean[c]), nm.std[c]);
+  }
+}
+
+// Mask and masked image (scripts/inference.py:311-318; ldm/data/test_bench_dataset.py:89-98):
+// mask = 1 - m/255 (scripts: then 0 / 1 at the 0.5 threshold), image = (u8/255 - 0.5)/0.5, inpaint = image * mask.
+__global__ void prepare_inpaint_u8_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                          float* __restrict__ image_out, float* __restrict__ mask_out,
+                                          float* __restrict__ inpaint_out, int Nb, int HW, int binarize) {
+  griddep_enter();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Nb) * HW) return;
+  const int n = static_cast<int>(idx / HW);
+  const int pix = static_cast<int>(idx % HW);
+  float m = __fsub_rn(1.0f, __fdiv_rn(static_cast<float>(mask[idx]), 255.0f));
+  if (binarize) m = (m < 0.5f) ? 0.0f : 1.0f;
+  if (mask_out != nullptr) mask_out[idx] = m;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(img[idx * 3 + c]), 255.0f), 0.5f), 0.5f);
+    const long long o = (static_cast<long long>(n) * 3 + c) * HW + pix;
+    if (image_out != nullptr) image_out[o] = v;
+    inpaint_out[o] = __fmul_rn(v, m);
+  }
+}
+
+// torchvision Resize([h, w]) of a float tensor = F.interpolate(mode="bilinear", align_corners=False) (scripts/inference.py:332,
+// the latent-resolution mask).  ATen upsample_bilinear2d: src = scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out.
+__global__ void resize_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H, int W, int h, int w) {
+  griddep_enter();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(NC) * h * w) return;
+  const int ox = static_cast<int>(idx % w), oy = static_cast<int>((idx / w) % h);
+  const long long nc = idx / (static_cast<long long>(w) * h);
+  const float sy = static_cast<float>(H) / static_cast<float>(h), sx = static_cast<float>(W) / static_cast<float>(w);
+  float fy = __fsub_rn(__fmul_rn(sy, __fadd_rn(static_cast<float>(oy), 0.5f)), 0.5f);
+  float fx = __fsub_rn(__fmul_rn(sx, __fadd_rn(static_cast<float>(ox), 0.5f)), 0.5f);
+  fy = fy < 0.0f ? 0.0f : fy;
+  fx = fx < 0.0f ? 0.0f : fx;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly1 = __fsub_rn(fy, static_cast<float>(y0)), lx1 = __fsub_rn(fx, static_cast<float>(x0));
+  const float ly0 = __fsub_rn(1.0f, ly1), lx0 = __fsub_rn(1.0f, lx1);
+  const float* src = in + nc * H * W;
+  const float top = __fadd_rn(__fmul_rn(lx0, src[static_cast<long long>(y0) * W + x0]), __fmul_rn(lx1, src[static_cast<long long>(y0) * W + x1]));
+  const float bot = __fadd_rn(__fmul_rn(lx0, src[static_cast<long long>(y1) * W + x0]), __fmul_rn(lx1, src[static_cast<long long>(y1) * W + x1]));
+  out[idx] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+}
+
+// The same with antialias=True (the default of torchvision >= 0.17 for tensors): ATen _upsample_bilinear2d_aa, a separable
+// triangle filter of support max(scale, 1) whose weights are normalised per output index; width pass, then height pass.
+__device__ __forceinline__ void aa_window(int i, int in_size, float scale, int& lo, int& size, float& center, float& invscale,
+                                          float& total) {
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  center = static_cast<float>(static_cast<double>(scale) * (static_cast<double>(i) + 0.5));
+  invscale = scale >= 1.0f ? static_cast<float>(1.0 / static_cast<double>(scale)) : 1.0f;
+  lo = max(static_cast<int>(static_cast<long long>(static_cast<double>(__fsub_rn(center, support)) + 0.5)), 0);
+  size = min(static_cast<int>(static_cast<long long>(static_cast<double>(__fadd_rn(center, support)) + 0.5)), in_size) - lo;
+  total = 0.0f;
+  for (int j = 0; j < size; ++j) {
+    float x = static_cast<float>((static_cast<double>(__fsub_rn(static_cast<float>(j + lo), center)) + 0.5) * static_cast<double>(invscale));
+    x = fabsf(x);
+    total = __fadd_rn(total, x < 1.0f ? __fsub_rn(1.0f, x) : 0.0f);
+  }
+}
+__device__ __forceinline__ float aa_weight(int j, int lo, float center, float invscale, float total) {
+  float x = static_cast<float>((static_cast<double>(__fsub_rn(static_cast<float>(j + lo), center)) + 0.5) * static_cast<double>(invscale));
+  x = fabsf(x);
+  const float wgt = x < 1.0f ? __fsub_rn(1.0f, x) : 0.0f;
+  return total != 0.0f ? __fdiv_rn(wgt, total) : wgt;
+}
+__global__ void resize_bilinear_aa_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H, int W, int h, int w) {
+  griddep_enter();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(NC) * h * w) return;
+  const int ox = static_cast<int>(idx % w), oy = static_cast<int>((idx / w) % h);
+  const long long nc = idx / (static_cast<long long>(w) * h);
+  const float sy = static_cast<float>(H) / static_cast<float>(h), sx = static_cast<float>(W) / static_cast<float>(w);
+  int xlo, xn, ylo, yn;
+  float xc, xi, xt, yc, yi, yt;
+  aa_window(ox, W, sx, xlo, xn, xc, xi, xt);
+  aa_window(oy, H, sy, ylo, yn, yc, yi, yt);
+  const float* src = in + nc * H * W;
+  float acc = 0.0f;
+  for (int jy = 0; jy < yn; ++jy) {
+    const float* row = src + static_cast<long long>(ylo + jy) * W + xlo;
+    float t = __fmul_rn(row[0], aa_weight(0, xlo, xc, xi, xt));                       // width pass of this source row
+    for (int jx = 1; jx < xn; ++jx) t = __fadd_rn(t, __fmul_rn(row[jx], aa_weight(jx, xlo, xc, xi, xt)));
+    const float v = __fmul_rn(t, aa_weight(jy, ylo, yc, yi, yt));                     // height pass
+    acc = jy == 0 ? v : __fadd_rn(acc, v);
+  }
+  out[idx] = acc;
+}
+
 // CLIP ViT patch embedding input (transformers CLIPVisionEmbeddings.patch_embedding: Conv2d(3, C, patch, stride=patch,
 // bias=False)): one row per patch, columns in the conv weight's (c, kh, kw) order, zero padded to Kpad
 __global__ void clip_pack_patches_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W, int patch,
@@ -388,6 +495,33 @@ int launch_postprocess_u8(const float* x, uint8_t* out, int Nb, int C, int H, in
   const long long total = static_cast<long long>(Nb) * H * W;
   PBE_CHECK_CUDA(launch_k(postprocess_u8_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x,
                           out, Nb, C, H * W));
+  return 0;
+}
+
+int launch_normalize_u8(const uint8_t* in, float* out, int Nb, int H, int W, const float* mean, const float* stdv,
+                        cudaStream_t stream) {
+  Norm3 nm;
+  for (int c = 0; c < 3; ++c) { nm.mean[c] = mean[c]; nm.std[c] = stdv[c]; }
+  const long long total = static_cast<long long>(Nb) * H * W;
+  PBE_CHECK_CUDA(launch_k(normalize_u8_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, in, out,
+                          Nb, H * W, nm));
+  return 0;
+}
+
+int launch_prepare_inpaint_u8(const uint8_t* img, const uint8_t* mask, float* image_out, float* mask_out, float* inpaint_out,
+                              int Nb, int H, int W, int binarize, cudaStream_t stream) {
+  const long long total = static_cast<long long>(Nb) * H * W;
+  PBE_CHECK_CUDA(launch_k(prepare_inpaint_u8_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, img,
+                          mask, image_out, mask_out, inpaint_out, Nb, H * W, binarize));
+  return 0;
+}
+
+int launch_resize_bilinear(const float* in, float* out, int NC, int H, int W, int h, int w, int antialias, cudaStream_t stream) {
+  PBE_REQUIRE(NC > 0 && H > 0 && W > 0 && h > 0 && w > 0, "resize_bilinear: empty geometry");
+  const long long total = static_cast<long long>(NC) * h * w;
+  const dim3 grid(static_cast<unsigned>((total + 127) / 128));
+  if (antialias) PBE_CHECK_CUDA(launch_k(resize_bilinear_aa_kernel, grid, dim3(128), 0, stream, in, out, NC, H, W, h, w));
+  else PBE_CHECK_CUDA(launch_k(resize_bilinear_kernel, grid, dim3(128), 0, stream, in, out, NC, H, W, h, w));
   return 0;
 }
 

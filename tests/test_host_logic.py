@@ -200,3 +200,21 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_preprocess_mirror_has_no_cpu_path_and_keeps_reference_errors():
+    """pbe_b200.preprocess mirrors get_tensor / get_tensor_clip / Resize (scripts/inference.py:106-124,332): CPU tensors and
+    wrong dtypes are refused loudly, torchvision's zero-std error is kept."""
+    from pbe_b200 import preprocess as P
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        P.get_tensor()(torch.zeros(8, 8, 3, dtype=torch.uint8))
+    with pytest.raises(TypeError):
+        P.get_tensor_clip()(torch.zeros(8, 8, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        P.prepare_inpaint(torch.zeros(8, 8, 3, dtype=torch.uint8), torch.zeros(8, 8, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        P.Resize([4, 4])(torch.zeros(1, 1, 8, 8))
+    with pytest.raises(ValueError, match="std evaluated to zero"):
+        P._Normalize((0.5, 0.5, 0.5), (0.5, 0.0, 0.5))
+    with pytest.raises(NotImplementedError):
+        P.Resize(64)

@@ -195,3 +195,56 @@ def test_clip_oracle_matches_live_reference():
     with torch.no_grad():
         a, b = enc(x), K.encode(sd, cfg, x)
     assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pre-processing oracle (oracle/preprocess_ref.py) against the LIVE torchvision transforms / torch interpolate the reference
+# scripts call (scripts/inference.py:106-124, 305-332).  These are library functions present on every box, not /root/reference.
+def test_preprocess_oracle_matches_live_torchvision_transforms():
+    import numpy as np
+    import torchvision
+    from PIL import Image
+    from oracle import preprocess_ref as P
+    img_u8, mask_u8 = P.synthetic_u8_request(2, 48, 40, seed=5)
+    for mean, std in ((P.HALF, P.HALF), (P.CLIP_MEAN, P.CLIP_STD)):
+        tf = torchvision.transforms.Compose([torchvision.transforms.ToTensor(), torchvision.transforms.Normalize(mean, std)])
+        ref = torch.stack([tf(Image.fromarray(img_u8[b].numpy())) for b in range(2)])
+        assert torch.equal(P.normalize_u8(img_u8, mean, std), ref)
+    # scripts/inference.py:311-318, restated literally on the PIL objects
+    for b in range(2):
+        image_tensor = torchvision.transforms.Compose([torchvision.transforms.ToTensor(), torchvision.transforms.Normalize(
+            (0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])(Image.fromarray(img_u8[b].numpy())).unsqueeze(0)
+        mask = np.array(Image.fromarray(mask_u8[b].numpy()).convert("L"))[None, None]
+        mask = 1 - mask.astype(np.float32) / 255.0
+        mask[mask < 0.5] = 0
+        mask[mask >= 0.5] = 1
+        mask_tensor = torch.from_numpy(mask)
+        image, m, inpaint = P.prepare_inpaint(img_u8[b:b + 1], mask_u8[b:b + 1], binarize=True)
+        assert torch.equal(image, image_tensor) and torch.equal(m, mask_tensor) and torch.equal(inpaint, image_tensor * mask_tensor)
+        # ldm/data/test_bench_dataset.py:89-98
+        mask_tensor = 1 - torchvision.transforms.ToTensor()(Image.fromarray(mask_u8[b].numpy()).convert("L"))
+        image, m, inpaint = P.prepare_inpaint(img_u8[b:b + 1], mask_u8[b:b + 1], binarize=False)
+        assert torch.equal(m[0], mask_tensor) and torch.equal(inpaint[0], image_tensor[0] * mask_tensor)
+        assert ((m > 0) & (m < 1)).any()           # the soft border survives without the threshold
+
+
+@pytest.mark.parametrize("H,W,h,w", [(512, 512, 64, 64), (768, 768, 96, 96), (96, 80, 12, 10), (100, 60, 13, 7), (30, 30, 45, 50)])
+@pytest.mark.parametrize("antialias", [False, True])
+def test_resize_oracle_matches_live_interpolate(H, W, h, w, antialias):
+    """Resize([h, w]) on a tensor = F.interpolate(bilinear, align_corners=False[, antialias]); ATen may contract to FMA, so
+    general inputs agree to an ulp and {0, 1} masks at the reference's power-of-two factors agree exactly."""
+    import torch.nn.functional as F
+    import torchvision
+    from oracle import preprocess_ref as P
+    g = torch.Generator().manual_seed(H + w)
+    x = torch.rand(2, 1, H, W, generator=g)
+    ref = F.interpolate(x, size=(h, w), mode="bilinear", align_corners=False, antialias=antialias)
+    assert (P.resize_bilinear(x, (h, w), antialias) - ref).abs().max().item() <= 5e-7
+    assert torch.equal(torchvision.transforms.Resize([h, w], antialias=antialias)(x), ref)
+    m = (x > 0.6).float()
+    m[:, :, H // 4: H // 2, W // 3:] = 1.0
+    ref = F.interpolate(m, size=(h, w), mode="bilinear", align_corners=False, antialias=antialias)
+    out = P.resize_bilinear(m, (h, w), antialias)
+    if not antialias and H % h == 0 and W % w == 0:
+        assert torch.equal(out, ref)
+    assert (out - ref).abs().max().item() <= 5e-7
