@@ -218,7 +218,9 @@ class PLMSSampler(_SamplerBase):
             raise KeyError("test_model_kwargs")   # plms.py:220 reads kwargs['test_model_kwargs'] unconditionally
         z_inp, m_inp = (t.to(device=device, dtype=torch.float32).contiguous() for t in pair)
 
-        if timesteps is None:
+        if "_decode_timesteps" in kwargs:          # DDIMSampler.decode: an explicit prefix of ddim_timesteps (ddim.py:266-267)
+            timesteps = kwargs["_decode_timesteps"]
+        elif timesteps is None:
             timesteps = self.ddim_timesteps
         else:
             subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
@@ -316,7 +318,9 @@ class DDIMSampler(_SamplerBase):
         if pair is None:
             raise Exception("kwargs must contain either 'test_model_kwargs' or 'rest' key")   # ddim.py:203-204
         z_inp, m_inp = (t.to(device=device, dtype=torch.float32).contiguous() for t in pair)
-        if timesteps is None:
+        if "_decode_timesteps" in kwargs:          # DDIMSampler.decode: an explicit prefix of ddim_timesteps (ddim.py:266-267)
+            timesteps = kwargs["_decode_timesteps"]
+        elif timesteps is None:
             timesteps = self.ddim_timesteps
         else:
             subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
@@ -362,6 +366,24 @@ class DDIMSampler(_SamplerBase):
                 intermediates["x_inter"].append(img)
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
+
+    @torch.no_grad()
+    def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
+               use_original_steps=False, disable_tqdm=False, **kwargs):
+        """ddim.py:262-283: run the last `t_start` DDIM steps from `x_latent` (after make_schedule / a sample() call).
+        In this fork p_sample_ddim insists on the inpainting inputs (ddim.py:198-204) and decode() does not forward any,
+        so the reference's decode always raises; the same exception is raised here when no `test_model_kwargs` / `rest`
+        is given, and -- as an extension -- the steps run when one is."""
+        if use_original_steps:
+            raise NotImplementedError("use_original_steps=True is not part of the hot path")
+        if _inpaint_kwargs(kwargs) is None:
+            raise Exception("kwargs must contain either 'test_model_kwargs' or 'rest' key")   # ddim.py:203-204
+        timesteps = self.ddim_timesteps[:t_start]
+        x_dec, _ = self.ddim_sampling(cond, tuple(x_latent.shape), x_T=x_latent,
+                                      unconditional_guidance_scale=unconditional_guidance_scale,
+                                      unconditional_conditioning=unconditional_conditioning, disable_tqdm=disable_tqdm,
+                                      _decode_timesteps=timesteps, **kwargs)
+        return x_dec
 
     @torch.no_grad()
     def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):

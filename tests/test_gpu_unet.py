@@ -173,6 +173,26 @@ def test_small_ddim_vs_reference_golden(small, dev, golden_dir):
     assert _psnr(out.cpu(), g) >= PSNR_DB
 
 
+def test_ddim_decode_continues_a_trajectory_bit_exactly(small, dev):
+    """DDIMSampler.decode (ddim.py:262-283) given the inpainting inputs: the last t_start steps from an intermediate latent
+    reproduce the end of the full eta = 0 trajectory bit for bit (same kernels, no randomness)."""
+    from pbe_b200.samplers import DDIMSampler
+    cfg, sd, req, model = small
+    d = lambda t: t.to(dev)
+    rest = d(torch.cat((req["z_inpaint"], req["mask"]), 1))
+    sampler = DDIMSampler(model)
+    kw = dict(unconditional_guidance_scale=5.0, unconditional_conditioning=d(req["uc"]))
+    out, inter = sampler.sample(S=5, conditioning=d(req["c"]), batch_size=2, shape=[4, 32, 32], verbose=False, eta=0.0,
+                                x_T=d(req["x_T"]), rest=rest, log_every_t=1, **kw)
+    xs = inter["x_inter"]                      # x_T, then the latent after each of the 5 steps
+    assert len(xs) == 6 and torch.equal(xs[-1], out)
+    for done in (1, 3):
+        tail = sampler.decode(xs[done].clone(), d(req["c"]), 5 - done, rest=rest, **kw)
+        assert torch.equal(tail, out)
+    with pytest.raises(Exception, match="kwargs must contain"):
+        sampler.decode(xs[1], d(req["c"]), 4, **kw)
+
+
 def test_sampler_generic_model_path(small, dev):
     """A model that is not the accelerated U-Net goes through its own apply_model; only the update kernel is ours."""
     from oracle import sampler_ref as S

@@ -100,6 +100,9 @@ def test_plms_rejects_eta_and_ddim_rejects_batch_mismatch():
         PLMSSampler(m).make_schedule(10, ddim_eta=0.5, verbose=False)
     with pytest.raises(ValueError):                                            # ddim.py:99-106
         DDIMSampler(m).sample(S=4, batch_size=2, shape=[4, 32, 32], conditioning=torch.zeros(1, 1, 768), verbose=False)
+    # ddim.py:262-283: decode() forwards no inpainting kwargs, so p_sample_ddim's check (:203-204) always fires in this fork
+    with pytest.raises(Exception, match="kwargs must contain either 'test_model_kwargs' or 'rest' key"):
+        DDIMSampler(m).decode(torch.zeros(1, 4, 32, 32), torch.zeros(1, 1, 768), 3)
 
 
 def test_inpaint_kwargs_spellings():
