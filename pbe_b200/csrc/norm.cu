@@ -164,27 +164,36 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const fl
     const float* src = (c < C0) ? st0 + (static_cast<long long>(b) * blocks * C0 + c) * 2
                                 : st1 + (static_cast<long long>(b) * blocks * C1 + (c - C0)) * 2;
     const long long ld = static_cast<long long>((c < C0) ? C0 : C1) * 2;
+    // every load of this thread is issued before the first add (the kernel is one wave of tiny CTAs: pure latency);
+    // the order of the additions is fixed (k ascending), so the result does not depend on timing
+    constexpr int MAXL = 16;
     int k = sub;
-    for (; k + 3 * nsub < blocks; k += 4 * nsub) {   // four independent loads in flight
-      const float2 v0 = *reinterpret_cast<const float2*>(src + k * ld);
-      const float2 v1 = *reinterpret_cast<const float2*>(src + (k + nsub) * ld);
-      const float2 v2 = *reinterpret_cast<const float2*>(src + (k + 2 * nsub) * ld);
-      const float2 v3 = *reinterpret_cast<const float2*>(src + (k + 3 * nsub) * ld);
-      a += (static_cast<double>(v0.x) + static_cast<double>(v1.x)) + (static_cast<double>(v2.x) + static_cast<double>(v3.x));
-      q += (static_cast<double>(v0.y) + static_cast<double>(v1.y)) + (static_cast<double>(v2.y) + static_cast<double>(v3.y));
-    }
-    for (; k < blocks; k += nsub) {
-      const float2 v = *reinterpret_cast<const float2*>(src + k * ld);
-      a += static_cast<double>(v.x);
-      q += static_cast<double>(v.y);
+    while (k < blocks) {
+      float2 v[MAXL];
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < MAXL; ++i) {
+        const int kk = k + i * nsub;
+        if (kk < blocks) { v[i] = *reinterpret_cast<const float2*>(src + kk * ld); n = i + 1; }
+      }
+#pragma unroll
+      for (int i = 0; i < MAXL; ++i) {
+        if (i < n) { a += static_cast<double>(v[i].x); q += static_cast<double>(v[i].y); }
+      }
+      k += MAXL * nsub;
     }
   }
-  s_a[t] = a;
-  s_q[t] = q;
+  // fixed-order tree: butterfly inside each warp, then the four warp totals in order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((t & 31) == 0) { s_a[t >> 5] = a; s_q[t >> 5] = q; }
   __syncthreads();
   if (t == 0) {
     double sa = 0.0, sq = 0.0;
-    for (int i = 0; i < cpg * nsub; ++i) {
+    for (int i = 0; i < GNF_THREADS / 32; ++i) {
       sa += s_a[i];
       sq += s_q[i];
     }
