@@ -62,6 +62,13 @@ int64_t pbe_op_groupnorm_workspace_bytes(int Nb, int HW);
 int pbe_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int C, float eps,
                      void* stream);
 
+/* fp32 Linear on a handful of rows: y[B,O] = act(bias + W[O,K] . f(x[B,K])) (+ residual[B,O]), f = SiLU when pre_silu,
+ * act = 0 none / 1 SiLU / 2 erf-GELU; y_silu (optional) also receives SiLU(y).  The CUDA-core GEMV behind time_embed
+ * (openaimodel.py:623-628), the folded single-key cross-attention to_out(to_v(c)) (attention.py:207-230) and the one-token
+ * mapper of the conditioning front-end (encoders/xf.py:31-130).  K % 4 == 0; bias / residual / y_silu may be NULL. */
+int pbe_op_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
+                        int post_act, const float* residual, float* y_silu, void* stream);
+
 /* nearest-2x upsample fp32 NHWC -> bf16 NHWC. Replaces F.interpolate in Upsample.forward, openaimodel.py:109-119. */
 int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C, void* stream);
 

@@ -58,6 +58,7 @@ _OPTIONAL_SIGS: dict = {
     "pbe_op_groupnorm_workspace_bytes": (c_int64, [_i, _i]),
     "pbe_op_layernorm": (c_int, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "pbe_op_upsample2x": (c_int, [_p, _p, _i, _i, _i, _i, _p]),
+    "pbe_op_small_linear": (c_int, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "pbe_sampler_step": (c_int, [_p, _p, _f, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p, _i64, _p]),
     "pbe_build_unet_input": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "pbe_create": (c_int, [_p, _p]),

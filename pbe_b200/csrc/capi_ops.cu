@@ -90,6 +90,12 @@ int pbe_op_layernorm(const float* x, const float* gamma, const float* beta, void
   return launch_layernorm(x, gamma, beta, static_cast<bf16*>(y_bf16), M, C, eps, static_cast<cudaStream_t>(stream));
 }
 
+int pbe_op_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
+                        int post_act, const float* residual, float* y_silu, void* stream) {
+  if (x == nullptr || W == nullptr || y == nullptr) { set_error("pbe_op_small_linear: null argument"); return -1; }
+  return launch_small_linear(x, W, bias, y, B, K, O, pre_silu, post_act, static_cast<cudaStream_t>(stream), y_silu, residual);
+}
+
 int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C, void* stream) {
   return launch_upsample2x_bf16(x, static_cast<bf16*>(y_bf16), Nb, H, W, C, static_cast<cudaStream_t>(stream));
 }

@@ -87,25 +87,27 @@ __global__ void unpack_output_kernel(const float* __restrict__ y, float* __restr
 
 __device__ __forceinline__ float silu_f(float t) { return t / (1.0f + expf(-t)); }
 
-// y[b][o] = act(bias[o] + sum_k W[o][k] x[b][k]) for a handful of batch rows (timestep / context embeddings: fp32).
-// One warp owns SL_OW outputs and SL_RB batch rows at a time; lanes split K.  Every x float4 is loaded once per warp and
-// reused by the SL_OW weight rows (the first version, one output per warp and 8 rows per pass, re-read x for every
-// output: the 22 concatenated emb_layers of one U-Net call took 190 us for 92 MB of weights).  The SL_OW * SL_RB partial
-// sums are combined by a halving butterfly: 62 shuffles instead of 5 per value.
-constexpr int SL_OW = 4, SL_RB = 16;
-__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+// y[b][o] = act(bias[o] + sum_k W[o][k] x[b][k]) for a handful of batch rows (timestep / context embeddings, the CLIP
+// mapper: fp32).  One CTA of SL_WARPS warps owns SL_OW outputs and SL_RB batch rows at a time; the warps take interleaved
+// 128-float slices of K, lanes the float4s of a slice, so a CTA has all of its weight loads in flight at once and there
+// are O / SL_OW CTAs (the previous version gave a WARP the whole K loop -- 10 dependent round trips to HBM at K = 1280 --
+// and filled 40 SMs: 43 us for the 6.5 MB of time_embed.2).  Every x float4 is loaded once per warp and reused by the
+// SL_OW weight rows.  The SL_OW * SL_RB partial sums of a warp are combined by a halving butterfly (62 shuffles instead of
+// 5 per value), the warps' results through shared memory in warp order: a fixed summation order, no atomics.
+constexpr int SL_OW = 4, SL_RB = 16, SL_WARPS = 8;
+__global__ void __launch_bounds__(SL_WARPS * 32) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ y,
                                                            float* __restrict__ y_silu, int B, int K, int O,
                                                            int pre_silu, int post_act, const float* __restrict__ residual) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
-  const int o0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SL_OW;
-  const int lane = threadIdx.x & 31;
-  if (o0 >= O) return;
+  __shared__ float s_part[SL_WARPS][SL_OW * SL_RB];
+  const int o0 = blockIdx.x * SL_OW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b0 = 0; b0 < B; b0 += SL_RB) {
     float acc[SL_OW * SL_RB];
 #pragma unroll
     for (int n = 0; n < SL_OW * SL_RB; ++n) acc[n] = 0.0f;
-    for (int k = lane * 4; k < K; k += 128) {
+    for (int k = (warp * 32 + lane) * 4; k < K; k += SL_WARPS * 128) {
       float4 xv[SL_RB];
 #pragma unroll
       for (int i = 0; i < SL_RB; ++i) {
@@ -134,12 +136,18 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
       }
     }
     // lane bits 4..0 picked halves of 64, 32, ..., 4 values: this lane holds n = 2 * lane + {0, 1}, n = j * SL_RB + i
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int n = 2 * lane + e;
+    if (b0 > 0) __syncthreads();   // the previous pass has been read
+    s_part[warp][2 * lane] = acc[0];
+    s_part[warp][2 * lane + 1] = acc[1];
+    __syncthreads();
+    if (threadIdx.x < SL_OW * SL_RB) {
+      const int n = threadIdx.x;
       const int j = n / SL_RB, i = n % SL_RB;
       if (o0 + j < O && b0 + i < B) {
-        float v = acc[e] + (bias ? bias[o0 + j] : 0.0f);
+        float v = s_part[0][n];
+#pragma unroll
+        for (int w = 1; w < SL_WARPS; ++w) v += s_part[w][n];
+        v += bias ? bias[o0 + j] : 0.0f;
         if (post_act == 1) v = silu_f(v);
         else if (post_act == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // nn.GELU() (erf)
         if (residual != nullptr) v += residual[static_cast<long long>(b0 + i) * O + o0 + j];
@@ -467,7 +475,7 @@ int launch_unpack_output(const float* y, float* out, int Nb, int Cout, int H, in
 int launch_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
                         int post_act, cudaStream_t stream, float* y_silu, const float* residual) {
   PBE_REQUIRE(K % 4 == 0, "small_linear K % 4");
-  PBE_CHECK_CUDA(launch_k(small_linear_kernel, dim3((O + 8 * SL_OW - 1) / (8 * SL_OW)), dim3(256), 0, stream, x, W, bias, y, y_silu, B, K, O, pre_silu, post_act, residual));
+  PBE_CHECK_CUDA(launch_k(small_linear_kernel, dim3((O + SL_OW - 1) / SL_OW), dim3(SL_WARPS * 32), 0, stream, x, W, bias, y, y_silu, B, K, O, pre_silu, post_act, residual));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

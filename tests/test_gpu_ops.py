@@ -330,3 +330,34 @@ def test_build_unet_input(lib):
     torch.cuda.synchronize()
     ref = torch.cat([torch.cat((x, z, m), 1)] * 2)
     assert torch.equal(out, ref)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,K,O,pre,act,res", [(16, 1280, 1280, 0, 0, False), (16, 320, 1280, 0, 1, False), (2, 768, 320, 0, 0, False),
+                                               (32, 1280, 1280, 1, 0, True), (1, 1024, 4096, 0, 2, False), (8, 4096, 1024, 0, 0, True),
+                                               (3, 100, 7, 1, 1, True), (17, 132, 33, 0, 2, False)])
+def test_small_linear_matches_fp32_linear(lib, B, K, O, pre, act, res):
+    """The fp32 GEMV of time_embed (openaimodel.py:623-628), the folded cross-attention (attention.py:207-230) and the
+    one-token mapper (encoders/xf.py): K split across the warps of a CTA, fixed summation order."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 7 + K + O)
+    x = torch.randn(B, K, generator=g).to(dev)
+    W = (torch.randn(O, K, generator=g) / math.sqrt(K)).to(dev)
+    bias = (0.1 * torch.randn(O, generator=g)).to(dev)
+    r = torch.randn(B, O, generator=g).to(dev) if res else None
+    y = torch.full((B, O), float("nan"), device=dev)
+    ys = torch.full((B, O), float("nan"), device=dev)
+    rc = lib.pbe_op_small_linear(x.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), B, K, O, pre, act, _p(r), ys.data_ptr(),
+                                 _stream())
+    assert rc == 0, _err(lib)
+    torch.cuda.synchronize()
+    ref = F.linear((F.silu(x) if pre else x).double(), W.double(), bias.double())
+    ref = F.silu(ref) if act == 1 else (F.gelu(ref) if act == 2 else ref)
+    if res:
+        ref = ref + r.double()
+    assert (y.double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (ys.double() - F.silu(ref)).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    y2 = torch.empty_like(y)
+    lib.pbe_op_small_linear(x.data_ptr(), W.data_ptr(), bias.data_ptr(), y2.data_ptr(), B, K, O, pre, act, _p(r), None, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)          # fixed summation order: bit-identical from run to run
