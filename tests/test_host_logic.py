@@ -221,3 +221,33 @@ def test_preprocess_mirror_has_no_cpu_path_and_keeps_reference_errors():
         P._Normalize((0.5, 0.5, 0.5), (0.5, 0.0, 0.5))
     with pytest.raises(NotImplementedError):
         P.Resize(64)
+
+
+def test_cited_reference_lines_exist():
+    """Every `file.py:line[-line]` citation in the C header, the kernels, the host mirror, the oracle and the design documents
+    points at lines that exist in the reference tree (authoring container only; the tree is not on the GPU box)."""
+    import glob
+    import re
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("/root/reference not mounted")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    by_name = {}
+    for path in glob.glob(os.path.join(ref, "**", "*.py"), recursive=True):
+        by_name.setdefault(os.path.basename(path), []).append(path)
+    sources = [os.path.join(root, "include", "pbe_b200.h")] + glob.glob(os.path.join(root, "pbe_b200", "*.py")) + \
+        glob.glob(os.path.join(root, "oracle", "*.py")) + glob.glob(os.path.join(root, "pbe_b200", "csrc", "*.*")) + \
+        [os.path.join(root, "DESIGN.md"), os.path.join(root, "INTEGRATION.md")]
+    pat = re.compile(r"([A-Za-z_0-9/]+\.py):(\d+)(?:-(\d+))?")
+    checked, bad = 0, []
+    for src in sources:
+        for m in pat.finditer(open(src).read()):
+            name, lo, hi = m.group(1), int(m.group(2)), int(m.group(3) or m.group(2))
+            cands = [p for p in by_name.get(os.path.basename(name), []) if p.endswith(name)]
+            if not cands:
+                continue        # not a reference file (e.g. a citation of this repository or of a third-party library)
+            n_lines = max(sum(1 for _ in open(p)) for p in cands)
+            checked += 1
+            if not (1 <= lo <= hi <= n_lines):
+                bad.append((os.path.relpath(src, root), m.group(0), n_lines))
+    assert checked > 50 and not bad, bad
