@@ -10,7 +10,7 @@
 // 128x128 fp32 TMEM tile, the softmax warps read it with tcgen05.ld, keep the reference maximum / row sum in registers,
 // write P (bf16 pairs) into a fourth TMEM region, and the MMA warp accumulates O += P V (A operand from tensor memory)
 // into a third.  TMEM: S0 [0,128) S1 [128,256) O [256, 256+dv <= 416) P [448,512).
-// flash_attn2_kernel (head dims <= 64, the 64x64-latent level): 256 queries per CTA, 19 warps -- see its comment.
+// flash_attn2_kernel (head dims <= 64, the 64x64-latent level): 256 queries per CTA, 20 warps on five warpgroups -- see its comment.
 // Q and K come from the fused projection output [B, N, 2C];
 // V arrives transposed ([B, C, N], written by the projection GEMM's epilogue) so both MMAs take K-major operands.
 // Head dims that are not a multiple of 64 (40, 80, 160) rely on TMA out-of-bounds zero fill.
@@ -494,7 +494,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       mbar_wait(s_full(g), j & 1);
       tc_fence_after();
       // pass 1: partial row maximum over my 64 columns, 32 at a time (values are re-read from TMEM in pass 2:
-      // 32 live registers instead of 64 keeps the 18-warp CTA free of spills)
+      // 32 live registers instead of 64 keeps this rarely used path small)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
