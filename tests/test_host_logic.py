@@ -251,3 +251,29 @@ def test_cited_reference_lines_exist():
             if not (1 <= lo <= hi <= n_lines):
                 bad.append((os.path.relpath(src, root), m.group(0), n_lines))
     assert checked > 50 and not bad, bad
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """profiles/ holds the evidence the design document quotes: the final bench lines must carry every key of the measurement
+    contract (metric / value / e2e with copy bytes / roofline / cpu_baseline / clocks / gpu_launches), and the ncu launch
+    list must summarise (tools/launch_summary.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prof = os.path.join(root, "profiles")
+    d = json.load(open(os.path.join(prof, "r01_bench_v26.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "images_per_sec_512px_plms50_cfg" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("BASELINE configs[1]") and "model" not in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    d2 = json.load(open(os.path.join(prof, "r01_bench_v26_2gpu.json")))
+    assert d2["n_gpus"] == 2 and d2["cpu_baseline"] is None and 1.8 < d2["value"] / d["value"] < 2.2
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), os.path.join(prof, "r01_launches_v23.csv")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "conv_gemm_kernel" in out.stdout and "flash_attn2_kernel" in out.stdout
