@@ -277,3 +277,19 @@ def test_committed_bench_lines_follow_the_contract():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), os.path.join(prof, "r01_launches_v23.csv")],
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "conv_gemm_kernel" in out.stdout and "flash_attn2_kernel" in out.stdout
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the product package may import it (statically checked)."""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "pbe_b200", "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
