@@ -23,10 +23,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "WARN")
-# stdout carries exactly ONE line, the JSON result: libraries write to file descriptor 1 behind Python's back (NCCL prints
-# "NCCL version ..." there at WARN level when the first communicator is created), so fd 1 is pointed at stderr for the
-# whole run and the JSON line goes to a private duplicate of the original stdout.
+# NCCL's own log (communicator, rank count, transport) goes to stderr at INFO level so a driver can check the ranks;
+# PBE_NCCL_DEBUG overrides.  stdout carries exactly ONE line, the JSON result: libraries write to file descriptor 1 behind
+# Python's back (NCCL prints its log there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
 _JSON_OUT = os.fdopen(os.dup(1), "w")
 sys.stdout.flush()
 os.dup2(2, 1)
@@ -44,8 +45,23 @@ F64_MIN = 771.3e9   # algorithmic FLOPs per sample-eval at 64x64 with the dead c
 # run once per (uncond, cond) pair -- conv_in 0.212 + first ResBlock 15.099 + proj_in 0.839 + qkv 2.517 + self-attention
 # 21.475 = 40.142 GFLOP per pair, i.e. half of that per sample-eval.  Only executed work is claimed below.
 F64_PAIR_SHARED = 40.142e9 / 2
-NCU_TRAFFIC_CONV1 = 43869440 + 36049152   # dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_conv1_pair_summary.txt)
-UNET_CALLS = 51     # PLMS-50: the first step evaluates twice (plms.py:230-235)
+
+
+def _ncu_traffic():
+    """DRAM read + write bytes of the dominant kernel's representative launch, from the `ncu --set full` capture of the
+    CURRENT build (tools/ncu_summary.py writes profiles/ncu_traffic.json next to the summary); None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def unet_calls(args) -> int:
+    """U-Net evaluations per image: PLMS evaluates the first step twice (plms.py:230-235), DDIM once per step."""
+    return args.sampler_steps + 1 if args.sampler == "plms" else args.sampler_steps
 
 
 def _peaks():
@@ -93,25 +109,48 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_call_seconds(n_calls=1, threads=None):
-    """Time the reference algorithm (oracle port, fp32 torch on the host cores) for one CFG U-Net call of one image
-    (batch 2, 64x64). Returns (median seconds per call, threads)."""
+def _reference_root():
+    """Where an importable copy of the unmodified reference lives on this box, if anywhere."""
+    for cand in (os.environ.get("PBE_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "ldm", "modules", "diffusionmodules")):
+            return cand
+    return None
+
+
+def cpu_reference_call_seconds(n_calls=1, threads=None, hw=64):
+    """Time the reference's CPU implementation of one CFG U-Net call of ONE image (batch 2): the reference's own
+    `UNetModel` when a copy of the reference is importable on this box (kind "reference"), otherwise the fp32 oracle port
+    (kind "port"; torch.equal to the live reference in tests/test_oracle_pinned.py).  Returns (median s per call, threads, kind)."""
     from oracle import sampler_ref as S, unet_ref as U
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     cfg = U.V1_CFG
     sd = U.make_state_dict(cfg, 321)
-    req = S.synthetic_request(1, 64, 64, seed=321)
+    req = S.synthetic_request(1, hw, hw, seed=321)
     x9 = torch.cat((req["x_T"], req["z_inpaint"], req["mask"]), 1)
     x_in = torch.cat([x9] * 2)
     c_in = torch.cat((req["uc"], req["c"]))
     t = torch.full((2,), 981, dtype=torch.int64)
+    kind, fn = "port", (lambda: U.unet_forward(sd, cfg, x_in, t, c_in))
+    root = _reference_root()
+    if root is not None:
+        try:
+            os.environ["PBE_REFERENCE"] = root
+            from oracle import reference_bridge as R
+            ref = R.build_reference_unet(cfg, sd)
+
+            def fn():
+                with torch.no_grad():
+                    return ref(x_in, t, context=c_in)
+            kind = "reference"
+        except Exception as e:   # an incomplete copy: say so on stderr and time the port
+            print(f"[bench] reference at {root} not importable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
     times = []
     for _ in range(n_calls):
         t0 = time.perf_counter()
-        U.unet_forward(sd, cfg, x_in, t, c_in)
+        fn()
         times.append(time.perf_counter() - t0)
-    return statistics.median(times), threads
+    return statistics.median(times), threads, kind
 
 
 def workload_string(args) -> str:
@@ -124,28 +163,119 @@ def workload_string(args) -> str:
             f"guidance scale 5")
 
 
+def base_config(args, world) -> dict:
+    """`config` of the JSON line -- the same dict for every arm, so the driver compares like with like."""
+    return {"workload": workload_string(args), "global_batch": world * args.batch,
+            "parallelism": f"dp{world} (independent requests, no collective)",
+            "l2": "working set per step (1.7 GB bf16 weights + >1 GB activations per U-Net call) exceeds the "
+                  "126 MB L2; no explicit flush"}
+
+
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores (all threads).  Each "step"
+    is a bounded sample of the workload: ONE CFG U-Net call of one image (batch 2) at the workload's latent size; images/s
+    = 1 / (calls per image x median call time), the way BASELINE.md section 4 extrapolates.  Rank 0 only under torchrun."""
     if rank != 0:
         return
     total = args.steps + args.warmup
-    per_call, threads = cpu_reference_call_seconds(n_calls=max(1, total))
-    ips = 1.0 / (UNET_CALLS * per_call)
+    calls = unet_calls(args)
+    per_call, threads, kind = cpu_reference_call_seconds(n_calls=max(1, total), hw=args.latent)
+    ips = 1.0 / (calls * per_call)
+    what = ("the reference's own ldm UNetModel.forward (fp32, CPU)" if kind == "reference"
+            else "the fp32 oracle port of ldm UNetModel.forward (CPU)")
     line = {
         "impl": "reference", "metric": "images_per_sec_512px_plms50_cfg", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_call * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(args),
-                   "global_batch": args.gpus * args.batch,
-                   "reference_sample": "each step times ONE CFG U-Net call of one image (batch 2) of the reference algorithm "
-                                       "(fp32 oracle port of ldm UNetModel.forward) on all host cores; value = 1 / "
-                                       f"({UNET_CALLS} calls x median call time); ms_per_step is that call time"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"median of {max(1, total)} CFG U-Net call(s) (batch 2, 64x64 latent) x {UNET_CALLS} "
-                                   f"calls per image (extrapolated); {per_call:.2f} s per call"},
+        "config": base_config(args, args.gpus),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"median of {max(1, total)} CFG U-Net call(s) of ONE image (batch 2, {args.latent}x{args.latent} "
+                                   f"latent) through {what} on {threads} host threads x {calls} calls per image "
+                                   f"(extrapolated); {per_call:.2f} s per call; ms_per_step is that call time",
+                         "arm_batch": 2, "unet_calls_per_image": calls},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_torch_eager(args, rank, world):
+    """--impl torch-eager: the GPU-side bar the reference itself would set on this box (SURVEY.md
+    section 2.2): the reference algorithm (fp32 oracle restatement of UNetModel.forward) through PyTorch library kernels on
+    the same B200 -- eager fp32 (TF32 off / on), under torch.autocast as scripts/inference.py:301-303 runs it (fp16) and with
+    bf16, and with F.scaled_dot_product_attention in place of the literal softmax(QK^T)V -- per U-Net call at CFG batch 2 and
+    at the workload's CFG batch.  Not the product and not the reference arm: a context line for profiles/."""
+    if rank != 0:
+        return
+    import torch.nn.functional as F
+    from oracle import unet_ref as U
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    cfg = U.V1_CFG
+    sd = {k: v.to(dev) for k, v in U.make_state_dict(cfg, 321).items()}
+    hw = args.latent
+    literal_attention = U.cross_attention
+
+    def sdpa_attention(sd_, p, x, context, heads):
+        q = F.linear(x, sd_[p + ".to_q.weight"])
+        ctx = x if context is None else context
+        k, v = F.linear(ctx, sd_[p + ".to_k.weight"]), F.linear(ctx, sd_[p + ".to_v.weight"])
+        b, n, c = q.shape
+        sp = lambda t_: t_.view(b, t_.shape[1], heads, c // heads).transpose(1, 2)
+        o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(b, n, c)
+        return F.linear(o, sd_[p + ".to_out.0.weight"], sd_[p + ".to_out.0.bias"])
+
+    def time_variant(Bc, tf32, autocast_dtype, sdpa):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        U.cross_attention = sdpa_attention if sdpa else literal_attention
+        g = torch.Generator().manual_seed(Bc)
+        x = torch.randn(Bc, 9, hw, hw, generator=g).to(dev)
+        t = torch.full((Bc,), 501, dtype=torch.int64, device=dev)
+        c = torch.randn(Bc, 1, 768, generator=g).to(dev)
+
+        def call():
+            if autocast_dtype is None:
+                return U.unet_forward(sd, cfg, x, t, c)
+            with torch.autocast("cuda", dtype=autocast_dtype):
+                return U.unet_forward(sd, cfg, x, t, c)
+        try:
+            for _ in range(2):
+                call()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = max(3, args.steps)
+            e0.record()
+            for _ in range(n):
+                call()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / n
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            return None
+        finally:
+            U.cross_attention = literal_attention
+
+    rows = []
+    for Bc in (2, 2 * args.batch):
+        for name, tf32, ac, sdpa in (("fp32 eager, TF32 off (the oracle as the parity tests run it)", False, None, False),
+                                     ("fp32 eager, TF32 on (PyTorch defaults for conv)", True, None, False),
+                                     ("fp32 eager + SDPA, TF32 on", True, None, True),
+                                     ("autocast fp16 (scripts/inference.py:301-303)", True, torch.float16, False),
+                                     ("autocast fp16 + SDPA", True, torch.float16, True),
+                                     ("autocast bf16 + SDPA", True, torch.bfloat16, True)):
+            ms = time_variant(Bc, tf32, ac, sdpa)
+            rows.append({"cfg_batch": Bc, "variant": name, "ms_per_unet_call": ms})
+            print(f"[torch-eager] CFG batch {Bc:3d} {name}: {ms if ms is None else round(ms, 2)} ms", file=sys.stderr)
+    calls = unet_calls(args)
+    best = min((r["ms_per_unet_call"] for r in rows if r["cfg_batch"] == 2 * args.batch and r["ms_per_unet_call"]), default=None)
+    emit({"impl": "torch-eager", "metric": "images_per_sec_512px_plms50_cfg",
+          "value": (args.batch / (calls * best * 1e-3)) if best else None, "unit": "images/s", "n_gpus": 1,
+          "higher_is_better": True, "dtype": "fp32 / fp16 / bf16 (see variants)", "data": "synthetic",
+          "config": base_config(args, 1),
+          "note": "value = batch / (U-Net calls per image x the FASTEST variant's call time at the workload's CFG batch): U-Net "
+                  "calls only, no sampler arithmetic -- an upper bound for a PyTorch-library implementation of the reference",
+          "variants": rows})
 
 
 def main():
@@ -153,7 +283,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--batch", type=int, default=8, help="edit requests per GPU per step (CFG doubles it)")
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--sampler-steps", type=int, default=50)
@@ -168,6 +298,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.impl == "torch-eager":
+        return run_torch_eager(args, rank, world)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
@@ -195,7 +327,7 @@ def main():
     pin = {k: v.contiguous().pin_memory() for k, v in req.items()}
     d = {k: v.to(dev) for k, v in req.items()}
     sampler = PLMSSampler(model) if args.sampler == "plms" else DDIMSampler(model)
-    calls = Sn + 1 if args.sampler == "plms" else Sn   # PLMS evaluates the first step twice (plms.py:230-235)
+    calls = unet_calls(args)
     flops_per_eval = F64_MIN * (hw * hw) / 4096.0 if hw == 64 else None   # SURVEY 8(d) gives F only for 64 and 96
     if hw == 96:
         flops_per_eval = 2079.9e9
@@ -290,18 +422,18 @@ def main():
     gemm_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
-        per_call, threads = cpu_reference_call_seconds(n_calls=5)
-        cpu_baseline = {"value": 1.0 / (UNET_CALLS * per_call), "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": f"median of 5 CFG U-Net calls (batch 2, 64x64 latent) of the fp32 oracle port x "
-                                  f"{UNET_CALLS} calls per image (extrapolated); {per_call:.2f} s per call"}
+        per_call, threads, kind = cpu_reference_call_seconds(n_calls=5, hw=hw)
+        cpu_baseline = {"value": 1.0 / (calls * per_call), "unit": "images/s", "cores": threads, "kind": kind,
+                        "sample": f"median of 5 CFG U-Net calls of ONE image (batch 2, {hw}x{hw} latent) of the "
+                                  f"{'reference UNetModel' if kind == 'reference' else 'fp32 oracle port'} x {calls} calls per "
+                                  f"image (extrapolated); {per_call:.2f} s per call",
+                        "arm_batch": 2, "unet_calls_per_image": calls}
+    traffic = _ncu_traffic()
     line = {
         "metric": "images_per_sec_512px_plms50_cfg", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_string(args),
-                   "global_batch": world * B, "parallelism": f"dp{world} (independent requests, no collective)",
-                   "l2": "working set per step (1.7 GB bf16 weights + >1 GB activations per U-Net call) exceeds the "
-                         "126 MB L2; no explicit flush"},
+        "config": base_config(args, world),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches * args.steps,
@@ -314,10 +446,9 @@ def main():
                                          "peak_tflops_sustained": peaks["tf_sustained"], "peak_source": peaks["src"]},
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM conv / linear, tcgen05)",
                      "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tf / peaks["tf_sustained"], "traffic": NCU_TRAFFIC_CONV1,
-                     "traffic_note": "DRAM read+write bytes of ONE representative launch (64x64 320->320 3x3 conv, CFG batch "
-                                     "16; algorithmic 127.7 MB, fp32 output still in L2 at kernel end) from ncu --set full: "
-                                     "profiles/r01_ncu_conv1_pair_summary.txt; achieved/peak aggregate all launches",
+                     "frac": gemm_tf / peaks["tf_sustained"],
+                     "traffic": (traffic or {}).get("dram_bytes"),
+                     "traffic_note": (traffic or {}).get("note", "no ncu --set full capture of the current build under profiles/"),
                      "how": f"sum of algorithmic FLOPs of the {gemm['launches']} conv_gemm launches of one U-Net call "
                             f"(CFG batch {Bc}) / sum of their CUDA-event durations (eager pass after the timed region); "
                             f"peak = {peaks['src']} sustained bf16",

@@ -75,16 +75,18 @@ int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C,
 /* Fused CFG combine + PLMS/DDIM multistep + x_prev/pred_x0 update over n fp32 elements (K11).
  * Replaces plms.py:185-189,202-219,230-246 and ddim.py:209-242.  order: 0 DDIM/plain, 1..3 Adams-Bashforth with
  * h1 (most recent) .. h3, 4 = PLMS first-step average (h1 = first eps, eps_* = second evaluation).
- * eps_c may be NULL when cfg == 0; noise may be NULL when sigma_t == 0; e_out / pred_x0 may be NULL. */
+ * eps_c may be NULL when cfg == 0; noise may be NULL when sigma_t == 0; e_out / pred_x0 may be NULL.
+ * The noise term is (sigma_t * noise) * temperature, rounded in the reference's order (plms.py:214, ddim.py:238). */
 int pbe_sampler_step(const float* eps_uc, const float* eps_c, float scale, int cfg, int order, const float* h1,
                      const float* h2, const float* h3, const float* x, float a_t, float a_prev, float sigma_t,
-                     float sqrt_one_minus_at, const float* noise, float* e_out, float* x_prev, float* pred_x0,
-                     int64_t n, void* stream);
+                     float sqrt_one_minus_at, const float* noise, float temperature, float* e_out, float* x_prev,
+                     float* pred_x0, int64_t n, void* stream);
 
-/* out[dup*B, 9, H*W] = cat(x[B,4,HW], z_inpaint[B,4,HW], mask[B,1,HW]) repeated `dup` (1 or 2) times along batch.
+/* out[dup*B, Cx+Cz+Cm, H*W] = cat(x[B,Cx,HW], z_inpaint[B,Cz,HW], mask[B,Cm,HW]) repeated `dup` (1 or 2) times along the
+ * batch (Paint-by-Example: 4 + 4 + 1 channels).  All three inputs must share B and HW -- the caller checks, as torch.cat would.
  * Replaces torch_cat((x, images_inpaint, images_mask), 1) and torch_cat([x]*2): plms.py:185-186,225; ddim.py:200,209. */
-int pbe_build_unet_input(const float* x, const float* z_inpaint, const float* mask, float* out, int B, int HW, int dup,
-                         void* stream);
+int pbe_build_unet_input(const float* x, const float* z_inpaint, const float* mask, float* out, int B, int Cx, int Cz,
+                         int Cm, int HW, int dup, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Engine: the whole UNetModel.forward (ldm/modules/diffusionmodules/openaimodel.py:852-889) behind

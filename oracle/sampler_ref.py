@@ -19,7 +19,9 @@ def make_schedule_buffers(timesteps=1000, linear_start=0.00085, linear_end=0.012
     alphas_cumprod = np.cumprod(alphas, axis=0)
     alphas_cumprod_prev = np.append(1.0, alphas_cumprod[:-1])
     f32 = lambda a: torch.tensor(a, dtype=torch.float32)
-    return dict(betas=f32(betas), alphas_cumprod=f32(alphas_cumprod), alphas_cumprod_prev=f32(alphas_cumprod_prev))
+    return dict(betas=f32(betas), alphas_cumprod=f32(alphas_cumprod), alphas_cumprod_prev=f32(alphas_cumprod_prev),
+                sqrt_alphas_cumprod=f32(np.sqrt(alphas_cumprod)),                     # ddpm.py:200-201: float64 sqrt, then fp32
+                sqrt_one_minus_alphas_cumprod=f32(np.sqrt(1. - alphas_cumprod)))
 
 
 def ddim_tables(alphas_cumprod: torch.Tensor, S: int, eta: float = 0.0, num_ddpm=1000):
@@ -62,15 +64,25 @@ class OracleModel:
         return unet_forward(self.sd, self.cfg, x_noisy, t, cond)
 
 
-def _x_prev_and_pred_x0(x, e, a_t, a_prev, sigma_t, sqrt_one_minus_at):
-    """get_x_prev_and_pred_x0, plms.py:202-219 (eta = 0 path draws noise that is multiplied by sigma_t)."""
+def _x_prev_and_pred_x0(x, e, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise=None, temperature=1.):
+    """get_x_prev_and_pred_x0, plms.py:202-219 / the tail of p_sample_ddim, ddim.py:221-242.
+    noise: the N(0,1) draw of noise_like(); None = the term is dropped (it is sigma_t * randn = +-0 when eta = 0)."""
     b = x.shape[0]
     full = lambda v: torch.full((b, 1, 1, 1), float(v), device=x.device)
     a_t, a_prev, sigma_t, s1m = full(a_t), full(a_prev), full(sigma_t), full(sqrt_one_minus_at)
     pred_x0 = (x - s1m * e) / a_t.sqrt()
     dir_xt = (1. - a_prev - sigma_t ** 2).sqrt() * e
     x_prev = a_prev.sqrt() * pred_x0 + dir_xt
+    if noise is not None:
+        x_prev = x_prev + sigma_t * noise * temperature        # plms.py:214,217 / ddim.py:238,241
     return x_prev, pred_x0
+
+
+def q_sample(model, x_start, t, noise):
+    """DDPM.q_sample, ddpm.py:348-351 (extract_into_tensor of the two sqrt tables)."""
+    shape = (x_start.shape[0],) + (1,) * (x_start.dim() - 1)
+    sac, s1m = model.sqrt_alphas_cumprod.to(x_start.device), model.sqrt_one_minus_alphas_cumprod.to(x_start.device)
+    return sac.gather(-1, t).reshape(shape) * x_start + s1m.gather(-1, t).reshape(shape) * noise
 
 
 def _cfg_eps(model, x9, t, c, uc, scale):
@@ -87,8 +99,10 @@ def _cfg_eps(model, x9, t, c, uc, scale):
 
 
 @torch.no_grad()
-def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None):
-    """PLMSSampler.plms_sampling + p_sample_plms, plms.py:118-248 (eta = 0)."""
+def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, blend_mask=None, x0=None, rng_device=None):
+    """PLMSSampler.plms_sampling + p_sample_plms, plms.py:118-248 (eta = 0).  With blend_mask / x0 (plms.py:150-153) the
+    generator of `rng_device` is consumed exactly as the reference does: q_sample's randn_like, then one (unused, sigma_t = 0)
+    noise_like() draw per get_x_prev_and_pred_x0 call (plms.py:214) -- two on the first step."""
     tab = ddim_tables(model.alphas_cumprod, S)
     ts = tab["timesteps"]
     time_range = np.flip(ts)
@@ -96,15 +110,21 @@ def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None):
     img = x_T
     b = img.shape[0]
     old_eps = []
+    rdev = img.device if rng_device is None else torch.device(rng_device)
+    draw = (lambda: torch.randn(img.shape, device=rdev)) if blend_mask is not None else (lambda: None)
     for i, step in enumerate(time_range):
         index = total - i - 1
         t = torch.full((b,), int(step), device=img.device, dtype=torch.int64)
         t_next = torch.full((b,), int(time_range[min(i + 1, total - 1)]), device=img.device, dtype=torch.int64)
         coef = (tab["alphas"][index], tab["alphas_prev"][index], tab["sigmas"][index],
                 tab["sqrt_one_minus_alphas"][index])
+        if blend_mask is not None:
+            img_orig = q_sample(model, x0, t, torch.randn(x0.shape, device=rdev).to(img.device))
+            img = img_orig * blend_mask + (1 - blend_mask) * img
         x9 = torch.cat((img, z_inpaint, mask), dim=1)
         e_t = _cfg_eps(model, x9, t, c, uc, scale)
         if len(old_eps) == 0:
+            draw()
             x_prev, _ = _x_prev_and_pred_x0(img, e_t, *coef)
             e_next = _cfg_eps(model, torch.cat((x_prev, z_inpaint, mask), dim=1), t_next, c, uc, scale)
             e_prime = (e_t + e_next) / 2
@@ -114,6 +134,7 @@ def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None):
             e_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
         else:
             e_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        draw()
         x_prev, pred_x0 = _x_prev_and_pred_x0(img, e_prime, *coef)
         if record is not None:
             record.append(dict(index=index, e_t=e_t.clone(), x_prev=x_prev.clone(), pred_x0=pred_x0.clone()))
@@ -125,25 +146,42 @@ def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None):
 
 
 @torch.no_grad()
-def ddim_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None):
-    """DDIMSampler.ddim_sampling + p_sample_ddim, ddim.py:136-242 (eta = 0)."""
-    tab = ddim_tables(model.alphas_cumprod, S)
+def ddim_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, eta=0.0, temperature=1., blend_mask=None,
+                x0=None, rng_device=None):
+    """DDIMSampler.ddim_sampling + p_sample_ddim, ddim.py:136-242.  With eta > 0 (or blend_mask / x0, ddim.py:168-171) the
+    noise is drawn from torch's global generator of `rng_device` (default: the latent's device) at the reference's points
+    and in its order: q_sample's randn_like first, then noise_like() after the model call."""
+    tab = ddim_tables(model.alphas_cumprod, S, eta=eta)
     ts = tab["timesteps"]
     time_range = np.flip(ts)
     total = len(ts)
     img = x_T
     b = img.shape[0]
+    rdev = img.device if rng_device is None else torch.device(rng_device)
     for i, step in enumerate(time_range):
         index = total - i - 1
         t = torch.full((b,), int(step), device=img.device, dtype=torch.int64)
+        if blend_mask is not None:
+            img_orig = q_sample(model, x0, t, torch.randn(x0.shape, device=rdev).to(img.device))
+            img = img_orig * blend_mask + (1. - blend_mask) * img
         x9 = torch.cat((img, z_inpaint, mask), dim=1)
         e_t = _cfg_eps(model, x9, t, c, uc, scale)
+        noise = torch.randn(img.shape, device=rdev).to(img.device) if (eta != 0.0 or blend_mask is not None) else None
         x_prev, pred_x0 = _x_prev_and_pred_x0(img, e_t, tab["alphas"][index], tab["alphas_prev"][index],
-                                              tab["sigmas"][index], tab["sqrt_one_minus_alphas"][index])
+                                              tab["sigmas"][index], tab["sqrt_one_minus_alphas"][index], noise, temperature)
         if record is not None:
             record.append(dict(index=index, e_t=e_t.clone(), x_prev=x_prev.clone(), pred_x0=pred_x0.clone()))
         img = x_prev
     return img
+
+
+def stochastic_encode(model, S, x0, t, noise, eta=0.0):
+    """DDIMSampler.stochastic_encode, ddim.py:245-258 (use_original_steps=False): t indexes the DDIM tables."""
+    tab = ddim_tables(model.alphas_cumprod, S, eta=eta)
+    shape = (x0.shape[0],) + (1,) * (x0.dim() - 1)
+    sac = torch.sqrt(tab["alphas"]).to(x0.device)
+    s1m = tab["sqrt_one_minus_alphas"].to(x0.device)
+    return sac.gather(-1, t).reshape(shape) * x0 + s1m.gather(-1, t).reshape(shape) * noise
 
 
 def synthetic_request(B, h, w, seed=321, ctx_dim=768, device="cpu"):

@@ -25,11 +25,15 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists():
-        if not build_if_missing:
-            raise PbeError(f"{_LIB_PATH} is missing: run `python -m pbe_b200.build` (nvcc, sm_100a)")
-        from .build import build_native
-        build_native()
+    if not os.environ.get("PBE_B200_LIB"):
+        # the in-tree library must match the in-tree sources: a stale .so would be called through the wrong signatures
+        from .build import build_native, library_is_current
+        if not library_is_current():
+            if not build_if_missing:
+                raise PbeError(f"{_LIB_PATH} is missing or older than csrc/: run `python -m pbe_b200.build` (nvcc, sm_100a)")
+            build_native()
+    elif not _LIB_PATH.exists():
+        raise PbeError(f"PBE_B200_LIB={_LIB_PATH} does not exist")
     lib = ctypes.CDLL(str(_LIB_PATH))
     _declare(lib)
     _lib = lib
@@ -59,8 +63,8 @@ _OPTIONAL_SIGS: dict = {
     "pbe_op_layernorm": (c_int, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "pbe_op_upsample2x": (c_int, [_p, _p, _i, _i, _i, _i, _p]),
     "pbe_op_small_linear": (c_int, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "pbe_sampler_step": (c_int, [_p, _p, _f, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _p, _p, _p, _p, _i64, _p]),
-    "pbe_build_unet_input": (c_int, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "pbe_sampler_step": (c_int, [_p, _p, _f, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _p, _f, _p, _p, _p, _i64, _p]),
+    "pbe_build_unet_input": (c_int, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pbe_create": (c_int, [_p, _p]),
     "pbe_destroy": (None, [_p]),
     "pbe_load_weight": (c_int, [_p, c_char_p, _p, _p, _i]),

@@ -46,10 +46,43 @@ def _digest(src: Path) -> str:
     return h.hexdigest()
 
 
+def tree_digest() -> str:
+    """One digest over the compile flags and every source / header the library is built from.  It is written next to the
+    library at link time (``lib/libpbe_b200.sha``, which travels with the .so) and compared at load time, so a library
+    that no longer matches the sources is rebuilt (or refused) instead of being loaded with stale signatures."""
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) +
+                    list((ROOT.parent / "include").glob("*.h"))):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+LIB_STAMP = LIBDIR / "libpbe_b200.sha"
+
+
+def library_is_current() -> bool:
+    return LIB.exists() and LIB_STAMP.exists() and LIB_STAMP.read_text().strip() == tree_digest()
+
+
 def build_native(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library. Incremental by content hash."""
-    nvcc = _nvcc()
+    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library. Incremental by content hash; serialised across
+    processes by a file lock (several ranks importing at once build once)."""
+    import fcntl
     LIBDIR.mkdir(exist_ok=True)
+    with open(LIBDIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and library_is_current():
+                return LIB
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    nvcc = _nvcc()
     OBJDIR.mkdir(exist_ok=True)
     srcs = _sources()
     jobs = []
@@ -81,6 +114,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    LIB_STAMP.write_text(tree_digest())
     return LIB
 
 

@@ -102,12 +102,12 @@ int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C,
 
 int pbe_sampler_step(const float* eps_uc, const float* eps_c, float scale, int cfg, int order, const float* h1,
                      const float* h2, const float* h3, const float* x, float a_t, float a_prev, float sigma_t,
-                     float sqrt_one_minus_at, const float* noise, float* e_out, float* x_prev, float* pred_x0,
-                     int64_t n, void* stream) {
+                     float sqrt_one_minus_at, const float* noise, float temperature, float* e_out, float* x_prev,
+                     float* pred_x0, int64_t n, void* stream) {
   SamplerStepArgs a{};
   a.eps_uc = eps_uc; a.eps_c = eps_c; a.scale = scale; a.cfg = cfg; a.order = order;
   a.h1 = h1; a.h2 = h2; a.h3 = h3; a.x = x; a.a_t = a_t; a.a_prev = a_prev; a.sigma_t = sigma_t;
-  a.sqrt_one_minus_at = sqrt_one_minus_at; a.noise = noise; a.e_out = e_out; a.x_prev = x_prev; a.pred_x0 = pred_x0;
+  a.sqrt_one_minus_at = sqrt_one_minus_at; a.noise = noise; a.temperature = temperature; a.e_out = e_out; a.x_prev = x_prev; a.pred_x0 = pred_x0;
   a.n = static_cast<size_t>(n);
   if (cfg && eps_c == nullptr) { set_error("pbe_sampler_step: cfg set but eps_c is NULL"); return -1; }
   if (order >= 1 && h1 == nullptr) { set_error("pbe_sampler_step: history missing"); return -1; }
@@ -117,10 +117,15 @@ int pbe_sampler_step(const float* eps_uc, const float* eps_c, float scale, int c
   return launch_sampler_step(a, static_cast<cudaStream_t>(stream));
 }
 
-int pbe_build_unet_input(const float* x, const float* z_inpaint, const float* mask, float* out, int B, int HW, int dup,
-                         void* stream) {
+int pbe_build_unet_input(const float* x, const float* z_inpaint, const float* mask, float* out, int B, int Cx, int Cz,
+                         int Cm, int HW, int dup, void* stream) {
   if (dup != 1 && dup != 2) { set_error("pbe_build_unet_input: dup must be 1 or 2"); return -1; }
-  return launch_build_unet_input(x, z_inpaint, mask, out, B, HW, dup, static_cast<cudaStream_t>(stream));
+  if (x == nullptr || out == nullptr || (Cz > 0 && z_inpaint == nullptr) || (Cm > 0 && mask == nullptr)) {
+    set_error("pbe_build_unet_input: NULL tensor");
+    return -1;
+  }
+  if (B <= 0 || Cx <= 0 || Cz < 0 || Cm < 0 || HW <= 0) { set_error("pbe_build_unet_input: bad extents"); return -1; }
+  return launch_build_unet_input(x, z_inpaint, mask, out, B, Cx, Cz, Cm, HW, dup, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

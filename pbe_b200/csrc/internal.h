@@ -256,14 +256,15 @@ struct SamplerStepArgs {
   const float* x;        // current latent [B,4,H,W]
   float a_t, a_prev, sigma_t, sqrt_one_minus_at;
   const float* noise;    // optional [B,4,H,W], multiplied by sigma_t (null when sigma_t == 0)
+  float temperature;     // the noise term is (sigma_t * noise) * temperature
   float* e_out;          // CFG-combined eps (history entry); may be null
   float* x_prev;         // may alias nothing else
   float* pred_x0;        // may be null
   size_t n;              // elements
 };
 int launch_sampler_step(const SamplerStepArgs& a, cudaStream_t stream);
-// x9[b] = cat(x[b], z[b], mask[b]) duplicated for both CFG halves: out [2B or B, 9, H, W]
-int launch_build_unet_input(const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup,
-                            cudaStream_t stream);
+// out[b] = cat(x[b] (Cx ch), z[b] (Cz ch), mask[b] (Cm ch)) duplicated for both CFG halves: out [2B or B, Cx+Cz+Cm, H, W]
+int launch_build_unet_input(const float* x, const float* z, const float* mask, float* out, int B, int Cx, int Cz, int Cm,
+                            int HW, int dup, cudaStream_t stream);
 
 }  // namespace pbe

@@ -19,6 +19,7 @@ struct Coef {
   float sqrt_aprev;    // a_prev.sqrt()
   float dir_coef;      // (1 - a_prev - sigma_t**2).sqrt()
   float sigma_t;
+  float temperature;   // noise = (sigma_t * randn) * temperature, in the reference's order (plms.py:214, ddim.py:238)
   int cfg, order;
 };
 
@@ -43,7 +44,7 @@ __device__ __forceinline__ float step_one(float eu, float ec, float h1, float h2
   const float pred_x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sqrt_one_minus_at, ep)), k.sqrt_at);
   const float dir_xt = __fmul_rn(k.dir_coef, ep);
   float xp = __fadd_rn(__fmul_rn(k.sqrt_aprev, pred_x0), dir_xt);
-  if (k.sigma_t != 0.0f) xp = __fadd_rn(xp, __fmul_rn(k.sigma_t, nz));
+  if (k.sigma_t != 0.0f) xp = __fadd_rn(xp, __fmul_rn(__fmul_rn(k.sigma_t, nz), k.temperature));
   *e_out = e;
   *x0_out = pred_x0;
   return xp;
@@ -73,19 +74,19 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(SamplerStepArgs a, Co
 }
 
 __global__ void build_unet_input_kernel(const float* __restrict__ x, const float* __restrict__ z,
-                                        const float* __restrict__ mask, float* __restrict__ out, int B, int HW,
-                                        int dup) {
+                                        const float* __restrict__ mask, float* __restrict__ out, int B, int Cx,
+                                        int Cz, int Cm, int HW, int dup) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long per = static_cast<long long>(9) * HW;
+  const long long per = static_cast<long long>(Cx + Cz + Cm) * HW;
   if (idx >= static_cast<long long>(B) * per) return;
   const int b = static_cast<int>(idx / per);
   const int r = static_cast<int>(idx % per);
   const int c = r / HW, pix = r % HW;
   float v;
-  if (c < 4) v = x[(static_cast<long long>(b) * 4 + c) * HW + pix];
-  else if (c < 8) v = z[(static_cast<long long>(b) * 4 + (c - 4)) * HW + pix];
-  else v = mask[static_cast<long long>(b) * HW + pix];
+  if (c < Cx) v = x[(static_cast<long long>(b) * Cx + c) * HW + pix];
+  else if (c < Cx + Cz) v = z[(static_cast<long long>(b) * Cz + (c - Cx)) * HW + pix];
+  else v = mask[(static_cast<long long>(b) * Cm + (c - Cx - Cz)) * HW + pix];
   out[idx] = v;
   if (dup == 2) out[static_cast<long long>(B) * per + idx] = v;
 }
@@ -101,6 +102,7 @@ int launch_sampler_step(const SamplerStepArgs& a, cudaStream_t stream) {
   k.order = a.order;
   k.sqrt_one_minus_at = a.sqrt_one_minus_at;
   k.sigma_t = a.sigma_t;
+  k.temperature = a.temperature;
   // fp32 IEEE ops, same as torch.full(..., fp32).sqrt() / (1. - a_prev - sigma_t**2).sqrt()
   k.sqrt_at = sqrtf(a.a_t);
   k.sqrt_aprev = sqrtf(a.a_prev);
@@ -114,10 +116,11 @@ int launch_sampler_step(const SamplerStepArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-int launch_build_unet_input(const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup,
-                            cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * 9 * HW;
-  PBE_CHECK_CUDA(launch_k(build_unet_input_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, z, mask, out, B, HW, dup));
+int launch_build_unet_input(const float* x, const float* z, const float* mask, float* out, int B, int Cx, int Cz, int Cm,
+                            int HW, int dup, cudaStream_t stream) {
+  PBE_REQUIRE(B > 0 && Cx > 0 && Cz >= 0 && Cm >= 0 && HW > 0, "build_unet_input: empty tensor");
+  const long long total = static_cast<long long>(B) * (Cx + Cz + Cm) * HW;
+  PBE_CHECK_CUDA(launch_k(build_unet_input_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, z, mask, out, B, Cx, Cz, Cm, HW, dup));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,18 +35,41 @@ class DiffusionWrapper(nn.Module):
 class LatentDiffusion(nn.Module):
     def __init__(self, unet_config=None, timesteps=1000, linear_start=0.00085, linear_end=0.0120,
                  scale_factor=0.18215, channels=4, image_size=64, conditioning_key="crossattn",
-                 parameterization="eps", **ignored):
+                 parameterization="eps", first_stage_config=None, cond_stage_config=None, cond_stage_forward=None,
+                 first_stage_key="inpaint", cond_stage_key="image", use_ema=False, ckpt_path=None, **ignored):
+        """Accepts everything ``configs/v1.yaml:4-73`` passes (training-only keys -- scheduler_config, monitor,
+        u_cond_percent, cond_stage_trainable, num_timesteps_cond, log_every_t ... -- land in ``ignored``).  The first / cond
+        stages are built from their configs exactly as ``instantiate_first_stage`` / ``instantiate_cond_stage`` do
+        (latent_diffusion.py:215-240): through ``instantiate_from_config`` on the ``target:`` the yaml names, which resolves to
+        this package's VAE / CLIP mirrors once ``pbe_b200.install()`` has run (or when the yaml names them directly)."""
         super().__init__()
+        if use_ema:
+            raise NotImplementedError("use_ema=True is a training feature (configs/v1.yaml:19 sets False)")
+        if ckpt_path is not None:
+            raise NotImplementedError("load weights with load_state_dict (scripts/inference.py:60-65), not ckpt_path")
+        if unet_config is not None and "target" in unet_config and not str(unet_config["target"]).endswith(".UNetModel"):
+            raise NotImplementedError(f"unet_config.target {unet_config['target']!r}: only UNetModel is accelerated")
         params = dict(unet_config.get("params", unet_config)) if unet_config is not None else {}
+        params.pop("target", None)
         self.model = DiffusionWrapper(params, conditioning_key)
         self.parameterization = parameterization
         self.channels = channels
         self.image_size = image_size
         self.scale_factor = scale_factor
+        self.first_stage_key, self.cond_stage_key = first_stage_key, cond_stage_key
+        self.cond_stage_forward = cond_stage_forward
         self.learnable_vector = nn.Parameter(torch.randn((1, 1, 768)), requires_grad=False)
         self.proj_out = nn.Linear(1024, 768)
         self.first_stage_model = None
         self.cond_stage_model = None
+        if first_stage_config is not None:
+            from .dropin import instantiate_from_config
+            self.first_stage_model = instantiate_from_config(first_stage_config).eval()
+        if cond_stage_config is not None and cond_stage_config not in ("__is_first_stage__", "__is_unconditional__"):
+            from .dropin import instantiate_from_config
+            self.cond_stage_model = instantiate_from_config(cond_stage_config).eval()
+        elif cond_stage_config == "__is_first_stage__":
+            self.cond_stage_model = self.first_stage_model
         self.register_schedule(timesteps, linear_start, linear_end)
 
     # ---- ddpm.py:175-228 --------------------------------------------------------------------------------------
@@ -102,9 +125,21 @@ class LatentDiffusion(nn.Module):
                                   f"module as `first_stage_model` / `cond_stage_model` to use it")
 
     def get_learned_conditioning(self, c):
-        if self.cond_stage_model is None:
+        """latent_diffusion.py:264-276."""
+        m = self.cond_stage_model
+        if m is None:
             self._need("CLIP exemplar encoder")
-        return self.cond_stage_model(c)
+        if self.cond_stage_forward is None:
+            if hasattr(m, "encode") and callable(m.encode):
+                c = m.encode(c)
+                if hasattr(c, "mode") and callable(c.mode) and not isinstance(c, torch.Tensor):
+                    c = c.mode()
+            else:
+                c = m(c)
+        else:
+            assert hasattr(m, self.cond_stage_forward)
+            c = getattr(m, self.cond_stage_forward)(c)
+        return c
 
     def encode_first_stage(self, x):
         if self.first_stage_model is None:
@@ -112,7 +147,13 @@ class LatentDiffusion(nn.Module):
         return self.first_stage_model.encode(x)
 
     def get_first_stage_encoding(self, encoder_posterior):
-        z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
+        """latent_diffusion.py:255-262."""
+        if isinstance(encoder_posterior, torch.Tensor):
+            z = encoder_posterior
+        elif hasattr(encoder_posterior, "sample"):
+            z = encoder_posterior.sample()
+        else:
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
         return self.scale_factor * z
 
     def decode_first_stage(self, z, **kw):

@@ -64,9 +64,14 @@ def _inpaint_kwargs(kwargs):
 
 
 class _SamplerBase:
-    def __init__(self, model, schedule="linear", **kwargs):
+    def __init__(self, model, schedule="linear", match_reference_rng=False, **kwargs):
         super().__init__()
         self.model = model
+        # The reference draws noise_like(x.shape) on every x_prev computation even when sigma_t == 0 (plms.py:214 -- twice on
+        # the first PLMS step -- and ddim.py:238); the mirror only draws noise it uses.  With match_reference_rng=True the
+        # unused draws are made (and discarded) at the same points, so a seeded multi-batch run consumes the CUDA generator
+        # exactly like the reference and later internally drawn x_T match.
+        self.match_reference_rng = bool(match_reference_rng)
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
 
@@ -129,9 +134,14 @@ class _SamplerBase:
             return unet.run(x9_in, t_in, out=eps_out)
         return self.model.apply_model(x9_in, t_in, c_in).to(torch.float32).contiguous()
 
-    def _step_kernel(self, eps, B, cfg, scale, order, hist, x, index, noise, e_out, x_prev, pred_x0):
+    def _step_kernel(self, eps, B, cfg, scale, order, hist, x, index, noise, e_out, x_prev, pred_x0, temperature=1.0):
         lib = _lib.load()
         n = x.numel()
+        dup = 2 if cfg else 1
+        if tuple(eps.shape) != (dup * B,) + tuple(x.shape[1:]) or eps.dtype != torch.float32 or not eps.is_contiguous():
+            # the kernel reads n elements per half: anything else would be an out-of-bounds device read
+            raise RuntimeError(f"model output has shape {tuple(eps.shape)} ({eps.dtype}), expected "
+                               f"{(dup * B,) + tuple(x.shape[1:])} contiguous float32")
         e_uc = eps[:B] if cfg else eps
         e_c = eps[B:] if cfg else None
         h = [(t.data_ptr() if t is not None else None) for t in hist] + [None] * (3 - len(hist))
@@ -141,7 +151,7 @@ class _SamplerBase:
             _lib.check(lib.pbe_sampler_step(
                 e_uc.data_ptr(), None if e_c is None else e_c.data_ptr(), float(scale), int(cfg), int(order),
                 h[0], h[1], h[2], x.data_ptr(), c["a_t"][index], c["a_prev"][index], c["sigma"][index],
-                c["sqrt_one_minus_at"][index], None if noise is None else noise.data_ptr(),
+                c["sqrt_one_minus_at"][index], None if noise is None else noise.data_ptr(), float(temperature),
                 None if e_out is None else e_out.data_ptr(), x_prev.data_ptr(),
                 None if pred_x0 is None else pred_x0.data_ptr(), n, st), "pbe_sampler_step")
 
@@ -150,8 +160,23 @@ class _SamplerBase:
         B, _, H, W = x.shape
         st = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            _lib.check(lib.pbe_build_unet_input(x.data_ptr(), z.data_ptr(), mask.data_ptr(), out.data_ptr(), B, H * W,
-                                                dup, st), "pbe_build_unet_input")
+            _lib.check(lib.pbe_build_unet_input(x.data_ptr(), z.data_ptr(), mask.data_ptr(), out.data_ptr(), B,
+                                                x.shape[1], z.shape[1], mask.shape[1], H * W, dup, st),
+                       "pbe_build_unet_input")
+
+    @staticmethod
+    def _check_inputs(img, z, m, shape):
+        """What torch.cat((x, images_inpaint, images_mask), dim=1) (plms.py:222-225, ddim.py:198-200) would refuse, refused
+        here: the kernels take raw pointers and B / H / W from x only."""
+        if img.dim() != 4 or tuple(img.shape) != tuple(shape):
+            raise RuntimeError(f"x_T has shape {tuple(img.shape)}, expected {tuple(shape)} (batch_size, C, H, W)")
+        for k, t in ((1, z), (2, m)):
+            if t.dim() != 4:
+                raise RuntimeError(f"Tensors must have same number of dimensions: got 4 and {t.dim()}")
+            for dim in (0, 2, 3):
+                if t.shape[dim] != img.shape[dim]:
+                    raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size "
+                                       f"{img.shape[dim]} but got size {t.shape[dim]} for tensor number {k} in the list.")
 
     def _setup(self, cond, shape, x_T, unconditional_guidance_scale, unconditional_conditioning, kwargs):
         device = self.model.betas.device
@@ -231,6 +256,7 @@ class PLMSSampler(_SamplerBase):
 
         unet = self._fast_unet()
         dup = 2 if cfg else 1
+        self._check_inputs(img, z_inp, m_inp, shape)
         _, C, H, W = img.shape
         if unet is not None:
             unet.set_context(c_in)
@@ -239,7 +265,13 @@ class PLMSSampler(_SamplerBase):
         eps_buf = torch.empty((dup * b, C, H, W), device=device, dtype=torch.float32)
         ts_dev = torch.as_tensor(np.ascontiguousarray(time_range), device=device, dtype=torch.int64)
         ts_all = ts_dev[:, None].expand(total_steps, dup * b).contiguous()   # one row per step, no per-step H2D
+        # step buffers, allocated once per call: two latents (ping-pong), four eps history slots, one pred_x0.  Tensors
+        # handed out (intermediates, img_callback) are clones, so reuse is invisible to the caller.
+        xbuf = [torch.empty_like(img), torch.empty_like(img)]
+        ebuf = [torch.empty_like(img) for _ in range(4)]
+        x0buf = torch.empty_like(img)
         old_eps = []
+        rng_match = getattr(self, "match_reference_rng", False)
 
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
@@ -250,11 +282,13 @@ class PLMSSampler(_SamplerBase):
                 img = (img_orig * mask + (1 - mask) * img).contiguous()
             self._build_input(img, z_inp, m_inp, x9, in_dup)
             eps = self._model_eps(unet, x9, ts_all[i], c_in, eps_buf)
-            x_prev = torch.empty_like(img)
-            pred_x0 = torch.empty_like(img)
-            e_t = torch.empty_like(img)
+            x_prev = xbuf[i & 1]
+            pred_x0 = torch.empty_like(img) if img_callback else x0buf
+            e_t = ebuf[i & 3]
             if len(old_eps) == 0:
                 # Pseudo Improved Euler (plms.py:230-235): provisional x_prev from e_t, second U-Net call at t_next
+                if rng_match:
+                    torch.randn(img.shape, device=device)      # the reference's unused noise_like() draw (plms.py:214)
                 self._step_kernel(eps, b, cfg, unconditional_guidance_scale, 0, [], img, index, None, e_t, x_prev, None)
                 self._build_input(x_prev, z_inp, m_inp, x9, in_dup)
                 eps2 = self._model_eps(unet, x9, ts_all[min(i + 1, total_steps - 1)], c_in, eps_buf)
@@ -265,6 +299,8 @@ class PLMSSampler(_SamplerBase):
                 hist = list(reversed(old_eps))[:order]   # h1 = most recent
                 self._step_kernel(eps, b, cfg, unconditional_guidance_scale, order, hist, img, index, None, e_t,
                                   x_prev, pred_x0)
+            if rng_match:
+                torch.randn(img.shape, device=device)
             img = x_prev
             old_eps.append(e_t)
             if len(old_eps) >= 4:
@@ -274,8 +310,8 @@ class PLMSSampler(_SamplerBase):
             if img_callback:
                 img_callback(pred_x0, i)
             if index % log_every_t == 0 or index == total_steps - 1:
-                intermediates["x_inter"].append(img)
-                intermediates["pred_x0"].append(pred_x0)
+                intermediates["x_inter"].append(img.clone() if index else img)
+                intermediates["pred_x0"].append(pred_x0 if img_callback else pred_x0.clone())
         return img, intermediates
 
 
@@ -331,6 +367,7 @@ class DDIMSampler(_SamplerBase):
 
         unet = self._fast_unet()
         dup = 2 if cfg else 1
+        self._check_inputs(img, z_inp, m_inp, shape)
         _, C, H, W = img.shape
         if unet is not None:
             unet.set_context(c_in)
@@ -339,6 +376,9 @@ class DDIMSampler(_SamplerBase):
         eps_buf = torch.empty((dup * b, C, H, W), device=device, dtype=torch.float32)
         ts_dev = torch.as_tensor(np.ascontiguousarray(time_range), device=device, dtype=torch.int64)
         ts_all = ts_dev[:, None].expand(total_steps, dup * b).contiguous()
+        xbuf = [torch.empty_like(img), torch.empty_like(img)]   # per-call step buffers (see plms_sampling)
+        x0buf = torch.empty_like(img)
+        rng_match = getattr(self, "match_reference_rng", False)
 
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
@@ -350,21 +390,25 @@ class DDIMSampler(_SamplerBase):
             eps = self._model_eps(unet, x9, ts_all[i], c_in, eps_buf)
             noise = None
             if self._coef["sigma"][index] != 0.0:
-                noise = torch.randn(img.shape, device=device) * temperature      # ddim.py:238 (sigma_t applied in-kernel)
+                # ddim.py:238: noise = sigma_t * noise_like(...) * temperature -- both products happen in the kernel, in that order
+                noise = torch.randn(img.shape, device=device)
                 if noise_dropout > 0.:
                     noise = torch.nn.functional.dropout(noise, p=noise_dropout)
                 noise = noise.contiguous()
-            x_prev = torch.empty_like(img)
-            pred_x0 = torch.empty_like(img)
-            self._step_kernel(eps, b, cfg, unconditional_guidance_scale, 0, [], img, index, noise, None, x_prev, pred_x0)
+            elif rng_match:
+                torch.randn(img.shape, device=device)          # the reference draws even when sigma_t == 0
+            x_prev = xbuf[i & 1]
+            pred_x0 = torch.empty_like(img) if img_callback else x0buf
+            self._step_kernel(eps, b, cfg, unconditional_guidance_scale, 0, [], img, index, noise, None, x_prev, pred_x0,
+                              temperature=temperature)
             img = x_prev
             if callback:
                 callback(i)
             if img_callback:
                 img_callback(pred_x0, i)
             if index % log_every_t == 0 or index == total_steps - 1:
-                intermediates["x_inter"].append(img)
-                intermediates["pred_x0"].append(pred_x0)
+                intermediates["x_inter"].append(img.clone() if index else img)
+                intermediates["pred_x0"].append(pred_x0 if img_callback else pred_x0.clone())
         return img, intermediates
 
     @torch.no_grad()

@@ -3,6 +3,7 @@
 Run in the authoring container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py small      # seconds..a minute
     python tests/golden/make_golden.py v1         # one full-size U-Net call (~10 s) + PLMS-50 C1 trajectory (~10 min)
+    python tests/golden/make_golden.py v1_ddim20  # DDIM-20 C4 trajectory at v1.yaml size (~4 min)
     python tests/golden/make_golden.py vae        # VAE decode: small config + the v1.yaml decoder on a 16x16 latent
     python tests/golden/make_golden.py clip       # conditioning front-end: live transformers CLIPVisionModel + reference mapper
 
@@ -92,6 +93,20 @@ def main(which):
         save("v1_plms50_final", out, dict(cfg="V1_CFG", S=50, scale=5.0, B=1, hw=64, unet_calls=model.calls,
                                           cpu_seconds=time.time() - t0, cpu_threads=torch.get_num_threads(),
                                           source="reference PLMSSampler.sample (BASELINE config C1)"), index)
+    elif which == "v1_ddim20":
+        # BASELINE config C4: DDIM 20 steps, batch 1, 64x64 latent, scale 5 (test.sh:1-9; ddim.py:136-242) -- 20 CFG U-Net calls
+        cfg = U.V1_CFG
+        sd = U.make_state_dict(cfg, 321)
+        ref = R.build_reference_unet(cfg, sd)
+        B, hw = 1, 64
+        req = S.synthetic_request(B, hw, hw, seed=321)
+        model = R.StubLatentDiffusion(ref)
+        t0 = time.time()
+        out, inter = run_sampler("ddim", model, req, 20, hw, B)
+        print("v1 ddim20", time.time() - t0, "s, unet calls", model.calls, flush=True)
+        save("v1_ddim20_final", out, dict(cfg="V1_CFG", S=20, scale=5.0, B=1, hw=64, unet_calls=model.calls,
+                                          cpu_seconds=time.time() - t0, cpu_threads=torch.get_num_threads(),
+                                          source="reference DDIMSampler.sample (BASELINE config C4)"), index)
     elif which == "vae":
         for tag, cfg, B, hw in (("small", V.SMALL_VAE_CFG, 2, 16), ("v1", V.V1_VAE_CFG, 1, 16)):
             sd = V.make_state_dict(cfg, 321)

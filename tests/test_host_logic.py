@@ -185,7 +185,8 @@ def test_clip_embedder_state_dict_keys_and_no_cpu_fallback(golden_dir):
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """The measurement contract: `bench.py --impl reference` times the reference algorithm (the oracle port -- one of the
+    """The measurement contract: `bench.py --impl reference` times the reference's CPU implementation of the path (its own
+    UNetModel where /root/reference is mounted -- kind "reference" --, the oracle port otherwise -- kind "port", one of the
     places allowed to execute oracle/) on the host cores and prints exactly ONE line on stdout, a JSON object carrying the
     base keys, the arm's own cpu_baseline and an e2e block with zero copy bytes; everything else goes to stderr."""
     import subprocess
@@ -200,7 +201,10 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "images_per_sec_512px_plms50_cfg" and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
     assert d["config"]["workload"].startswith("BASELINE configs[1]") and "model" not in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.isdir(os.path.join(os.environ.get("PBE_REFERENCE", "/root/reference"), "ldm"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["unet_calls_per_image"] == 51 and d["cpu_baseline"]["arm_batch"] == 2
+    assert set(d["config"]) == {"workload", "global_batch", "parallelism", "l2"}     # the same keys as our arm's config
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 

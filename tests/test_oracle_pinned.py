@@ -103,6 +103,55 @@ def test_oracle_bit_equals_live_reference(small):
     assert torch.equal(out, out_ref)
 
 
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
+@pytest.mark.parametrize("case", ["eta", "eta_temperature", "mask_x0", "plms_mask_x0"])
+def test_oracle_stochastic_paths_bit_equal_live_reference(small, case):
+    """The sampler paths that draw noise -- DDIM eta > 0 (ddim.py:229-241), temperature != 1 (the (sigma * randn) * T order),
+    and the mask / x0 blend of both samplers (ddim.py:168-171, plms.py:150-153) -- consume torch's generator at the same
+    points and in the same order as the unmodified reference: same seed, bit-identical latents."""
+    cfg, sd, req = small
+    model = R.StubLatentDiffusion(R.build_reference_unet(cfg, sd))
+    om = S.OracleModel(sd, cfg)
+    g = torch.Generator().manual_seed(99)
+    x0 = torch.randn(2, 4, 32, 32, generator=g)
+    bm = (torch.rand(2, 1, 32, 32, generator=g) > 0.5).float()
+    kw = dict(conditioning=req["c"], batch_size=2, shape=[4, 32, 32], verbose=False, unconditional_guidance_scale=5.0,
+              unconditional_conditioning=req["uc"].expand(2, 1, 768), x_T=req["x_T"],
+              test_model_kwargs=dict(images_inpaint=req["z_inpaint"], images_mask=req["mask"]))
+    args = (req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"])
+    torch.manual_seed(1234)
+    if case == "eta":
+        out_ref, _ = R.reference_sampler("ddim", model).sample(S=4, eta=0.7, disable_tqdm=True, **kw)
+        torch.manual_seed(1234)
+        out = S.ddim_sample(om, 4, *args, eta=0.7)
+    elif case == "eta_temperature":
+        out_ref, _ = R.reference_sampler("ddim", model).sample(S=4, eta=0.5, temperature=0.8, disable_tqdm=True, **kw)
+        torch.manual_seed(1234)
+        out = S.ddim_sample(om, 4, *args, eta=0.5, temperature=0.8)
+    elif case == "mask_x0":
+        out_ref, _ = R.reference_sampler("ddim", model).sample(S=4, eta=0.0, mask=bm, x0=x0, disable_tqdm=True, **kw)
+        torch.manual_seed(1234)
+        out = S.ddim_sample(om, 4, *args, blend_mask=bm, x0=x0)
+    else:
+        out_ref, _ = R.reference_sampler("plms", model).sample(S=4, eta=0.0, mask=bm, x0=x0, **kw)
+        torch.manual_seed(1234)
+        out = S.plms_sample(om, 4, *args, blend_mask=bm, x0=x0)
+    assert torch.equal(out, out_ref)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
+def test_oracle_stochastic_encode_bit_equals_live_reference(small):
+    cfg, sd, req = small
+    smp = R.reference_sampler("ddim", R.StubLatentDiffusion(R.build_reference_unet(cfg, sd)))
+    smp.make_schedule(ddim_num_steps=10, ddim_eta=0.0, verbose=False)
+    g = torch.Generator().manual_seed(5)
+    x0, noise = torch.randn(2, 4, 32, 32, generator=g), torch.randn(2, 4, 32, 32, generator=g)
+    t = torch.tensor([7, 2])
+    ref = smp.stochastic_encode(x0, t, noise=noise)
+    out = S.stochastic_encode(S.OracleModel(sd, cfg), 10, x0, t, noise)
+    assert torch.equal(out, ref)
+
+
 # ---- VAE decode (SURVEY.md §8f rank 1): oracle/vae_ref.py ------------------------------------------------------------
 @pytest.mark.parametrize("tag", ["small", "v1"])
 def test_vae_oracle_matches_reference_golden(golden_dir, tag):
