@@ -19,7 +19,11 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 
 namespace pbe {
 
@@ -35,8 +39,17 @@ struct AttnParams {
   int N, heads, d, dv, ksteps, C;
   float scale_log2;
   bf16* out;
-  int two_pass;   // flash_attn2_kernel: 1 = exact running maximum in every tile (PBE_ATTN_TWO_PASS=1), 0 = single-pass tiles
+  int two_pass;   // 1 = exact running maximum in every tile (PBE_ATTN_TWO_PASS=1, and the overflow re-run), 0 = single-pass tiles
+  // overflow handling of the single-pass tiles: a work item (one CTA's query block) whose row sum left the safe range sets
+  // flags[item]; the exact re-run launched right behind (check_flags = 1) recomputes exactly those items and clears the flags
+  int* flags;
+  int check_flags;
+  int qtiles, total_items;   // flash_attn3_kernel (persistent): 256-query blocks per (sample, head), work items in total
 };
+
+// Row sums are kept ATT2_BIAS powers of two below 1; a row sum above this bound means some exponential ran far above the
+// reference maximum (the single-pass tiles' failure mode) and P / O may have overflowed: the item is recomputed exactly.
+constexpr float ATT_L_SAFE = 1.1529215e18f;   // 2^60
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -63,6 +76,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                   const __grid_constant__ AttnParams p) {
   griddep_launch_dependents();   // PDL (ptx.cuh): successor may be scheduled; griddep_wait() after the prologue
+  // work item = this CTA's (query tile, head, sample); the exact re-run (check_flags) only recomputes flagged items
+  const int item = static_cast<int>((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+  if (p.check_flags) {
+    griddep_wait();
+    if (__ldg(p.flags + item) == 0) return;   // whole CTA, before any barrier / TMEM allocation
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -219,14 +238,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           if (i >= kvalid) s[i] = -INFINITY;
       }
       float alpha = 1.0f;
-      if (j == 0) {
+      if (j == 0 || p.two_pass) {
+        // exact row maximum: tile 0 always; every tile in the exact re-run of a flagged item (classic online softmax)
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < KT; i += 4) {
           mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
           mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
         }
-        mrs = fmaxf(mx0, mx1) * sl2;
+        const float mt = fmaxf(mx0, mx1) * sl2;
+        if (j == 0) {
+          mrs = mt;
+        } else if (__any_sync(0xffffffffu, mt > mrs)) {
+          const float m_new = fmaxf(mrs, mt);
+          alpha = ex2(mrs - m_new);
+          mrs = m_new;
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
+        }
       } else {
         const float est = rf1 + ATT2_BIAS + __log2f(sm1);
         if (__any_sync(0xffffffffu, est - mrs > 8.0f)) {
@@ -280,6 +310,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int tok = q0 + row;
+    if (!p.two_pass && p.flags != nullptr) {   // single-pass tiles left their safe range: have the item recomputed exactly
+      const bool bad = (tok < p.N) && !(l_run < ATT_L_SAFE);
+      if (__any_sync(0xffffffffu, bad) && lane == 0) p.flags[item] = 1;
+    }
     bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
     for (int c = 0; c < p.dv; c += 16) {
       uint32_t o[16];
@@ -303,6 +337,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.check_flags && threadIdx.x == 0) p.flags[item] = 0;   // consumed
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -721,8 +756,510 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// flash_attn3_kernel: flash_attn2_kernel (same roles, same TMEM map, same single-pass tiles) with the two changes its ncu
+// profile asked for (profiles/r01_ncu_attn2_v6_summary.txt: XU pipe 76.5 %, issue slots 47 %, tensor pipe 28 %):
+//  * PERSISTENT.  One CTA per SM walks work items (256-query block, head, sample), block index fastest so that the CTAs
+//    running at the same time share K / V in L2.  Barrier phases run on a global tile counter, Q is double-buffered, so the
+//    service warps run ahead across items: the next item's Q / K / V loads and its first Q.K^T overlap the current item's
+//    last exponentials and its O / l epilogue.  Launch, TMEM allocation, barrier set-up and the first load round trip
+//    (about 7 % of a 48 us CTA before) are paid once per SM instead of once per item.
+//  * PART OF THE EXPONENTIALS ON THE FMA PIPE.  At d = 40 the MUFU pipe (16 ex2 / clk / SM) is the floor: 2048 clk per
+//    128-key tile pair against ~800 clk of tensor work.  POLY16 of every 16 exponentials are evaluated as
+//    2^x = 2^n * p(f), n = round(x), f = x - n in [-1/2, 1/2], p a degree-3 minimax polynomial (max relative error 1.0e-4
+//    in fp32 -- P is rounded to bf16, 3.9e-3, right after): magic-number rounding, three FFMA2 (two logits per
+//    instruction) and one integer shift-add into the exponent field; 5 issue slots per exponential instead of 1, on pipes
+//    that were half empty.  (The same idea as FlashAttention-4's software exp2; here the share is a template parameter.)
+// Overflow of the single-pass tiles (a logit more than ~132 nats above every earlier key of the row) is DETECTED: the
+// row sum leaves its safe range, the item's flag is set and launch_attn3 runs the exact (two-pass) variant over the
+// flagged items right behind -- the row is recomputed instead of coming out as NaN.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr float EXP2_C0 = 0.9999281168f, EXP2_C1 = 0.6932609677f, EXP2_C2 = 0.2426108569f, EXP2_C3 = 0.05517145991f;
+
+// 2^x for two logits on the FMA / ALU pipes.  t = x + 1.5 * 2^23 holds round(x) in its low mantissa bits; t - 1.5 * 2^23
+// and x - round(x) are exact; (bits(t) << 23) is n << 23 (the constant's bits leave the word), added to p's bits it scales
+// p(f) in [0.707, 1.414] by 2^n.  x is clamped at -125 so the exponent field cannot wrap (2^-125 is 0 next to any row sum).
+__device__ __forceinline__ void exp2_fma2(f32x2 x, uint32_t& o0, uint32_t& o1) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const f32x2 xc = pk2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const f32x2 t = add2(xc, pk2(12582912.0f, 12582912.0f));
+  const f32x2 r = add2(t, pk2(-12582912.0f, -12582912.0f));
+  const f32x2 f = fma2(r, pk2(-1.0f, -1.0f), xc);
+  f32x2 pl = fma2(pk2(EXP2_C3, EXP2_C3), f, pk2(EXP2_C2, EXP2_C2));
+  pl = fma2(pl, f, pk2(EXP2_C1, EXP2_C1));
+  pl = fma2(pl, f, pk2(EXP2_C0, EXP2_C0));
+  float p0, p1, t0, t1;
+  upk2(pl, p0, p1);
+  upk2(t, t0, t1);
+  o0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  o1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+}
+
+// which of every 8 logit pairs take the FMA-pipe path, spread so the two kinds interleave in program order
+template <int POLY16> struct PolyMask;
+template <> struct PolyMask<0> { static constexpr unsigned value = 0x00u; };
+template <> struct PolyMask<2> { static constexpr unsigned value = 0x08u; };
+template <> struct PolyMask<4> { static constexpr unsigned value = 0x22u; };
+template <> struct PolyMask<6> { static constexpr unsigned value = 0x4Au; };
+template <> struct PolyMask<8> { static constexpr unsigned value = 0xAAu; };
+
+constexpr int ATT3_ST = 3;   // K / V ring depth
+// shared memory: 2 Q buffers x 2 query tiles | K ring | V ring | exchange (tile-0 maxima + 16-bit sums, final sums) | barriers
+constexpr int ATT3_V_STAGE_BYTES = 2 * 64 * 128;
+constexpr int ATT3_NBAR = 4 + 2 * ATT3_ST + 12;   // q_full[2] q_free[2] kv_full[ST] kv_empty[ST] s_full[2] p_full[2] pv_done[4] s_free[2] + tmem ptr + pad
+constexpr size_t ATT3_SMEM = 4 * CHUNK_BYTES + ATT3_ST * CHUNK_BYTES + ATT3_ST * ATT3_V_STAGE_BYTES + 2048 + 2048 + 8 * ATT3_NBAR;
+
+template <int POLY16>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ AttnParams p) {
+  griddep_launch_dependents();
+  extern __shared__ __align__(1024) uint8_t smem_att3[];
+  uint8_t* smem_gen = smem_att3;
+  const uint32_t smem_base = smem_u32(smem_gen);
+  if ((smem_base & 1023u) != 0u) __trap();
+  const int v_chunk_bytes = p.dv * 128;
+  const uint32_t sQ = smem_base;                              // [2 buffers][2 query tiles]
+  const uint32_t sK = sQ + 4 * CHUNK_BYTES;
+  const uint32_t sV = sK + ATT3_ST * CHUNK_BYTES;
+  const uint32_t sX = sV + ATT3_ST * ATT3_V_STAGE_BYTES;      // tile-0 maxima (fp32) / running 16-bit sums, as in flash_attn2_kernel
+  const uint32_t sXF = sX + 2048;                             // final row sums: [2 wg][2 halves][128] floats (own region: the
+                                                              // next item's tile-0 exchange must not overwrite them mid-read)
+  const uint32_t sBar = sXF + 2048;
+  float* x_gen = reinterpret_cast<float*>(smem_gen + (sX - smem_base));
+  float* xf_gen = reinterpret_cast<float*>(smem_gen + (sXF - smem_base));
+  constexpr int ST = ATT3_ST;
+  auto q_full = [&](int qb) { return sBar + 8u * qb; };
+  auto q_free = [&](int qb) { return sBar + 8u * (2 + qb); };
+  auto kv_full = [&](int s) { return sBar + 8u * (4 + s); };
+  auto kv_empty = [&](int s) { return sBar + 8u * (4 + ST + s); };
+  auto s_full = [&](int g) { return sBar + 8u * (4 + 2 * ST + g); };
+  auto p_full = [&](int g) { return sBar + 8u * (6 + 2 * ST + g); };
+  auto pv_done = [&](int g, uint32_t par) { return sBar + 8u * (8 + 2 * ST + g * 2 + par); };
+  auto s_free = [&](int g) { return sBar + 8u * (12 + 2 * ST + g); };
+  const uint32_t tmem_ptr_addr = sBar + 8u * (14 + 2 * ST);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
+
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
+  const int lane = threadIdx.x & 31;
+  const int T = (p.N + KT - 1) / KT;
+  const int total = p.total_items;
+  const int step = static_cast<int>(gridDim.x);
+  // exact re-run: only the items the single-pass launch flagged.  Every role walks the same list: the flags are only read
+  // here (they are cleared after the final __syncthreads below).
+  auto live = [&](int item) { return p.check_flags == 0 || __ldg(p.flags + item) != 0; };
+  auto next_live = [&](int item) {
+    while (item < total && !live(item)) item += step;
+    return item;
+  };
+  auto coords = [&](int item, int& q0, int& head, int& b) {
+    const int qt = item % p.qtiles;
+    const int r = item / p.qtiles;
+    head = r % p.heads;
+    b = r / p.heads;
+    q0 = qt * 2 * QT;
+  };
+
+  if (warp == 17 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full(i), 1);
+      mbar_init(q_free(i), 2);       // one tcgen05.commit per MMA warp
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 8);
+      mbar_init(pv_done(i, 0), 1);
+      mbar_init(pv_done(i, 1), 1);
+      mbar_init(s_free(i), 8);
+    }
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 16) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
+  griddep_wait();
+
+  const int first = next_live(static_cast<int>(blockIdx.x));
+
+  if (warp == 16 || warp == 17) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
+    // ================= MMA issue for warpgroup g: one flat sequence of tiles over all items of this CTA =================
+    const int g = warp - 16;
+    const uint32_t idesc_qk = umma_idesc_bf16(128, KT);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, p.dv);
+    const uint32_t tmem_S = tmem_base + g * 128;
+    const uint32_t tmem_O = tmem_base + 256 + g * 64;
+    const uint32_t tmem_P = tmem_base + 384 + g * 64;
+    auto issue_qk = [&](int qb, int st) {
+      const uint64_t qdesc = umma_desc_sw128(sQ + (qb * 2 + g) * CHUNK_BYTES);
+      const uint64_t kdesc = umma_desc_sw128(sK + st * CHUNK_BYTES);
+      for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16_ss_elect(tmem_S, qdesc + 2u * ks, kdesc + 2u * ks, idesc_qk, ks > 0 ? 1u : 0u);
+      umma_commit_elect(s_full(g));
+    };
+    if (first < total) {
+      int item = first;
+      uint32_t k = 0;                      // live items so far
+      uint32_t gt = 0;                     // tiles so far
+      int st = 0, st_next = (ST > 1) ? 1 : 0;
+      uint32_t ph_next = (ST > 1) ? 0u : 1u;   // kv_full parity of tile gt + 1
+      mbar_wait(q_full(0), 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      if (T == 1) umma_commit_elect(q_free(0));
+      while (true) {
+        const int nxt = next_live(item + step);
+        for (int j = 0; j < T; ++j, ++gt) {
+          const bool last = (j + 1 == T);
+          if (!last || nxt < total) {
+            // S(gt + 1): as soon as every softmax warp has read S(gt) for the last time
+            mbar_wait(s_free(g), gt & 1u);
+            const uint32_t kk = last ? k + 1 : k;          // the item tile gt + 1 belongs to
+            if (last) mbar_wait(q_full(kk & 1u), (kk >> 1) & 1u);
+            mbar_wait(kv_full(st_next), ph_next);
+            tc_fence_after();
+            issue_qk(static_cast<int>(kk & 1u), st_next);
+            // the last Q.K^T of an item: its Q buffer may be refilled once these MMAs have retired
+            if (last ? (T == 1) : (j + 2 == T)) umma_commit_elect(q_free(kk & 1u));
+          }
+          mbar_wait(p_full(g), gt & 1u);      // P(gt) is in tensor memory
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < KT / 16; ++ks) {
+            const uint64_t vdesc = umma_desc_sw128(sV + st * ATT3_V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
+            umma_bf16_ts_elect(tmem_O, tmem_P + 8u * ks, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit_elect(pv_done(g, gt & 1u));
+          umma_commit_elect(kv_empty(st));
+          st = st_next;
+          if (++st_next == ST) { st_next = 0; ph_next ^= 1u; }
+        }
+        if (nxt >= total) break;
+        item = nxt;
+        ++k;
+      }
+    }
+  } else if (warp == 19) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
+  } else if (warp == 18) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
+    // ================= Q / K / V loads, running ahead of the other roles across items =================
+    uint32_t k = 0, gt = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int item = first; item < total; item = next_live(item + step), ++k) {
+      int q0, head, b;
+      coords(item, q0, head, b);
+      const int qb = static_cast<int>(k & 1u);
+      if (k >= 2) mbar_wait(q_free(qb), ((k >> 1) - 1u) & 1u);   // the Q.K^T MMAs of item k - 2 have retired
+      mbar_expect_tx_elect(q_full(qb), 2 * CHUNK_BYTES);
+      tma_load_4d_elect(sQ + (qb * 2) * CHUNK_BYTES, &tmQK, q_full(qb), 0, head, q0, b);
+      tma_load_4d_elect(sQ + (qb * 2 + 1) * CHUNK_BYTES, &tmQK, q_full(qb), 0, head, q0 + QT, b);
+      for (int t = 0; t < T; ++t, ++gt) {
+        if (gt >= static_cast<uint32_t>(ST)) mbar_wait(kv_empty(st), ph ^ 1u);   // both P.V of the tile that used this stage retired
+        mbar_expect_tx_elect(kv_full(st), CHUNK_BYTES + 2 * v_chunk_bytes);
+        tma_load_4d_elect(sK + st * CHUNK_BYTES, &tmQK, kv_full(st), 0, p.heads + head, t * KT, b);
+        tma_load_3d_elect<false>(sV + st * ATT3_V_STAGE_BYTES, &tmV, kv_full(st), t * KT, head * p.d, b);
+        tma_load_3d_elect<false>(sV + st * ATT3_V_STAGE_BYTES + v_chunk_bytes, &tmV, kv_full(st), t * KT + 64, head * p.d, b);
+        if (++st == ST) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT2_SOFTMAX_REGS));
+    // ================= softmax (16 warps: warpgroup g = query tile, two threads per row) =================
+    const int g = warp >> 3;
+    const int sub = (warp >> 2) & 1;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tmem_S = tmem_base + g * 128 + sub * 64;
+    const uint32_t tmem_O = tmem_base + 256 + g * 64;
+    const uint32_t tmem_P = tmem_base + 384 + g * 64 + sub * 32;
+    auto store_p = [&](const uint32_t (&v)[32], int h) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      tmem_st_x16(tmem_P + lane_off + h * 16, pk);
+    };
+    float* xmine = x_gen + (g * 2 + sub) * 128 + row;
+    float* xpeer = x_gen + (g * 2 + (sub ^ 1)) * 128 + row;
+    float* xfmine = xf_gen + (g * 2 + sub) * 128 + row;
+    float* xfpeer = xf_gen + (g * 2 + (sub ^ 1)) * 128 + row;
+    const int bar_id = 1 + g;
+    const float sl2 = p.scale_log2;
+    const float bias = p.two_pass ? 0.0f : ATT2_BIAS;
+    const f32x2 sl2_2 = pk2(sl2, sl2);
+    const uint32_t xs_mine = sX + (((g * 2 + 0) * 2 + sub) * 128 + row) * 2;
+    const uint32_t xs_peer = sX + (((g * 2 + 0) * 2 + (sub ^ 1)) * 128 + row) * 2;
+    const int T_full = p.N / KT;
+    uint32_t gt = 0;   // tiles so far (barrier phases)
+
+    for (int item = first; item < total; item = next_live(item + step)) {
+      int q0, head, b;
+      coords(item, q0, head, b);
+      float m_run = -INFINITY;   // reference maximum of the two-pass tiles
+      float l_run = 0.0f;        // partial row sum over this thread's columns
+      float mrs = 0.0f;          // reference maximum in log2 units (single-pass tiles)
+      float sm1 = 0.0f, sm2 = 0.0f, rf1 = 0.0f, rf2 = 0.0f;
+
+      // exact tile (tile 0 of every item; every tile of the exact re-run): see flash_attn2_kernel
+      auto tile = [&](int j, auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        mbar_wait(s_full(g), gt & 1u);
+        tc_fence_after();
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_S + lane_off + h * 32, v);
+          tmem_ld_wait();
+          if (MASKED) {
+            const int kvalid = p.N - j * KT - sub * 64 - h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i >= kvalid) v[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 4])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[i + 1]), __uint_as_float(v[i + 5])));
+            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 6])));
+            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[i + 3]), __uint_as_float(v[i + 7])));
+          }
+        }
+        const float mpart = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        *xmine = mpart;
+        named_bar_sync(bar_id, 256);
+        const float mx = fmaxf(mpart, *xpeer);
+        float alpha = 1.0f;
+        if (__any_sync(0xffffffffu, (mx - m_run) * sl2 > 8.0f)) {
+          const float m_new = fmaxf(m_run, mx);
+          alpha = ex2((m_run - m_new) * sl2);
+          m_run = m_new;
+          if (j > 0 && sub == 0) {
+            mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
+            tc_fence_after();
+            rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
+          }
+        }
+        const float mneg = fmaf(-m_run, sl2, -bias);
+        float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_S + lane_off + h * 32, v);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(g));
+          }
+          if (MASKED) {
+            const int kvalid = p.N - j * KT - sub * 64 - h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i >= kvalid) v[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2(fmaf(__uint_as_float(v[i]), sl2, mneg)));
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            sum0 += __uint_as_float(v[c + 0]) + __uint_as_float(v[c + 4]);
+            sum1 += __uint_as_float(v[c + 1]) + __uint_as_float(v[c + 5]);
+            sum2 += __uint_as_float(v[c + 2]) + __uint_as_float(v[c + 6]);
+            sum3 += __uint_as_float(v[c + 3]) + __uint_as_float(v[c + 7]);
+          }
+          if (h == 0 && j > 0) {   // P is single-buffered: P.V of the previous tile must have read it.  (Tile 0 of an item:
+                                   // every softmax thread waited for the previous item's last P.V in its epilogue.)
+            mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
+            tc_fence_after();
+          }
+          store_p(v, h);
+        }
+        l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+        ++gt;
+      };
+
+      // single-pass tile (flash_attn2_kernel's tile1p) with PolyMask<POLY16> of the exponentials on the FMA pipe
+      auto tile1p = [&](int j, auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        mbar_wait(s_full(g), gt & 1u);
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(tmem_S + lane_off, va);
+        tmem_ld_x32(tmem_S + lane_off + 32, vb);
+        float alpha = 1.0f;
+        if (j >= 2) {
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(xs_mine + (((j - 1) & 1) << 9)),
+                       "h"(static_cast<unsigned short>(__float_as_uint(sm1) >> 16)) : "memory");
+          if (j >= 3) {
+            unsigned short peer_bits;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(peer_bits) : "r"(xs_peer + ((j & 1) << 9)) : "memory");
+            const float peer = __uint_as_float(static_cast<uint32_t>(peer_bits) << 16);
+            const float est = rf2 + ATT2_BIAS + __log2f(sm2 + peer);
+            if (__any_sync(0xffffffffu, est - mrs > 8.0f)) {
+              const float m_new = fmaxf(mrs, est);
+              alpha = ex2(mrs - m_new);
+              mrs = m_new;
+              if (sub == 0) {
+                mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
+                tc_fence_after();
+                rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
+              }
+            }
+          }
+        }
+        const float mneg = -mrs - ATT2_BIAS;
+        const f32x2 mneg_2 = pk2(mneg, mneg);
+        f32x2 acc0 = pk2(0.0f, 0.0f), acc1 = acc0;
+        auto half = [&](uint32_t (&v)[32], int h) {
+          if (MASKED) {
+            const int kvalid = p.N - j * KT - sub * 64 - h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i >= kvalid) v[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2_2, mneg_2);
+            if ((PolyMask<POLY16>::value >> ((i >> 1) & 7)) & 1u) {
+              exp2_fma2(x, v[i], v[i + 1]);
+            } else {
+              float x0, x1;
+              upk2(x, x0, x1);
+              v[i] = __float_as_uint(ex2(x0));
+              v[i + 1] = __float_as_uint(ex2(x1));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            acc0 = add2(acc0, pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            acc1 = add2(acc1, pk2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+          }
+          if (h == 0) {   // j >= 1 here
+            mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
+            tc_fence_after();
+          }
+          store_p(v, h);
+        };
+        tmem_ld_wait_x32x2(va, vb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free(g));
+        half(va, 0);
+        half(vb, 1);
+        float t0, t1, t2, t3;
+        upk2(acc0, t0, t1);
+        upk2(acc1, t2, t3);
+        const float tsum = (t0 + t1) + (t2 + t3);
+        l_run = l_run * alpha + tsum;
+        sm2 = sm1; rf2 = rf1;
+        sm1 = __bfloat162float(__float2bfloat16_rn(tsum)); rf1 = mrs;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+        ++gt;
+      };
+
+      if (p.two_pass) {
+        for (int j = 0; j < T_full; ++j) tile(j, std::false_type{});
+        if (T_full < T) tile(T_full, std::true_type{});
+      } else {
+        tile(0, std::false_type{});          // N > 128 here: the first tile is always full
+        mrs = m_run * sl2;
+        for (int j = 1; j < T_full; ++j) tile1p(j, std::false_type{});
+        if (T_full < T) tile1p(T_full, std::true_type{});
+      }
+
+      // ---- row sums of the two halves, overflow check, O / l -> out ----
+      *xfmine = l_run;
+      named_bar_sync(bar_id, 256);
+      const float l_tot = l_run + *xfpeer;
+      mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
+      tc_fence_after();
+      const int tok = q0 + g * QT + row;
+      if (!p.two_pass && p.flags != nullptr) {
+        const bool bad = (tok < p.N) && !(l_tot < ATT_L_SAFE);       // also true for NaN
+        if (__any_sync(0xffffffffu, bad) && lane == 0) p.flags[item] = 1;
+      }
+      if (sub == 0) {
+        const float inv_l = 1.0f / l_tot;
+        bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
+        for (int c = 0; c < p.dv; c += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(tmem_O + lane_off + c, o);
+          tmem_ld_wait();
+          if (tok < p.N) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              if (c + i < p.d) {
+                uint4 pk;
+                pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+                pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+                pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+                pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c + i) = pk;
+              }
+            }
+          }
+        }
+        tc_fence_before();   // these reads of O precede the next item's first P.V (ordered through p_full)
+      }
+      // the final sums are read; the next item's tile 0 reuses the max-exchange slots only after its own barrier
+      named_bar_sync(bar_id, 256);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.check_flags) {   // exact re-run: the flags it consumed are cleared for the next launch
+    for (int item = static_cast<int>(blockIdx.x) + static_cast<int>(threadIdx.x) * step; item < total; item += step * ATT2_THREADS)
+      p.flags[item] = 0;
+  }
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
 constexpr size_t ATT2_SMEM = 2 * CHUNK_BYTES + ATT2_KV_STAGES * CHUNK_BYTES + ATT2_KV_STAGES * (2 * 64 * 128) +
                              2048 + 8 * (12 + 2 * ATT2_KV_STAGES);
+
+void fill_params(const AttnPlan& plan, AttnParams* p) {
+  p->N = plan.N; p->heads = plan.heads; p->d = plan.d;
+  p->dv = (plan.d + 15) / 16 * 16;
+  p->ksteps = (plan.d + 15) / 16;
+  p->C = plan.heads * plan.d;
+  p->scale_log2 = plan.scale_log2;
+  p->out = plan.out;
+  p->flags = plan.flags;
+  p->check_flags = 0;
+  p->two_pass = 0;
+  p->qtiles = (plan.N + 2 * QT - 1) / (2 * QT);
+  p->total_items = p->qtiles * plan.heads * plan.B;
+}
+
+// PBE_ATTN_TWO_PASS=1: exact running maximum in every tile (no single-pass tiles, no re-run); PBE_ATTN_KERNEL=2: the
+// round-1 non-persistent kernel for head dims <= 64 (A/B comparisons); PBE_ATTN_POLY=0|2|4|6|8: exponentials per 16 on the
+// FMA pipe (default 4); PBE_ATTN_RERUN=0: skip the exact re-run launch (overflowing rows then stay NaN, as in round 1).
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+bool attn_two_pass() { static const int v = env_int("PBE_ATTN_TWO_PASS", 0); return v != 0; }
+bool attn_rerun() { static const int v = env_int("PBE_ATTN_RERUN", 1); return v != 0; }
 
 int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
@@ -733,18 +1270,65 @@ int launch_attn2(const AttnPlan& plan, cudaStream_t stream) {
     attr_set = true;
   }
   AttnParams p;
-  p.N = plan.N; p.heads = plan.heads; p.d = plan.d;
-  p.dv = (plan.d + 15) / 16 * 16;
-  p.ksteps = (plan.d + 15) / 16;
-  p.C = plan.heads * plan.d;
-  p.scale_log2 = plan.scale_log2;
-  p.out = plan.out;
-  static const int two_pass = [] { const char* e = getenv("PBE_ATTN_TWO_PASS"); return (e && atoi(e) != 0) ? 1 : 0; }();
-  p.two_pass = two_pass;
+  fill_params(plan, &p);
+  p.flags = nullptr;
+  p.two_pass = attn_two_pass() ? 1 : 0;
   dim3 grid((plan.N + 2 * QT - 1) / (2 * QT), plan.heads, plan.B);
   PBE_CHECK_CUDA(launch_k(flash_attn2_kernel, dim3(grid), dim3(ATT2_THREADS), ATT2_SMEM, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int attn_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int POLY16>
+int launch_attn3_t(const AttnPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  static_assert(ATT3_SMEM <= 227 * 1024, "attention smem");
+  if (!attr_set) {
+    PBE_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<POLY16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(ATT3_SMEM)));
+    attr_set = true;
+  }
+  AttnParams p;
+  fill_params(plan, &p);
+  const dim3 grid(static_cast<unsigned>(std::min(p.total_items, attn_num_sms())));
+  if (attn_two_pass()) {   // exact everywhere: one launch, nothing to re-run
+    p.two_pass = 1;
+    p.flags = nullptr;
+    PBE_CHECK_CUDA(launch_k(flash_attn3_kernel<POLY16>, grid, dim3(ATT2_THREADS), ATT3_SMEM, stream, plan.tmQ, plan.tmV, p));
+    return 0;
+  }
+  if (!attn_rerun()) p.flags = nullptr;
+  PBE_CHECK_CUDA(launch_k(flash_attn3_kernel<POLY16>, grid, dim3(ATT2_THREADS), ATT3_SMEM, stream, plan.tmQ, plan.tmV, p));
+  if (p.flags != nullptr) {
+    // exact re-run of the (normally zero) items whose single-pass tiles overflowed: every CTA scans its items' flags
+    p.two_pass = 1;
+    p.check_flags = 1;
+    PBE_CHECK_CUDA(launch_k(flash_attn3_kernel<POLY16>, grid, dim3(ATT2_THREADS), ATT3_SMEM, stream, plan.tmQ, plan.tmV, p));
+  }
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_attn3(const AttnPlan& plan, cudaStream_t stream) {
+  static const int poly = env_int("PBE_ATTN_POLY", 4);
+  switch (poly) {
+    case 0: return launch_attn3_t<0>(plan, stream);
+    case 2: return launch_attn3_t<2>(plan, stream);
+    case 6: return launch_attn3_t<6>(plan, stream);
+    case 8: return launch_attn3_t<8>(plan, stream);
+    default: return launch_attn3_t<4>(plan, stream);
+  }
 }
 
 template <int DK_CHUNKS, int KV_STAGES>
@@ -764,24 +1348,50 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
     attr_set = true;
   }
   AttnParams p;
-  p.N = plan.N; p.heads = plan.heads; p.d = plan.d;
-  p.dv = (plan.d + 15) / 16 * 16;
-  p.ksteps = (plan.d + 15) / 16;
-  p.C = plan.heads * plan.d;
-  p.scale_log2 = plan.scale_log2;
-  p.out = plan.out;
-  p.two_pass = 1;
+  fill_params(plan, &p);
+  if (attn_two_pass()) { p.two_pass = 1; p.flags = nullptr; }
+  else if (!attn_rerun()) p.flags = nullptr;
   PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
+  if (p.flags != nullptr && !p.two_pass) {
+    p.two_pass = 1;
+    p.check_flags = 1;
+    PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
+  }
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// Overflow flags: one int per work item, zero between launches (the exact re-run clears what it consumed).  Plans built by
+// an engine get their own slice of a per-device pool; one-off plans (pbe_op_self_attention) share the first slice, which is
+// safe for launches on one stream.
+constexpr int FLAG_POOL_INTS = 1 << 20, FLAG_SHARED_INTS = 1 << 16;
+int* attn_flags(int n, bool own) {
+  static std::mutex mu;
+  static std::map<int, std::pair<int*, int>> pools;   // device -> (base, next free)
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = pools.find(dev);
+  if (it == pools.end()) {
+    int* base = nullptr;
+    if (cudaMalloc(&base, sizeof(int) * FLAG_POOL_INTS) != cudaSuccess) return nullptr;
+    cudaMemset(base, 0, sizeof(int) * FLAG_POOL_INTS);
+    it = pools.emplace(dev, std::make_pair(base, FLAG_SHARED_INTS)).first;
+  }
+  if (n > FLAG_SHARED_INTS) return nullptr;           // no flags: such a plan runs without the re-run
+  if (!own || it->second.second + n > FLAG_POOL_INTS) return it->second.first;
+  int* r = it->second.first + it->second.second;
+  it->second.second += n;
+  return r;
+}
+
 }  // namespace
 
-int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan) {
+int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan, bool own_flags) {
   PBE_REQUIRE(d % 8 == 0 && d <= 160, "head dim must be a multiple of 8, <= 160");
   const int C = heads * d;
   plan->B = B; plan->N = N; plan->heads = heads; plan->d = d;
+  plan->flags = attn_flags(((N + QT - 1) / QT) * heads * B, own_flags);
   plan->scale_log2 = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(d)));
   plan->out = out;
   plan->grid = dim3((N + QT - 1) / QT, heads, B);
@@ -812,9 +1422,14 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
   return 0;
 }
 
+int attn_num_launches(const AttnPlan& plan) {
+  return (plan.flags != nullptr && !attn_two_pass() && attn_rerun()) ? 2 : 1;
+}
+
 int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream) {
   const int chunks = (plan.d + 63) / 64;
-  if (chunks == 1 && plan.N > QT) return launch_attn2(plan, stream);
+  static const int which = env_int("PBE_ATTN_KERNEL", 3);
+  if (chunks == 1 && plan.N > QT) return which == 2 ? launch_attn2(plan, stream) : launch_attn3(plan, stream);
   switch (chunks) {
     case 1: return launch_attn_t<1, 2>(plan, stream);
     case 2: return launch_attn_t<2, 2>(plan, stream);

@@ -625,12 +625,12 @@ int Engine::build(Prepared& P, bool dry) {
         bf16* ao = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
         if (!dry) {
           auto plan = std::make_shared<AttnPlan>();
-          int rc = build_attn_plan(qk, vt, ao, Bc, N, s.heads, s.d, plan.get());
+          int rc = build_attn_plan(qk, vt, ao, Bc, N, s.heads, s.d, plan.get(), true);
           if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + tag + ".attn]"; }
-          add_op_meta(tag + ".attn1", 1, [plan](cudaStream_t st) { return launch_attn_plan(*plan, st); }, "attention",
+          add_op_meta(tag + ".attn1", attn_num_launches(*plan), [plan](cudaStream_t st) { return launch_attn_plan(*plan, st); }, "attention",
                       4.0 * Bc * static_cast<double>(N) * N * C, static_cast<double>(M) * C * 2.0 * 4.0);
         } else {
-          launches += 1;
+          launches += 2;
         }
         float* t1 = static_cast<float*>(SA(M * (diverged ? 1 : 2) * C * sizeof(float)));
         for (int half = 0; half < (diverged ? 1 : 2); ++half) {

@@ -170,12 +170,16 @@ struct AttnPlan {
   bf16* out;
   dim3 grid;
   size_t smem;
+  int* flags;   // per-item overflow flags of the single-pass softmax (attn_tc.cu); null = no exact re-run
 };
 // Row pitch (elements) of the transposed V buffer [B][C][vt_pitch(N)]: token counts that are not multiples of 8 are padded
 // so that every row starts 16-byte aligned (TMA global stride requirement); the pad columns are never read.
 inline int vt_pitch(int N) { return (N + 7) & ~7; }
-int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan);
+// own_flags: give the plan its own overflow-flag slice (long-lived engine plans); false = the shared slice (one-off plans)
+int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int heads, int d, AttnPlan* plan,
+                    bool own_flags = false);
 int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream);
+int attn_num_launches(const AttnPlan& plan);   // 2 with the exact re-run of overflowed items behind the single-pass kernel
 
 // ------------------------------------------------------------------------------------------------
 // Normalisation / elementwise kernels (norm.cu, misc.cu)

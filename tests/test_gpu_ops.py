@@ -227,6 +227,63 @@ def test_self_attention_drifting_maximum(lib, N, d, heads, drift):
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("N,d,heads,kind", [(4096, 40, 8, "ramp80"), (4096, 40, 8, "step"), (1035, 40, 8, "step"),
+                                           (257, 64, 16, "step"), (1024, 80, 8, "ramp150"), (1024, 80, 8, "step"),
+                                           (576, 160, 8, "step"), (4096, 40, 8, "late_step")])
+def test_self_attention_overflow_is_recomputed_exactly(lib, N, d, heads, kind):
+    """Logits that outrun the single-pass tiles' stale reference by more than its headroom (> 132 nats above every earlier
+    key): round 1 documented the row as NaN.  Now the kernel notices (the row sum leaves its safe range), flags the work item,
+    and the exact (running-maximum) variant launched right behind recomputes exactly those items: finite and equal to the fp32
+    softmax (attention.py:217-229) -- which at such logits is a one-hot on the last keys.  B = 2 with only sample 0
+    pathological: the re-run must touch flagged items only and leave the rest bit-identical to a plain run."""
+    dev = torch.device("cuda:0")
+    B = 2
+    g = torch.Generator().manual_seed(11 + N + d)
+    C = heads * d
+    q = torch.randn(B, N, heads, d, generator=g)
+    k = torch.randn(B, N, heads, d, generator=g) * 0.5
+    u = torch.nn.functional.normalize(torch.randn(heads, d, generator=g), dim=-1)
+    idx = torch.arange(N, dtype=torch.float32)
+    if kind.startswith("ramp"):            # a sustained climb of 80 / 150 nats per 128 keys
+        prof = idx / 128.0 * float(kind[4:])
+    elif kind == "step":                    # flat, then +400 nats from the middle on
+        prof = (idx >= N // 2).float() * 400.0
+    else:                                   # the jump sits in the very last keys (the masked / final tile)
+        prof = (idx >= N - 3).float() * 300.0
+    comp = prof * math.sqrt(d) / 4.0
+    q0 = q[0] - (q[0] * u).sum(-1, keepdim=True) * u + 4.0 * u
+    k0 = k[0] - (k[0] * u).sum(-1, keepdim=True) * u + comp.view(N, 1, 1) * u
+    q = torch.stack((q0, q[1]))
+    k = torch.stack((k0, k[1]))
+    q = q.reshape(B, N, C).to(dev).bfloat16()
+    k = k.reshape(B, N, C).to(dev).bfloat16()
+    v = torch.randn(B, N, C, generator=g).to(dev).bfloat16()
+    qk = torch.cat((q, k), dim=-1).contiguous()
+    Np = (N + 7) // 8 * 8
+    vt = torch.zeros(B, C, Np, device=dev, dtype=torch.bfloat16)
+    vt[:, :, :N] = v.transpose(1, 2)
+    out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
+    rc = lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, _stream())
+    assert rc == 0, _err(lib)
+    torch.cuda.synchronize()
+
+    def split(t):
+        return t.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+
+    sim = torch.einsum("bhid,bhjd->bhij", split(q).double(), split(k).double()) * d ** -0.5
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), split(v).double()).permute(0, 2, 1, 3).reshape(B, N, C).float()
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out[0], ref[0]) < 1e-2, _rel(out[0], ref[0])
+    assert _rel(out[1], ref[1]) < 1e-2, _rel(out[1], ref[1])
+    # the benign sample alone gives the same bits: the re-run did not touch it, and the flags were left clean
+    out1 = torch.zeros(1, N, C, device=dev, dtype=torch.bfloat16)
+    rc = lib.pbe_op_self_attention(qk[1:].contiguous().data_ptr(), vt[1:].contiguous().data_ptr(), out1.data_ptr(), 1, N, heads, d,
+                                   _stream())
+    assert rc == 0, _err(lib)
+    torch.cuda.synchronize()
+    assert torch.equal(out1[0], out[1])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Nb,HW,C0,C1,eps,silu", [(2, 4096, 320, 0, 1e-5, 1), (2, 1024, 640, 320, 1e-5, 1),
                                                   (2, 256, 1280, 640, 1e-5, 1), (3, 64, 1280, 1280, 1e-5, 1),
@@ -312,8 +369,8 @@ def test_sampler_step_bit_exact_vs_oracle(lib, order, cfg):
     e_out, xp, x0 = (torch.empty(shape, device=dev) for _ in range(3))
     rc = lib.pbe_sampler_step(eu_d.data_ptr(), ec_d.data_ptr() if cfg else None, ctypes.c_float(scale), cfg, order,
                               h1_d.data_ptr(), h2_d.data_ptr(), h3_d.data_ptr(), x_d.data_ptr(), ctypes.c_float(a_t),
-                              ctypes.c_float(a_prev), ctypes.c_float(sig), ctypes.c_float(s1m), None, e_out.data_ptr(),
-                              xp.data_ptr(), x0.data_ptr(), x.numel(), _stream())
+                              ctypes.c_float(a_prev), ctypes.c_float(sig), ctypes.c_float(s1m), None, ctypes.c_float(1.0),
+                              e_out.data_ptr(), xp.data_ptr(), x0.data_ptr(), x.numel(), _stream())
     assert rc == 0, _err(lib)
     torch.cuda.synchronize()
     assert torch.equal(e_out.cpu(), e)
@@ -325,7 +382,7 @@ def test_build_unet_input(lib):
     dev = torch.device("cuda:0")
     x, z, m = torch.randn(3, 4, 32, 32, device=dev), torch.randn(3, 4, 32, 32, device=dev), torch.rand(3, 1, 32, 32, device=dev)
     out = torch.empty(6, 9, 32, 32, device=dev)
-    rc = lib.pbe_build_unet_input(x.data_ptr(), z.data_ptr(), m.data_ptr(), out.data_ptr(), 3, 32 * 32, 2, _stream())
+    rc = lib.pbe_build_unet_input(x.data_ptr(), z.data_ptr(), m.data_ptr(), out.data_ptr(), 3, 4, 4, 1, 32 * 32, 2, _stream())
     assert rc == 0, _err(lib)
     torch.cuda.synchronize()
     ref = torch.cat([torch.cat((x, z, m), 1)] * 2)

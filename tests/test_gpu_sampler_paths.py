@@ -158,18 +158,18 @@ def _kw(req, dev, B):
 @pytest.mark.parametrize("eta,temperature", [(0.5, 1.0), (0.7, 0.8), (1.0, 1.3)])
 def test_ddim_eta_and_temperature_bit_exact(toy, dev, eta, temperature):
     """DDIM with eta > 0 and a temperature: the noise drawn from the CUDA generator at the reference's point (after the model
-    call, ddim.py:238) enters as (sigma_t * noise) * temperature; 12 steps, every intermediate compared."""
+    call, ddim.py:238) enters as (sigma_t * noise) * temperature; 10 steps, every intermediate compared."""
     from oracle import sampler_ref as S
     from pbe_b200.samplers import DDIMSampler
     prod, orc, req, _, _ = toy
     torch.manual_seed(2024)
-    out, inter = DDIMSampler(prod).sample(S=12, eta=eta, temperature=temperature, log_every_t=1, **_kw(req, dev, 3))
+    out, inter = DDIMSampler(prod).sample(S=10, eta=eta, temperature=temperature, log_every_t=1, **_kw(req, dev, 3))
     torch.manual_seed(2024)
     rec = []
-    ref = S.ddim_sample(orc, 12, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"], record=rec, eta=eta,
+    ref = S.ddim_sample(orc, 10, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"], record=rec, eta=eta,
                         temperature=temperature, rng_device=dev)
     assert torch.equal(out.cpu(), ref)
-    assert len(inter["x_inter"]) == 13 and len(inter["pred_x0"]) == 13
+    assert len(inter["x_inter"]) == 11 and len(inter["pred_x0"]) == 11
     for k, r in enumerate(rec):      # buffers are reused between steps: the logged tensors must be snapshots
         assert torch.equal(inter["x_inter"][k + 1].cpu(), r["x_prev"]), k
         assert torch.equal(inter["pred_x0"][k + 1].cpu(), r["pred_x0"]), k
@@ -199,25 +199,25 @@ def test_mask_x0_blend_bit_exact(toy, dev, kind):
 
 
 def test_plms_plain_loop_and_callbacks_bit_exact(toy, dev):
-    """PLMS-9 (first-step double evaluation, AB2..AB4) with the reused step buffers: final latent, every logged
+    """PLMS-8 (first-step double evaluation, AB2..AB4) with the reused step buffers: final latent, every logged
     intermediate and the tensors handed to img_callback equal the oracle's."""
     from oracle import sampler_ref as S
     from pbe_b200.samplers import PLMSSampler
     prod, orc, req, _, _ = toy
     rec = []
-    ref = S.plms_sample(orc, 9, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"], record=rec)
+    ref = S.plms_sample(orc, 8, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"], record=rec)
     seen, steps = [], []
-    out, inter = PLMSSampler(prod).sample(S=9, eta=0.0, log_every_t=2, img_callback=lambda p, i: seen.append(p),
+    out, inter = PLMSSampler(prod).sample(S=8, eta=0.0, log_every_t=2, img_callback=lambda p, i: seen.append(p),
                                           callback=steps.append, **_kw(req, dev, 3))
     assert torch.equal(out.cpu(), ref)
-    assert steps == list(range(9)) and len(seen) == 9
+    assert steps == list(range(8)) and len(seen) == 8
     for k, r in enumerate(rec):
         assert torch.equal(seen[k].cpu(), r["pred_x0"]), k       # callback tensors are not overwritten by later steps
-    logged = [r for r in rec if r["index"] % 2 == 0 or r["index"] == 8]
+    logged = [r for r in rec if r["index"] % 2 == 0 or r["index"] == 7]
     assert len(inter["x_inter"]) == 1 + len(logged)
     for a, r in zip(inter["x_inter"][1:], logged):
         assert torch.equal(a.cpu(), r["x_prev"])
-    out_b, _ = PLMSSampler(prod).sample(S=9, eta=0.0, **_kw(req, dev, 3))
+    out_b, _ = PLMSSampler(prod).sample(S=8, eta=0.0, **_kw(req, dev, 3))
     assert torch.equal(out_b, out)
 
 
@@ -248,23 +248,23 @@ def test_sampler_shape_checks(toy, dev):
         kw = _kw(req, dev, 3)
         kw["test_model_kwargs"] = dict(images_inpaint=d(req["z_inpaint"][:1]), images_mask=d(req["mask"]))   # batch-1 z
         with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
-            cls(prod).sample(S=3, eta=0.0, **kw)
+            cls(prod).sample(S=4, eta=0.0, **kw)
         kw = _kw(req, dev, 3)
         kw["test_model_kwargs"] = dict(images_inpaint=d(req["z_inpaint"]),
                                        images_mask=d(torch.ones(3, 1, 128, 192)))                          # image-resolution mask
         with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
-            cls(prod).sample(S=3, eta=0.0, **kw)
+            cls(prod).sample(S=4, eta=0.0, **kw)
         kw = _kw(req, dev, 3)
         kw["x_T"] = d(req["x_T"][:2])                                                                      # x_T batch != batch_size
         with pytest.raises(RuntimeError, match="x_T has shape"):
-            cls(prod).sample(S=3, eta=0.0, **kw)
+            cls(prod).sample(S=4, eta=0.0, **kw)
 
     class Bad(_ToyProduct):
         def apply_model(self, x, t, c):
             return _toy_eps(x, t, c)[:, :, :8]          # wrong spatial size
 
     with pytest.raises(RuntimeError, match="model output has shape"):
-        PLMSSampler(Bad(dev)).sample(S=3, eta=0.0, **_kw(req, dev, 3))
+        PLMSSampler(Bad(dev)).sample(S=4, eta=0.0, **_kw(req, dev, 3))
 
 
 # ---- the real U-Net on the stochastic path ---------------------------------------------------------------------------
