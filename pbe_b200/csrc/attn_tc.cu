@@ -40,10 +40,10 @@ struct AttnParams {
   float scale_log2;
   bf16* out;
   int two_pass;   // 1 = exact running maximum in every tile (PBE_ATTN_TWO_PASS=1, and the overflow re-run), 0 = single-pass tiles
-  // overflow handling of the single-pass tiles: a work item (one CTA's query block) whose row sum left the safe range sets
-  // flags[item]; the exact re-run launched right behind (check_flags = 1) recomputes exactly those items and clears the flags
+  // overflow handling of the single-pass tiles: a work item (one CTA's query block) whose row sum left the safe range is
+  // recomputed by the same CTA, in the same launch, with the exact running maximum (flags: per-item marks of the persistent
+  // kernel, null = no second pass)
   int* flags;
-  int check_flags;
   int qtiles, total_items;   // flash_attn3_kernel (persistent): 256-query blocks per (sample, head), work items in total
 };
 
@@ -76,12 +76,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                   const __grid_constant__ AttnParams p) {
   griddep_launch_dependents();   // PDL (ptx.cuh): successor may be scheduled; griddep_wait() after the prologue
-  // work item = this CTA's (query tile, head, sample); the exact re-run (check_flags) only recomputes flagged items
-  const int item = static_cast<int>((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
-  if (p.check_flags) {
-    griddep_wait();
-    if (__ldg(p.flags + item) == 0) return;   // whole CTA, before any barrier / TMEM allocation
-  }
+  // One work item per CTA (query tile, head, sample).  If its single-pass tiles overflow (row sum out of the safe range) the
+  // CTA runs the item a second time with the exact running maximum (pass 1) -- same launch, Q still in shared memory; the
+  // barrier phases simply continue (tile index jb = pass * T + j).
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -103,6 +100,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   const uint32_t pv_done = sBar + 8u * (6 + 3 * KV_STAGES);
   const uint32_t tmem_ptr_addr = sBar + 8u * (7 + 3 * KV_STAGES);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (7 + 3 * KV_STAGES));
+  volatile int* cta_flagged = reinterpret_cast<volatile int*>(bar_gen + 8 * (7 + 3 * KV_STAGES) + 4);
 
   const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
@@ -126,6 +124,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     }
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
+    *cta_flagged = 0;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -139,15 +138,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   griddep_wait();   // PDL: the prologue above overlapped the previous kernel; no dependent global access before this
   const uint32_t tmem_O = tmem_base + 256;
 
+  for (int pass = 0; pass < 2; ++pass) {
+  const int base = pass * T;                       // tiles before this pass (barrier phases / ring stages continue)
+  const bool exact = (p.two_pass != 0) || pass == 1;
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      mbar_expect_tx(q_full, DK_CHUNKS * CHUNK_BYTES);
-      for (int kc = 0; kc < DK_CHUNKS; ++kc)
-        tma_load_4d(sQ + kc * CHUNK_BYTES, &tmQK, q_full, kc * 64, head, q0, b);
+      if (pass == 0) {
+        mbar_expect_tx(q_full, DK_CHUNKS * CHUNK_BYTES);
+        for (int kc = 0; kc < DK_CHUNKS; ++kc)
+          tma_load_4d(sQ + kc * CHUNK_BYTES, &tmQK, q_full, kc * 64, head, q0, b);
+      }
       for (int j = 0; j < T; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
+        const int st = (base + j) % KV_STAGES;
+        const uint32_t ph = ((base + j) / KV_STAGES) & 1;
         mbar_wait(kv_empty(st), ph ^ 1u);
         mbar_expect_tx(k_full(st), DK_CHUNKS * CHUNK_BYTES);
         for (int kc = 0; kc < DK_CHUNKS; ++kc)
@@ -162,10 +166,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     const uint32_t idesc_qk = umma_idesc_bf16(128, KT);
     const uint32_t idesc_pv = umma_idesc_bf16(128, p.dv);
     auto issue_qk = [&](int j) {
-      const int st = j % KV_STAGES;
-      const int sb = j & 1;
-      mbar_wait(k_full(st), (j / KV_STAGES) & 1);
-      mbar_wait(s_free(sb), ((j >> 1) & 1) ^ 1u);
+      const int jb = base + j;
+      const int st = jb % KV_STAGES;
+      const int sb = jb & 1;
+      mbar_wait(k_full(st), (jb / KV_STAGES) & 1);
+      mbar_wait(s_free(sb), ((jb >> 1) & 1) ^ 1u);
       tc_fence_after();
       {
         for (int ks = 0; ks < p.ksteps; ++ks) {
@@ -177,13 +182,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
+    if (pass == 0) mbar_wait(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < T; ++j) {
       if (KV_STAGES >= 2 && j + 1 < T) issue_qk(j + 1);
-      const int st = j % KV_STAGES;
-      mbar_wait(v_full(st), (j / KV_STAGES) & 1);
-      mbar_wait(p_full, j & 1);
+      const int jb = base + j;
+      const int st = jb % KV_STAGES;
+      mbar_wait(v_full(st), (jb / KV_STAGES) & 1);
+      mbar_wait(p_full, jb & 1);
       tc_fence_after();
       {
 #pragma unroll
@@ -215,8 +221,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     const f32x2 sl2_2 = pk2(sl2, sl2);
 
     for (int j = 0; j < T; ++j) {
-      const int sb = j & 1;
-      mbar_wait(s_full(sb), (j >> 1) & 1);
+      const int jb = base + j;
+      const int sb = jb & 1;
+      mbar_wait(s_full(sb), (jb >> 1) & 1);
       tc_fence_after();
       float s[KT];
 #pragma unroll
@@ -238,7 +245,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           if (i >= kvalid) s[i] = -INFINITY;
       }
       float alpha = 1.0f;
-      if (j == 0 || p.two_pass) {
+      if (j == 0 || exact) {
         // exact row maximum: tile 0 always; every tile in the exact re-run of a flagged item (classic online softmax)
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -253,7 +260,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           const float m_new = fmaxf(mrs, mt);
           alpha = ex2(mrs - m_new);
           mrs = m_new;
-          mbar_wait(pv_done, (j - 1) & 1);
+          mbar_wait(pv_done, (jb - 1) & 1);
           tc_fence_after();
           rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
         }
@@ -263,7 +270,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           const float m_new = fmaxf(mrs, est);
           alpha = ex2(mrs - m_new);
           mrs = m_new;
-          mbar_wait(pv_done, (j - 1) & 1);
+          mbar_wait(pv_done, (jb - 1) & 1);
           tc_fence_after();
           rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
         }
@@ -288,8 +295,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       sm1 = tsum;
       rf1 = mrs;
 
-      if (j > 0) {   // P is single-buffered: P.V(j-1) must have read it
-        mbar_wait(pv_done, (j - 1) & 1);
+      if (j > 0) {   // P is single-buffered: P.V(j-1) must have read it (pass 1, tile 0: waited for in pass 0's epilogue)
+        mbar_wait(pv_done, (jb - 1) & 1);
         tc_fence_after();
       }
 #pragma unroll
@@ -306,13 +313,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     }
 
     // ---- final: O / l -> out[b, q0+row, head*d + :] ----
-    mbar_wait(pv_done, (T - 1) & 1);
+    mbar_wait(pv_done, (base + T - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int tok = q0 + row;
-    if (!p.two_pass && p.flags != nullptr) {   // single-pass tiles left their safe range: have the item recomputed exactly
+    if (!exact && p.flags != nullptr) {   // single-pass tiles left their safe range: recompute the item exactly (pass 1)
       const bool bad = (tok < p.N) && !(l_run < ATT_L_SAFE);
-      if (__any_sync(0xffffffffu, bad) && lane == 0) p.flags[item] = 1;
+      if (__any_sync(0xffffffffu, bad) && lane == 0) *cta_flagged = 1;
     }
     bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
     for (int c = 0; c < p.dv; c += 16) {
@@ -335,9 +342,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     }
   }
 
+  if (pass == 1 || p.flags == nullptr || p.two_pass) break;
   tc_fence_before();
   __syncthreads();
-  if (p.check_flags && threadIdx.x == 0) p.flags[item] = 0;   // consumed
+  if (*cta_flagged == 0) break;
+  tc_fence_after();
+  }   // pass
+
+  tc_fence_before();
+  __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -846,12 +859,21 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const int T = (p.N + KT - 1) / KT;
   const int total = p.total_items;
   const int step = static_cast<int>(gridDim.x);
-  // exact re-run: only the items the single-pass launch flagged.  Every role walks the same list: the flags are only read
-  // here (they are cleared after the final __syncthreads below).
-  auto live = [&](int item) { return p.check_flags == 0 || __ldg(p.flags + item) != 0; };
-  auto next_live = [&](int item) {
-    while (item < total && !live(item)) item += step;
+  // Two passes over this CTA's items inside ONE launch: pass 0 = every item with single-pass tiles; pass 1 = the items
+  // whose row sums left the safe range in pass 0 (normally none: the CTA then leaves after one barrier), recomputed with
+  // the exact running maximum.  The flags are written by this CTA's softmax warps in pass 0, read by every role in pass 1
+  // (after a CTA barrier) and cleared at the end.
+  volatile int* cta_flagged = reinterpret_cast<volatile int*>(smem_gen + (tmem_ptr_addr + 4u - smem_base));
+  auto next_live = [&](int item, int pass) {
+    if (pass != 0)
+      while (item < total && *reinterpret_cast<volatile int*>(p.flags + item) == 0) item += step;
     return item;
+  };
+  // between the passes: every thread of the CTA meets here; true = some item of this CTA needs the exact pass
+  auto second_pass = [&]() {
+    if (p.flags == nullptr || p.two_pass) return false;
+    named_bar_sync(3, ATT2_THREADS);
+    return *cta_flagged != 0;
   };
   auto coords = [&](int item, int& q0, int& head, int& b) {
     const int qt = item % p.qtiles;
@@ -877,6 +899,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 2);
     }
+    *cta_flagged = 0;
     fence_barrier_init();
   }
   if (warp == 16) {
@@ -889,7 +912,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const uint32_t tmem_base = uniform_u32(*tmem_ptr_gen);
   griddep_wait();
 
-  const int first = next_live(static_cast<int>(blockIdx.x));
+  const int first = static_cast<int>(blockIdx.x);
 
   if (warp == 16 || warp == 17) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
@@ -906,73 +929,84 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16_ss_elect(tmem_S, qdesc + 2u * ks, kdesc + 2u * ks, idesc_qk, ks > 0 ? 1u : 0u);
       umma_commit_elect(s_full(g));
     };
-    if (first < total) {
-      int item = first;
-      uint32_t k = 0;                      // live items so far
-      uint32_t gt = 0;                     // tiles so far
-      int st = 0, st_next = (ST > 1) ? 1 : 0;
-      uint32_t ph_next = (ST > 1) ? 0u : 1u;   // kv_full parity of tile gt + 1
-      mbar_wait(q_full(0), 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      if (T == 1) umma_commit_elect(q_free(0));
-      while (true) {
-        const int nxt = next_live(item + step);
-        for (int j = 0; j < T; ++j, ++gt) {
-          const bool last = (j + 1 == T);
-          if (!last || nxt < total) {
-            // S(gt + 1): as soon as every softmax warp has read S(gt) for the last time
-            mbar_wait(s_free(g), gt & 1u);
-            const uint32_t kk = last ? k + 1 : k;          // the item tile gt + 1 belongs to
-            if (last) mbar_wait(q_full(kk & 1u), (kk >> 1) & 1u);
-            mbar_wait(kv_full(st_next), ph_next);
+    uint32_t k = 0;                      // items so far (Q buffer / phase)
+    uint32_t gt = 0;                     // tiles so far
+    int st = 0;                          // K / V stage of tile gt ...
+    uint32_t ph = 0;                     // ... and its kv_full parity
+    for (int pass = 0; pass < 2; ++pass) {
+      int item = next_live(first, pass);
+      if (item < total) {
+        // first tile of the pass: nothing is in flight
+        if (gt > 0) mbar_wait(s_free(g), (gt - 1u) & 1u);
+        mbar_wait(q_full(k & 1u), (k >> 1) & 1u);
+        mbar_wait(kv_full(st), ph);
+        tc_fence_after();
+        issue_qk(static_cast<int>(k & 1u), st);
+        if (T == 1) umma_commit_elect(q_free(k & 1u));
+        while (true) {
+          const int nxt = next_live(item + step, pass);
+          for (int j = 0; j < T; ++j, ++gt) {
+            const bool last = (j + 1 == T);
+            const int st_next = (st + 1 == ST) ? 0 : st + 1;
+            const uint32_t ph_next = (st + 1 == ST) ? (ph ^ 1u) : ph;
+            if (!last || nxt < total) {
+              // S(gt + 1): as soon as every softmax warp has read S(gt) for the last time
+              mbar_wait(s_free(g), gt & 1u);
+              const uint32_t kk = last ? k + 1 : k;          // the item tile gt + 1 belongs to
+              if (last) mbar_wait(q_full(kk & 1u), (kk >> 1) & 1u);
+              mbar_wait(kv_full(st_next), ph_next);
+              tc_fence_after();
+              issue_qk(static_cast<int>(kk & 1u), st_next);
+              // the last Q.K^T of an item: its Q buffer may be refilled once these MMAs have retired
+              if (last ? (T == 1) : (j + 2 == T)) umma_commit_elect(q_free(kk & 1u));
+            }
+            mbar_wait(p_full(g), gt & 1u);      // P(gt) is in tensor memory
             tc_fence_after();
-            issue_qk(static_cast<int>(kk & 1u), st_next);
-            // the last Q.K^T of an item: its Q buffer may be refilled once these MMAs have retired
-            if (last ? (T == 1) : (j + 2 == T)) umma_commit_elect(q_free(kk & 1u));
-          }
-          mbar_wait(p_full(g), gt & 1u);      // P(gt) is in tensor memory
-          tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < KT / 16; ++ks) {
-            const uint64_t vdesc = umma_desc_sw128(sV + st * ATT3_V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
-            umma_bf16_ts_elect(tmem_O, tmem_P + 8u * ks, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < KT / 16; ++ks) {
+              const uint64_t vdesc = umma_desc_sw128(sV + st * ATT3_V_STAGE_BYTES + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
+              umma_bf16_ts_elect(tmem_O, tmem_P + 8u * ks, vdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit_elect(pv_done(g, gt & 1u));
+            umma_commit_elect(kv_empty(st));
+            st = st_next;
+            ph = ph_next;
           }
-          umma_commit_elect(pv_done(g, gt & 1u));
-          umma_commit_elect(kv_empty(st));
-          st = st_next;
-          if (++st_next == ST) { st_next = 0; ph_next ^= 1u; }
+          ++k;
+          if (nxt >= total) break;
+          item = nxt;
         }
-        if (nxt >= total) break;
-        item = nxt;
-        ++k;
       }
+      if (pass == 1 || !second_pass()) break;
     }
   } else if (warp == 19) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
+    second_pass();
   } else if (warp == 18) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_SERVICE_REGS));
     // ================= Q / K / V loads, running ahead of the other roles across items =================
     uint32_t k = 0, gt = 0;
     int st = 0;
     uint32_t ph = 0;
-    for (int item = first; item < total; item = next_live(item + step), ++k) {
-      int q0, head, b;
-      coords(item, q0, head, b);
-      const int qb = static_cast<int>(k & 1u);
-      if (k >= 2) mbar_wait(q_free(qb), ((k >> 1) - 1u) & 1u);   // the Q.K^T MMAs of item k - 2 have retired
-      mbar_expect_tx_elect(q_full(qb), 2 * CHUNK_BYTES);
-      tma_load_4d_elect(sQ + (qb * 2) * CHUNK_BYTES, &tmQK, q_full(qb), 0, head, q0, b);
-      tma_load_4d_elect(sQ + (qb * 2 + 1) * CHUNK_BYTES, &tmQK, q_full(qb), 0, head, q0 + QT, b);
-      for (int t = 0; t < T; ++t, ++gt) {
-        if (gt >= static_cast<uint32_t>(ST)) mbar_wait(kv_empty(st), ph ^ 1u);   // both P.V of the tile that used this stage retired
-        mbar_expect_tx_elect(kv_full(st), CHUNK_BYTES + 2 * v_chunk_bytes);
-        tma_load_4d_elect(sK + st * CHUNK_BYTES, &tmQK, kv_full(st), 0, p.heads + head, t * KT, b);
-        tma_load_3d_elect<false>(sV + st * ATT3_V_STAGE_BYTES, &tmV, kv_full(st), t * KT, head * p.d, b);
-        tma_load_3d_elect<false>(sV + st * ATT3_V_STAGE_BYTES + v_chunk_bytes, &tmV, kv_full(st), t * KT + 64, head * p.d, b);
-        if (++st == ST) { st = 0; ph ^= 1u; }
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int item = next_live(first, pass); item < total; item = next_live(item + step, pass), ++k) {
+        int q0, head, b;
+        coords(item, q0, head, b);
+        const int qb = static_cast<int>(k & 1u);
+        if (k >= 2) mbar_wait(q_free(qb), ((k >> 1) - 1u) & 1u);   // the Q.K^T MMAs of item k - 2 have retired
+        mbar_expect_tx_elect(q_full(qb), 2 * CHUNK_BYTES);
+        tma_load_4d_elect(sQ + (qb * 2) * CHUNK_BYTES, &tmQK, q_full(qb), 0, head, q0, b);
+        tma_load_4d_elect(sQ + (qb * 2 + 1) * CHUNK_BYTES, &tmQK, q_full(qb), 0, head, q0 + QT, b);
+        for (int t = 0; t < T; ++t, ++gt) {
+          if (gt >= static_cast<uint32_t>(ST)) mbar_wait(kv_empty(st), ph ^ 1u);   // both P.V of the tile that used this stage retired
+          mbar_expect_tx_elect(kv_full(st), CHUNK_BYTES + 2 * v_chunk_bytes);
+          tma_load_4d_elect(sK + st * CHUNK_BYTES, &tmQK, kv_full(st), 0, p.heads + head, t * KT, b);
+          tma_load_3d_elect<false>(sV + st * ATT3_V_STAGE_BYTES, &tmV, kv_full(st), t * KT, head * p.d, b);
+          tma_load_3d_elect<false>(sV + st * ATT3_V_STAGE_BYTES + v_chunk_bytes, &tmV, kv_full(st), t * KT + 64, head * p.d, b);
+          if (++st == ST) { st = 0; ph ^= 1u; }
+        }
       }
+      if (pass == 1 || !second_pass()) break;
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT2_SOFTMAX_REGS));
@@ -997,14 +1031,16 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     float* xfpeer = xf_gen + (g * 2 + (sub ^ 1)) * 128 + row;
     const int bar_id = 1 + g;
     const float sl2 = p.scale_log2;
-    const float bias = p.two_pass ? 0.0f : ATT2_BIAS;
     const f32x2 sl2_2 = pk2(sl2, sl2);
     const uint32_t xs_mine = sX + (((g * 2 + 0) * 2 + sub) * 128 + row) * 2;
     const uint32_t xs_peer = sX + (((g * 2 + 0) * 2 + (sub ^ 1)) * 128 + row) * 2;
     const int T_full = p.N / KT;
     uint32_t gt = 0;   // tiles so far (barrier phases)
 
-    for (int item = first; item < total; item = next_live(item + step)) {
+    for (int pass = 0; pass < 2; ++pass) {
+    const bool exact = (p.two_pass != 0) || pass == 1;
+    const float bias = exact ? 0.0f : ATT2_BIAS;
+    for (int item = next_live(first, pass); item < total; item = next_live(item + step, pass)) {
       int q0, head, b;
       coords(item, q0, head, b);
       float m_run = -INFINITY;   // reference maximum of the two-pass tiles
@@ -1176,7 +1212,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         ++gt;
       };
 
-      if (p.two_pass) {
+      if (exact) {
         for (int j = 0; j < T_full; ++j) tile(j, std::false_type{});
         if (T_full < T) tile(T_full, std::true_type{});
       } else {
@@ -1193,9 +1229,12 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
       tc_fence_after();
       const int tok = q0 + g * QT + row;
-      if (!p.two_pass && p.flags != nullptr) {
+      if (!exact && p.flags != nullptr) {
         const bool bad = (tok < p.N) && !(l_tot < ATT_L_SAFE);       // also true for NaN
-        if (__any_sync(0xffffffffu, bad) && lane == 0) p.flags[item] = 1;
+        if (__any_sync(0xffffffffu, bad) && lane == 0) {
+          *reinterpret_cast<volatile int*>(p.flags + item) = 1;
+          *cta_flagged = 1;
+        }
       }
       if (sub == 0) {
         const float inv_l = 1.0f / l_tot;
@@ -1223,11 +1262,13 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       // the final sums are read; the next item's tile 0 reuses the max-exchange slots only after its own barrier
       named_bar_sync(bar_id, 256);
     }
+    if (pass == 1 || !second_pass()) break;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.check_flags) {   // exact re-run: the flags it consumed are cleared for the next launch
+  if (*cta_flagged != 0) {   // the flags this CTA raised are consumed: clean for the next launch
     for (int item = static_cast<int>(blockIdx.x) + static_cast<int>(threadIdx.x) * step; item < total; item += step * ATT2_THREADS)
       p.flags[item] = 0;
   }
@@ -1245,7 +1286,6 @@ void fill_params(const AttnPlan& plan, AttnParams* p) {
   p->scale_log2 = plan.scale_log2;
   p->out = plan.out;
   p->flags = plan.flags;
-  p->check_flags = 0;
   p->two_pass = 0;
   p->qtiles = (plan.N + 2 * QT - 1) / (2 * QT);
   p->total_items = p->qtiles * plan.heads * plan.B;
@@ -1308,14 +1348,8 @@ int launch_attn3_t(const AttnPlan& plan, cudaStream_t stream) {
     PBE_CHECK_CUDA(launch_k(flash_attn3_kernel<POLY16>, grid, dim3(ATT2_THREADS), ATT3_SMEM, stream, plan.tmQ, plan.tmV, p));
     return 0;
   }
-  if (!attn_rerun()) p.flags = nullptr;
+  if (!attn_rerun()) p.flags = nullptr;   // no exact second pass: an overflowing row stays NaN (round-1 behaviour)
   PBE_CHECK_CUDA(launch_k(flash_attn3_kernel<POLY16>, grid, dim3(ATT2_THREADS), ATT3_SMEM, stream, plan.tmQ, plan.tmV, p));
-  if (p.flags != nullptr) {
-    // exact re-run of the (normally zero) items whose single-pass tiles overflowed: every CTA scans its items' flags
-    p.two_pass = 1;
-    p.check_flags = 1;
-    PBE_CHECK_CUDA(launch_k(flash_attn3_kernel<POLY16>, grid, dim3(ATT2_THREADS), ATT3_SMEM, stream, plan.tmQ, plan.tmV, p));
-  }
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1352,11 +1386,6 @@ int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   if (attn_two_pass()) { p.two_pass = 1; p.flags = nullptr; }
   else if (!attn_rerun()) p.flags = nullptr;
   PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
-  if (p.flags != nullptr && !p.two_pass) {
-    p.two_pass = 1;
-    p.check_flags = 1;
-    PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
-  }
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1423,7 +1452,8 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
 }
 
 int attn_num_launches(const AttnPlan& plan) {
-  return (plan.flags != nullptr && !attn_two_pass() && attn_rerun()) ? 2 : 1;
+  (void)plan;
+  return 1;   // the exact pass over overflowed items runs inside the same launch
 }
 
 int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream) {

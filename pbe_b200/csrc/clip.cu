@@ -195,7 +195,7 @@ int ClipEncoder::build(ClipPrepared& P, bool dry) {
         int rc = build_attn_plan(qk, vt, ao, B, N, heads, d, plan.get(), true);
         if (rc && !err) { err = rc; last_error = std::string(get_error()) + " [" + tag + ".attn]"; }
       }
-      add_op(tag + ".attn", 2, [plan](cudaStream_t s) { return launch_attn_plan(*plan, s); });
+      add_op(tag + ".attn", 1, [plan](cudaStream_t s) { return launch_attn_plan(*plan, s); });
     }
     {
       ConvGemmDesc dsc = linear(ao, M, C, L.out_proj);

@@ -630,7 +630,7 @@ int Engine::build(Prepared& P, bool dry) {
           add_op_meta(tag + ".attn1", attn_num_launches(*plan), [plan](cudaStream_t st) { return launch_attn_plan(*plan, st); }, "attention",
                       4.0 * Bc * static_cast<double>(N) * N * C, static_cast<double>(M) * C * 2.0 * 4.0);
         } else {
-          launches += 2;
+          launches += 1;
         }
         float* t1 = static_cast<float*>(SA(M * (diverged ? 1 : 2) * C * sizeof(float)));
         for (int half = 0; half < (diverged ? 1 : 2); ++half) {
