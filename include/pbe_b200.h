@@ -69,6 +69,15 @@ int pbe_op_layernorm(const float* x, const float* gamma, const float* beta, void
 int pbe_op_small_linear(const float* x, const float* W, const float* bias, float* y, int B, int K, int O, int pre_silu,
                         int post_act, const float* residual, float* y_silu, void* stream);
 
+/* Format of the 16-bit tensor-core operands this library writes and reads (activations produced by the normalisation
+ * kernels and GEMM epilogues, repacked weights, and the 16-bit tensors of the pbe_op_* entry points): 1 = fp16 (default),
+ * 0 = bf16 (also: environment PBE_OPERANDS=bf16).  Same MMA rate, fp32 accumulation either way; fp16 has three more mantissa
+ * bits and is what the reference runs at under torch.autocast (scripts/inference.py:301-303); conversions saturate at
+ * +-65504.  Process-wide: set it before creating engines (an engine refuses to run under a format other than the one it was
+ * built with).  The self-attention entry point always takes bf16 Q | K | V^T and writes its output in this format. */
+int pbe_set_operand_format(int f16);
+int pbe_get_operand_format(void);
+
 /* nearest-2x upsample fp32 NHWC -> bf16 NHWC. Replaces F.interpolate in Upsample.forward, openaimodel.py:109-119. */
 int pbe_op_upsample2x(const float* x, void* y_bf16, int Nb, int H, int W, int C, void* stream);
 

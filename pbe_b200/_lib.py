@@ -57,6 +57,8 @@ _f, _i, _p, _i64 = c_float, c_int, c_void_p, c_int64
 _OPTIONAL_SIGS: dict = {
     "pbe_op_self_attention": (c_int, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "pbe_debug_gemm_counters": (c_int, [_p]),
+    "pbe_set_operand_format": (c_int, [_i]),
+    "pbe_get_operand_format": (c_int, []),
     "pbe_debug_set_gemm_stats_out": (None, [_p]),
     "pbe_op_groupnorm": (c_int, [_p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p]),
     "pbe_op_groupnorm_workspace_bytes": (c_int64, [_i, _i]),

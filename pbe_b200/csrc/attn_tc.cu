@@ -44,6 +44,7 @@ struct AttnParams {
   // recomputed by the same CTA, in the same launch, with the exact running maximum (flags: per-item marks of the persistent
   // kernel, null = no second pass)
   int* flags;
+  int out_f16;               // the output feeds a GEMM: written in the library's operand format (fp16 unless PBE_OPERANDS=bf16)
   int qtiles, total_items;   // flash_attn3_kernel (persistent): 256-query blocks per (sample, head), work items in total
 };
 
@@ -331,10 +332,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         for (int i = 0; i < 16; i += 8) {
           if (c + i < p.d) {  // d % 8 == 0
             uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-            pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-            pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            pk.x = pack_op2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l, p.out_f16);
+            pk.y = pack_op2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l, p.out_f16);
+            pk.z = pack_op2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l, p.out_f16);
+            pk.w = pack_op2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l, p.out_f16);
             *reinterpret_cast<uint4*>(orow + c + i) = pk;
           }
         }
@@ -752,10 +753,10 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           for (int i = 0; i < 16; i += 8) {
             if (c + i < p.d) {
               uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-              pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-              pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-              pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+              pk.x = pack_op2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l, p.out_f16);
+              pk.y = pack_op2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l, p.out_f16);
+              pk.z = pack_op2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l, p.out_f16);
+              pk.w = pack_op2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l, p.out_f16);
               *reinterpret_cast<uint4*>(orow + c + i) = pk;
             }
           }
@@ -1186,13 +1187,14 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
             acc0 = add2(acc0, pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
             acc1 = add2(acc1, pk2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
           }
-          if (h == 0) {   // j >= 1 here
-            mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
-            tc_fence_after();
-          }
           store_p(v, h);
         };
+        // P is single-buffered: P.V of the previous tile (issued a whole tile of exponentials ago) must have read it.  Waited
+        // for HERE, in front of both halves, so that the two halves form one straight-line block and the scheduler can run
+        // the FMA-pipe work of one under the MUFU work of the other.
+        mbar_wait(pv_done(g, (gt - 1u) & 1u), ((gt - 1u) >> 1) & 1u);
         tmem_ld_wait_x32x2(va, vb);
+        tc_fence_after();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free(g));
@@ -1248,10 +1250,10 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
             for (int i = 0; i < 16; i += 8) {
               if (c + i < p.d) {
                 uint4 pk;
-                pk.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-                pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-                pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-                pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+                pk.x = pack_op2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l, p.out_f16);
+                pk.y = pack_op2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l, p.out_f16);
+                pk.z = pack_op2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l, p.out_f16);
+                pk.w = pack_op2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l, p.out_f16);
                 *reinterpret_cast<uint4*>(orow + c + i) = pk;
               }
             }
@@ -1286,6 +1288,7 @@ void fill_params(const AttnPlan& plan, AttnParams* p) {
   p->scale_log2 = plan.scale_log2;
   p->out = plan.out;
   p->flags = plan.flags;
+  p->out_f16 = plan.out_f16;
   p->two_pass = 0;
   p->qtiles = (plan.N + 2 * QT - 1) / (2 * QT);
   p->total_items = p->qtiles * plan.heads * plan.B;
@@ -1293,7 +1296,7 @@ void fill_params(const AttnPlan& plan, AttnParams* p) {
 
 // PBE_ATTN_TWO_PASS=1: exact running maximum in every tile (no single-pass tiles, no re-run); PBE_ATTN_KERNEL=2: the
 // round-1 non-persistent kernel for head dims <= 64 (A/B comparisons); PBE_ATTN_POLY=0|2|4|6|8: exponentials per 16 on the
-// FMA pipe (default 4); PBE_ATTN_RERUN=0: skip the exact re-run launch (overflowing rows then stay NaN, as in round 1).
+// FMA pipe (default 6); PBE_ATTN_RERUN=0: skip the exact re-run launch (overflowing rows then stay NaN, as in round 1).
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -1355,13 +1358,13 @@ int launch_attn3_t(const AttnPlan& plan, cudaStream_t stream) {
 }
 
 int launch_attn3(const AttnPlan& plan, cudaStream_t stream) {
-  static const int poly = env_int("PBE_ATTN_POLY", 4);
+  static const int poly = env_int("PBE_ATTN_POLY", 6);
   switch (poly) {
     case 0: return launch_attn3_t<0>(plan, stream);
     case 2: return launch_attn3_t<2>(plan, stream);
-    case 6: return launch_attn3_t<6>(plan, stream);
+    case 4: return launch_attn3_t<4>(plan, stream);
     case 8: return launch_attn3_t<8>(plan, stream);
-    default: return launch_attn3_t<4>(plan, stream);
+    default: return launch_attn3_t<6>(plan, stream);
   }
 }
 
@@ -1421,6 +1424,7 @@ int build_attn_plan(const bf16* qk, const bf16* vt, bf16* out, int B, int N, int
   const int C = heads * d;
   plan->B = B; plan->N = N; plan->heads = heads; plan->d = d;
   plan->flags = attn_flags(((N + QT - 1) / QT) * heads * B, own_flags);
+  plan->out_f16 = operand_f16();
   plan->scale_log2 = static_cast<float>(1.4426950408889634 / sqrt(static_cast<double>(d)));
   plan->out = out;
   plan->grid = dim3((N + QT - 1) / QT, heads, B);

@@ -61,6 +61,12 @@ extern "C" {
 
 int pbe_debug_gemm_counters(long long* out8) { return gemm_read_debug_counters(out8); }
 
+int pbe_set_operand_format(int f16) {
+  set_operand_f16(f16);
+  return 0;
+}
+int pbe_get_operand_format(void) { return operand_f16(); }
+
 int pbe_op_self_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int B, int N, int heads, int d,
                           void* stream) {
   AttnPlan plan;

@@ -187,6 +187,7 @@ int ClipEncoder::build(ClipPrepared& P, bool dry) {
     {
       ConvGemmDesc dsc = linear(a16, M, C, L.qkv);
       dsc.mode = EPI_QKV; dsc.out_bf16 = qk; dsc.ld_out = 2 * C; dsc.out_vt = vt; dsc.qk_cols = 2 * C; dsc.vt_tokens = N;
+      dsc.out16_bf16 = 1;   // read by the flash-attention kernel (bf16 Q / K / V)
       add_gemm(tag + ".qkv", dsc);
     }
     {

@@ -80,9 +80,31 @@ int WeightLoader::upload_f32(const std::vector<float>& v, float** dst) {
   return 0;
 }
 
+// fp32 -> fp16, round to nearest even, saturating at +-65504 (the same rule as the device conversions)
+static uint16_t f32_to_f16_rn_sat(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return static_cast<uint16_t>(sign | 0x7e00u);              // NaN
+  if (a >= 0x477ff000u) return static_cast<uint16_t>(sign | 0x7bffu);             // >= 65520 rounds past the largest finite
+  if (a < 0x33000001u) return static_cast<uint16_t>(sign);                        // < 2^-25: rounds to zero
+  const int e = static_cast<int>(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;
+  if (e < -14) {                                                                  // subnormal result
+    const int sh = 13 + (-14 - e);
+    const uint32_t q = m >> sh, rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+    return static_cast<uint16_t>(sign | (q + ((rem > half || (rem == half && (q & 1u))) ? 1u : 0u)));
+  }
+  const uint32_t q = (static_cast<uint32_t>(e + 15) << 10) | ((m >> 13) & 0x3ffu), rem = m & 0x1fffu;
+  return static_cast<uint16_t>(sign | (q + ((rem > 0x1000u || (rem == 0x1000u && (q & 1u))) ? 1u : 0u)));
+}
+
+// GEMM weights in the library's operand format (fp16 by default, internal.h: operand_f16)
 int WeightLoader::upload_bf16(const std::vector<float>& v, bf16** dst) {
   std::vector<uint16_t> h(v.size());
-  for (size_t i = 0; i < v.size(); ++i) h[i] = f32_to_bf16_rn(v[i]);
+  if (fmt_f16_) for (size_t i = 0; i < v.size(); ++i) h[i] = f32_to_f16_rn_sat(v[i]);
+  else for (size_t i = 0; i < v.size(); ++i) h[i] = f32_to_bf16_rn(v[i]);
   void* p = nullptr;
   PBE_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(h.size(), 1) * sizeof(uint16_t)));
   dev_allocs_.push_back(p);
@@ -619,6 +641,7 @@ int Engine::build(Prepared& P, bool dry) {
           d.act = n1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.qkv.w; d.Cout = 3 * C; d.mode = EPI_QKV; d.out_bf16 = qk; d.ld_out = 2 * C; d.out_vt = vt;
           d.qk_cols = 2 * C;
+          d.out16_bf16 = 1;   // Q | K | V^T feed the flash-attention kernels, which work in bf16 (P lives far below the fp16 range)
           d.block_n = (C % 160 == 0) ? 160 : ((C % 128 == 0) ? 128 : 64);
           add_gemm(tag + ".qkv", d);
         }
@@ -789,6 +812,7 @@ bool Engine::pair_plan_possible() const {
 
 int Engine::prepare(int Bc, int H, int W, bool pair) {
   PBE_REQUIRE(finalized_, "weights not finalized");
+  PBE_REQUIRE(fmt_f16_ == operand_f16(), "the operand format (pbe_set_operand_format / PBE_OPERANDS) changed after this engine was built");
   PBE_REQUIRE(Bc >= 1 && Bc <= MAX_BC, "batch out of range");
   int down = 1;
   for (int i = 1; i < cfg_.num_levels; ++i) down *= 2;

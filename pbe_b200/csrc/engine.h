@@ -110,6 +110,7 @@ class WeightLoader {
   int upload_f32(const std::vector<float>& v, float** dst);
   int upload_bf16(const std::vector<float>& v, bf16** dst);
   std::unordered_map<std::string, HostTensor> host_;
+  int fmt_f16_ = operand_f16();   // operand format the weights are repacked in (fixed at construction)
   bool finalized_ = false;
   std::vector<void*> dev_allocs_;
 };

@@ -260,7 +260,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (dbg && lane == 0) g_gemm_dbg[3] = t_empty;
   } else if (warp == 1 && (CL == 1 || crank == 0)) {
     // ================= MMA issuer (pair: the leader CTA only) =================
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CL, BLOCK_N);
+    const uint32_t idesc = umma_idesc_f16(BLOCK_M * CL, BLOCK_N) | p.idesc_fmt;   // operand format bits from the plan
     int stage = 0;
     uint32_t phase = 0;
     int ti = 0;
@@ -435,7 +435,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n_base + c * 32 + j));
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j * tokens] = __float2bfloat16(__uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              reinterpret_cast<unsigned short*>(dst)[j * tokens] = to_op16(__uint_as_float(v[j]), p.out16_f16);
           }
         }
         continue;
@@ -576,16 +577,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (((p.n_total | p.ld_out) & 7) != 0) {  // narrow / unaligned rows: scalar stores
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col + j < p.n_total) dst[j] = __float2bfloat16(o[j]);
+                if (col + j < p.n_total) reinterpret_cast<unsigned short*>(dst)[j] = to_op16(o[j], p.out16_f16);
             } else
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (col + 8 * u < p.n_total) {
                 uint4 pk;
-                pk.x = pack_bf16x2(o[8 * u + 0], o[8 * u + 1]);
-                pk.y = pack_bf16x2(o[8 * u + 2], o[8 * u + 3]);
-                pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
-                pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
+                pk.x = pack_op2(o[8 * u + 0], o[8 * u + 1], p.out16_f16);
+                pk.y = pack_op2(o[8 * u + 2], o[8 * u + 3], p.out16_f16);
+                pk.z = pack_op2(o[8 * u + 4], o[8 * u + 5], p.out16_f16);
+                pk.w = pack_op2(o[8 * u + 6], o[8 * u + 7], p.out16_f16);
                 *reinterpret_cast<uint4*>(dst + 8 * u) = pk;
               }
             }
@@ -594,14 +595,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // bf16-only output: compact [128 rows x 64 B] layout (64B swizzle) overlaps other rows' fp32 residual
           if (p.has_res) named_bar_sync(bar_id, 128);
           uint8_t* my_row64 = slot_gen + row * 64;
+          if (p.out16_f16) {   // warp-uniform: one conversion per pair on either path
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 pk;
-            pk.x = pack_bf16x2(o[8 * u + 0], o[8 * u + 1]);
-            pk.y = pack_bf16x2(o[8 * u + 2], o[8 * u + 3]);
-            pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
-            pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
-            *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+            for (int u = 0; u < 4; ++u) {
+              uint4 pk;
+              pk.x = pack_f16x2(o[8 * u + 0], o[8 * u + 1]);
+              pk.y = pack_f16x2(o[8 * u + 2], o[8 * u + 3]);
+              pk.z = pack_f16x2(o[8 * u + 4], o[8 * u + 5]);
+              pk.w = pack_f16x2(o[8 * u + 6], o[8 * u + 7]);
+              *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 pk;
+              pk.x = pack_bf16x2(o[8 * u + 0], o[8 * u + 1]);
+              pk.y = pack_bf16x2(o[8 * u + 2], o[8 * u + 3]);
+              pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
+              pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
+              *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+            }
           }
         }
         fence_async_smem();
@@ -754,8 +767,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitKReduce r) {
   if (r.out_f32) *reinterpret_cast<float4*>(r.out_f32 + o) = acc;
   if (r.out_bf16) {
     uint2 pk;
-    pk.x = pack_bf16x2(acc.x, acc.y);
-    pk.y = pack_bf16x2(acc.z, acc.w);
+    pk.x = pack_op2(acc.x, acc.y, r.out16_f16);
+    pk.y = pack_op2(acc.z, acc.w, r.out16_f16);
     *reinterpret_cast<uint2*>(r.out_bf16 + o) = pk;
   }
 }
@@ -869,6 +882,11 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.qk_cols = d.qk_cols;
   p.vt_tokens = d.vt_tokens;
   p.act = d.epi_act;
+  {
+    const int f16 = operand_f16();
+    p.idesc_fmt = (f16 && !d.operands_bf16) ? 0u : ((1u << 7) | (1u << 10));
+    p.out16_f16 = (f16 && !d.out16_bf16) ? 1 : 0;
+  }
   PBE_REQUIRE(d.epi_act == 0 || d.mode == EPI_STD, "activation epilogue needs mode STD");
   p.ld_out = d.ld_out ? d.ld_out : (d.mode == EPI_GEGLU ? d.Cout / 2 : d.Cout);
 
@@ -882,6 +900,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   }
   plan->red = SplitKReduce{};
   plan->red.S = p.split_k;
+  plan->red.out16_f16 = p.out16_f16;
   PBE_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
   if (d.mode == EPI_GEGLU) PBE_REQUIRE(bn == 256 && d.Cout % 256 == 0, "GEGLU needs BLOCK_N=256 | Cout");
   if (d.mode == EPI_QKV) PBE_REQUIRE(d.qk_cols % bn == 0 && d.Cout % bn == 0, "QKV split must align with BLOCK_N");

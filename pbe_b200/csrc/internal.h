@@ -8,7 +8,17 @@
 
 namespace pbe {
 
-typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat16 bf16;   // "a 16-bit GEMM operand": the bits are fp16 or bf16 depending on operand_f16() below
+
+// Format of the 16-bit tensor-core operands (activations written by the norm kernels / GEMM epilogues, repacked weights):
+// fp16 (default) or bf16 (PBE_OPERANDS=bf16 or pbe_set_operand_format(0)).  Both run kind::f16 MMAs at the same rate with
+// fp32 accumulation; fp16 carries three more mantissa bits (operand rounding 2^-12 instead of 2^-9: the U-Net's eps error
+// against the fp32 reference drops from 9.8e-3 to 1.8e-3, tools/parity_attribution.py) and is the precision the reference
+// itself runs at under torch.autocast (scripts/inference.py:301-303); conversions saturate at +-65504 instead of
+// overflowing.  The flash-attention kernels keep bf16 Q / K / V / P (P is kept 2^-64 below 1, outside the fp16 range).
+// Process-wide; engines record the format they were built with and refuse to run under another.
+int operand_f16();
+void set_operand_f16(int f16);
 
 // Thread-local error string (also copied into the handle by the C-ABI layer).
 void set_error(const std::string& msg);
@@ -77,11 +87,14 @@ struct ConvGemmParams {
   int qk_cols;
   int vt_tokens;          // EPI_QKV: tokens per sample of the V^T store when the activation is one flat row range (0: H*W)
   int act;                // EPI_STD: 0 none, 1 quick_gelu x * sigmoid(1.702 x) (CLIP MLP), applied after the biases
+  uint32_t idesc_fmt;     // operand-format bits of the MMA instruction descriptor (bf16: A and B format 1; fp16: 0)
+  int out16_f16;          // 16-bit outputs (out_bf16 / out_vt) are written as fp16 (else bf16)
 };
 
 // Deterministic split-K: slice s of the K range writes its partial tile to ws[s]; a second small kernel sums the
 // slices in fixed order and applies the fused epilogue terms.
 struct SplitKReduce {
+  int out16_f16;                                   // format of out_bf16
   const float* ws; int S; long long slice_stride;  // floats between slices
   long long M; int N; int HW;                      // rows, columns, rows per sample
   const float* bias; const float* rowbias; int rowbias_ld; const float* residual;
@@ -148,6 +161,8 @@ struct ConvGemmDesc {
                            // must accumulate in the same order as the same layer over the full 2B batch
   int pad_end;             // stride-2 3x3 only: 1 = zero padding (0,1,0,1) as the VAE Downsample (model.py:74-76)
                            // instead of the symmetric padding 1 of the U-Net Downsample
+  int out16_bf16;          // 1: the 16-bit outputs are bf16 whatever the operand format (Q | K | V^T read by the flash kernels)
+  int operands_bf16;       // 1: act / wt are bf16 whatever the operand format
 };
 // Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
 int gemm_read_debug_counters(long long* out8);
@@ -170,6 +185,7 @@ struct AttnPlan {
   bf16* out;
   dim3 grid;
   size_t smem;
+  int out_f16;  // output format: the library's operand format at plan-build time
   int* flags;   // per-item overflow flags of the single-pass softmax (attn_tc.cu); null = no exact re-run
 };
 // Row pitch (elements) of the transposed V buffer [B][C][vt_pitch(N)]: token counts that are not multiples of 8 are padded
@@ -192,7 +208,7 @@ struct GroupNormArgs {
   int Nb, HW;
   const float* gamma; const float* beta;
   float eps; int silu;
-  bf16* y; bf16* raw;        // raw may be null
+  bf16* y; bf16* raw;        // raw may be null; 16-bit operands in the library's operand format (operand_f16())
   float* partial;            // workspace of gn_workspace_floats(Nb, HW, C0+C1) floats (16-B aligned)
   // optional statistics fused into the producers' GEMM epilogues: [Nb*HW/32][C_i][2]; when every live source has
   // them the stats pass over x is skipped

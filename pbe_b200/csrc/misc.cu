@@ -7,7 +7,7 @@ namespace pbe {
 
 namespace {
 
-__global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict__ y, int Nb, int H, int W, int C) {
+__global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict__ y, int Nb, int H, int W, int C, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   // one thread per input float4
   const long long total = static_cast<long long>(Nb) * H * W * (C / 4);
@@ -20,11 +20,9 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict_
   const int h = static_cast<int>(pix % H);
   const int n = static_cast<int>(pix / H);
   const float4 v = *reinterpret_cast<const float4*>(x + idx * 4);
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
   uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&lo);
-  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  pk.x = pack_op2(v.x, v.y, f16);
+  pk.y = pack_op2(v.z, v.w, f16);
   const int W2 = 2 * W, H2 = 2 * H;
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy)
@@ -35,22 +33,20 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict_
     }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
+__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[i];
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
   uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&lo);
-  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  pk.x = pack_op2(v.x, v.y, f16);
+  pk.y = pack_op2(v.z, v.w, f16);
   reinterpret_cast<uint2*>(y)[i] = pk;
 }
 
 // thread per (n, pixel): gathers Cin channel planes (coalesced across threads), writes Cpad bf16 contiguous
 __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ y, int Nb, int Cin, int HW,
-                                  int Cpad) {
+                                  int Cpad, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Nb) * HW) return;
@@ -65,12 +61,10 @@ __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict_
       v[i] = (c < Cin) ? x[(static_cast<long long>(n) * Cin + c) * HW + pix] : 0.0f;
     }
     uint4 pk;
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]),
-                   c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&a);
-    pk.y = *reinterpret_cast<uint32_t*>(&b);
-    pk.z = *reinterpret_cast<uint32_t*>(&c);
-    pk.w = *reinterpret_cast<uint32_t*>(&d);
+    pk.x = pack_op2(v[0], v[1], f16);
+    pk.y = pack_op2(v[2], v[3], f16);
+    pk.z = pack_op2(v[4], v[5], f16);
+    pk.w = pack_op2(v[6], v[7], f16);
     *reinterpret_cast<uint4*>(dst + c0) = pk;
   }
 }
@@ -185,7 +179,7 @@ __global__ void add_rowvec_kernel(const float* __restrict__ a, const float* __re
 // ---- VAE decode helpers (AutoencoderKL.decode, ldm/models/autoencoder.py:66-69; AttnBlock model.py:152-182) ----
 // post_quant_conv (1x1, embed_dim -> z_channels, fp32) fused with the NCHW -> NHWC bf16 pack (channels padded with zeros)
 __global__ void vae_pack_input_kernel(const float* __restrict__ z, const float* __restrict__ Wp, const float* __restrict__ bp,
-                                      bf16* __restrict__ y, int Nb, int Cin, int Cz, int HW, int Cpad) {
+                                      bf16* __restrict__ y, int Nb, int Cin, int Cz, int HW, int Cpad, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Nb) * HW) return;
@@ -200,7 +194,7 @@ __global__ void vae_pack_input_kernel(const float* __restrict__ z, const float* 
       v = bp[o];
       for (int i = 0; i < Cin; ++i) v += Wp[o * Cin + i] * zin[i];
     }
-    dst[o] = __float2bfloat16(v);
+    reinterpret_cast<unsigned short*>(dst)[o] = to_op16(v, f16);
   }
 }
 
@@ -347,7 +341,7 @@ __global__ void resize_bilinear_aa_kernel(const float* __restrict__ in, float* _
 // CLIP ViT patch embedding input (transformers CLIPVisionEmbeddings.patch_embedding: Conv2d(3, C, patch, stride=patch,
 // bias=False)): one row per patch, columns in the conv weight's (c, kh, kw) order, zero padded to Kpad
 __global__ void clip_pack_patches_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W, int patch,
-                                         int Kpad) {
+                                         int Kpad, int f16) {
   griddep_enter();
   const int pw = W / patch, ph = H / patch;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -363,7 +357,7 @@ __global__ void clip_pack_patches_kernel(const float* __restrict__ img, bf16* __
     const int c = k / (patch * patch), r = k % (patch * patch), kh = r / patch, kw = r % patch;
     v = img[((static_cast<long long>(b) * 3 + c) * H + py * patch + kh) * W + px * patch + kw];
   }
-  out[idx] = __float2bfloat16(v);
+  reinterpret_cast<unsigned short*>(out)[idx] = to_op16(v, f16);
 }
 
 // tokens[b, 0] = class_embedding + pos[0]; tokens[b, 1 + p] = patch_emb[b, p] + pos[1 + p]  (CLIPVisionEmbeddings.forward)
@@ -383,7 +377,7 @@ __global__ void clip_embed_kernel(const float* __restrict__ patch_emb, const flo
 // P[r][:] = softmax(S[r][:] * scale), fp32 in, bf16 out; one 256-thread block per row, the row lives in registers
 constexpr int SM_MAXV = 16;   // float4 per thread -> rows of up to 16384
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int N,
-                                                           float scale_log2) {
+                                                           float scale_log2, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   __shared__ float s_red[8];
   const long long row = blockIdx.x;
@@ -432,9 +426,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int i = 0; i < SM_MAXV; ++i) {
     const int k = threadIdx.x + i * 256;
     if (k < nv) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
-      dst[k] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      dst[k] = make_uint2(pack_op2(v[i].x * inv, v[i].y * inv, f16), pack_op2(v[i].z * inv, v[i].w * inv, f16));
     }
   }
 }
@@ -444,7 +436,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream) {
   PBE_REQUIRE(C % 4 == 0, "upsample channels % 4");
   const long long total = static_cast<long long>(Nb) * H * W * (C / 4);
-  PBE_CHECK_CUDA(launch_k(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, y, Nb, H, W, C));
+  PBE_CHECK_CUDA(launch_k(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, y, Nb, H, W, C, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -452,7 +444,7 @@ int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C,
 int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
   PBE_REQUIRE(n % 4 == 0, "cast length % 4");
   const size_t n4 = n / 4;
-  PBE_CHECK_CUDA(launch_k(cast_bf16_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, stream, x, y, n4));
+  PBE_CHECK_CUDA(launch_k(cast_bf16_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, stream, x, y, n4, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -460,7 +452,7 @@ int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
 int launch_pack_input(const float* x, bf16* y, int Nb, int Cin, int H, int W, int Cpad, cudaStream_t stream) {
   PBE_REQUIRE(Cpad % 8 == 0 && Cpad >= Cin, "padded channel count");
   const long long total = static_cast<long long>(Nb) * H * W;
-  PBE_CHECK_CUDA(launch_k(pack_input_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, x, y, Nb, Cin, H * W, Cpad));
+  PBE_CHECK_CUDA(launch_k(pack_input_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, x, y, Nb, Cin, H * W, Cpad, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -484,7 +476,7 @@ int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16
                           int Cpad, cudaStream_t stream) {
   PBE_REQUIRE(Cin <= 8 && Cz <= Cpad, "vae_pack_input: embed_dim <= 8");
   const long long total = static_cast<long long>(Nb) * H * W;
-  PBE_CHECK_CUDA(launch_k(vae_pack_input_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, z, Wp, bp, y, Nb, Cin, Cz, H * W, Cpad));
+  PBE_CHECK_CUDA(launch_k(vae_pack_input_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, z, Wp, bp, y, Nb, Cin, Cz, H * W, Cpad, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -537,7 +529,7 @@ int launch_clip_pack_patches(const float* img, bf16* out, int B, int H, int W, i
   PBE_REQUIRE(H % patch == 0 && W % patch == 0 && Kpad >= 3 * patch * patch, "clip_pack_patches: image / patch geometry");
   const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * Kpad;
   PBE_CHECK_CUDA(launch_k(clip_pack_patches_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, img,
-                          out, B, H, W, patch, Kpad));
+                          out, B, H, W, patch, Kpad, operand_f16()));
   return 0;
 }
 
@@ -551,7 +543,7 @@ int launch_clip_embed(const float* patch_emb, const float* cls, const float* pos
 
 int launch_softmax_rows(const float* S, bf16* P, long long rows, int N, float scale, cudaStream_t stream) {
   PBE_REQUIRE(N % 4 == 0 && N <= 4 * 256 * SM_MAXV, "softmax_rows: row length % 4 == 0, <= 16384");
-  PBE_CHECK_CUDA(launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, S, P, N, scale * 1.4426950408889634f));
+  PBE_CHECK_CUDA(launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, S, P, N, scale * 1.4426950408889634f, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -16,10 +16,6 @@ namespace pbe {
 
 namespace {
 
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_C = 2560;
@@ -221,7 +217,7 @@ __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f 
 
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
                                                         int C1, int HW, int rows_par, const float2* __restrict__ ab,
-                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw) {
+                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int C = C0 + C1;
   const int vpp = C / 4;
@@ -251,8 +247,9 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
       float o2 = fmaf(v[u].z, s23.x, s23.y), o3 = fmaf(v[u].w, s23.z, s23.w);
       if (silu) { o0 = silu_fast(o0); o1 = silu_fast(o1); o2 = silu_fast(o2); o3 = silu_fast(o3); }
       const long long off = obase + static_cast<long long>(pix) * C;
-      *reinterpret_cast<uint2*>(y + off) = make_uint2(pack2(o0, o1), pack2(o2, o3));
-      if (raw != nullptr) *reinterpret_cast<uint2*>(raw + off) = make_uint2(pack2(v[u].x, v[u].y), pack2(v[u].z, v[u].w));
+      *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_op2(o0, o1, f16), pack_op2(o2, o3, f16));
+      if (raw != nullptr)
+        *reinterpret_cast<uint2*>(raw + off) = make_uint2(pack_op2(v[u].x, v[u].y, f16), pack_op2(v[u].z, v[u].w, f16));
     }
   }
 }
@@ -279,7 +276,7 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
                                                                const float* __restrict__ x1, int C1, int HW, int rows_par,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, int silu,
-                                                               bf16* __restrict__ y, bf16* __restrict__ raw) {
+                                                               bf16* __restrict__ y, bf16* __restrict__ raw, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   extern __shared__ float2 s_x[];  // [HW][cpg / 2]
   __shared__ double s_red[GNS_THREADS / 32];
@@ -340,8 +337,8 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
       const float2 v = s_x[pix * hv + cv];
       float o0 = fmaf(v.x, a0, b0), o1 = fmaf(v.y, a1, b1);
       if (silu) { o0 = silu_fast(o0); o1 = silu_fast(o1); }
-      *reinterpret_cast<uint32_t*>(yo + static_cast<long long>(pix) * C) = pack2(o0, o1);
-      if (ro != nullptr) *reinterpret_cast<uint32_t*>(ro + static_cast<long long>(pix) * C) = pack2(v.x, v.y);
+      *reinterpret_cast<uint32_t*>(yo + static_cast<long long>(pix) * C) = pack_op2(o0, o1, f16);
+      if (ro != nullptr) *reinterpret_cast<uint32_t*>(ro + static_cast<long long>(pix) * C) = pack_op2(v.x, v.y, f16);
     }
   }
 }
@@ -353,7 +350,7 @@ constexpr int LN_MAX_VEC = 10;
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, int M,
-                                                        int C, float eps, float* __restrict__ y32, long long ld_x) {
+                                                        int C, float eps, float* __restrict__ y32, long long ld_x, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -397,7 +394,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       const float4 g = __ldg(gr + k), bb = __ldg(br + k);
       const float4 o = make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
                                    (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
-      if (y != nullptr) yr[k] = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+      if (y != nullptr) yr[k] = make_uint2(pack_op2(o.x, o.y, f16), pack_op2(o.z, o.w, f16));
       if (y32 != nullptr) reinterpret_cast<float4*>(y32 + static_cast<long long>(row) * C)[k] = o;
     }
   }
@@ -439,7 +436,7 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
     const int hv = C / 64;
     const int rows_par = std::min(GNS_THREADS / hv, a.HW);
     PBE_CHECK_CUDA(launch_k(gn_small_kernel, dim3(dim3(32, a.Nb)), dim3(GNS_THREADS), small_smem, stream, a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, a.gamma,
-                                                                        a.beta, a.eps, a.silu, a.y, a.raw));
+                                                                        a.beta, a.eps, a.silu, a.y, a.raw, operand_f16()));
     PBE_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -460,7 +457,7 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   const int rows_par = vpp >= 256 ? 1 : 256 / vpp;
   const int pix_per_block = rows_par * GN_UNROLL;
   PBE_CHECK_CUDA(launch_k(gn_apply_kernel, dim3(dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb)), dim3(vpp * rows_par), 0, stream, 
-      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw));
+      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -471,9 +468,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
   PBE_REQUIRE(ld_x % 4 == 0 && (y != nullptr || y32 != nullptr), "LayerNorm: row stride % 4, at least one output");
   PBE_REQUIRE(C % 4 == 0 && C / 4 <= 32 * LN_MAX_VEC, "LayerNorm width must be a multiple of 4, <= 1280");
   const int nv = (C / 4 + 31) / 32;
-  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x));
-  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x));
-  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x));
+  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16()));
+  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16()));
+  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -163,6 +163,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// The same with A/B = fp16 (format field 0 instead of 1 for both operands)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by one thread.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -401,6 +405,19 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp16 pair, round to nearest, SATURATING (|x| > 65504 -> +-65504, never inf): one F2FP, the same cost as the bf16 pack
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit GEMM operand pair in the library's operand format (f16 != 0: fp16, else bf16); f16 is warp-uniform
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi, int f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ unsigned short to_op16(float v, int f16) {
+  return static_cast<unsigned short>(pack_op2(v, 0.0f, f16) & 0xffffu);
 }
 
 }  // namespace pbe

@@ -71,6 +71,18 @@ int make_tmap(CUtensorMap* out, const void* base, bool is_f32, int rank, const u
 }
 
 namespace {
+int g_operand_f16 = -1;   // -1: not decided yet (PBE_OPERANDS)
+}
+int operand_f16() {
+  if (g_operand_f16 < 0) {
+    const char* e = getenv("PBE_OPERANDS");
+    g_operand_f16 = (e != nullptr && (e[0] == 'b' || e[0] == 'B')) ? 0 : 1;
+  }
+  return g_operand_f16;
+}
+void set_operand_f16(int f16) { g_operand_f16 = f16 ? 1 : 0; }
+
+namespace {
 thread_local int g_pdl_scope = -1;   // -1: no preference from the engine that is building / capturing a launch plan
 }
 void pdl_set_scope(int v) { g_pdl_scope = v; }

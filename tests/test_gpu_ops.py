@@ -8,15 +8,31 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+# The 16-bit GEMM operand format is a process-wide library setting (include/pbe_b200.h: pbe_set_operand_format): fp16 by
+# default, bf16 on request.  Every test of this module runs in both; OP16 is the torch dtype of the current one.  (The
+# self-attention entry point always READS bf16 Q | K | V^T -- its P matrix lives far below the fp16 range -- and writes its
+# output in the operand format.)
+_FMT = {"dtype": torch.float16}
 
-@pytest.fixture(scope="module")
-def lib():
+
+def OP16():
+    return _FMT["dtype"]
+
+
+@pytest.fixture(scope="module", params=["f16", "bf16"])
+def lib(request):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     from pbe_b200 import _lib
-    return _lib.load()
+    handle = _lib.load()
+    f16 = request.param == "f16"
+    assert handle.pbe_set_operand_format(1 if f16 else 0) == 0
+    _FMT["dtype"] = torch.float16 if f16 else torch.bfloat16
+    yield handle
+    handle.pbe_set_operand_format(1)          # the library default
+    _FMT["dtype"] = torch.float16
 
 
 def _stream():
@@ -59,15 +75,15 @@ def test_conv_gemm_matches_conv2d(lib, case):
     Nb, H, W, C, k, stride, Cout, bn, use_rb, use_res = case
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(1234 + sum(case[:7]))
-    x = torch.randn(Nb, H, W, C, generator=g).to(dev).bfloat16()
-    w = (torch.randn(Cout, C, k, k, generator=g) / math.sqrt(C * k * k)).to(dev).bfloat16()
+    x = torch.randn(Nb, H, W, C, generator=g).to(dev).to(OP16())
+    w = (torch.randn(Cout, C, k, k, generator=g) / math.sqrt(C * k * k)).to(dev).to(OP16())
     wt = w.permute(2, 3, 0, 1).contiguous().view(k * k, Cout, C)
     bias = torch.randn(Cout, generator=g).to(dev)
     Ho, Wo = H // stride, W // stride
     rb = torch.randn(Nb, Cout, generator=g).to(dev) if use_rb else None
     res = torch.randn(Nb, Ho, Wo, Cout, generator=g).to(dev) if use_res else None
     out = torch.full((Nb, Ho, Wo, Cout), float("nan"), device=dev)
-    outb = torch.zeros((Nb, Ho, Wo, Cout), device=dev, dtype=torch.bfloat16)
+    outb = torch.zeros((Nb, Ho, Wo, Cout), device=dev, dtype=OP16())
     rc = lib.pbe_op_conv_gemm(x.data_ptr(), Nb, H, W, C, k, stride, wt.data_ptr(), Cout, 0, _p(bias), _p(rb), _p(res),
                               out.data_ptr(), outb.data_ptr(), None, 0, bn, _stream())
     assert rc == 0, _err(lib)
@@ -88,8 +104,8 @@ def test_gemm_fused_groupnorm_statistics(lib, case):
     Nb, H, W, C, k, Cout, use_res = case
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(77 + sum(case[:6]))
-    x = torch.randn(Nb, H, W, C, generator=g).to(dev).bfloat16()
-    w = (torch.randn(Cout, C, k, k, generator=g) / math.sqrt(C * k * k)).to(dev).bfloat16()
+    x = torch.randn(Nb, H, W, C, generator=g).to(dev).to(OP16())
+    w = (torch.randn(Cout, C, k, k, generator=g) / math.sqrt(C * k * k)).to(dev).to(OP16())
     wt = w.permute(2, 3, 0, 1).contiguous().view(k * k, Cout, C)
     bias = torch.randn(Cout, generator=g).to(dev)
     res = torch.randn(Nb, H, W, Cout, generator=g).to(dev) if use_res else None
@@ -115,14 +131,14 @@ def test_gemm_geglu_epilogue(lib):
     g = torch.Generator().manual_seed(7)
     M, C = 640, 128
     inner = 4 * C
-    x = torch.randn(M, C, generator=g).to(dev).bfloat16()
-    w = (torch.randn(2 * inner, C, generator=g) / math.sqrt(C)).to(dev).bfloat16()
+    x = torch.randn(M, C, generator=g).to(dev).to(OP16())
+    w = (torch.randn(2 * inner, C, generator=g) / math.sqrt(C)).to(dev).to(OP16())
     b = torch.randn(2 * inner, generator=g).to(dev)
     # interleave: tile t = 128 value rows then 128 gate rows (engine.cu add_st)
     wv, wg = w[:inner].view(inner // 128, 128, C), w[inner:].view(inner // 128, 128, C)
     wi = torch.cat((wv, wg), dim=1).reshape(2 * inner, C).contiguous()
     bi = torch.cat((b[:inner].view(-1, 128), b[inner:].view(-1, 128)), dim=1).reshape(-1).contiguous()
-    out = torch.zeros(M, inner, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(M, inner, device=dev, dtype=OP16())
     rc = lib.pbe_op_conv_gemm(x.data_ptr(), 1, 1, M, C, 1, 1, wi.data_ptr(), 2 * inner, 1, bi.data_ptr(), None, None,
                               None, out.data_ptr(), None, 0, 0, _stream())
     assert rc == 0, _err(lib)
@@ -139,10 +155,10 @@ def test_gemm_qkv_split_store(lib):
     g = torch.Generator().manual_seed(9)
     B, H, W, C = 2, 16, 16, 128
     N = H * W
-    x = torch.randn(B, H, W, C, generator=g).to(dev).bfloat16()
-    w = (torch.randn(3 * C, C, generator=g) / math.sqrt(C)).to(dev).bfloat16()
-    qk = torch.zeros(B, N, 2 * C, device=dev, dtype=torch.bfloat16)
-    vt = torch.zeros(B, C, N, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(B, H, W, C, generator=g).to(dev).to(OP16())
+    w = (torch.randn(3 * C, C, generator=g) / math.sqrt(C)).to(dev).to(OP16())
+    qk = torch.zeros(B, N, 2 * C, device=dev, dtype=OP16())
+    vt = torch.zeros(B, C, N, device=dev, dtype=OP16())
     rc = lib.pbe_op_conv_gemm(x.data_ptr(), B, H, W, C, 1, 1, w.data_ptr(), 3 * C, 2, None, None, None, None,
                               qk.data_ptr(), vt.data_ptr(), 2 * C, 128, _stream())
     assert rc == 0, _err(lib)
@@ -169,7 +185,7 @@ def test_self_attention_matches_softmax_reference(lib, B, N, heads, d):
     Np = (N + 7) // 8 * 8                       # V^T rows are pitched to a multiple of 8 tokens (pad never read)
     vt = torch.full((B, C, Np), float("nan"), device=dev, dtype=torch.bfloat16)
     vt[:, :, :N] = v.transpose(1, 2)
-    out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, C, device=dev, dtype=OP16())
     rc = lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, _stream())
     assert rc == 0, _err(lib)
     torch.cuda.synchronize()
@@ -213,7 +229,7 @@ def test_self_attention_drifting_maximum(lib, N, d, heads, drift):
     Np = (N + 7) // 8 * 8
     vt = torch.zeros(B, C, Np, device=dev, dtype=torch.bfloat16)
     vt[:, :, :N] = v.transpose(1, 2)
-    out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, C, device=dev, dtype=OP16())
     rc = lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, _stream())
     assert rc == 0, _err(lib)
     torch.cuda.synchronize()
@@ -262,7 +278,7 @@ def test_self_attention_overflow_is_recomputed_exactly(lib, N, d, heads, kind):
     Np = (N + 7) // 8 * 8
     vt = torch.zeros(B, C, Np, device=dev, dtype=torch.bfloat16)
     vt[:, :, :N] = v.transpose(1, 2)
-    out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(B, N, C, device=dev, dtype=OP16())
     rc = lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, _stream())
     assert rc == 0, _err(lib)
     torch.cuda.synchronize()
@@ -276,7 +292,7 @@ def test_self_attention_overflow_is_recomputed_exactly(lib, N, d, heads, kind):
     assert _rel(out[0], ref[0]) < 1e-2, _rel(out[0], ref[0])
     assert _rel(out[1], ref[1]) < 1e-2, _rel(out[1], ref[1])
     # the benign sample alone gives the same bits: the re-run did not touch it, and the flags were left clean
-    out1 = torch.zeros(1, N, C, device=dev, dtype=torch.bfloat16)
+    out1 = torch.zeros(1, N, C, device=dev, dtype=OP16())
     rc = lib.pbe_op_self_attention(qk[1:].contiguous().data_ptr(), vt[1:].contiguous().data_ptr(), out1.data_ptr(), 1, N, heads, d,
                                    _stream())
     assert rc == 0, _err(lib)
@@ -296,8 +312,8 @@ def test_groupnorm_concat_silu(lib, Nb, HW, C0, C1, eps, silu):
     C = C0 + C1
     gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(dev)
     beta = (0.1 * torch.randn(C, generator=g)).to(dev)
-    y = torch.zeros(Nb, HW, C, device=dev, dtype=torch.bfloat16)
-    raw = torch.zeros(Nb, HW, C, device=dev, dtype=torch.bfloat16)
+    y = torch.zeros(Nb, HW, C, device=dev, dtype=OP16())
+    raw = torch.zeros(Nb, HW, C, device=dev, dtype=OP16())
     ws = torch.zeros(lib.pbe_op_groupnorm_workspace_bytes(Nb, HW) // 4 + 16, device=dev)
     rc = lib.pbe_op_groupnorm(x0.data_ptr(), C0, _p(x1), C1, Nb, HW, gamma.data_ptr(), beta.data_ptr(),
                               ctypes.c_float(eps), silu, y.data_ptr(), raw.data_ptr(), ws.data_ptr(), _stream())
@@ -308,7 +324,7 @@ def test_groupnorm_concat_silu(lib, Nb, HW, C0, C1, eps, silu):
     if silu:
         ref = F.silu(ref)
     assert (y.float() - ref).abs().max().item() < 0.04 and _rel(y, ref) < 4e-3
-    assert torch.equal(raw, xc.bfloat16())
+    assert torch.equal(raw, xc.to(OP16()))
 
 
 @pytest.mark.parametrize("M,C", [(8192, 320), (2048, 640), (515, 1280), (64, 64)])
@@ -318,7 +334,7 @@ def test_layernorm(lib, M, C):
     x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(dev)
     gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(dev)
     beta = (0.1 * torch.randn(C, generator=g)).to(dev)
-    y = torch.zeros(M, C, device=dev, dtype=torch.bfloat16)
+    y = torch.zeros(M, C, device=dev, dtype=OP16())
     rc = lib.pbe_op_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), M, C,
                               ctypes.c_float(1e-5), _stream())
     assert rc == 0, _err(lib)
@@ -330,11 +346,11 @@ def test_layernorm(lib, M, C):
 def test_upsample2x(lib):
     dev = torch.device("cuda:0")
     x = torch.randn(2, 8, 8, 128, device=dev)
-    y = torch.zeros(2, 16, 16, 128, device=dev, dtype=torch.bfloat16)
+    y = torch.zeros(2, 16, 16, 128, device=dev, dtype=OP16())
     rc = lib.pbe_op_upsample2x(x.data_ptr(), y.data_ptr(), 2, 8, 8, 128, _stream())
     assert rc == 0, _err(lib)
     torch.cuda.synchronize()
-    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).bfloat16()
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).to(OP16())
     assert torch.equal(y, ref)
 
 

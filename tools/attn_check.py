@@ -18,7 +18,7 @@ qk = torch.cat((q, k), dim=-1).contiguous()
 Np = (N + 7) // 8 * 8
 vt = torch.zeros(B, C, Np, device=dev, dtype=torch.bfloat16)
 vt[:, :, :N] = v.transpose(1, 2)
-out = torch.zeros(B, N, C, device=dev, dtype=torch.bfloat16)
+out = torch.zeros(B, N, C, device=dev, dtype=torch.float16 if lib.pbe_get_operand_format() else torch.bfloat16)
 assert lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, st) == 0
 torch.cuda.synchronize()
 sp = lambda t: t.float().view(B, N, heads, d).permute(0, 2, 1, 3)

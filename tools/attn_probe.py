@@ -18,7 +18,7 @@ g = torch.Generator().manual_seed(1)
 qk = torch.randn(B, N, 2 * C, generator=g).to(dev).bfloat16()
 Np = (N + 7) // 8 * 8
 vt = torch.randn(B, C, Np, generator=g).to(dev).bfloat16()
-out = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+out = torch.empty(B, N, C, device=dev, dtype=torch.float16 if lib.pbe_get_operand_format() else torch.bfloat16)
 for _ in range(3):
     assert lib.pbe_op_self_attention(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), B, N, heads, d, st) == 0, lib.pbe_last_error()
 torch.cuda.synchronize()
