@@ -85,3 +85,27 @@ def test_inference_script_flow_vs_oracle_pipeline():
     assert rel(c, c_ref) <= 1e-2 and rel(z_inp, z_ref) <= 1e-2
     assert _psnr(samples, lat_ref) >= 35.0 and _psnr(img, img_ref) >= 30.0
     assert u8.shape == (B, H, W, 3) and u8.dtype == torch.uint8
+
+
+def test_test_bench_tool_with_png_io_overlapped(tmp_path):
+    """tools/test_bench.py (BASELINE config C3 loop, scripts/inference_test_bench.py:295-397) on the CI-size networks with
+    the real host I/O: PNG triples in the reference's folder layout are decoded by the loader threads, results are PNG-
+    encoded by the writer threads; every request comes back as a readable 128x128 RGB file named <id:012d>.png."""
+    import json
+    import subprocess
+    import sys
+    import numpy as np
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ds, out = tmp_path / "tb", tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "test_bench.py"), "--small", "--requests", "10", "--batch", "4",
+                        "--steps", "4", "--size", "128", "--dataset", str(ds), "--save", str(out), "--io-workers", "4"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["n_gpus"] == 1 and line["requests_timed"] == 6 and line["images_per_sec"] > 0      # batch 0 (4 requests) builds the plans
+    ids = np.load(ds / "id_list.npy").tolist()
+    files = sorted(os.listdir(out / "results"))
+    assert files == sorted(str(i).zfill(12) + ".png" for i in ids)
+    img = np.asarray(Image.open(out / "results" / files[0]))
+    assert img.shape == (128, 128, 3) and img.dtype == np.uint8 and img.std() > 0

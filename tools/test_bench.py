@@ -1,16 +1,20 @@
-"""BASELINE config C3 end to end: a COCOEE-shaped test bench of synthetic edit triples (image bytes, bbox-mask bytes, exemplar
-bytes), sharded request i -> rank i mod world (scripts/inference_test_bench.py:295-397 is the loop being mirrored), every
-stage on the GPU through the library:
+"""BASELINE config C3 end to end: a COCOEE-shaped test bench of edit triples (image, bbox mask, exemplar), sharded
+request i -> rank i mod world (scripts/inference_test_bench.py:295-397 is the loop being mirrored), every device stage
+through the library and the host I/O overlapped with it (pbe_b200/io.py):
 
-    uint8 bytes -> prepare_inpaint / get_tensor_clip (pbe_b200.preprocess) -> encode_first_stage (VAE) ->
-    get_learned_conditioning + proj_out (CLIP front-end) -> Resize(mask) -> PLMSSampler.sample (50 steps, scale 5) ->
-    decode_to_uint8 (VAE + post-processing) -> bytes back on the host
+    loader threads: PNG decode (or synthetic bytes) -> pinned uint8          [RequestLoader, 2 batches ahead]
+    main thread   : H2D -> prepare_inpaint / get_tensor_clip (pbe_b200.preprocess) -> encode_first_stage (VAE) ->
+                    get_learned_conditioning + proj_out (CLIP front-end) -> Resize(mask) -> PLMSSampler.sample (50 steps,
+                    scale 5) -> decode_to_uint8 (VAE + post-processing) -> async D2H          [never synchronises]
+    writer threads: wait for the copy's event -> PNG encode -> results/<id>.png              [ResultWriter]
 
-    python tools/test_bench.py --requests 16 --batch 8            # one GPU
-    torchrun --nproc-per-node 8 tools/test_bench.py --requests 3500 --batch 8
+    python tools/test_bench.py --requests 16 --batch 8                       # one GPU, synthetic bytes, no files
+    python tools/test_bench.py --requests 64 --dataset /tmp/tb --save /tmp/out   # PNG triples on disk in, PNGs out
+    torchrun --nproc-per-node 8 tools/test_bench.py --requests 3500 --batch 8 --save /tmp/out
 
-Weights are the seeded synthetic ones of the oracles (there is no checkpoint in this sandbox); what is measured is the
-whole-request throughput including host<->device copies, per stage with CUDA events.  Rank 0 prints one JSON line."""
+Weights are the seeded synthetic ones of the oracles (there is no checkpoint in this sandbox) and so is the data; what is
+measured is whole-request throughput including host<->device copies and the host I/O, plus per-stage CUDA-event times.
+Rank 0 prints one JSON line."""
 import argparse
 import json
 import math
@@ -29,6 +33,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--small", action="store_true", help="narrow CI networks instead of v1.yaml (quick functional check)")
+    ap.add_argument("--dataset", default=None, help="test-bench directory in the reference's layout (created with synthetic PNG "
+                                                    "triples if it has no id_list.npy); default: synthetic bytes, no files")
+    ap.add_argument("--save", default=None, help="write results/<id>.png here (threaded PNG writer)")
+    ap.add_argument("--io-workers", type=int, default=8)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
@@ -64,31 +72,43 @@ def main():
     sampler = PLMSSampler(model)
     setup_s = time.perf_counter() - t0
 
+    from pbe_b200 import io as IO
     f = 2 ** (len(vcfg["ch_mult"]) - 1)
     H = W = args.size
     h, w = H // f, W // f
-    mine = shard_requests(args.requests, rank, world)
-    batches = [mine[i:i + args.batch] for i in range(0, len(mine), args.batch)]
+    S_ref = kcfg["image_size"]
+    if args.dataset:
+        if rank == 0 and not os.path.exists(os.path.join(args.dataset, "id_list.npy")):
+            IO.write_synthetic_test_bench(args.dataset, args.requests, size=args.size, seed=7)     # no dataset in the sandbox
+        if world > 1:
+            dist.barrier()
+        loader = IO.RequestLoader.from_test_bench(args.dataset, args.batch, rank, world, prefetch=2, workers=args.io_workers)
+        loader.fetch = lambda rid, root=args.dataset: IO.load_triple(root, rid, ref_size=S_ref)
+    else:
+        def synth(i):   # what PIL would hand over for request i (bytes only; generated on the loader threads)
+            img_u8, mask_u8 = R.synthetic_u8_request(1, H, W, seed=321 + i)
+            gg = torch.Generator().manual_seed(1000 + i)
+            return img_u8[0], torch.randint(0, 256, (S_ref, S_ref, 3), generator=gg, dtype=torch.uint8), mask_u8[0]
+        loader = IO.RequestLoader(shard_requests(args.requests, rank, world), args.batch, synth, prefetch=2, workers=args.io_workers)
+    writer = IO.ResultWriter(os.path.join(args.save, "results"), workers=args.io_workers, max_in_flight=4) if args.save else None
     stages = ("h2d", "preprocess", "vae_encode", "clip", "sample", "decode_u8", "d2h")
-    acc = {s: 0.0 for s in stages}
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    done, checksum = 0, 0
+    torch.manual_seed(4321 + rank)                    # x_T is drawn on the device by the sampler (start_code = None in the script)
+    all_marks, done, checksum_t = [], 0, torch.zeros((), dtype=torch.int64, device=dev)
     wall0 = None
-    for bi, ids in enumerate(batches):
+    host_keep = []
+    nb = len(loader)
+    for bi, (ids, img_u8, ref_u8, mask_u8) in enumerate(loader):
         B = len(ids)
-        img_u8, mask_u8 = R.synthetic_u8_request(B, H, W, seed=321 + ids[0])          # what PIL would hand over
-        gg = torch.Generator().manual_seed(1000 + ids[0])
-        ref_u8 = torch.randint(0, 256, (B, kcfg["image_size"], kcfg["image_size"], 3), generator=gg, dtype=torch.uint8)
-        x_T = torch.randn(B, 4, h, w, generator=gg)
-        pinned = [t.pin_memory() for t in (img_u8, mask_u8, ref_u8, x_T)]
-        if bi == 1 or len(batches) == 1:
+        if bi == 1 or nb == 1:
             torch.cuda.synchronize()
             wall0 = time.perf_counter()                                                 # the first batch builds the plans
             done = 0
+            all_marks = []
         marks = [ev() for _ in range(len(stages) + 1)]
         with torch.no_grad():
             marks[0].record()
-            img_d, mask_d, ref_d, xT_d = (t.to(dev, non_blocking=True) for t in pinned)
+            img_d, mask_d, ref_d = (t.to(dev, non_blocking=True) for t in (img_u8, mask_u8, ref_u8))
             marks[1].record()
             _, m_full, inpaint = P.prepare_inpaint(img_d, mask_d, binarize=False)       # test_bench_dataset.py:89-98
             ref_t = P.get_tensor_clip()(ref_d)
@@ -100,21 +120,30 @@ def main():
             marks[4].record()
             samples, _ = sampler.sample(S=args.steps, conditioning=c, batch_size=B, shape=[4, h, w], verbose=False,
                                         unconditional_guidance_scale=5.0, unconditional_conditioning=model.learnable_vector,
-                                        eta=0.0, x_T=xT_d, test_model_kwargs=dict(inpaint_image=z_inp, inpaint_mask=m_lat))
+                                        eta=0.0, x_T=None, test_model_kwargs=dict(inpaint_image=z_inp, inpaint_mask=m_lat))
             marks[5].record()
             u8 = model.first_stage_model.decode_to_uint8(samples / model.scale_factor)
             marks[6].record()
-            out = u8.cpu()
+            if writer is not None:
+                writer.submit([str(i).zfill(12) for i in ids], u8)                      # async D2H + PNG encode off-thread
+            else:
+                hb = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+                hb.copy_(u8, non_blocking=True)
+                host_keep = [hb]
             marks[7].record()
-        torch.cuda.synchronize()
-        assert out.shape == (B, H, W, 3) and out.dtype == torch.uint8
-        checksum = (checksum + int(out.long().sum())) % (1 << 31)
-        if wall0 is not None:
-            for i, s in enumerate(stages):
-                acc[s] += marks[i].elapsed_time(marks[i + 1])
-            done += B
+            checksum_t += u8.sum(dtype=torch.int64)
+        assert u8.shape == (B, H, W, 3) and u8.dtype == torch.uint8
+        all_marks.append((B, marks))
+        done += B
     torch.cuda.synchronize()
+    if writer is not None:
+        writer.close()
     wall = time.perf_counter() - (wall0 or time.perf_counter())
+    checksum = int(checksum_t.item()) % (1 << 31)
+    acc = {s: 0.0 for s in stages}
+    for B, marks in all_marks:
+        for i, s in enumerate(stages):
+            acc[s] += marks[i].elapsed_time(marks[i + 1])
     total_done = done
     if world > 1:
         t = torch.tensor([float(done), wall], device=dev)
@@ -129,6 +158,11 @@ def main():
                         f"micro-batch {args.batch}, request i -> rank i mod {world}; whole request on the GPU from uint8 bytes "
                         f"to uint8 bytes ({'CI-size' if args.small else 'v1.yaml'} networks, seeded random weights)",
             "n_gpus": world, "requests_timed": total_done, "images_per_sec": round(total_done / wall, 3) if wall > 0 else None,
+            "host_io": {"input": "PNG triples decoded by loader threads" if args.dataset else "synthetic bytes from loader threads",
+                        "output": (f"{writer.written} PNGs, {writer.bytes_written / 1e6:.1f} MB written by {args.io_workers} "
+                                   f"writer threads (rank 0)") if writer is not None else "none (D2H copy only)",
+                        "overlap": "loader 2 batches ahead; D2H + PNG encode asynchronous; the main thread never synchronises "
+                                   "the stream inside the timed loop"},
             "stage_ms_per_image_rank0": per_img, "setup_s": round(setup_s, 1), "checksum_rank0": checksum}))
     if world > 1:
         dist.destroy_process_group()
