@@ -459,6 +459,7 @@ int Engine::build(Prepared& P, bool dry) {
     if (d.out_f32) bytes += Mrows * out_cols * 4.0;
     if (d.out_bf16 || d.out_vt) bytes += Mrows * out_cols * 2.0;
     if (d.residual) bytes += Mrows * out_cols * 4.0;
+    if (d.residual16) bytes += Mrows * out_cols * 2.0;
     add_op_meta(name, ws_bytes ? 2 : 1, [plan](cudaStream_t s) { return launch_gemm_plan(*plan, s); }, "conv_gemm", flops,
                 bytes);
   };
@@ -466,8 +467,9 @@ int Engine::build(Prepared& P, bool dry) {
     a.partial = static_cast<float*>(SA(static_cast<size_t>(gn_workspace_floats(a.Nb, a.HW, a.C0 + a.C1)) * sizeof(float)));
     const double n = static_cast<double>(a.Nb) * a.HW * (a.C0 + a.C1);
     const int launches = gn_num_launches(a);
+    const double in_b = a.in16 ? 2.0 : 4.0;
     add_op_meta(name, launches, [a](cudaStream_t s) { return launch_groupnorm(a, s); }, "groupnorm", 0.0,
-                n * ((launches == 3 ? 8.0 : 4.0) + 2.0 + (a.raw ? 2.0 : 0.0)));
+                n * ((launches == 3 ? 2.0 * in_b : in_b) + 2.0 + (a.raw ? 2.0 : 0.0)));
   };
 
   P.x_stage = static_cast<float*>(PA(static_cast<size_t>(BcFull) * cfg_.in_channels * H0 * W0 * sizeof(float)));
@@ -502,15 +504,38 @@ int Engine::build(Prepared& P, bool dry) {
     }
   }
 
+  // The residual stream between ops (block outputs, skip tensors, ResBlock h, transformer t0 / t1) is 16-bit in the
+  // operand format (fp16 by default) -- what the reference itself carries under torch.autocast -- unless PBE_STREAM=fp32:
+  // every GEMM then stores 16-bit only (rounded once from its fp32 accumulator + bias + residual), GroupNorm / LayerNorm
+  // read 2 bytes per element instead of 4, residuals enter the epilogues as 64-byte rows, and no raw 16-bit side copies
+  // are needed for the stride-2 and 1x1 skip convs (the stream IS the operand).  Statistics stay fp32.
+  const bool s16 = stream16_;
+  const size_t esz = s16 ? sizeof(bf16) : sizeof(float);
   struct Act {
     float* f32;
-    bf16* b16;  // optional bf16 copy
+    bf16* b16;  // fp32 stream: optional 16-bit copy; 16-bit stream: the tensor itself
     int C, H, W;
     bool has16 = false;
     float* stats = nullptr;   // fused GroupNorm statistics written by the producing GEMM (or null)
     bool has_stats = false;
   };
-  // Attach fused GroupNorm statistics to a GEMM whose fp32 output `o` is normalised by the next op.
+  auto new_act = [&](bool persistent, size_t elems, int C, int H, int W) {
+    Act a{nullptr, nullptr, C, H, W};
+    void* ptr = persistent ? PA(elems * esz) : SA(elems * esz);
+    if (s16) { a.b16 = static_cast<bf16*>(ptr); a.has16 = true; }
+    else a.f32 = static_cast<float*>(ptr);
+    return a;
+  };
+  auto as_f32ptr = [&](const Act& a) { return s16 ? reinterpret_cast<const float*>(a.b16) : a.f32; };   // GroupNormArgs / LayerNorm source
+  auto set_out = [&](ConvGemmDesc& d, const Act& a) {
+    if (s16) d.out_bf16 = a.b16;
+    else { d.out_f32 = a.f32; d.out_bf16 = a.b16; }
+  };
+  auto set_res = [&](ConvGemmDesc& d, const Act& a) {
+    if (s16) d.residual16 = a.b16;
+    else d.residual = a.f32;
+  };
+  // Attach fused GroupNorm statistics to a GEMM whose output `o` is normalised by the next op.
   auto want_stats = [&](ConvGemmDesc& d, Act& o, bool persistent) {
     d.splitk_ws = nullptr;
     if (!diverged) d.split_batch = 2 * d.Nb;   // as in add_gemm: decide like the full CFG batch would
@@ -528,8 +553,8 @@ int Engine::build(Prepared& P, bool dry) {
     const Module& m = modules_[mi];
     const size_t smark = P.scratch.mark();
     const std::string tag = "m" + std::to_string(mi);
-    // does the next module consume a raw bf16 copy of this module's output? (stride-2 conv reads raw activations)
-    const bool next_is_down = (mi + 1 < modules_.size() && modules_[mi + 1].kind == Module::DOWN);
+    // does the next module consume a raw 16-bit copy of this module's output? (fp32 stream only: a stride-2 conv reads raw activations)
+    const bool next_is_down = !s16 && (mi + 1 < modules_.size() && modules_[mi + 1].kind == Module::DOWN);
     switch (m.kind) {
       case Module::CONV_IN: {
         const ConvW& c = convs_[m.idx];
@@ -538,10 +563,11 @@ int Engine::build(Prepared& P, bool dry) {
         const float* xs = P.x_stage;
         const int cin = cfg_.in_channels;
         add_op(tag + ".pack_input", 1, [=](cudaStream_t s) { return launch_pack_input(xs, xin, Bc, cin, H0, W0, 64, s); });
-        Act o{static_cast<float*>(PA(M * (diverged ? 1 : 2) * c.cout * sizeof(float))), nullptr, c.cout, H0, W0};
+        Act o = new_act(true, M * (diverged ? 1 : 2) * c.cout, c.cout, H0, W0);
         ConvGemmDesc d{};
         d.act = xin; d.Nb = Bc; d.H = H0; d.W = W0; d.C = 64; d.c_real = cin; d.ksize = 3; d.stride = 1;
-        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b;
+        set_out(d, o);
         want_stats(d, o, true);
         add_gemm(tag + ".conv_in", d);
         h = o;
@@ -562,47 +588,52 @@ int Engine::build(Prepared& P, bool dry) {
           return err;
         }
         bf16* a1 = static_cast<bf16*>(SA(M * cin * sizeof(bf16)));
-        bf16* raw = r.has_skip ? static_cast<bf16*>(SA(M * cin * sizeof(bf16))) : nullptr;
+        // the 1x1 skip conv reads the raw (un-normalised) input: with a 16-bit stream and no concat that is h itself
+        const bool raw_needed = r.has_skip && !(s16 && skip.C == 0);
+        bf16* raw = raw_needed ? static_cast<bf16*>(SA(M * cin * sizeof(bf16))) : nullptr;
         GroupNormArgs g1{};
-        g1.x0 = h.f32; g1.C0 = h.C; g1.x1 = skip.f32; g1.C1 = skip.C; g1.Nb = Bc; g1.HW = h.H * h.W;
+        g1.x0 = as_f32ptr(h); g1.C0 = h.C; g1.x1 = skip.C ? as_f32ptr(skip) : nullptr; g1.C1 = skip.C; g1.Nb = Bc; g1.HW = h.H * h.W;
+        g1.in16 = s16 ? 1 : 0;
         g1.gamma = r.gn1.g; g1.beta = r.gn1.b; g1.eps = 1e-5f; g1.silu = 1; g1.y = a1; g1.raw = raw;
         g1.stats0 = h.has_stats ? h.stats : nullptr;
         g1.stats1 = (skip.C > 0 && skip.has_stats) ? skip.stats : nullptr;
         if (skip.C > 0 && !(h.has_stats && skip.has_stats)) g1.stats0 = g1.stats1 = nullptr;
         add_gn(tag + ".gn1", g1);
-        float* h1 = static_cast<float*>(SA(M * r.cout * sizeof(float)));
-        Act h1act{h1, nullptr, r.cout, h.H, h.W};
+        Act h1act = new_act(false, M * r.cout, r.cout, h.H, h.W);
         {
           ConvGemmDesc d{};
           d.act = a1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 3; d.stride = 1;
           d.wt = r.conv1.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv1.b;
           d.rowbias = emb_all + r.emb_off; d.rowbias_ld = emb_total_;
-          d.out_f32 = h1;
+          set_out(d, h1act);
           want_stats(d, h1act, false);
           add_gemm(tag + ".conv1", d);
         }
         bf16* a2 = static_cast<bf16*>(SA(M * r.cout * sizeof(bf16)));
         GroupNormArgs g2{};
-        g2.x0 = h1; g2.C0 = r.cout; g2.x1 = nullptr; g2.C1 = 0; g2.Nb = Bc; g2.HW = h.H * h.W;
+        g2.x0 = as_f32ptr(h1act); g2.C0 = r.cout; g2.x1 = nullptr; g2.C1 = 0; g2.Nb = Bc; g2.HW = h.H * h.W;
+        g2.in16 = s16 ? 1 : 0;
         g2.gamma = r.gn2.g; g2.beta = r.gn2.b; g2.eps = 1e-5f; g2.silu = 1; g2.y = a2; g2.raw = nullptr;
         g2.stats0 = h1act.has_stats ? h1act.stats : nullptr;
         add_gn(tag + ".gn2", g2);
-        const float* resid = h.f32;
+        Act resid = h;
         if (r.has_skip) {
-          float* sk = static_cast<float*>(SA(M * r.cout * sizeof(float)));
+          Act sk = new_act(false, M * r.cout, r.cout, h.H, h.W);
           ConvGemmDesc d{};
-          d.act = raw; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 1; d.stride = 1;
-          d.wt = r.skip.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.skip.b; d.out_f32 = sk;
+          d.act = raw_needed ? raw : h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 1; d.stride = 1;
+          d.wt = r.skip.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.skip.b;
+          set_out(d, sk);
           add_gemm(tag + ".skip", d);
           resid = sk;
         }
-        Act o{static_cast<float*>(PA(M * (diverged ? 1 : 2) * r.cout * sizeof(float))), nullptr, r.cout, h.H, h.W};
+        Act o = new_act(true, M * (diverged ? 1 : 2) * r.cout, r.cout, h.H, h.W);
         if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * (diverged ? 1 : 2) * r.cout * sizeof(bf16))); o.has16 = true; }
         {
           ConvGemmDesc d{};
           d.act = a2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = r.cout; d.ksize = 3; d.stride = 1;
-          d.wt = r.conv2.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv2.b; d.residual = resid;
-          d.out_f32 = o.f32; d.out_bf16 = o.b16;
+          d.wt = r.conv2.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.conv2.b;
+          set_res(d, resid);
+          set_out(d, o);
           want_stats(d, o, true);
           add_gemm(tag + ".conv2", d);
         }
@@ -616,23 +647,27 @@ int Engine::build(Prepared& P, bool dry) {
         if (C != h.C) { err = -5; last_error = "channel mismatch at " + tag; return err; }
         bf16* a = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
         GroupNormArgs g{};
-        g.x0 = h.f32; g.C0 = C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = N;
+        g.x0 = as_f32ptr(h); g.C0 = C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = N;
+        g.in16 = s16 ? 1 : 0;
         g.gamma = s.gn.g; g.beta = s.gn.b; g.eps = 1e-6f; g.silu = 0; g.y = a; g.raw = nullptr;
         g.stats0 = h.has_stats ? h.stats : nullptr;
         add_gn(tag + ".norm", g);
-        float* t0 = static_cast<float*>(SA(M * C * sizeof(float)));
+        Act t0 = new_act(false, M * C, C, h.H, h.W);
         {
           ConvGemmDesc d{};
           d.act = a; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
-          d.wt = s.proj_in.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_in.b; d.out_f32 = t0;
+          d.wt = s.proj_in.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_in.b;
+          set_out(d, t0);
           add_gemm(tag + ".proj_in", d);
         }
         bf16* n1 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
         {
           const float *gg = s.ln1.g, *bb = s.ln1.b;
           const int Mi = static_cast<int>(M);
-          add_op_meta(tag + ".ln1", 1, [=](cudaStream_t st) { return launch_layernorm(t0, gg, bb, n1, Mi, C, 1e-5f, st); },
-                      "layernorm", 0.0, static_cast<double>(M) * C * 6.0);
+          const float* src = as_f32ptr(t0);
+          const int in16 = s16 ? 1 : 0;
+          add_op_meta(tag + ".ln1", 1, [=](cudaStream_t st) { return launch_layernorm(src, gg, bb, n1, Mi, C, 1e-5f, st, nullptr, 0, in16); },
+                      "layernorm", 0.0, static_cast<double>(M) * C * (esz + 2.0));
         }
         bf16* qk = static_cast<bf16*>(SA(M * 2 * C * sizeof(bf16)));
         bf16* vt = static_cast<bf16*>(SA(static_cast<size_t>(Bc) * C * vt_pitch(N) * sizeof(bf16)));   // [Bc][C][pitch]
@@ -655,7 +690,7 @@ int Engine::build(Prepared& P, bool dry) {
         } else {
           launches += 1;
         }
-        float* t1 = static_cast<float*>(SA(M * (diverged ? 1 : 2) * C * sizeof(float)));
+        Act t1 = new_act(false, M * (diverged ? 1 : 2) * C, C, h.H, h.W);
         for (int half = 0; half < (diverged ? 1 : 2); ++half) {
           // x1 = to_out(attn) + b + x ; x2 = x1 + to_out2(to_v2(ctx))  (single-key cross-attention, folded).
           // CFG pair plan: this is where the context enters -- the shared activations feed one GEMM per half, each
@@ -665,7 +700,11 @@ int Engine::build(Prepared& P, bool dry) {
           d.wt = s.to_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.to_out.b;
           d.rowbias = ctx_vecs_ + static_cast<size_t>(MAX_BC) * s.ctx_vec_off + static_cast<size_t>(half) * Bc * C;
           d.rowbias_ld = C;
-          d.residual = t0; d.out_f32 = t1 + static_cast<size_t>(half) * M * C;
+          set_res(d, t0);
+          Act dst = t1;
+          if (s16) dst.b16 = t1.b16 + static_cast<size_t>(half) * M * C;
+          else dst.f32 = t1.f32 + static_cast<size_t>(half) * M * C;
+          set_out(d, dst);
           add_gemm(tag + (half ? ".attn1.to_out+attn2[cond]" : ".attn1.to_out+attn2"), d);
         }
         if (!diverged) {
@@ -676,11 +715,13 @@ int Engine::build(Prepared& P, bool dry) {
           dup.push_back(&h);
           for (Act* a0 : dup) {
             const size_t elems = static_cast<size_t>(Bc) * a0->H * a0->W * a0->C;
-            float* f = a0->f32;
-            add_op(tag + ".dup_f32", 0, [=](cudaStream_t st) {
-              PBE_CHECK_CUDA(cudaMemcpyAsync(f + elems, f, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
-              return 0;
-            });
+            if (a0->f32) {
+              float* f = a0->f32;
+              add_op(tag + ".dup_f32", 0, [=](cudaStream_t st) {
+                PBE_CHECK_CUDA(cudaMemcpyAsync(f + elems, f, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                return 0;
+              });
+            }
             if (a0->has_stats) {
               const size_t sel = static_cast<size_t>(Bc) * a0->H * a0->W / 32 * a0->C * 2;
               float* sp = a0->stats;
@@ -705,8 +746,10 @@ int Engine::build(Prepared& P, bool dry) {
         {
           const float *gg = s.ln3.g, *bb = s.ln3.b;
           const int Mi = static_cast<int>(M);
-          add_op_meta(tag + ".ln3", 1, [=](cudaStream_t st) { return launch_layernorm(t1, gg, bb, n3, Mi, C, 1e-5f, st); },
-                      "layernorm", 0.0, static_cast<double>(M) * C * 6.0);
+          const float* src = as_f32ptr(t1);
+          const int in16 = s16 ? 1 : 0;
+          add_op_meta(tag + ".ln3", 1, [=](cudaStream_t st) { return launch_layernorm(src, gg, bb, n3, Mi, C, 1e-5f, st, nullptr, 0, in16); },
+                      "layernorm", 0.0, static_cast<double>(M) * C * (esz + 2.0));
         }
         bf16* gg = static_cast<bf16*>(SA(M * 4 * C * sizeof(bf16)));
         {
@@ -719,16 +762,18 @@ int Engine::build(Prepared& P, bool dry) {
         {
           ConvGemmDesc d{};
           d.act = gg; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = 4 * C; d.ksize = 1; d.stride = 1;
-          d.wt = s.ff2.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.ff2.b; d.residual = t1; d.out_bf16 = t2;
+          d.wt = s.ff2.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.ff2.b; d.out_bf16 = t2;
+          set_res(d, t1);
           add_gemm(tag + ".ff.out", d);
         }
-        Act o{static_cast<float*>(PA(M * C * sizeof(float))), nullptr, C, h.H, h.W};
+        Act o = new_act(true, M * C, C, h.H, h.W);
         if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * C * sizeof(bf16))); o.has16 = true; }
         {
           ConvGemmDesc d{};
           d.act = t2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
-          d.wt = s.proj_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_out.b; d.residual = h.f32;
-          d.out_f32 = o.f32; d.out_bf16 = o.b16;
+          d.wt = s.proj_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_out.b;
+          set_res(d, h);
+          set_out(d, o);
           want_stats(d, o, true);
           add_gemm(tag + ".proj_out", d);
         }
@@ -739,14 +784,15 @@ int Engine::build(Prepared& P, bool dry) {
         const ConvW& c = convs_[m.idx];
         if (!h.has16 || (h.H & 1) || (h.W & 1)) {
           err = -5;
-          last_error = "downsample needs a bf16 copy and even H, W at " + tag;
+          last_error = "downsample needs a 16-bit copy and even H, W at " + tag;
           return err;
         }
         const size_t M = static_cast<size_t>(Bc) * (h.H / 2) * (h.W / 2);
-        Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, h.H / 2, h.W / 2};
+        Act o = new_act(true, M * c.cout, c.cout, h.H / 2, h.W / 2);
         ConvGemmDesc d{};
         d.act = h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = h.C; d.ksize = 3; d.stride = 2;
-        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b;
+        set_out(d, o);
         want_stats(d, o, true);
         add_gemm(tag + ".downsample", d);
         h = o;
@@ -758,15 +804,19 @@ int Engine::build(Prepared& P, bool dry) {
         bf16* up = static_cast<bf16*>(SA(M * h.C * sizeof(bf16)));
         {
           const float* src = h.f32;
+          const bf16* src16 = h.b16;
           const int hh = h.H, ww = h.W, cc = h.C;
           add_op_meta(tag + ".upsample2x", 1,
-                      [=](cudaStream_t st) { return launch_upsample2x_bf16(src, up, Bc, hh, ww, cc, st); }, "upsample",
-                      0.0, static_cast<double>(Bc) * hh * ww * cc * (4.0 + 8.0));
+                      [=](cudaStream_t st) {
+                        return s16 ? launch_upsample2x_16(src16, up, Bc, hh, ww, cc, st) : launch_upsample2x_bf16(src, up, Bc, hh, ww, cc, st);
+                      },
+                      "upsample", 0.0, static_cast<double>(Bc) * hh * ww * cc * (esz + 8.0));
         }
-        Act o{static_cast<float*>(PA(M * c.cout * sizeof(float))), nullptr, c.cout, 2 * h.H, 2 * h.W};
+        Act o = new_act(true, M * c.cout, c.cout, 2 * h.H, 2 * h.W);
         ConvGemmDesc d{};
         d.act = up; d.Nb = Bc; d.H = 2 * h.H; d.W = 2 * h.W; d.C = h.C; d.ksize = 3; d.stride = 1;
-        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = o.f32;
+        d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b;
+        set_out(d, o);
         want_stats(d, o, true);
         add_gemm(tag + ".upsample.conv", d);
         h = o;
@@ -777,11 +827,12 @@ int Engine::build(Prepared& P, bool dry) {
         const size_t M = static_cast<size_t>(Bc) * h.H * h.W;
         bf16* a = static_cast<bf16*>(SA(M * h.C * sizeof(bf16)));
         GroupNormArgs g{};
-        g.x0 = h.f32; g.C0 = h.C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = h.H * h.W;
+        g.x0 = as_f32ptr(h); g.C0 = h.C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = h.H * h.W;
+        g.in16 = s16 ? 1 : 0;
         g.gamma = out_norm_.g; g.beta = out_norm_.b; g.eps = 1e-5f; g.silu = 1; g.y = a; g.raw = nullptr;
         g.stats0 = h.has_stats ? h.stats : nullptr;
         add_gn(tag + ".out.norm", g);
-        float* y = static_cast<float*>(SA(M * c.cout * sizeof(float)));
+        float* y = static_cast<float*>(SA(M * c.cout * sizeof(float)));       // eps leaves the network in fp32
         ConvGemmDesc d{};
         d.act = a; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = h.C; d.ksize = 3; d.stride = 1;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b; d.out_f32 = y; d.block_n = 32;

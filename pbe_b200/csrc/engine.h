@@ -1,6 +1,8 @@
 // U-Net engine: owns repacked weights, per-shape launch plans and workspaces; runs UNetModel.forward
 // (ldm/modules/diffusionmodules/openaimodel.py:852-889) as a fixed list of sm_100a kernel launches (CUDA-graph replayed).
 #pragma once
+#include <stdlib.h>
+
 #include <functional>
 #include <map>
 #include <memory>
@@ -135,6 +137,8 @@ class Engine : public WeightLoader {
                       float* ms, int max_ops);
   const Prepared* current() const { return cur_; }
   bool use_graph = true;
+  // 16-bit residual stream (operand format) between ops; PBE_STREAM=fp32 keeps the round-1 fp32 stream (A/B, debugging)
+  bool stream16_ = [] { const char* e = getenv("PBE_STREAM"); return !(e != nullptr && (e[0] == 'f' || e[0] == 'F')); }();
   std::string last_error;
 
  private:

@@ -358,7 +358,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!tile_is_vt(n_tile) && chunk_valid(n_tile, pf_c)) {
           const int slot = ws * 2 + (pf_seq & 1);
           if (p.has_res) {
-            mbar_expect_tx(res_full_bar(slot), SLOT_BYTES);
+            mbar_expect_tx(res_full_bar(slot), p.res16 ? SLOT_BYTES / 2 : SLOT_BYTES);   // 16-bit residual: 128 rows x 64 B
             tma_load_4d(slot_base + slot * SLOT_BYTES, &tmR, res_full_bar(slot), n_tile * tile_out_cols + pf_c * chunk_cols,
                         w0, h0, n0);
           } else {
@@ -528,7 +528,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.has_res) mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
         if (edbg) e_slot += clock64() - te;
         uint8_t* my_row128 = slot_gen + row * 128;
-        if (p.has_res) {
+        if (p.has_res && p.res16) {
+          // 16-bit residual stream: the box landed in the compact [128 rows x 64 B] layout (64B swizzle) the 16-bit output
+          // uses -- a thread reads its own row here and overwrites exactly those bytes below: no barrier in between
+          const uint8_t* rrow = slot_gen + row * 64;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(rrow + ((u ^ ((row >> 1) & 3)) << 4));
+            const float2 r0 = unpack_op2(rr.x, p.out16_f16), r1 = unpack_op2(rr.y, p.out16_f16),
+                         r2 = unpack_op2(rr.z, p.out16_f16), r3 = unpack_op2(rr.w, p.out16_f16);
+            o[8 * u + 0] += r0.x; o[8 * u + 1] += r0.y; o[8 * u + 2] += r1.x; o[8 * u + 3] += r1.y;
+            o[8 * u + 4] += r2.x; o[8 * u + 5] += r2.y; o[8 * u + 6] += r3.x; o[8 * u + 7] += r3.y;
+          }
+        } else if (p.has_res) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float4 rr = *reinterpret_cast<const float4*>(my_row128 + ((u ^ (row & 7)) << 4));
@@ -592,8 +604,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else {
-          // bf16-only output: compact [128 rows x 64 B] layout (64B swizzle) overlaps other rows' fp32 residual
-          if (p.has_res) named_bar_sync(bar_id, 128);
+          // 16-bit-only output: compact [128 rows x 64 B] layout (64B swizzle) overlaps other rows' fp32 residual
+          if (p.has_res && !p.res16) named_bar_sync(bar_id, 128);
           uint8_t* my_row64 = slot_gen + row * 64;
           if (p.out16_f16) {   // warp-uniform: one conversion per pair on either path
 #pragma unroll
@@ -614,6 +626,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
               pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
               *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+            }
+          }
+          if (p.stats_out != nullptr) {
+            // GroupNorm statistics of the 16-bit tensor being written, taken from the ROUNDED values in the slot (they are
+            // the statistics of what the next GroupNorm will read): lane = column, walk my warp's 32 rows.  Fixed order.
+            __syncwarp();
+            const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
+            const long long m_first = __shfl_sync(0xffffffffu, my_m, 0);
+            const int col = n_base + c * 32 + lane;
+            if (vmask != 0u && col < p.n_total) {
+              float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+              const uint32_t wbase = slot_addr + (q * 32) * 64 + ((lane & 7) << 1);
+              const int unit = lane >> 3;
+#pragma unroll
+              for (int r = 0; r < 32; r += 2) {
+                const int ra = q * 32 + r, rb2 = ra + 1;
+                unsigned short ha, hb;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ha) : "r"(wbase + r * 64 + ((unit ^ ((ra >> 1) & 3)) << 4)));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hb) : "r"(wbase + (r + 1) * 64 + ((unit ^ ((rb2 >> 1) & 3)) << 4)));
+                float xa = op16_to_float(ha, p.out16_f16), xb = op16_to_float(hb, p.out16_f16);
+                if (vmask != 0xffffffffu) {
+                  xa = ((vmask >> r) & 1u) ? xa : 0.0f;
+                  xb = ((vmask >> (r + 1)) & 1u) ? xb : 0.0f;
+                }
+                s0 += xa; q0 = fmaf(xa, xa, q0);
+                s1 += xb; q1 = fmaf(xb, xb, q1);
+              }
+              *reinterpret_cast<float2*>(p.stats_out + ((m_first >> 5) * p.n_total + col) * 2) = make_float2(s0 + s1, q0 + q1);
             }
           }
         }
@@ -764,6 +804,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitKReduce r) {
     const float4 b = *reinterpret_cast<const float4*>(r.residual + o);
     acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
   }
+  if (r.residual16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(r.residual16 + o);
+    const float2 b0 = unpack_op2(u.x, r.out16_f16), b1 = unpack_op2(u.y, r.out16_f16);
+    acc.x += b0.x; acc.y += b0.y; acc.z += b1.x; acc.w += b1.y;
+  }
   if (r.out_f32) *reinterpret_cast<float4*>(r.out_f32 + o) = acc;
   if (r.out_bf16) {
     uint2 pk;
@@ -875,7 +920,9 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.bias = d.bias;
   p.rowbias = d.rowbias;
   p.rowbias_ld = d.rowbias_ld ? d.rowbias_ld : d.Cout;
-  p.residual = d.residual;
+  p.residual = d.residual16 ? reinterpret_cast<const float*>(d.residual16) : d.residual;
+  p.res16 = d.residual16 != nullptr;
+  PBE_REQUIRE(!(d.residual16 && (d.residual || d.out_f32)), "a 16-bit residual goes with a 16-bit-only output");
   p.out_f32 = d.out_f32;
   p.out_bf16 = d.out_bf16;
   p.out_vt = d.out_vt;
@@ -895,7 +942,8 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.debug = getenv("PBE_GEMM_DEBUG") ? 1 : 0;
   p.stats_out = nullptr;
   if (d.stats_out != nullptr) {
-    PBE_REQUIRE(gemm_can_fuse_stats(d) && p.split_k == 1 && d.out_f32 != nullptr, "fused GroupNorm statistics not available for this GEMM");
+    PBE_REQUIRE(gemm_can_fuse_stats(d) && p.split_k == 1 && (d.out_f32 != nullptr || d.out_bf16 != nullptr),
+                "fused GroupNorm statistics not available for this GEMM");
     p.stats_out = d.stats_out;
   }
   plan->red = SplitKReduce{};
@@ -950,7 +998,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     const uint64_t Wo = p.Wo, Ho = p.Ho, Nb = p.Nb;
     const uint64_t dims[4] = {static_cast<uint64_t>(out_cols), Wo, Ho, Nb};
     const uint32_t box[4] = {32u, static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.tn)};
-    p.has_res = d.residual != nullptr;
+    p.has_res = d.residual != nullptr || d.residual16 != nullptr;
     p.has_o32 = d.out_f32 != nullptr;
     p.has_o16 = d.out_bf16 != nullptr;
     PBE_REQUIRE(p.has_o32 || p.has_o16, "GEMM needs an output");
@@ -964,8 +1012,9 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
       r.N = d.Cout;
       r.HW = p.Ho * p.Wo;
       r.bias = d.bias; r.rowbias = d.rowbias; r.rowbias_ld = p.rowbias_ld; r.residual = d.residual;
+      r.residual16 = d.residual16;
       r.out_f32 = d.out_f32; r.out_bf16 = d.out_bf16; r.ld_out = p.ld_out;
-      p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr; p.out_bf16 = nullptr;
+      p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr; p.res16 = 0; p.out_bf16 = nullptr;
       p.out_f32 = d.splitk_ws;
       p.has_res = 0; p.has_o32 = 1; p.has_o16 = 0;
       const uint64_t wdims[4] = {static_cast<uint64_t>(d.Cout), Wo, Ho, nb_pad * p.split_k};
@@ -980,7 +1029,8 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     const uint64_t s32[3] = {ld * 4, Wo * ld * 4, Ho * Wo * ld * 4};
     const uint64_t s16[3] = {ld * 2, Wo * ld * 2, Ho * Wo * ld * 2};
     int rc = 0;
-    if (p.has_res) rc = make_tmap(&plan->tmR, d.residual, true, 4, dims, s32, box, 128);
+    if (p.has_res && p.res16) rc = make_tmap(&plan->tmR, d.residual16, false, 4, dims, s16, box, 64);
+    else if (p.has_res) rc = make_tmap(&plan->tmR, d.residual, true, 4, dims, s32, box, 128);
     if (rc) return rc;
     if (p.has_o32) rc = make_tmap(&plan->tmO32, d.out_f32, true, 4, dims, s32, box, 128);
     if (rc) return rc;

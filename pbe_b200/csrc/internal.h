@@ -79,6 +79,7 @@ struct ConvGemmParams {
   const float* rowbias;   // [Nb, rowbias_ld] or null (timestep-embedding / folded cross-attention term)
   int rowbias_ld;
   const float* residual;  // [M, ld_out] fp32 or null
+  int res16;              // 1: `residual` points to 16-bit data (operand format) -- the 16-bit residual stream of the U-Net
   float* out_f32;         // [M, ld_out] or null
   bf16* out_bf16;         // [M, ld_out] or null
   int ld_out;
@@ -98,6 +99,7 @@ struct SplitKReduce {
   const float* ws; int S; long long slice_stride;  // floats between slices
   long long M; int N; int HW;                      // rows, columns, rows per sample
   const float* bias; const float* rowbias; int rowbias_ld; const float* residual;
+  const bf16* residual16;                          // 16-bit residual (operand format, same ld_out) instead of `residual`
   float* out_f32; bf16* out_bf16; int ld_out;
 };
 
@@ -145,6 +147,7 @@ struct ConvGemmDesc {
   const float* rowbias;
   int rowbias_ld;  // 0 -> Cout
   const float* residual;
+  const bf16* residual16;  // 16-bit residual in the operand format (the U-Net's 16-bit residual stream); excludes `residual` / out_f32
   float* out_f32;
   bf16* out_bf16;
   int ld_out;  // 0 -> Cout (or Cout/2 for GEGLU)
@@ -205,6 +208,7 @@ int attn_num_launches(const AttnPlan& plan);   // 2 with the exact re-run of ove
 struct GroupNormArgs {
   const float* x0; int C0;
   const float* x1; int C1;   // x1 may be null (C1 = 0)
+  int in16;                  // 1: x0 / x1 point to 16-bit data in the operand format (the U-Net's 16-bit residual stream)
   int Nb, HW;
   const float* gamma; const float* beta;
   float eps; int silu;
@@ -221,11 +225,14 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream);
 
 // LayerNorm over the last dim of fp32 [M, C] -> bf16 [M, C]
 // y (bf16) and / or y32 (fp32), row r of x at x + r * ld_x (ld_x = 0: contiguous rows of C)
+// in16: x points to 16-bit rows in the operand format
 int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16* y, int M, int C, float eps,
-                     cudaStream_t stream, float* y32 = nullptr, long long ld_x = 0);
+                     cudaStream_t stream, float* y32 = nullptr, long long ld_x = 0, int in16 = 0);
 
 // nearest 2x upsample, fp32 NHWC [Nb,H,W,C] -> bf16 NHWC [Nb,2H,2W,C]
 int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
+// the same from a 16-bit source (a pure copy: [Nb,H,W,C] 16-bit -> [Nb,2H,2W,C] 16-bit)
+int launch_upsample2x_16(const bf16* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream);
 // images fp32 NCHW in [-1, 1] -> uint8 NHWC (clamp((x+1)/2) * 255, truncated)
 int launch_postprocess_u8(const float* x, uint8_t* out, int Nb, int C, int H, int W, cudaStream_t stream);
 int launch_normalize_u8(const uint8_t* in, float* out, int Nb, int H, int W, const float* mean, const float* stdv,

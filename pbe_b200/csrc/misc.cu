@@ -33,6 +33,29 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, bf16* __restrict_
     }
 }
 
+// nearest 2x from a 16-bit source: a pure copy, one thread per 8 channels (16 bytes) of an input pixel
+__global__ void upsample2x_16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int Nb, int H, int W, int C) {
+  griddep_enter();
+  const long long total = static_cast<long long>(Nb) * H * W * (C / 8);
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % (C / 8));
+  long long pix = idx / (C / 8);
+  const int w = static_cast<int>(pix % W);
+  pix /= W;
+  const int h = static_cast<int>(pix % H);
+  const int n = static_cast<int>(pix / H);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + idx);
+  const int W2 = 2 * W, H2 = 2 * H;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const long long o = ((static_cast<long long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dx) * C + cv * 8;
+      *reinterpret_cast<uint4*>(y + o) = v;
+    }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -437,6 +460,14 @@ int launch_upsample2x_bf16(const float* x, bf16* y, int Nb, int H, int W, int C,
   PBE_REQUIRE(C % 4 == 0, "upsample channels % 4");
   const long long total = static_cast<long long>(Nb) * H * W * (C / 4);
   PBE_CHECK_CUDA(launch_k(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, y, Nb, H, W, C, operand_f16()));
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_upsample2x_16(const bf16* x, bf16* y, int Nb, int H, int W, int C, cudaStream_t stream) {
+  PBE_REQUIRE(C % 8 == 0, "upsample channels % 8");
+  const long long total = static_cast<long long>(Nb) * H * W * (C / 8);
+  PBE_CHECK_CUDA(launch_k(upsample2x_16_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, y, Nb, H, W, C));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -20,11 +20,22 @@ namespace {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_C = 2560;
 
+// four consecutive channels starting at element index `idx` of a tensor that holds fp32 (in16 = 0) or 16-bit operands
+__device__ __forceinline__ float4 ld4e(const float* __restrict__ x, long long idx, int in16, int f16) {
+  if (!in16) return __ldg(reinterpret_cast<const float4*>(x + idx));
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(x) + idx));
+  const float2 a = unpack_op2(u.x, f16), b = unpack_op2(u.y, f16);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float2 ld2e(const float* __restrict__ x, long long idx, int in16, int f16) {
+  if (!in16) return __ldg(reinterpret_cast<const float2*>(x + idx));
+  return unpack_op2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned short*>(x) + idx)), f16);
+}
 __device__ __forceinline__ float4 ld4(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-                                      long long pix, int c) {
+                                      long long pix, int c, int in16, int f16) {
   // c % 4 == 0, C0 % 4 == 0: a float4 never straddles the concat seam
-  if (c < C0) return __ldg(reinterpret_cast<const float4*>(x0 + pix * C0 + c));
-  return __ldg(reinterpret_cast<const float4*>(x1 + pix * C1 + (c - C0)));
+  if (c < C0) return ld4e(x0, pix * C0 + c, in16, f16);
+  return ld4e(x1, pix * C1 + (c - C0), in16, f16);
 }
 
 // grid (slabs, Nb). partial[b][slab][g] = (sum, sumsq) over the slab's pixels and the group's channels.
@@ -33,7 +44,7 @@ __device__ __forceinline__ float4 ld4(const float* __restrict__ x0, int C0, cons
 // rows; four pixels are in flight per thread.
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x0, int C0,
                                                               const float* __restrict__ x1, int C1, int HW, int slabs,
-                                                              float* __restrict__ partial) {
+                                                              float* __restrict__ partial, int in16, int f16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   __shared__ float s_sum[GN_MAX_C];
   __shared__ float s_sq[GN_MAX_C];
@@ -57,17 +68,17 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
       const int c = col * 4;
       int pix = p0 + prow;
       for (; pix + 3 * rows_par < p1; pix += 4 * rows_par) {
-        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c);
-        const float4 a1 = ld4(x0, C0, x1, C1, base + pix + rows_par, c);
-        const float4 a2 = ld4(x0, C0, x1, C1, base + pix + 2 * rows_par, c);
-        const float4 a3 = ld4(x0, C0, x1, C1, base + pix + 3 * rows_par, c);
+        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c, in16, f16);
+        const float4 a1 = ld4(x0, C0, x1, C1, base + pix + rows_par, c, in16, f16);
+        const float4 a2 = ld4(x0, C0, x1, C1, base + pix + 2 * rows_par, c, in16, f16);
+        const float4 a3 = ld4(x0, C0, x1, C1, base + pix + 3 * rows_par, c, in16, f16);
         sx += (a0.x + a1.x) + (a2.x + a3.x); qx += (a0.x * a0.x + a1.x * a1.x) + (a2.x * a2.x + a3.x * a3.x);
         sy += (a0.y + a1.y) + (a2.y + a3.y); qy += (a0.y * a0.y + a1.y * a1.y) + (a2.y * a2.y + a3.y * a3.y);
         sz += (a0.z + a1.z) + (a2.z + a3.z); qz += (a0.z * a0.z + a1.z * a1.z) + (a2.z * a2.z + a3.z * a3.z);
         sw += (a0.w + a1.w) + (a2.w + a3.w); qw += (a0.w * a0.w + a1.w * a1.w) + (a2.w * a2.w + a3.w * a3.w);
       }
       for (; pix < p1; pix += rows_par) {
-        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c);
+        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c, in16, f16);
         sx += a0.x; qx += a0.x * a0.x;
         sy += a0.y; qy += a0.y * a0.y;
         sz += a0.z; qz += a0.z * a0.z;
@@ -217,7 +228,7 @@ __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f 
 
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
                                                         int C1, int HW, int rows_par, const float2* __restrict__ ab,
-                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw, int f16) {
+                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw, int f16, int in16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int C = C0 + C1;
   const int vpp = C / 4;
@@ -226,10 +237,11 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
   const int c = (t - prow * vpp) * 4;
   const int b = blockIdx.y;
   const int p_begin = blockIdx.x * (rows_par * GN_UNROLL) + prow;
-  const float* __restrict__ src;
+  const float* __restrict__ src;     // element-indexed through ld4e (fp32 or 16-bit source)
+  long long sbase;
   int ld;
-  if (c < C0) { src = x0 + static_cast<long long>(b) * HW * C0 + c; ld = C0; }
-  else { src = x1 + static_cast<long long>(b) * HW * C1 + (c - C0); ld = C1; }
+  if (c < C0) { src = x0; sbase = static_cast<long long>(b) * HW * C0 + c; ld = C0; }
+  else { src = x1; sbase = static_cast<long long>(b) * HW * C1 + (c - C0); ld = C1; }
   const float4 s01 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c));
   const float4 s23 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
   const long long obase = static_cast<long long>(b) * HW * C + c;
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
 #pragma unroll
   for (int u = 0; u < GN_UNROLL; ++u) {
     const int pix = p_begin + u * rows_par;
-    if (pix < HW) v[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(pix) * ld));
+    if (pix < HW) v[u] = ld4e(src, sbase + static_cast<long long>(pix) * ld, in16, f16);
   }
 #pragma unroll
   for (int u = 0; u < GN_UNROLL; ++u) {
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
                                                                const float* __restrict__ x1, int C1, int HW, int rows_par,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, int silu,
-                                                               bf16* __restrict__ y, bf16* __restrict__ raw, int f16) {
+                                                               bf16* __restrict__ y, bf16* __restrict__ raw, int f16, int in16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   extern __shared__ float2 s_x[];  // [HW][cpg / 2]
   __shared__ double s_red[GNS_THREADS / 32];
@@ -289,18 +301,19 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
   const int cv = threadIdx.x - prow * hv;
   const bool active = prow < rows_par;
   const int c = g * cpg + cv * 2;
-  const float* __restrict__ src;
+  const float* __restrict__ src;     // element-indexed through ld2e (fp32 or 16-bit source)
+  long long sbase;
   int ld;
-  if (c < C0) { src = x0 + static_cast<long long>(b) * HW * C0 + c; ld = C0; }
-  else { src = x1 + static_cast<long long>(b) * HW * C1 + (c - C0); ld = C1; }
+  if (c < C0) { src = x0; sbase = static_cast<long long>(b) * HW * C0 + c; ld = C0; }
+  else { src = x1; sbase = static_cast<long long>(b) * HW * C1 + (c - C0); ld = C1; }
   float ps = 0.0f;
   if (active) {
     int pix = prow;
     for (; pix + 3 * rows_par < HW; pix += 4 * rows_par) {
-      const float2 v0 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix) * ld));
-      const float2 v1 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix + rows_par) * ld));
-      const float2 v2 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix + 2 * rows_par) * ld));
-      const float2 v3 = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix + 3 * rows_par) * ld));
+      const float2 v0 = ld2e(src, sbase + static_cast<long long>(pix) * ld, in16, f16);
+      const float2 v1 = ld2e(src, sbase + static_cast<long long>(pix + rows_par) * ld, in16, f16);
+      const float2 v2 = ld2e(src, sbase + static_cast<long long>(pix + 2 * rows_par) * ld, in16, f16);
+      const float2 v3 = ld2e(src, sbase + static_cast<long long>(pix + 3 * rows_par) * ld, in16, f16);
       s_x[pix * hv + cv] = v0;
       s_x[(pix + rows_par) * hv + cv] = v1;
       s_x[(pix + 2 * rows_par) * hv + cv] = v2;
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
       ps += ((v0.x + v0.y) + (v1.x + v1.y)) + ((v2.x + v2.y) + (v3.x + v3.y));
     }
     for (; pix < HW; pix += rows_par) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(src + static_cast<long long>(pix) * ld));
+      const float2 v = ld2e(src, sbase + static_cast<long long>(pix) * ld, in16, f16);
       s_x[pix * hv + cv] = v;
       ps += v.x + v.y;
     }
@@ -350,19 +363,20 @@ constexpr int LN_MAX_VEC = 10;
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, int M,
-                                                        int C, float eps, float* __restrict__ y32, long long ld_x, int f16) {
+                                                        int C, float eps, float* __restrict__ y32, long long ld_x, int f16,
+                                                        int in16) {
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int nvec = C / 4;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ld_x);
+  const long long xbase = static_cast<long long>(row) * ld_x;
   float4 v[NV];
   float sum = 0.0f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int k = lane + i * 32;
-    if (k < nvec) v[i] = __ldg(xr + k);
+    if (k < nvec) v[i] = ld4e(x, xbase + 4 * k, in16, f16);
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -436,7 +450,7 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
     const int hv = C / 64;
     const int rows_par = std::min(GNS_THREADS / hv, a.HW);
     PBE_CHECK_CUDA(launch_k(gn_small_kernel, dim3(dim3(32, a.Nb)), dim3(GNS_THREADS), small_smem, stream, a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, a.gamma,
-                                                                        a.beta, a.eps, a.silu, a.y, a.raw, operand_f16()));
+                                                                        a.beta, a.eps, a.silu, a.y, a.raw, operand_f16(), a.in16));
     PBE_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -448,7 +462,7 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
                                                                         a.beta, a.eps, ab));
     PBE_CHECK_CUDA(cudaGetLastError());
   } else {
-    PBE_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(dim3(slabs, a.Nb)), dim3(GN_THREADS), 0, stream, a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial));
+    PBE_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(dim3(slabs, a.Nb)), dim3(GN_THREADS), 0, stream, a.x0, a.C0, a.x1, a.C1, a.HW, slabs, partial, a.in16, operand_f16()));
     PBE_CHECK_CUDA(cudaGetLastError());
     PBE_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(a.Nb), dim3(GN_THREADS), 0, stream, partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab));
     PBE_CHECK_CUDA(cudaGetLastError());
@@ -457,20 +471,20 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   const int rows_par = vpp >= 256 ? 1 : 256 / vpp;
   const int pix_per_block = rows_par * GN_UNROLL;
   PBE_CHECK_CUDA(launch_k(gn_apply_kernel, dim3(dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb)), dim3(vpp * rows_par), 0, stream, 
-      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw, operand_f16()));
+      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw, operand_f16(), a.in16));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16* y, int M, int C, float eps,
-                     cudaStream_t stream, float* y32, long long ld_x) {
+                     cudaStream_t stream, float* y32, long long ld_x, int in16) {
   if (ld_x == 0) ld_x = C;
   PBE_REQUIRE(ld_x % 4 == 0 && (y != nullptr || y32 != nullptr), "LayerNorm: row stride % 4, at least one output");
   PBE_REQUIRE(C % 4 == 0 && C / 4 <= 32 * LN_MAX_VEC, "LayerNorm width must be a multiple of 4, <= 1280");
   const int nv = (C / 4 + 31) / 32;
-  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16()));
-  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16()));
-  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16()));
+  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16(), in16));
+  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16(), in16));
+  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16(), in16));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

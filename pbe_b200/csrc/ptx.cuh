@@ -416,6 +416,16 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack_op2(float lo, float hi, int f16) {
   return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
+// two 16-bit operands (fp16 if f16 else bf16) -> fp32
+__device__ __forceinline__ float2 unpack_op2(uint32_t bits, int f16) {
+  if (f16) {
+    float2 r;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(bits));
+    return r;
+  }
+  return make_float2(__uint_as_float(bits << 16), __uint_as_float(bits & 0xffff0000u));
+}
+__device__ __forceinline__ float op16_to_float(unsigned short h, int f16) { return unpack_op2(h, f16).x; }
 __device__ __forceinline__ unsigned short to_op16(float v, int f16) {
   return static_cast<unsigned short>(pack_op2(v, 0.0f, f16) & 0xffffu);
 }
