@@ -148,6 +148,39 @@ int WeightLoader::make_conv(const std::string& prefix, int k, int cin, int cout,
   return 0;
 }
 
+// "nearest-2x upsample, then 3x3 conv with padding 1" (Upsample.forward, openaimodel.py:109-119) == four 2x2 convs on the
+// LOW-resolution tensor, one per output-pixel parity (a, b): output row 2i+a sees upsampled rows 2i+a-1 .. 2i+a+1, which are
+// the low-resolution rows {i-1, i, i} (a = 0) or {i, i, i+1} (a = 1) -- taps that read the same source row are summed
+// (in fp32, before the one rounding to the operand format).  Same for columns.  [phase = 2a+b][tap = 2*th+tw][cout][cin].
+int WeightLoader::make_upconv_phases(const std::string& prefix, int cin, int cout, ConvW* w) {
+  const HostTensor* W;
+  int rc = get(prefix + ".weight", &W);
+  if (rc) return rc;
+  if (W->data.size() != static_cast<size_t>(cout) * cin * 9) { set_error("weight " + prefix + ".weight has the wrong size"); return -4; }
+  std::vector<float> packed(static_cast<size_t>(16) * cout * cin, 0.0f);
+  auto src_taps = [](int parity, int t, int* lo, int* hi) {   // which of the 3 original taps fold into effective tap t
+    if (parity == 0) { if (t == 0) { *lo = 0; *hi = 0; } else { *lo = 1; *hi = 2; } }
+    else             { if (t == 0) { *lo = 0; *hi = 1; } else { *lo = 2; *hi = 2; } }
+  };
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      for (int th = 0; th < 2; ++th)
+        for (int tw = 0; tw < 2; ++tw) {
+          int h0, h1, w0, w1;
+          src_taps(a, th, &h0, &h1);
+          src_taps(b, tw, &w0, &w1);
+          float* dst = packed.data() + (static_cast<size_t>((a * 2 + b) * 4 + th * 2 + tw) * cout) * cin;
+          for (int o = 0; o < cout; ++o)
+            for (int i = 0; i < cin; ++i) {
+              float acc = 0.0f;
+              for (int kh = h0; kh <= h1; ++kh)
+                for (int kw = w0; kw <= w1; ++kw) acc += W->data[(static_cast<size_t>(o) * cin + i) * 9 + kh * 3 + kw];
+              dst[static_cast<size_t>(o) * cin + i] = acc;
+            }
+        }
+  return upload_bf16(packed, &w->wup);
+}
+
 int WeightLoader::make_norm(const std::string& prefix, int c, NormW* n) {
   const HostTensor *G, *B;
   int rc = get(prefix + ".weight", &G);
@@ -356,6 +389,7 @@ int Engine::finalize() {
       if (level && i == cfg_.num_res_blocks) {
         ConvW c;
         if ((rc = make_conv(pfx + "." + std::to_string(sub) + ".conv", 3, ch, ch, &c))) return rc;
+        if ((rc = make_upconv_phases(pfx + "." + std::to_string(sub) + ".conv", ch, ch, &c))) return rc;
         convs_.push_back(c);
         modules_.push_back({Module::UP, static_cast<int>(convs_.size()) - 1, false, false});
         ds /= 2;
@@ -445,7 +479,7 @@ int Engine::build(Prepared& P, bool dry) {
   int err = 0;
   auto add_gemm = [&](const std::string& name, ConvGemmDesc d) {
     if (!diverged) d.split_batch = 2 * d.Nb;   // CFG-pair prefix: same split-K decision (summation order) as the full batch
-    const size_t ws_bytes = d.stats_out ? 0 : gemm_splitk_ws_bytes(d);
+    const size_t ws_bytes = (d.stats_out || d.up_phase) ? 0 : gemm_splitk_ws_bytes(d);
     d.splitk_ws = ws_bytes ? static_cast<float*>(SA(ws_bytes)) : nullptr;
     if (dry) { launches += ws_bytes ? 2 : 1; return; }
     auto plan = std::make_shared<GemmPlan>();
@@ -801,6 +835,30 @@ int Engine::build(Prepared& P, bool dry) {
       case Module::UP: {
         const ConvW& c = convs_[m.idx];
         const size_t M = static_cast<size_t>(Bc) * (2 * h.H) * (2 * h.W);
+        Act o = new_act(true, M * c.cout, c.cout, 2 * h.H, 2 * h.W);
+        // Each phase is its own launch over the low-resolution pixel grid: worth it when one such launch still fills the GPU
+        // (CFG batch 16: the 16->32 and 32->64 levels); small batches keep the literal form, whose single launch has 4x the tiles.
+        const long up_tiles = ((static_cast<long>(Bc) * h.H * h.W + 127) / 128) * ((c.cout + 159) / 160);
+        if (s16 && subpixel_up_ && (up_tiles >= 100 || subpixel_up_ >= 2)) {
+          // four sub-pixel phase GEMMs on the low-resolution stream tensor itself (no upsampled copy, 4/9 of the FLOPs)
+          ConvGemmDesc d{};
+          d.act = h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = h.C; d.ksize = 2; d.stride = 1;
+          d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b;
+          set_out(d, o);
+          d.up_phase = 1;
+          if (gemm_can_fuse_stats(d)) {
+            o.stats = static_cast<float*>(PA(M / 32 * c.cout * 2 * sizeof(float)));
+            o.has_stats = true;
+          }
+          for (int ph = 0; ph < 4; ++ph) {
+            d.up_phase = ph + 1;
+            d.wt = c.wup + static_cast<size_t>(ph) * 4 * c.cout * h.C;
+            d.stats_out = o.has_stats ? o.stats : nullptr;
+            add_gemm(tag + ".upsample.conv[phase " + std::to_string(ph) + "]", d);
+          }
+          h = o;
+          break;
+        }
         bf16* up = static_cast<bf16*>(SA(M * h.C * sizeof(bf16)));
         {
           const float* src = h.f32;
@@ -812,7 +870,6 @@ int Engine::build(Prepared& P, bool dry) {
                       },
                       "upsample", 0.0, static_cast<double>(Bc) * hh * ww * cc * (esz + 8.0));
         }
-        Act o = new_act(true, M * c.cout, c.cout, 2 * h.H, 2 * h.W);
         ConvGemmDesc d{};
         d.act = up; d.Nb = Bc; d.H = 2 * h.H; d.W = 2 * h.W; d.C = h.C; d.ksize = 3; d.stride = 1;
         d.wt = c.w; d.Cout = c.cout; d.mode = EPI_STD; d.bias = c.b;

@@ -21,6 +21,7 @@ struct HostTensor {
 };
 
 struct ConvW {
+  bf16* wup = nullptr; // Upsample convs: the four sub-pixel phases' combined 2x2 taps [phase][4][cout][cin] (ConvGemmDesc::up_phase)
   bf16* w = nullptr;   // [k*k][cout][cin_pad]
   float* b = nullptr;  // [cout]
   int cin = 0, cin_pad = 0, cout = 0, k = 1;
@@ -108,6 +109,7 @@ class WeightLoader {
   const HostTensor* find(const std::string& name);
   int get(const std::string& name, const HostTensor** out);
   int make_conv(const std::string& prefix, int k, int cin, int cout, ConvW* w, int cin_pad = 0, int cout_pad = 0);
+  int make_upconv_phases(const std::string& prefix, int cin, int cout, ConvW* w);   // fills w->wup
   int make_norm(const std::string& prefix, int c, NormW* n);
   int upload_f32(const std::vector<float>& v, float** dst);
   int upload_bf16(const std::vector<float>& v, bf16** dst);
@@ -139,6 +141,8 @@ class Engine : public WeightLoader {
   bool use_graph = true;
   // 16-bit residual stream (operand format) between ops; PBE_STREAM=fp32 keeps the round-1 fp32 stream (A/B, debugging)
   bool stream16_ = [] { const char* e = getenv("PBE_STREAM"); return !(e != nullptr && (e[0] == 'f' || e[0] == 'F')); }();
+  // nearest-2x upsample + 3x3 conv as four sub-pixel phase convs (16-bit stream only); PBE_SUBPIXEL_UP=0: the literal form
+  int subpixel_up_ = [] { const char* e = getenv("PBE_SUBPIXEL_UP"); return e == nullptr ? 1 : atoi(e); }();   // 2: at every size (tests)
   std::string last_error;
 
  private:

@@ -558,6 +558,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
             const long long m_first = __shfl_sync(0xffffffffu, my_m, 0);
+            const long long on_first = __shfl_sync(0xffffffffu, on, 0);
             const int col = n_base + c * 32 + lane;
             if (vmask != 0u && col < p.n_total) {
               // shared-space loads and branch-free accumulation into four independent chains (the first version --
@@ -579,7 +580,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s0 += x0; q0 = fmaf(x0, x0, q0); s1 += x1; q1 = fmaf(x1, x1, q1);
                 s2 += x2; q2 = fmaf(x2, x2, q2); s3 += x3; q3 = fmaf(x3, x3, q3);
               }
-              *reinterpret_cast<float2*>(p.stats_out + ((m_first >> 5) * p.n_total + col) * 2) =
+              *reinterpret_cast<float2*>(p.stats_out + (((m_first >> 5) + on_first * p.stats_sample_extra + p.stats_block_off) * p.n_total + col) * 2) =
                   make_float2((s0 + s1) + (s2 + s3), (q0 + q1) + (q2 + q3));
             }
           }
@@ -634,6 +635,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
             const long long m_first = __shfl_sync(0xffffffffu, my_m, 0);
+            const long long on_first = __shfl_sync(0xffffffffu, on, 0);
             const int col = n_base + c * 32 + lane;
             if (vmask != 0u && col < p.n_total) {
               float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
@@ -653,7 +655,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s0 += xa; q0 = fmaf(xa, xa, q0);
                 s1 += xb; q1 = fmaf(xb, xb, q1);
               }
-              *reinterpret_cast<float2*>(p.stats_out + ((m_first >> 5) * p.n_total + col) * 2) = make_float2(s0 + s1, q0 + q1);
+              *reinterpret_cast<float2*>(p.stats_out + (((m_first >> 5) + on_first * p.stats_sample_extra + p.stats_block_off) * p.n_total + col) * 2) = make_float2(s0 + s1, q0 + q1);
             }
           }
         }
@@ -875,7 +877,10 @@ size_t gemm_splitk_ws_bytes(const ConvGemmDesc& d) {
 
 int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   PBE_REQUIRE(d.C % 64 == 0, "activation channels must be a multiple of 64");
-  PBE_REQUIRE(d.ksize == 1 || d.ksize == 3, "kernel size 1 or 3");
+  PBE_REQUIRE(d.ksize == 1 || d.ksize == 3 || (d.ksize == 2 && d.up_phase >= 1 && d.up_phase <= 4), "kernel size 1 or 3 (2: sub-pixel phase)");
+  PBE_REQUIRE(d.up_phase == 0 || (d.ksize == 2 && d.stride == 1 && d.mode == EPI_STD && d.residual == nullptr && d.residual16 == nullptr &&
+                                  d.splitk_ws == nullptr && d.act_ld == 0),
+              "sub-pixel phase conv: ksize 2, stride 1, plain epilogue, no residual, no split-K");
   PBE_REQUIRE(d.Cout % 4 == 0 && d.ld_out % 4 == 0 && d.rowbias_ld % 4 == 0, "output columns / leading dims % 4");
   PBE_REQUIRE(d.stride == 1 || d.stride == 2, "stride 1 or 2");
   PBE_REQUIRE(d.stride == 1 || (d.H % 2 == 0 && d.W % 2 == 0 && d.ksize == 3), "stride-2 conv needs even H, W, k=3");
@@ -896,6 +901,13 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
       const int t = kh * d.ksize + kw;
       if (d.ksize == 1) {
         p.tap_dw[t] = p.tap_dh[t] = p.tap_ph[t] = 0;
+        p.tap_coff[t] = 0;
+      } else if (d.ksize == 2) {
+        // phase (a, b) of upsample + 3x3: output row 2i+a reads low-resolution rows {i-1, i} (a = 0) or {i, i+1} (a = 1)
+        const int a = (d.up_phase - 1) >> 1, b = (d.up_phase - 1) & 1;
+        p.tap_dh[t] = static_cast<int8_t>(a == 0 ? kh - 1 : kh);
+        p.tap_dw[t] = static_cast<int8_t>(b == 0 ? kw - 1 : kw);
+        p.tap_ph[t] = 0;
         p.tap_coff[t] = 0;
       } else if (d.stride == 1) {
         p.tap_dw[t] = static_cast<int8_t>(kw - 1);
@@ -941,6 +953,12 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.split_k = (d.splitk_ws != nullptr) ? gemm_split_k(d) : 1;
   p.debug = getenv("PBE_GEMM_DEBUG") ? 1 : 0;
   p.stats_out = nullptr;
+  p.stats_sample_extra = 0; p.stats_block_off = 0;
+  if (d.stats_out != nullptr && d.up_phase) {
+    const int blocks_low = p.Ho * p.Wo / 32;
+    p.stats_sample_extra = 3 * blocks_low;                       // a sample owns 4 * blocks_low row blocks of the full-res tensor
+    p.stats_block_off = (d.up_phase - 1) * blocks_low;
+  }
   if (d.stats_out != nullptr) {
     PBE_REQUIRE(gemm_can_fuse_stats(d) && p.split_k == 1 && (d.out_f32 != nullptr || d.out_bf16 != nullptr),
                 "fused GroupNorm statistics not available for this GEMM");
@@ -1026,16 +1044,20 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
       plan->tmO16 = plan->tmO32;
     } else {
     PBE_REQUIRE(!(d.mode != EPI_STD && (p.has_res || p.has_o32)), "GEGLU / QKV epilogues write bf16 only");
-    const uint64_t s32[3] = {ld * 4, Wo * ld * 4, Ho * Wo * ld * 4};
-    const uint64_t s16[3] = {ld * 2, Wo * ld * 2, Ho * Wo * ld * 2};
+    // sub-pixel phase (a, b): the same pixel grid, written to every second pixel / row of the full-resolution tensor
+    const uint64_t us = d.up_phase ? 2 : 1;
+    const uint64_t s32[3] = {us * ld * 4, us * (us * Wo) * ld * 4, (us * Ho) * (us * Wo) * ld * 4};
+    const uint64_t s16[3] = {us * ld * 2, us * (us * Wo) * ld * 2, (us * Ho) * (us * Wo) * ld * 2};
+    const size_t ph_off = d.up_phase ? (static_cast<size_t>((d.up_phase - 1) >> 1) * 2 * Wo + ((d.up_phase - 1) & 1)) * ld : 0;
+    PBE_REQUIRE(!(d.up_phase && p.has_o16 && p.has_o32), "sub-pixel phase conv writes one output tensor");
     int rc = 0;
     if (p.has_res && p.res16) rc = make_tmap(&plan->tmR, d.residual16, false, 4, dims, s16, box, 64);
     else if (p.has_res) rc = make_tmap(&plan->tmR, d.residual, true, 4, dims, s32, box, 128);
     if (rc) return rc;
-    if (p.has_o32) rc = make_tmap(&plan->tmO32, d.out_f32, true, 4, dims, s32, box, 128);
+    if (p.has_o32) rc = make_tmap(&plan->tmO32, d.out_f32 + ph_off, true, 4, dims, s32, box, 128);
     if (rc) return rc;
     const bool o16_tma = p.has_o16 && !p.has_o32;  // with both outputs the bf16 copy is a direct row store
-    if (o16_tma) rc = make_tmap(&plan->tmO16, d.out_bf16, false, 4, dims, s16, box, 64);
+    if (o16_tma) rc = make_tmap(&plan->tmO16, d.out_bf16 + ph_off, false, 4, dims, s16, box, 64);
     if (rc) return rc;
     if (!p.has_res) plan->tmR = p.has_o32 ? plan->tmO32 : plan->tmO16;
     if (!p.has_o32) plan->tmO32 = plan->tmO16;

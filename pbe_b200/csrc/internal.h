@@ -71,6 +71,7 @@ struct ConvGemmParams {
   int pair_dim;                   // 2-CTA clusters: tile dimension (0 w, 1 h, 2 n) whose neighbours form a cluster; -1 none
   int split_k;                    // >1: K range split over work units, partial sums to a workspace
   float* stats_out;               // optional [M/32][n_total][2] per-32-row (sum, sumsq) of the fp32 output (GroupNorm)
+  int stats_sample_extra, stats_block_off;   // sub-pixel phases: row-block index += sample * extra + off (full-resolution layout)
   int8_t tap_dw[9], tap_dh[9], tap_ph[9];
   int tap_coff[9];
   // epilogue
@@ -164,6 +165,11 @@ struct ConvGemmDesc {
                            // must accumulate in the same order as the same layer over the full 2B batch
   int pad_end;             // stride-2 3x3 only: 1 = zero padding (0,1,0,1) as the VAE Downsample (model.py:74-76)
                            // instead of the symmetric padding 1 of the U-Net Downsample
+  int up_phase;            // 0: ordinary conv.  1..4: sub-pixel phase (a, b) = ((up_phase-1) >> 1, (up_phase-1) & 1) of
+                           // "nearest-2x upsample, then 3x3 conv" (openaimodel.py:109-119): ksize = 2, `act` is the LOW-resolution
+                           // tensor [Nb,H,W,C], `wt` the phase's four combined taps [4][Cout][C], and the outputs / statistics
+                           // address the FULL-resolution tensor [Nb,2H,2W,Cout] at pixels (2i+a, 2j+b).  4/9 of the FLOPs of
+                           // the literal form, no upsampled copy of the input.
   int out16_bf16;          // 1: the 16-bit outputs are bf16 whatever the operand format (Q | K | V^T read by the flash kernels)
   int operands_bf16;       // 1: act / wt are bf16 whatever the operand format
 };

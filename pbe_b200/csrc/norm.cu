@@ -27,6 +27,13 @@ __device__ __forceinline__ float4 ld4e(const float* __restrict__ x, long long id
   const float2 a = unpack_op2(u.x, f16), b = unpack_op2(u.y, f16);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+__device__ __forceinline__ float4 cvt4(uint2 u, int f16) {
+  const float2 a = unpack_op2(u.x, f16), b = unpack_op2(u.y, f16);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 ldraw4(const float* __restrict__ x, long long idx) {   // four 16-bit operands, unconverted
+  return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(x) + idx));
+}
 __device__ __forceinline__ float2 ld2e(const float* __restrict__ x, long long idx, int in16, int f16) {
   if (!in16) return __ldg(reinterpret_cast<const float2*>(x + idx));
   return unpack_op2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned short*>(x) + idx)), f16);
@@ -226,9 +233,11 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const fl
 constexpr int GN_UNROLL = 8;
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
+template <int IN16>
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
                                                         int C1, int HW, int rows_par, const float2* __restrict__ ab,
-                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw, int f16, int in16) {
+                                                        int silu, bf16* __restrict__ y, bf16* __restrict__ raw, int f16) {
+  constexpr int in16 = IN16;
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int C = C0 + C1;
   const int vpp = C / 4;
@@ -246,10 +255,23 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
   const float4 s23 = __ldg(reinterpret_cast<const float4*>(ab + static_cast<long long>(b) * C + c + 2));
   const long long obase = static_cast<long long>(b) * HW * C + c;
   float4 v[GN_UNROLL];
+  if (in16) {
+    // every load is issued before the first conversion (a load whose result is converted on the spot reuses its
+    // destination registers and serialises on the previous one: 2 TB/s instead of 4)
+    uint2 r16[GN_UNROLL];
 #pragma unroll
-  for (int u = 0; u < GN_UNROLL; ++u) {
-    const int pix = p_begin + u * rows_par;
-    if (pix < HW) v[u] = ld4e(src, sbase + static_cast<long long>(pix) * ld, in16, f16);
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pix = p_begin + u * rows_par;
+      r16[u] = (pix < HW) ? ldraw4(src, sbase + static_cast<long long>(pix) * ld) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) v[u] = cvt4(r16[u], f16);
+  } else {
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const int pix = p_begin + u * rows_par;
+      if (pix < HW) v[u] = __ldg(reinterpret_cast<const float4*>(src + sbase + static_cast<long long>(pix) * ld));
+    }
   }
 #pragma unroll
   for (int u = 0; u < GN_UNROLL; ++u) {
@@ -360,11 +382,11 @@ constexpr int LN_MAX_VEC = 10;
 // One warp per row; row held in registers (C <= 1280).  NV = float4 per lane: instantiated for the widths the U-Net
 // uses so the 320-wide rows of the 64x64 level do not carry the 1280-wide register footprint (occupancy = bytes in
 // flight for this pure streaming pass).
-template <int NV>
+template <int NV, int IN16>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, int M,
-                                                        int C, float eps, float* __restrict__ y32, long long ld_x, int f16,
-                                                        int in16) {
+                                                        int C, float eps, float* __restrict__ y32, long long ld_x, int f16) {
+  constexpr int in16 = IN16;
   griddep_enter();   // PDL: let the successor start, wait for the predecessor (ptx.cuh)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -373,10 +395,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const long long xbase = static_cast<long long>(row) * ld_x;
   float4 v[NV];
   float sum = 0.0f;
+  if (in16) {
+    uint2 r16[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int k = lane + i * 32;
-    if (k < nvec) v[i] = ld4e(x, xbase + 4 * k, in16, f16);
+    for (int i = 0; i < NV; ++i) {
+      const int k = lane + i * 32;
+      r16[i] = (k < nvec) ? ldraw4(x, xbase + 4 * k) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = cvt4(r16[i], f16);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int k = lane + i * 32;
+      if (k < nvec) v[i] = __ldg(reinterpret_cast<const float4*>(x + xbase) + k);
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -470,8 +503,12 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
   const int vpp = C / 4;
   const int rows_par = vpp >= 256 ? 1 : 256 / vpp;
   const int pix_per_block = rows_par * GN_UNROLL;
-  PBE_CHECK_CUDA(launch_k(gn_apply_kernel, dim3(dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb)), dim3(vpp * rows_par), 0, stream, 
-      a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw, operand_f16(), a.in16));
+  if (a.in16)
+    PBE_CHECK_CUDA(launch_k(gn_apply_kernel<1>, dim3(dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb)), dim3(vpp * rows_par), 0, stream,
+        a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw, operand_f16()));
+  else
+    PBE_CHECK_CUDA(launch_k(gn_apply_kernel<0>, dim3(dim3((a.HW + pix_per_block - 1) / pix_per_block, a.Nb)), dim3(vpp * rows_par), 0, stream,
+        a.x0, a.C0, a.x1, a.C1, a.HW, rows_par, ab, a.silu, a.y, a.raw, operand_f16()));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -482,9 +519,15 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, bf16
   PBE_REQUIRE(ld_x % 4 == 0 && (y != nullptr || y32 != nullptr), "LayerNorm: row stride % 4, at least one output");
   PBE_REQUIRE(C % 4 == 0 && C / 4 <= 32 * LN_MAX_VEC, "LayerNorm width must be a multiple of 4, <= 1280");
   const int nv = (C / 4 + 31) / 32;
-  if (nv <= 3) PBE_CHECK_CUDA(launch_k(layernorm_kernel<3>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16(), in16));
-  else if (nv <= 5) PBE_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16(), in16));
-  else PBE_CHECK_CUDA(launch_k(layernorm_kernel<LN_MAX_VEC>, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, operand_f16(), in16));
+  const int f16 = operand_f16();
+  const dim3 grid((M + 7) / 8), block(256);
+#define PBE_LN_LAUNCH(NVV, I16) PBE_CHECK_CUDA(launch_k(layernorm_kernel<NVV, I16>, grid, block, 0, stream, x, gamma, beta, y, M, C, eps, y32, ld_x, f16))
+  if (in16) {
+    if (nv <= 3) PBE_LN_LAUNCH(3, 1); else if (nv <= 5) PBE_LN_LAUNCH(5, 1); else PBE_LN_LAUNCH(LN_MAX_VEC, 1);
+  } else {
+    if (nv <= 3) PBE_LN_LAUNCH(3, 0); else if (nv <= 5) PBE_LN_LAUNCH(5, 0); else PBE_LN_LAUNCH(LN_MAX_VEC, 0);
+  }
+#undef PBE_LN_LAUNCH
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

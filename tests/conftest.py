@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a); run with -m gpu on the GPU box")
+    # numpy 2 / swig deprecation chatter from third-party code buries the failure output of `pytest | tail`
+    config.addinivalue_line("filterwarnings", "ignore::DeprecationWarning")
 
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -322,6 +322,48 @@ torch.save(e2.cpu(), {str(out)!r})
     assert torch.equal(torch.load(out), eps.cpu())
 
 
+@pytest.mark.parametrize("env", [dict(PBE_SUBPIXEL_UP="2"), dict(PBE_SUBPIXEL_UP="0"), dict(PBE_STREAM="fp32"),
+                                 dict(PBE_OPERANDS="bf16"), dict(PBE_OPERANDS="bf16", PBE_STREAM="fp32")])
+def test_engine_variants_vs_oracle(small, dev, tmp_path, env):
+    """The engine's build-time switches, each in its own process (they are read once): the sub-pixel form of upsample + conv
+    forced at every level (PBE_SUBPIXEL_UP=2; by default only launches that fill the GPU use it) or off, the round-1 fp32
+    residual stream, bf16 operands.  Every variant is held to the parity bar against the fp32 oracle (odd batch, distinct
+    timesteps), and the fp16 variants to a much tighter one."""
+    import subprocess
+    import sys
+    from oracle import unet_ref as U
+    cfg, sd, req, model = small
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 9, 32, 32, generator=g)
+    t = torch.tensor([999, 500, 0], dtype=torch.int64)
+    c = torch.randn(3, 1, 768, generator=g)
+    ref = U.unet_forward(sd, cfg, x, t, c)
+    torch.save(dict(x=x, t=t, c=c), tmp_path / "in.pt")
+    out = tmp_path / "eps.pt"
+    code = f"""
+import sys, torch
+sys.path.insert(0, {str(ROOT)!r})
+from oracle import unet_ref as U
+from pbe_b200.diffusion import LatentDiffusion
+cfg = U.SMALL_CFG
+sd = U.make_state_dict(cfg, 321)
+m = LatentDiffusion(unet_config=dict(params=dict(cfg)))
+m.load_state_dict({{"model.diffusion_model." + k: v for k, v in sd.items()}}, strict=False)
+m = m.to("cuda:0").eval()
+i = torch.load({str(tmp_path / "in.pt")!r})
+e1 = m.apply_model(i["x"].cuda(), i["t"].cuda(), i["c"].cuda()); e2 = m.apply_model(i["x"].cuda(), i["t"].cuda(), i["c"].cuda())
+assert torch.equal(e1, e2)
+torch.save(e2.cpu(), {str(out)!r})
+"""
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    eps = torch.load(out)
+    rel = _rel(eps, ref)
+    print(f"variant {env}: rel-L2 vs fp32 oracle {rel:.3e}")
+    assert torch.isfinite(eps).all()
+    assert rel <= (SMALL_EPS_REL_L2 if env.get("PBE_OPERANDS") == "bf16" else 4e-3), (env, rel)
+
+
 @pytest.mark.parametrize("Bc,h,w", [(6, 64, 48), (10, 32, 32), (2, 40, 72)])
 def test_v1_ragged_batches_and_non_square_latents_vs_oracle_on_gpu(v1, dev, Bc, h, w):
     """Geometries off the benchmark grid: odd CFG batches (no even tile count for CTA pairs at some levels), non-square

@@ -1,6 +1,7 @@
 """Summarise an .ncu-rep (first kernel): key raw metrics + stall samples by opcode + hottest instructions."""
 import csv, subprocess, sys, collections, io
 rep = sys.argv[1]
+traffic_out = sys.argv[2] if len(sys.argv) > 2 else None     # optional: write {"dram_bytes": read + write, ...} (bench.py reads profiles/ncu_traffic.json)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[2]
@@ -14,6 +15,20 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.su
 for i, h in enumerate(hdr):
     if h in want or "issue_stalled" in h and "per_issue" not in h and False:
         print(f"{h:80s} {vals[i]} {rows[1][i]}")
+if traffic_out:
+    import json
+    col = {h: i for i, h in enumerate(hdr)}
+    def val(name):
+        v, u = float(vals[col[name]]), rows[1][col[name]]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    name_col = col.get("Kernel Name")
+    json.dump({"dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+               "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+               "kernel": vals[name_col] if name_col is not None else None,
+               "duration_us_under_ncu": float(vals[col["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(rows[1][col["gpu__time_duration.sum"]], 1),
+               "note": "DRAM read + write bytes of ONE launch of the dominant kernel (the longest conv_gemm launch of a U-Net call at "
+                       "CFG batch 16, 64x64: a 3x3 conv of the first level) from `ncu --set full` of the current build; "
+                       "source: " + rep.split("/")[-1]}, open(traffic_out, "w"), indent=1)
 for i, h in enumerate(hdr):
     if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and float(vals[i] or 0) > 0.15:
         print(f"{h:80s} {vals[i]}")

@@ -25,4 +25,19 @@ net.run(x, t, out=out)      # first call: eager warm pass + graph capture + repl
 torch.cuda.synchronize()
 net.run(x, t, out=out)      # steady state: one graph replay
 torch.cuda.synchronize()
+# the sampler's fused update (K11) and input builder at the same batch: the HBM-bound elementwise kernels of the path
+from pbe_b200 import _lib
+import ctypes
+lib = _lib.load()
+st = torch.cuda.current_stream().cuda_stream
+lat = [torch.randn(B, 4, hw, hw, device=dev) for _ in range(9)]
+x9 = torch.empty(Bc, 9, hw, hw, device=dev)
+f = ctypes.c_float
+for _ in range(3):
+    assert lib.pbe_build_unet_input(lat[0].data_ptr(), lat[1].data_ptr(), lat[2][:, :1].contiguous().data_ptr(), x9.data_ptr(), B, 4, 4, 1,
+                                    hw * hw, 2, st) == 0
+    assert lib.pbe_sampler_step(out[:B].data_ptr(), out[B:].data_ptr(), f(5.0), 1, 3, lat[3].data_ptr(), lat[4].data_ptr(),
+                                lat[5].data_ptr(), lat[0].data_ptr(), f(0.5), f(0.6), f(0.0), f(0.7), None, f(1.0), lat[6].data_ptr(),
+                                lat[7].data_ptr(), lat[8].data_ptr(), lat[0].numel(), st) == 0
+torch.cuda.synchronize()
 print("ok", float(out.abs().mean()))
