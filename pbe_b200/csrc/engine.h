@@ -140,7 +140,12 @@ class Engine : public WeightLoader {
   const Prepared* current() const { return cur_; }
   bool use_graph = true;
   // 16-bit residual stream (operand format) between ops; PBE_STREAM=fp32 keeps the round-1 fp32 stream (A/B, debugging)
-  bool stream16_ = [] { const char* e = getenv("PBE_STREAM"); return !(e != nullptr && (e[0] == 'f' || e[0] == 'F')); }();
+  // (bf16 operands keep the fp32 stream by default: bf16 rounding of operands AND stream together exceeds the 1e-2 parity bar)
+  bool stream16_ = [] {
+    const char* e = getenv("PBE_STREAM");
+    if (e != nullptr) return !(e[0] == 'f' || e[0] == 'F');
+    return operand_f16() != 0;
+  }();
   // nearest-2x upsample + 3x3 conv as four sub-pixel phase convs (16-bit stream only); PBE_SUBPIXEL_UP=0: the literal form
   int subpixel_up_ = [] { const char* e = getenv("PBE_SUBPIXEL_UP"); return e == nullptr ? 1 : atoi(e); }();   // 2: at every size (tests)
   std::string last_error;

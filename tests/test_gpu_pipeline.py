@@ -2,6 +2,7 @@
 proj_out -> conditioning; masked image -> VAE encode -> latent; PLMS under CFG over the U-Net; VAE decode -> uint8 —
 against the same pipeline composed from the fp32 oracles (small configurations of all three networks)."""
 import math
+import os
 
 import pytest
 import torch
