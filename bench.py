@@ -45,6 +45,9 @@ F64_MIN = 771.3e9   # algorithmic FLOPs per sample-eval at 64x64 with the dead c
 # run once per (uncond, cond) pair -- conv_in 0.212 + first ResBlock 15.099 + proj_in 0.839 + qkv 2.517 + self-attention
 # 21.475 = 40.142 GFLOP per pair, i.e. half of that per sample-eval.  Only executed work is claimed below.
 F64_PAIR_SHARED = 40.142e9 / 2
+# ... nor by the sub-pixel form of "nearest-2x upsample + 3x3 conv" (4/9 of the literal FLOPs) at the two levels whose phase
+# launches fill the GPU at CFG batch >= 8: 16->32 (1280 ch) and 32->64 (640 ch), 30.2 GFLOP each in the literal form
+F64_SUBPIXEL_SAVED = 2 * 30.199e9 * 5.0 / 9.0
 
 
 def _ncu_traffic():
@@ -332,6 +335,8 @@ def main():
     if hw == 96:
         flops_per_eval = 2079.9e9
     unet = model.model.diffusion_model
+    from pbe_b200 import _lib as _pl
+    fmt_f16 = bool(_pl.load().pbe_get_operand_format())
 
     def sample_device():
         out, _ = sampler.sample(S=Sn, conditioning=d["c"], batch_size=B, shape=[4, hw, hw], verbose=False,
@@ -432,17 +437,21 @@ def main():
     line = {
         "metric": "images_per_sec_512px_plms50_cfg", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16" if fmt_f16 else "bf16", "data": "synthetic",
+        "dtype_note": ("fp16 tensor-core operands (saturating conversions) and 16-bit fp16 residual stream, fp32 accumulation and "
+                       "statistics; bf16 Q/K/V/P inside self-attention -- the precision the reference runs at under torch.autocast"
+                       if fmt_f16 else "bf16 tensor-core operands, fp32 accumulation, statistics and residual stream (PBE_OPERANDS=bf16)"),
         "config": base_config(args, world),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches * args.steps,
         "unet_step_ms": {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                          "cfg_batch": Bc, "floor_ms_at_sustained_peak": (Bc * flops_per_eval / (peaks["tf_sustained"] * 1e12) * 1e3) if flops_per_eval else None},
-        "tensor_utilisation_whole_job": {"achieved_tflops": (B * args.steps * 2 * calls * (flops_per_eval - (F64_PAIR_SHARED if hw == 64 else 0.0))
+        "tensor_utilisation_whole_job": {"achieved_tflops": (B * args.steps * 2 * calls * (flops_per_eval - ((F64_PAIR_SHARED + (F64_SUBPIXEL_SAVED if (fmt_f16 and B >= 8) else 0.0)) if hw == 64 else 0.0))
                                                              / (total_ms / 1e3) / 1e12) if flops_per_eval else None,
                                          "note": "executed FLOPs only: the CFG-pair plan evaluates the layers in front of the "
-                                                 "first cross-attention once per (uncond, cond) pair",
+                                                 "first cross-attention once per (uncond, cond) pair, and two of the three "
+                                                 "upsample convs run in their sub-pixel form (4/9 of the literal FLOPs)",
                                          "peak_tflops_sustained": peaks["tf_sustained"], "peak_source": peaks["src"]},
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM conv / linear, tcgen05)",
                      "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",

@@ -85,21 +85,26 @@ def q_sample(model, x_start, t, noise):
     return sac.gather(-1, t).reshape(shape) * x_start + s1m.gather(-1, t).reshape(shape) * noise
 
 
-def _cfg_eps(model, x9, t, c, uc, scale):
-    """get_model_output, plms.py:181-189."""
+def _cfg_eps(model, x9, t, c, uc, scale, score_corrector=None, corrector_kwargs=None):
+    """get_model_output, plms.py:181-194 (ddim.py:205-218): CFG combine, then the optional score corrector."""
     if uc is None or scale == 1.:
-        return model.apply_model(x9, t, c)
-    if uc.shape[0] != c.shape[0]:
-        uc = uc.expand(c.shape[0], *uc.shape[1:])
-    x_in = torch.cat([x9] * 2)
-    t_in = torch.cat([t] * 2)
-    c_in = torch.cat((uc, c))
-    e_u, e_c = model.apply_model(x_in, t_in, c_in).chunk(2)
-    return e_u + scale * (e_c - e_u)
+        e_t = model.apply_model(x9, t, c)
+    else:
+        if uc.shape[0] != c.shape[0]:
+            uc = uc.expand(c.shape[0], *uc.shape[1:])
+        x_in = torch.cat([x9] * 2)
+        t_in = torch.cat([t] * 2)
+        c_in = torch.cat((uc, c))
+        e_u, e_c = model.apply_model(x_in, t_in, c_in).chunk(2)
+        e_t = e_u + scale * (e_c - e_u)
+    if score_corrector is not None:
+        e_t = score_corrector.modify_score(model, e_t, x9, t, c, **(corrector_kwargs or {}))
+    return e_t
 
 
 @torch.no_grad()
-def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, blend_mask=None, x0=None, rng_device=None):
+def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, blend_mask=None, x0=None, rng_device=None,
+                score_corrector=None, corrector_kwargs=None):
     """PLMSSampler.plms_sampling + p_sample_plms, plms.py:118-248 (eta = 0).  With blend_mask / x0 (plms.py:150-153) the
     generator of `rng_device` is consumed exactly as the reference does: q_sample's randn_like, then one (unused, sigma_t = 0)
     noise_like() draw per get_x_prev_and_pred_x0 call (plms.py:214) -- two on the first step."""
@@ -122,11 +127,12 @@ def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, blend
             img_orig = q_sample(model, x0, t, torch.randn(x0.shape, device=rdev).to(img.device))
             img = img_orig * blend_mask + (1 - blend_mask) * img
         x9 = torch.cat((img, z_inpaint, mask), dim=1)
-        e_t = _cfg_eps(model, x9, t, c, uc, scale)
+        e_t = _cfg_eps(model, x9, t, c, uc, scale, score_corrector, corrector_kwargs)
         if len(old_eps) == 0:
             draw()
             x_prev, _ = _x_prev_and_pred_x0(img, e_t, *coef)
-            e_next = _cfg_eps(model, torch.cat((x_prev, z_inpaint, mask), dim=1), t_next, c, uc, scale)
+            e_next = _cfg_eps(model, torch.cat((x_prev, z_inpaint, mask), dim=1), t_next, c, uc, scale, score_corrector,
+                              corrector_kwargs)
             e_prime = (e_t + e_next) / 2
         elif len(old_eps) == 1:
             e_prime = (3 * e_t - old_eps[-1]) / 2
@@ -147,7 +153,7 @@ def plms_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, blend
 
 @torch.no_grad()
 def ddim_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, eta=0.0, temperature=1., blend_mask=None,
-                x0=None, rng_device=None):
+                x0=None, rng_device=None, score_corrector=None, corrector_kwargs=None):
     """DDIMSampler.ddim_sampling + p_sample_ddim, ddim.py:136-242.  With eta > 0 (or blend_mask / x0, ddim.py:168-171) the
     noise is drawn from torch's global generator of `rng_device` (default: the latent's device) at the reference's points
     and in its order: q_sample's randn_like first, then noise_like() after the model call."""
@@ -165,7 +171,7 @@ def ddim_sample(model, S, x_T, c, uc, scale, z_inpaint, mask, record=None, eta=0
             img_orig = q_sample(model, x0, t, torch.randn(x0.shape, device=rdev).to(img.device))
             img = img_orig * blend_mask + (1. - blend_mask) * img
         x9 = torch.cat((img, z_inpaint, mask), dim=1)
-        e_t = _cfg_eps(model, x9, t, c, uc, scale)
+        e_t = _cfg_eps(model, x9, t, c, uc, scale, score_corrector, corrector_kwargs)
         noise = torch.randn(img.shape, device=rdev).to(img.device) if (eta != 0.0 or blend_mask is not None) else None
         x_prev, pred_x0 = _x_prev_and_pred_x0(img, e_t, tab["alphas"][index], tab["alphas_prev"][index],
                                               tab["sigmas"][index], tab["sqrt_one_minus_alphas"][index], noise, temperature)

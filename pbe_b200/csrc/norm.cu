@@ -231,7 +231,16 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_fused_kernel(const fl
 // with every load issued before the first use.  (The first version recomputed pixel / sample / channel with two 64-bit
 // divisions per float4 and re-read the scale / shift table per element: 2.2-3.4 TB/s.)
 constexpr int GN_UNROLL = 8;
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x * sigmoid(x) = x * rcp(1 + 2^(-x log2 e)): FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL.  (__fdividef carries a range fix-up for
+// denominators above 2^126 -- an FSETP and two more FMULs per element; here the denominator overflowing to +inf gives
+// rcp = 0 and the right limit.  ncu, profiles/r02_ncu_gnapply_v4_summary.txt: the pass was issue-bound at 24 instructions
+// per element, 75 % issue-active, not HBM-bound.)
+__device__ __forceinline__ float silu_fast(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
 
 template <int IN16>
 __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
@@ -277,8 +286,9 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
   for (int u = 0; u < GN_UNROLL; ++u) {
     const int pix = p_begin + u * rows_par;
     if (pix < HW) {
-      float o0 = fmaf(v[u].x, s01.x, s01.y), o1 = fmaf(v[u].y, s01.z, s01.w);
-      float o2 = fmaf(v[u].z, s23.x, s23.y), o3 = fmaf(v[u].w, s23.z, s23.w);
+      float o0, o1, o2, o3;
+      upk2(fma2(pk2(v[u].x, v[u].y), pk2(s01.x, s01.z), pk2(s01.y, s01.w)), o0, o1);
+      upk2(fma2(pk2(v[u].z, v[u].w), pk2(s23.x, s23.z), pk2(s23.y, s23.w)), o2, o3);
       if (silu) { o0 = silu_fast(o0); o1 = silu_fast(o1); o2 = silu_fast(o2); o3 = silu_fast(o3); }
       const long long off = obase + static_cast<long long>(pix) * C;
       *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_op2(o0, o1, f16), pack_op2(o2, o3, f16));
@@ -394,7 +404,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int nvec = C / 4;
   const long long xbase = static_cast<long long>(row) * ld_x;
   float4 v[NV];
-  float sum = 0.0f;
   if (in16) {
     uint2 r16[NV];
 #pragma unroll
@@ -411,26 +420,41 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       if (k < nvec) v[i] = __ldg(reinterpret_cast<const float4*>(x + xbase) + k);
     }
   }
+  // packed fp32x2 arithmetic (FADD2 / FFMA2 / FMUL2): the pass is issue-bound (ncu: 85 % issue-active, 29 instructions per
+  // element before), not HBM-bound, so instructions per element are what counts.  Lanes beyond the row hold zeros.
+  f32x2 acc = pk2(0.0f, 0.0f);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int k = lane + i * 32;
-    if (k < nvec) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    if (k >= nvec) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc = add2(acc, add2(pk2(v[i].x, v[i].y), pk2(v[i].z, v[i].w)));
   }
+  float s0, s1;
+  upk2(acc, s0, s1);
+  float sum = s0 + s1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / C;
-  float sq = 0.0f;
+  const f32x2 nmean = pk2(-mean, -mean);
+  f32x2 d[NV][2];
+  f32x2 sq2 = pk2(0.0f, 0.0f);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int k = lane + i * 32;
-    if (k < nvec) {
-      const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
-      sq += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+    d[i][0] = add2(pk2(v[i].x, v[i].y), nmean);
+    d[i][1] = add2(pk2(v[i].z, v[i].w), nmean);
+    if (k < nvec) {   // (padding lanes would contribute mean^2)
+      sq2 = fma2(d[i][0], d[i][0], sq2);
+      sq2 = fma2(d[i][1], d[i][1], sq2);
     }
   }
+  float q0, q1;
+  upk2(sq2, q0, q1);
+  float sq = q0 + q1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / C + eps);
+  const f32x2 rstd2 = pk2(rstd, rstd);
   const float4* gr = reinterpret_cast<const float4*>(gamma);
   const float4* br = reinterpret_cast<const float4*>(beta);
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(row) * C);
@@ -439,8 +463,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const int k = lane + i * 32;
     if (k < nvec) {
       const float4 g = __ldg(gr + k), bb = __ldg(br + k);
-      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
-                                   (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+      float4 o;
+      upk2(fma2(d[i][0], mul2(pk2(g.x, g.y), rstd2), pk2(bb.x, bb.y)), o.x, o.y);
+      upk2(fma2(d[i][1], mul2(pk2(g.z, g.w), rstd2), pk2(bb.z, bb.w)), o.z, o.w);
       if (y != nullptr) yr[k] = make_uint2(pack_op2(o.x, o.y, f16), pack_op2(o.z, o.w, f16));
       if (y32 != nullptr) reinterpret_cast<float4*>(y32 + static_cast<long long>(row) * C)[k] = o;
     }

@@ -107,6 +107,13 @@ class _SamplerBase:
         self.register_buffer("ddim_sigmas_for_original_num_steps", sig_orig)
         # Host-side per-step coefficients, rounded exactly as the reference's per-step torch.full(...) fp32 fills
         # (plms.py:204-207): no device->host sync inside the loop.
+        # use_original_steps=True (ddim.py:224-227): the 1000-step tables of the model itself
+        self._coef_orig = dict(
+            a_t=[float(v) for v in ac_cpu],
+            a_prev=[float(v) for v in acp],
+            sigma=[float(v) for v in sig_orig.to(torch.float32)],
+            sqrt_one_minus_at=[float(v) for v in torch.as_tensor(np.sqrt(1. - ac_cpu)).to(torch.float32)],
+        )
         a_cpu = ddim_alphas.detach().to("cpu", torch.float32)
         self._coef = dict(
             a_t=[float(v) for v in a_cpu],
@@ -134,7 +141,8 @@ class _SamplerBase:
             return unet.run(x9_in, t_in, out=eps_out)
         return self.model.apply_model(x9_in, t_in, c_in).to(torch.float32).contiguous()
 
-    def _step_kernel(self, eps, B, cfg, scale, order, hist, x, index, noise, e_out, x_prev, pred_x0, temperature=1.0):
+    def _step_kernel(self, eps, B, cfg, scale, order, hist, x, index, noise, e_out, x_prev, pred_x0, temperature=1.0,
+                     coef=None):
         lib = _lib.load()
         n = x.numel()
         dup = 2 if cfg else 1
@@ -145,7 +153,7 @@ class _SamplerBase:
         e_uc = eps[:B] if cfg else eps
         e_c = eps[B:] if cfg else None
         h = [(t.data_ptr() if t is not None else None) for t in hist] + [None] * (3 - len(hist))
-        c = self._coef
+        c = self._coef if coef is None else coef
         st = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
             _lib.check(lib.pbe_sampler_step(
@@ -154,6 +162,15 @@ class _SamplerBase:
                 c["sqrt_one_minus_at"][index], None if noise is None else noise.data_ptr(), float(temperature),
                 None if e_out is None else e_out.data_ptr(), x_prev.data_ptr(),
                 None if pred_x0 is None else pred_x0.data_ptr(), n, st), "pbe_sampler_step")
+
+    def _corrected_eps(self, eps, B, cfg, scale, score_corrector, corrector_kwargs, x9, t, cond):
+        """get_model_output's tail (plms.py:188-194, ddim.py:213-218): CFG combine, then
+        ``score_corrector.modify_score(model, e_t, x, t, c, **corrector_kwargs)``.  The corrector is user code, so this runs as
+        torch ops and the fused kernel is then called without CFG on the result."""
+        assert getattr(self.model, "parameterization", "eps") == "eps"
+        e_t = (eps[:B] + scale * (eps[B:] - eps[:B])) if cfg else eps
+        e_t = score_corrector.modify_score(self.model, e_t, x9[:B], t[:B], cond, **(corrector_kwargs or {}))
+        return e_t.to(torch.float32).contiguous()
 
     def _build_input(self, x, z, mask, out, dup):
         lib = _lib.load()
@@ -234,9 +251,13 @@ class PLMSSampler(_SamplerBase):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, **kwargs):
         if ddim_use_original_steps:
-            raise NotImplementedError("ddim_use_original_steps=True (1000-step PLMS) is not part of the hot path")
-        if quantize_denoised or score_corrector is not None:
-            raise NotImplementedError("quantize_denoised / score_corrector are not used by Paint-by-Example")
+            # plms.py:199 reads self.model.ddim_sigmas_for_original_num_steps, which no model has: the reference raises too
+            raise AttributeError("'LatentDiffusion' object has no attribute 'ddim_sigmas_for_original_num_steps' "
+                                 "(plms.py:199: use_original_steps is not usable with PLMSSampler)")
+        if quantize_denoised:
+            raise NotImplementedError("quantize_denoised needs a VQ first stage (first_stage_model.quantize, plms.py:211); "
+                                      "Paint-by-Example's first stage is AutoencoderKL")
+        cond_user = cond
         device, b, img, pair, cfg, c_in = self._setup(cond, shape, x_T, unconditional_guidance_scale,
                                                      unconditional_conditioning, kwargs)
         if pair is None:
@@ -282,6 +303,11 @@ class PLMSSampler(_SamplerBase):
                 img = (img_orig * mask + (1 - mask) * img).contiguous()
             self._build_input(img, z_inp, m_inp, x9, in_dup)
             eps = self._model_eps(unet, x9, ts_all[i], c_in, eps_buf)
+            kcfg = cfg
+            if score_corrector is not None:      # plms.py:191-193: user code between the CFG combine and the multistep update
+                eps = self._corrected_eps(eps, b, cfg, unconditional_guidance_scale, score_corrector, corrector_kwargs, x9,
+                                          ts_all[i], cond_user)
+                kcfg = False
             x_prev = xbuf[i & 1]
             pred_x0 = torch.empty_like(img) if img_callback else x0buf
             e_t = ebuf[i & 3]
@@ -289,15 +315,19 @@ class PLMSSampler(_SamplerBase):
                 # Pseudo Improved Euler (plms.py:230-235): provisional x_prev from e_t, second U-Net call at t_next
                 if rng_match:
                     torch.randn(img.shape, device=device)      # the reference's unused noise_like() draw (plms.py:214)
-                self._step_kernel(eps, b, cfg, unconditional_guidance_scale, 0, [], img, index, None, e_t, x_prev, None)
+                self._step_kernel(eps, b, kcfg, unconditional_guidance_scale, 0, [], img, index, None, e_t, x_prev, None)
                 self._build_input(x_prev, z_inp, m_inp, x9, in_dup)
-                eps2 = self._model_eps(unet, x9, ts_all[min(i + 1, total_steps - 1)], c_in, eps_buf)
-                self._step_kernel(eps2, b, cfg, unconditional_guidance_scale, 4, [e_t], img, index, None, None,
+                t_nx = ts_all[min(i + 1, total_steps - 1)]
+                eps2 = self._model_eps(unet, x9, t_nx, c_in, eps_buf)
+                if score_corrector is not None:
+                    eps2 = self._corrected_eps(eps2, b, cfg, unconditional_guidance_scale, score_corrector, corrector_kwargs, x9,
+                                               t_nx, cond_user)
+                self._step_kernel(eps2, b, kcfg, unconditional_guidance_scale, 4, [e_t], img, index, None, None,
                                   x_prev, pred_x0)
             else:
                 order = min(len(old_eps), 3)
                 hist = list(reversed(old_eps))[:order]   # h1 = most recent
-                self._step_kernel(eps, b, cfg, unconditional_guidance_scale, order, hist, img, index, None, e_t,
+                self._step_kernel(eps, b, kcfg, unconditional_guidance_scale, order, hist, img, index, None, e_t,
                                   x_prev, pred_x0)
             if rng_match:
                 torch.randn(img.shape, device=device)
@@ -345,17 +375,22 @@ class DDIMSampler(_SamplerBase):
                       quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100,
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, disable_tqdm=False, **kwargs):
-        if ddim_use_original_steps:
-            raise NotImplementedError("ddim_use_original_steps=True is not part of the hot path")
-        if quantize_denoised or score_corrector is not None:
-            raise NotImplementedError("quantize_denoised / score_corrector are not used by Paint-by-Example")
+        if quantize_denoised:
+            raise NotImplementedError("quantize_denoised needs a VQ first stage (first_stage_model.quantize, ddim.py:234); "
+                                      "Paint-by-Example's first stage is AutoencoderKL")
+        cond_user = cond
         device, b, img, pair, cfg, c_in = self._setup(cond, shape, x_T, unconditional_guidance_scale,
                                                      unconditional_conditioning, kwargs)
         if pair is None:
             raise Exception("kwargs must contain either 'test_model_kwargs' or 'rest' key")   # ddim.py:203-204
         z_inp, m_inp = (t.to(device=device, dtype=torch.float32).contiguous() for t in pair)
-        if "_decode_timesteps" in kwargs:          # DDIMSampler.decode: an explicit prefix of ddim_timesteps (ddim.py:266-267)
+        coef = None
+        if "_decode_timesteps" in kwargs:          # DDIMSampler.decode: an explicit prefix of the timesteps (ddim.py:266-267)
             timesteps = kwargs["_decode_timesteps"]
+            coef = self._coef_orig if ddim_use_original_steps else None
+        elif ddim_use_original_steps:              # ddim.py:152-153,159-160: all ddpm_num_timesteps steps, the model's own tables
+            timesteps = np.arange(self.ddpm_num_timesteps)
+            coef = self._coef_orig
         elif timesteps is None:
             timesteps = self.ddim_timesteps
         else:
@@ -364,6 +399,7 @@ class DDIMSampler(_SamplerBase):
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         time_range = np.flip(timesteps)
         total_steps = timesteps.shape[0]
+        sig_tab = (coef or self._coef)["sigma"]
 
         unet = self._fast_unet()
         dup = 2 if cfg else 1
@@ -388,8 +424,13 @@ class DDIMSampler(_SamplerBase):
                 img = (img_orig * mask + (1. - mask) * img).contiguous()
             self._build_input(img, z_inp, m_inp, x9, in_dup)
             eps = self._model_eps(unet, x9, ts_all[i], c_in, eps_buf)
+            kcfg = cfg
+            if score_corrector is not None:      # ddim.py:216-218
+                eps = self._corrected_eps(eps, b, cfg, unconditional_guidance_scale, score_corrector, corrector_kwargs, x9,
+                                          ts_all[i], cond_user)
+                kcfg = False
             noise = None
-            if self._coef["sigma"][index] != 0.0:
+            if sig_tab[index] != 0.0:
                 # ddim.py:238: noise = sigma_t * noise_like(...) * temperature -- both products happen in the kernel, in that order
                 noise = torch.randn(img.shape, device=device)
                 if noise_dropout > 0.:
@@ -399,8 +440,8 @@ class DDIMSampler(_SamplerBase):
                 torch.randn(img.shape, device=device)          # the reference draws even when sigma_t == 0
             x_prev = xbuf[i & 1]
             pred_x0 = torch.empty_like(img) if img_callback else x0buf
-            self._step_kernel(eps, b, cfg, unconditional_guidance_scale, 0, [], img, index, noise, None, x_prev, pred_x0,
-                              temperature=temperature)
+            self._step_kernel(eps, b, kcfg, unconditional_guidance_scale, 0, [], img, index, noise, None, x_prev, pred_x0,
+                              temperature=temperature, coef=coef)
             img = x_prev
             if callback:
                 callback(i)
@@ -418,12 +459,10 @@ class DDIMSampler(_SamplerBase):
         In this fork p_sample_ddim insists on the inpainting inputs (ddim.py:198-204) and decode() does not forward any,
         so the reference's decode always raises; the same exception is raised here when no `test_model_kwargs` / `rest`
         is given, and -- as an extension -- the steps run when one is."""
-        if use_original_steps:
-            raise NotImplementedError("use_original_steps=True is not part of the hot path")
         if _inpaint_kwargs(kwargs) is None:
             raise Exception("kwargs must contain either 'test_model_kwargs' or 'rest' key")   # ddim.py:203-204
-        timesteps = self.ddim_timesteps[:t_start]
-        x_dec, _ = self.ddim_sampling(cond, tuple(x_latent.shape), x_T=x_latent,
+        timesteps = (np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps)[:t_start]
+        x_dec, _ = self.ddim_sampling(cond, tuple(x_latent.shape), x_T=x_latent, ddim_use_original_steps=use_original_steps,
                                       unconditional_guidance_scale=unconditional_guidance_scale,
                                       unconditional_conditioning=unconditional_conditioning, disable_tqdm=disable_tqdm,
                                       _decode_timesteps=timesteps, **kwargs)

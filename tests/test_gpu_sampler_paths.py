@@ -225,6 +225,51 @@ def test_plms_plain_loop_and_callbacks_bit_exact(toy, dev):
     assert torch.equal(out_b, out)
 
 
+@pytest.mark.parametrize("kind", ["plms", "ddim"])
+def test_score_corrector_bit_exact(toy, dev, kind):
+    """score_corrector.modify_score between the CFG combine and the update (plms.py:191-193, ddim.py:216-218): user code, so the
+    combine runs as torch ops and the fused kernel takes the corrected eps without CFG -- bit-identical to the oracle."""
+    from oracle import sampler_ref as S
+    from pbe_b200.samplers import DDIMSampler, PLMSSampler
+    from test_oracle_pinned import ToyCorrector
+    prod, orc, req, _, _ = toy
+    cls, fn = (PLMSSampler, S.plms_sample) if kind == "plms" else (DDIMSampler, S.ddim_sample)
+    out, _ = cls(prod).sample(S=8, eta=0.0, score_corrector=ToyCorrector(), corrector_kwargs=dict(gain=2.0), **_kw(req, dev, 3))
+    ref = fn(orc, 8, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"], score_corrector=ToyCorrector(),
+             corrector_kwargs=dict(gain=2.0))
+    assert torch.equal(out.cpu(), ref)
+    plain, _ = cls(prod).sample(S=8, eta=0.0, **_kw(req, dev, 3))
+    assert not torch.equal(plain, out)
+
+
+def test_ddim_original_steps_decode(toy, dev):
+    """use_original_steps=True (ddim.py:152-160,224-227,262-267): the model's own 1000-step tables instead of the DDIM
+    sub-sequence.  In this fork both samplers read `self.model.ddim_sigmas_for_original_num_steps`, which no model has, so the
+    reference raises AttributeError on this path (PLMSSampler here raises the same); DDIMSampler implements what the line
+    means (upstream CompVis reads the sampler's own buffer).  Checked against a direct restatement of the update with the
+    model's tables: the last 6 of the 1000 steps, eta = 0."""
+    from oracle import sampler_ref as S
+    from pbe_b200.samplers import DDIMSampler, PLMSSampler
+    prod, orc, req, _, _ = toy
+    smp = DDIMSampler(prod)
+    smp.make_schedule(ddim_num_steps=10, ddim_eta=0.0, verbose=False)
+    d = lambda t: t.to(dev)
+    kw = dict(unconditional_guidance_scale=5.0, unconditional_conditioning=d(req["uc"]),
+              test_model_kwargs=dict(images_inpaint=d(req["z_inpaint"]), images_mask=d(req["mask"])))
+    out = smp.decode(d(req["x_T"]), d(req["c"]), 6, use_original_steps=True, **kw)
+    buf = S.make_schedule_buffers()
+    ac, acp = buf["alphas_cumprod"], buf["alphas_cumprod_prev"]
+    s1m = torch.tensor(np.sqrt(1. - ac.numpy().astype(np.float32)))
+    img = req["x_T"]
+    for step in range(5, -1, -1):
+        t = torch.full((3,), step, dtype=torch.int64)
+        e = S._cfg_eps(orc, torch.cat((img, req["z_inpaint"], req["mask"]), 1), t, req["c"], req["uc"], 5.0)
+        img, _ = S._x_prev_and_pred_x0(img, e, ac[step], acp[step], 0.0, s1m[step])
+    assert torch.equal(out.cpu(), img)
+    with pytest.raises(AttributeError, match="ddim_sigmas_for_original_num_steps"):
+        PLMSSampler(prod).plms_sampling(d(req["c"]), (3, 4, 16, 24), ddim_use_original_steps=True, **kw)
+
+
 def test_stochastic_encode_bit_exact(toy, dev):
     from oracle import sampler_ref as S
     from pbe_b200.samplers import DDIMSampler

@@ -139,6 +139,31 @@ def test_oracle_stochastic_paths_bit_equal_live_reference(small, case):
     assert torch.equal(out, out_ref)
 
 
+class ToyCorrector:
+    """A score corrector in the reference's calling convention (plms.py:191-193): elementwise fp32, so CPU == GPU bit for bit."""
+
+    def modify_score(self, model, e_t, x, t, c, gain=1.0):
+        return e_t * 0.875 + x[:, :4] * 0.0625 * gain
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
+@pytest.mark.parametrize("kind", ["plms", "ddim"])
+def test_oracle_score_corrector_bit_equals_live_reference(small, kind):
+    cfg, sd, req = small
+    model = R.StubLatentDiffusion(R.build_reference_unet(cfg, sd))
+    kw = dict(S=4, conditioning=req["c"], batch_size=2, shape=[4, 32, 32], verbose=False, unconditional_guidance_scale=5.0,
+              unconditional_conditioning=req["uc"].expand(2, 1, 768), x_T=req["x_T"], eta=0.0,
+              score_corrector=ToyCorrector(), corrector_kwargs=dict(gain=2.0),
+              test_model_kwargs=dict(images_inpaint=req["z_inpaint"], images_mask=req["mask"]))
+    if kind == "ddim":
+        kw["disable_tqdm"] = True
+    out_ref, _ = R.reference_sampler(kind, model).sample(**kw)
+    fn = S.plms_sample if kind == "plms" else S.ddim_sample
+    out = fn(S.OracleModel(sd, cfg), 4, req["x_T"], req["c"], req["uc"], 5.0, req["z_inpaint"], req["mask"],
+             score_corrector=ToyCorrector(), corrector_kwargs=dict(gain=2.0))
+    assert torch.equal(out, out_ref)
+
+
 @pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
 def test_oracle_stochastic_encode_bit_equals_live_reference(small):
     cfg, sd, req = small
