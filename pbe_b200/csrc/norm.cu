@@ -75,10 +75,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
       const int c = col * 4;
       int pix = p0 + prow;
       for (; pix + 3 * rows_par < p1; pix += 4 * rows_par) {
-        const float4 a0 = ld4(x0, C0, x1, C1, base + pix, c, in16, f16);
-        const float4 a1 = ld4(x0, C0, x1, C1, base + pix + rows_par, c, in16, f16);
-        const float4 a2 = ld4(x0, C0, x1, C1, base + pix + 2 * rows_par, c, in16, f16);
-        const float4 a3 = ld4(x0, C0, x1, C1, base + pix + 3 * rows_par, c, in16, f16);
+        float4 a0, a1, a2, a3;
+        if (in16) {   // all four loads in flight before the first conversion
+          const float* sp = (c < C0) ? x0 : x1;
+          const int cc = (c < C0) ? c : c - C0, cl = (c < C0) ? C0 : C1;
+          const uint2 r0 = ldraw4(sp, (base + pix) * cl + cc), r1 = ldraw4(sp, (base + pix + rows_par) * cl + cc),
+                      r2 = ldraw4(sp, (base + pix + 2 * rows_par) * cl + cc), r3 = ldraw4(sp, (base + pix + 3 * rows_par) * cl + cc);
+          a0 = cvt4(r0, f16); a1 = cvt4(r1, f16); a2 = cvt4(r2, f16); a3 = cvt4(r3, f16);
+        } else {
+          a0 = ld4(x0, C0, x1, C1, base + pix, c, 0, f16);
+          a1 = ld4(x0, C0, x1, C1, base + pix + rows_par, c, 0, f16);
+          a2 = ld4(x0, C0, x1, C1, base + pix + 2 * rows_par, c, 0, f16);
+          a3 = ld4(x0, C0, x1, C1, base + pix + 3 * rows_par, c, 0, f16);
+        }
         sx += (a0.x + a1.x) + (a2.x + a3.x); qx += (a0.x * a0.x + a1.x * a1.x) + (a2.x * a2.x + a3.x * a3.x);
         sy += (a0.y + a1.y) + (a2.y + a3.y); qy += (a0.y * a0.y + a1.y * a1.y) + (a2.y * a2.y + a3.y * a3.y);
         sz += (a0.z + a1.z) + (a2.z + a3.z); qz += (a0.z * a0.z + a1.z * a1.z) + (a2.z * a2.z + a3.z * a3.z);
@@ -342,10 +351,20 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const float* __re
   if (active) {
     int pix = prow;
     for (; pix + 3 * rows_par < HW; pix += 4 * rows_par) {
-      const float2 v0 = ld2e(src, sbase + static_cast<long long>(pix) * ld, in16, f16);
-      const float2 v1 = ld2e(src, sbase + static_cast<long long>(pix + rows_par) * ld, in16, f16);
-      const float2 v2 = ld2e(src, sbase + static_cast<long long>(pix + 2 * rows_par) * ld, in16, f16);
-      const float2 v3 = ld2e(src, sbase + static_cast<long long>(pix + 3 * rows_par) * ld, in16, f16);
+      float2 v0, v1, v2, v3;
+      if (in16) {   // all four loads in flight before the first conversion
+        const unsigned short* s16p = reinterpret_cast<const unsigned short*>(src) + sbase;
+        const uint32_t r0 = __ldg(reinterpret_cast<const uint32_t*>(s16p + static_cast<long long>(pix) * ld));
+        const uint32_t r1 = __ldg(reinterpret_cast<const uint32_t*>(s16p + static_cast<long long>(pix + rows_par) * ld));
+        const uint32_t r2 = __ldg(reinterpret_cast<const uint32_t*>(s16p + static_cast<long long>(pix + 2 * rows_par) * ld));
+        const uint32_t r3 = __ldg(reinterpret_cast<const uint32_t*>(s16p + static_cast<long long>(pix + 3 * rows_par) * ld));
+        v0 = unpack_op2(r0, f16); v1 = unpack_op2(r1, f16); v2 = unpack_op2(r2, f16); v3 = unpack_op2(r3, f16);
+      } else {
+        v0 = __ldg(reinterpret_cast<const float2*>(src + sbase + static_cast<long long>(pix) * ld));
+        v1 = __ldg(reinterpret_cast<const float2*>(src + sbase + static_cast<long long>(pix + rows_par) * ld));
+        v2 = __ldg(reinterpret_cast<const float2*>(src + sbase + static_cast<long long>(pix + 2 * rows_par) * ld));
+        v3 = __ldg(reinterpret_cast<const float2*>(src + sbase + static_cast<long long>(pix + 3 * rows_par) * ld));
+      }
       s_x[pix * hv + cv] = v0;
       s_x[(pix + rows_par) * hv + cv] = v1;
       s_x[(pix + 2 * rows_par) * hv + cv] = v2;
