@@ -8,6 +8,8 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -964,10 +966,24 @@ int Engine::profile_forward(const float* x, const int64_t* t, float* eps, int Bc
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) PBE_CHECK_CUDA(cudaEventCreate(&e));
   PBE_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+  // PBE_GEMM_DEBUG: in-situ wait counters of CTA 0 of every conv_gemm op (serialises the pass; times are then not comparable)
+  const bool gdbg = getenv("PBE_GEMM_DEBUG") != nullptr;
   for (size_t i = 0; i < n; ++i) {
+    if (gdbg && P.op_family[i] == "conv_gemm") gemm_reset_debug_counters();
     rc = P.ops[i](stream);
     if (rc) return rc;
     PBE_CHECK_CUDA(cudaEventRecord(ev[i + 1], stream));
+    if (gdbg && P.op_family[i] == "conv_gemm") {
+      long long c[16];
+      PBE_CHECK_CUDA(cudaStreamSynchronize(stream));
+      gemm_read_debug_counters16(c);
+      fprintf(stderr, "[gemm-dbg] %-34s mma %8lld cyc (wait tma %3.0f%% tmem %3.0f%%) %4lld k-it %5.0f cyc/it | prod wait-empty %8lld | epi %8lld cyc (wait acc %3.0f%% slot %3.0f%% bar %3.0f%%) %3lld chunks: ld+bias %5.0f pack %5.0f fence %5.0f cyc/chunk\n",
+              P.op_names[i].c_str(), c[0], c[0] ? 100.0 * c[1] / c[0] : 0.0, c[0] ? 100.0 * c[2] / c[0] : 0.0, c[4],
+              c[4] ? static_cast<double>(c[0]) / c[4] : 0.0, c[3], c[5], c[5] ? 100.0 * c[6] / c[5] : 0.0,
+              c[5] ? 100.0 * (c[7] >> 32) / c[5] : 0.0, c[5] ? 100.0 * (c[7] & 0xffffffffll) / c[5] : 0.0, c[11],
+              c[11] ? static_cast<double>(c[8]) / c[11] : 0.0, c[11] ? static_cast<double>(c[9]) / c[11] : 0.0,
+              c[11] ? static_cast<double>(c[10]) / c[11] : 0.0);
+    }
   }
   PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
                                  cudaMemcpyDeviceToDevice, stream));

@@ -28,7 +28,7 @@ namespace pbe {
 
 // Debug counters of CTA 0 (tools/gemm_probe.py): [0] MMA-warp cycles total, [1] waiting for smem stages (TMA),
 // [2] waiting for a free TMEM buffer (epilogue), [3] producer cycles waiting for free stages, [4] k iterations.
-__device__ long long g_gemm_dbg[8];
+__device__ long long g_gemm_dbg[16];   // [8..11]: epilogue warp per-chunk stages: ld+bias+add, residual+pack+stats, fence, chunks
 
 namespace {
 
@@ -40,6 +40,8 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int NUM_SLOTS = 4;
 constexpr int SLOT_BYTES = 128 * 32 * 4;  // one 32-column fp32 chunk of a 128-row tile
 constexpr int EPI_STAGING_BYTES = NUM_SLOTS * SLOT_BYTES;
+constexpr int BIAS_SCR_FLOATS = 128;                                  // per epilogue warp: this chunk's fused bias columns
+constexpr int BIAS_SCR_BYTES = NUM_EPI_WARPS * BIAS_SCR_FLOATS * 4;   // 4 KB behind the barriers
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -381,11 +383,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     const bool store_warp = (ew & 3) == 0;
 
+    // ---- fused bias columns of a chunk: lane = column, fetched one chunk ahead, broadcast through a per-warp scratch ----
+    // (Every thread used to load the chunk's 32 bias + 32 per-sample bias values itself: 16 LDG.128 per chunk whose results the
+    // adds consumed pair by pair -- a chain of global-load round trips in the middle of every chunk, and the reason the
+    // short-K GEMMs were epilogue-bound at 2-4 k cycles per chunk, tools/unet_gemm_dbg.py.)  Needs the sample index to be
+    // warp-uniform: a warp's 32 rows are 32 pixels of one sample whenever tw*th % 32 == 0 (or the tile is one sample).
+    // BLOCK_N = 256 (the GEGLU tile; 5 pair stages leave no room) keeps its scratch in the upper half of the slot, which its
+    // 16-bit-only epilogue never stages into; a plain epilogue on a 256-wide tile (op-level tests only) takes the per-thread loads
+    constexpr bool DEDICATED_SCR = BLOCK_N != 256;
+    float* wscr = reinterpret_cast<float*>(bar_gen + 8 * (2 * STAGES + 6 + NUM_SLOTS)) + ew * BIAS_SCR_FLOATS;
+    const bool bias_uniform = DEDICATED_SCR && ((rowbias == nullptr) || p.tn == 1 || ((p.tw * p.th) & 31) == 0);
+    const bool bias_any = (p.bias != nullptr) || (rowbias != nullptr);
+    int bpf_key = -1;
+    float bpf0 = 0.0f, bpf1 = 0.0f;
+    // columns [col0, col0 + 32) (+ the gate columns col0 + BLOCK_N/2 for GEGLU) of sample on_w
+    auto bias_fetch = [&](int key, int col0, int on_w) {
+      bpf_key = key;
+      bpf0 = 0.0f; bpf1 = 0.0f;
+      const int col = col0 + lane;
+      if (geglu) {
+        bpf0 = __ldg(p.bias + col);
+        bpf1 = __ldg(p.bias + col + BLOCK_N / 2);
+      } else if (col < p.n_total) {
+        // two registers, summed at the point of use one chunk later: an add here would stall the warp on both loads
+        if (p.bias != nullptr) bpf0 = __ldg(p.bias + col);
+        if (rowbias != nullptr && on_w < p.Nb) bpf1 = __ldg(rowbias + static_cast<long long>(on_w) * p.rowbias_ld + col);
+      }
+    };
+
     int ti = 0;
     int seq = 0;  // chunks consumed by this warp-set
     // debug counters of CTA 0, epilogue warp 3 (not the electing warp): total, waiting for an accumulator, slot, barrier
     const bool edbg = p.debug != 0 && blockIdx.x == 0 && warp == 3 && lane == 0;
-    long long e_all = edbg ? clock64() : 0, e_full = 0, e_slot = 0, e_bar = 0;
+    long long e_all = edbg ? clock64() : 0, e_full = 0, e_slot = 0, e_bar = 0, e_ld = 0, e_pack = 0, e_fence = 0, e_chunks = 0, tc0 = 0;
     // position of my accumulator row inside a tile: constant over all tiles
     const int wl = row % p.tw;
     const int hl = (row / p.tw) % p.th;
@@ -397,6 +427,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 n0 = (tc.ni * mn + cn) * p.tn;
       const int n_base = n_tile * BLOCK_N;
       const int ow = w0 + wl, oh = h0 + hl, on = n0 + nl;
+      const int on_w = __shfl_sync(0xffffffffu, on, 0);
+      // the chunk this warp-set handles first in its next tile (bias prefetch across the tile boundary)
+      TileCoord tcn = tc;
+      tile_coord_advance(tcn, tstep);
+      const bool next_tile_ok = tile + vgrid < total_tiles;
+      const int next_c_first = (ws + ti + 1) & 1;
+      const int next_on_w = __shfl_sync(0xffffffffu, (tcn.ni * mn + cn) * p.tn + nl, 0);
       const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
       const long long my_m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
 
@@ -447,6 +484,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (last_c < 0 && lane == 0) tmem_empty_arrive(buf);
 #pragma unroll 1
       for (int c = c_first; c <= last_c; c += 2, ++seq) {
+        if (edbg) { tc0 = clock64(); ++e_chunks; }
         const int slot = ws * 2 + (seq & 1);
         const uint32_t slot_addr = slot_base + slot * SLOT_BYTES;
         uint8_t* slot_gen = slot_gen_base + slot * SLOT_BYTES;
@@ -459,10 +497,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // this chunk's 32 value + 32 gate biases: one coalesced load per lane, broadcast through a per-warp scratch in
           // the unused upper half of the slot (bf16-only epilogues stage 8 KB of the 16 KB).  Sixteen float4 __ldg's
           // inside the GELU math stalled every group of four outputs on a global-load round trip.
-          float* bscr = reinterpret_cast<float*>(slot_gen + 8192 + (ew & 3) * 256);
+          float* bscr = DEDICATED_SCR ? wscr : reinterpret_cast<float*>(slot_gen + 8192 + (ew & 3) * 512);
           {
-            const float b_val = __ldg(p.bias + n_base + c * 32 + lane);
-            const float b_gate = __ldg(p.bias + n_base + HALF + c * 32 + lane);
+            if (bpf_key != tile * 8 + c) bias_fetch(tile * 8 + c, n_base + c * 32, on_w);   // warp-uniform; normally prefetched
+            const float b_val = bpf0, b_gate = bpf1;
+            if (c + 2 <= last_c) bias_fetch(tile * 8 + c + 2, n_base + (c + 2) * 32, on_w);
+            else if (next_tile_ok) bias_fetch((tile + vgrid) * 8 + next_c_first, tcn.nt * BLOCK_N + next_c_first * 32, next_on_w);
             __syncwarp();   // previous chunk's reads of the scratch are done
             bscr[lane] = b_val;
             bscr[32 + lane] = b_gate;
@@ -496,25 +536,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           uint32_t v[32];
           tmem_ld_x32(taddr + c * 32, v);
+          const int col = n_base + c * 32;
+          if (bias_uniform && bias_any) {
+            if (bpf_key != tile * 8 + c) bias_fetch(tile * 8 + c, col, on_w);   // warp-uniform; normally prefetched a chunk ago
+            const float cb = bpf0 + bpf1;
+            if (c + 2 <= last_c) bias_fetch(tile * 8 + c + 2, n_base + (c + 2) * 32, on_w);
+            else if (next_tile_ok) bias_fetch((tile + vgrid) * 8 + next_c_first, tcn.nt * BLOCK_N + next_c_first * 32, next_on_w);
+            __syncwarp();   // previous chunk's reads of the scratch are done
+            wscr[lane] = cb;
+            __syncwarp();
+          }
           tmem_ld_wait();
           if (c == last_c) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) tmem_empty_arrive(buf);
           }
-          const int col = n_base + c * 32;
+          if (bias_uniform) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias != nullptr && col + j < p.n_total) a = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-            if (rowbias != nullptr && my_valid && col + j < p.n_total) {
-              const float4 rb = __ldg(reinterpret_cast<const float4*>(rowbias + static_cast<long long>(on) * p.rowbias_ld + col + j));
-              a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
+            for (int j = 0; j < 32; j += 4) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias_any) a = *reinterpret_cast<const float4*>(wscr + j);
+              o[j + 0] = __uint_as_float(v[j + 0]) + a.x;
+              o[j + 1] = __uint_as_float(v[j + 1]) + a.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + a.z;
+              o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
             }
-            o[j + 0] = __uint_as_float(v[j + 0]) + a.x;
-            o[j + 1] = __uint_as_float(v[j + 1]) + a.y;
-            o[j + 2] = __uint_as_float(v[j + 2]) + a.z;
-            o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
+          } else {   // tiles whose warps straddle samples (tiny feature maps): per-thread loads
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias != nullptr && col + j < p.n_total) a = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+              if (rowbias != nullptr && my_valid && col + j < p.n_total) {
+                const float4 rb = __ldg(reinterpret_cast<const float4*>(rowbias + static_cast<long long>(on) * p.rowbias_ld + col + j));
+                a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
+              }
+              o[j + 0] = __uint_as_float(v[j + 0]) + a.x;
+              o[j + 1] = __uint_as_float(v[j + 1]) + a.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + a.z;
+              o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
+            }
           }
           if (p.act == 1) {   // quick_gelu (CLIP MLP): x * sigmoid(1.702 x)
 #pragma unroll
@@ -522,11 +583,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // the slot is ours once the residual prefetch (or the plain arrive that stands in for it) has landed
-        if (edbg) te = clock64();
+        if (edbg) { te = clock64(); e_ld += te - tc0; }
         // Without a residual nothing is prefetched into the slot: it is free once the store issued from it two
         // chunks ago has read it, which the storing warp checks before it joins the previous chunk's barrier (below).
         if (p.has_res) mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
-        if (edbg) e_slot += clock64() - te;
+        if (edbg) { tc0 = clock64(); e_slot += tc0 - te; }
         uint8_t* my_row128 = slot_gen + row * 128;
         if (p.has_res && p.res16) {
           // 16-bit residual stream: the box landed in the compact [128 rows x 64 B] layout (64B swizzle) the 16-bit output
@@ -659,11 +720,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        if (edbg) { te = clock64(); e_pack += te - tc0; }
         fence_async_smem();
         const int ocol = n_tile * tile_out_cols + c * chunk_cols;
-        if (edbg) te = clock64();
+        if (edbg) { tc0 = clock64(); e_fence += tc0 - te; te = tc0; }
         if (p.has_res) {
           named_bar_sync(bar_id, 128);
+          if (edbg) e_bar += clock64() - te;
           if (elected) {
             if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
             else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
@@ -690,6 +753,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       g_gemm_dbg[5] = clock64() - e_all;
       g_gemm_dbg[6] = e_full;
       g_gemm_dbg[7] = (e_slot << 32) | (e_bar & 0xffffffffll);
+      g_gemm_dbg[8] = e_ld; g_gemm_dbg[9] = e_pack; g_gemm_dbg[10] = e_fence; g_gemm_dbg[11] = e_chunks;
     }
     if (store_warp) tma_store_wait_all();
   }
@@ -705,7 +769,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BLOCK_N, int STAGES, int CL>
 constexpr size_t smem_bytes_for() {
-  return 1024 + STAGES * (A_STAGE_BYTES + (BLOCK_N / CL) * BLOCK_K * 2) + EPI_STAGING_BYTES + 8 * (2 * STAGES + 6 + NUM_SLOTS);
+  return 1024 + STAGES * (A_STAGE_BYTES + (BLOCK_N / CL) * BLOCK_K * 2) + EPI_STAGING_BYTES + 8 * (2 * STAGES + 6 + NUM_SLOTS) +
+         (BLOCK_N != 256 ? BIAS_SCR_BYTES : 0);
 }
 
 template <int BLOCK_N, int STAGES, int CL>
@@ -834,6 +899,17 @@ int auto_block_n(const ConvGemmDesc& d) {
 
 int gemm_read_debug_counters(long long* out8) {
   PBE_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(long long) * 8));
+  return 0;
+}
+
+int gemm_read_debug_counters16(long long* out16) {
+  PBE_CHECK_CUDA(cudaMemcpyFromSymbol(out16, g_gemm_dbg, sizeof(long long) * 16));
+  return 0;
+}
+
+int gemm_reset_debug_counters() {
+  const long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  PBE_CHECK_CUDA(cudaMemcpyToSymbol(g_gemm_dbg, z, sizeof(z)));
   return 0;
 }
 
@@ -1096,7 +1172,7 @@ static int launch_main(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.block_n) {
     // stages: single CTA / CTA pair (half weight tile per CTA)
     case 32: return launch_t<32, 6, 8>(plan, stream);
-    case 64: return launch_t<64, 6, 8>(plan, stream);
+    case 64: return launch_t<64, 6, 7>(plan, stream);
     case 128: return launch_t<128, 4, 6>(plan, stream);
     case 160: return launch_t<160, 4, 6>(plan, stream);
     case 256: return launch_t<256, 3, 5>(plan, stream);

@@ -175,6 +175,8 @@ struct ConvGemmDesc {
 };
 // Split factor build_gemm_plan will use for this problem when a workspace is supplied (1 = no split), and its size.
 int gemm_read_debug_counters(long long* out8);
+int gemm_reset_debug_counters();
+int gemm_read_debug_counters16(long long* out16);
 int gemm_split_k(const ConvGemmDesc& d);
 // True when the epilogue can emit per-32-row column statistics for this geometry (no split-K, aligned tiles).
 bool gemm_can_fuse_stats(const ConvGemmDesc& d);
