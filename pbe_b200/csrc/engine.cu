@@ -102,6 +102,52 @@ static uint16_t f32_to_f16_rn_sat(float f) {
   return static_cast<uint16_t>(sign | (q + ((rem > 0x1000u || (rem == 0x1000u && (q & 1u))) ? 1u : 0u)));
 }
 
+static float f16_bits_to_f32(uint16_t h) {
+  const uint32_t sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  uint32_t u;
+  if (e == 0) {
+    if (m == 0) u = sign;
+    else {   // subnormal: renormalise
+      int sh = 0;
+      uint32_t mm = m;
+      while (!(mm & 0x400u)) { mm <<= 1; ++sh; }
+      u = sign | (static_cast<uint32_t>(127 - 15 - sh + 1) << 23) | ((mm & 0x3ffu) << 13);
+    }
+  } else if (e == 31) u = sign | 0x7f800000u | (m << 13);
+  else u = sign | ((e + 112u) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+float WeightLoader::round_operand(float v) const {
+  if (fmt_f16_) return f16_bits_to_f32(f32_to_f16_rn_sat(v));
+  const uint32_t u = static_cast<uint32_t>(f32_to_bf16_rn(v)) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// LayerNorm folded into the linear layer behind it: y = W LN(x) + b with LN(x) = (x - mean) rstd gamma + beta becomes
+//   y = rstd * (W'' x) + b',   W''[o][i] = W[o][i] gamma[i] - mean_i(W[o][:] gamma[:]),   b'[o] = b[o] + sum_i W[o][i] beta[i]
+// (rows of W'' sum to zero, so W'' x = W'' (x - mean): the GEMM runs on the raw tensor and only rstd is left for its epilogue).
+void WeightLoader::fold_layernorm(std::vector<float>& w, std::vector<float>& bias, const std::vector<float>& gamma,
+                                  const std::vector<float>& beta, int rows, int c) const {
+  bias.resize(rows, 0.0f);
+  for (int o = 0; o < rows; ++o) {
+    float* wr = &w[static_cast<size_t>(o) * c];
+    double b = bias[o], cs = 0.0;
+    for (int i = 0; i < c; ++i) {
+      b += static_cast<double>(beta[i]) * wr[i];
+      wr[i] *= gamma[i];
+      cs += wr[i];
+    }
+    const float centre = static_cast<float>(cs / c);
+    for (int i = 0; i < c; ++i) wr[i] -= centre;
+    bias[o] = static_cast<float>(b);
+  }
+}
+
 // GEMM weights in the library's operand format (fp16 by default, internal.h: operand_f16)
 int WeightLoader::upload_bf16(const std::vector<float>& v, bf16** dst) {
   std::vector<uint16_t> h(v.size());
@@ -261,6 +307,32 @@ int Engine::finalize() {
       w.insert(w.end(), Q->data.begin(), Q->data.end());
       w.insert(w.end(), K->data.begin(), K->data.end());
       w.insert(w.end(), V->data.begin(), V->data.end());
+      {   // norm1 folded into the projection.  to_q / to_k / to_v have no bias of their own; beta's image under them is:
+          //   q: a real bias (kept: columns [0, c) of the GEMM);
+          //   k: q . b_k is constant over the keys of a query row and cancels in the softmax -> dropped;
+          //   v: sum_j p_j (v_j + b_v) = (sum_j p_j v_j) + b_v -> leaves the attention untouched and becomes W_out b_v in
+          //      attn1.to_out's bias (added to the host copy here, before to_out is repacked below).
+        const HostTensor *G, *Bt;
+        if ((e = get(tb + ".norm1.weight", &G))) return e;
+        if ((e = get(tb + ".norm1.bias", &Bt))) return e;
+        std::vector<float> bias;
+        fold_layernorm(w, bias, G->data, Bt->data, 3 * c, c);
+        std::vector<float> bq(bias.begin(), bias.begin() + c);
+        bq.resize(3 * c, 0.0f);
+        if ((e = upload_f32(bq, &s.qkv.b))) return e;
+        const HostTensor* WO;
+        if ((e = get(tb + ".attn1.to_out.0.weight", &WO))) return e;
+        auto ob = host_.find(tb + ".attn1.to_out.0.bias");
+        if (ob == host_.end() || ob->second.data.size() != static_cast<size_t>(c) || WO->data.size() != cc) {
+          set_error("attn1.to_out of " + pfx + " has wrong size");
+          return -4;
+        }
+        for (int o = 0; o < c; ++o) {
+          double acc = ob->second.data[o];
+          for (int i = 0; i < c; ++i) acc += static_cast<double>(WO->data[static_cast<size_t>(o) * c + i]) * bias[2 * c + i];
+          ob->second.data[o] = static_cast<float>(acc);
+        }
+      }
       if ((e = upload_bf16(w, &s.qkv.w))) return e;
       s.qkv.cin = s.qkv.cin_pad = c; s.qkv.cout = 3 * c; s.qkv.k = 1;
     }
@@ -285,6 +357,12 @@ int Engine::finalize() {
           b[dst_v] = B->data[src_v];
           b[dst_g] = B->data[src_g];
         }
+      {   // norm3 folded into the GEGLU projection
+        const HostTensor *G, *Bt;
+        if ((e = get(tb + ".norm3.weight", &G))) return e;
+        if ((e = get(tb + ".norm3.bias", &Bt))) return e;
+        fold_layernorm(w, b, G->data, Bt->data, 2 * inner, c);
+      }
       if ((e = upload_bf16(w, &s.ff1.w))) return e;
       if ((e = upload_f32(b, &s.ff1.b))) return e;
       s.ff1.cin = s.ff1.cin_pad = c; s.ff1.cout = 2 * inner; s.ff1.k = 1;
@@ -422,6 +500,9 @@ int Engine::finalize() {
     PBE_CHECK_CUDA(cudaMalloc(&p, static_cast<size_t>(MAX_BC) * cmax * sizeof(float)));
     dev_allocs_.push_back(p);
     ctx_tmp_ = static_cast<float*>(p);
+    std::vector<float> ones(cmax, 1.0f), zeros(cmax, 0.0f);
+    if ((rc = upload_f32(ones, &ln_ones_))) return rc;
+    if ((rc = upload_f32(zeros, &ln_zeros_))) return rc;
   }
   host_.clear();
   finalized_ = true;
@@ -582,6 +663,17 @@ int Engine::build(Prepared& P, bool dry) {
     o.has_stats = true;
     d.stats_out = o.stats;
   };
+  // LayerNorm fold: let GEMM `d` (writing a [rows_total, Cout] 16-bit tensor, of which it may cover a slice) emit per-row
+  // statistics partials; returns the number of partials (0: not available -> normalise-only pass)
+  auto want_ln_stats = [&](ConvGemmDesc& d, size_t rows_total, float2** stats) -> int {
+    if (!s16 || !ln_fold_) return 0;
+    const int parts = gemm_ln_parts(d);
+    if (parts <= 0 || parts > 16) return 0;
+    *stats = static_cast<float2*>(SA(static_cast<size_t>(parts) * rows_total * sizeof(float2)));
+    d.ln_stats_out = *stats;
+    d.ln_stats_stride = static_cast<long long>(rows_total);
+    return parts;
+  };
   std::vector<Act> hs;
   Act h{nullptr, nullptr, 0, H0, W0};
 
@@ -681,6 +773,8 @@ int Engine::build(Prepared& P, bool dry) {
         const int C = s.c, N = h.H * h.W;
         size_t M = static_cast<size_t>(Bc) * N;
         if (C != h.C) { err = -5; last_error = "channel mismatch at " + tag; return err; }
+        float2 *ln1_stats = nullptr, *ln3_stats = nullptr;
+        int ln1_parts = 0, ln3_parts = 0;
         bf16* a = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
         GroupNormArgs g{};
         g.x0 = as_f32ptr(h); g.C0 = C; g.x1 = nullptr; g.C1 = 0; g.Nb = Bc; g.HW = N;
@@ -694,11 +788,14 @@ int Engine::build(Prepared& P, bool dry) {
           d.act = a; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.proj_in.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_in.b;
           set_out(d, t0);
+          ln1_parts = want_ln_stats(d, M, &ln1_stats);
           add_gemm(tag + ".proj_in", d);
         }
-        bf16* n1 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
-        {
-          const float *gg = s.ln1.g, *bb = s.ln1.b;
+        // norm1 (attention.py:271): gamma / beta live in the qkv weights; either the row statistics come out of proj_in's
+        // epilogue and qkv finishes the normalisation in its own (no pass over the tensor at all), or a normalise-only pass
+        bf16* n1 = ln1_parts ? t0.b16 : static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        if (!ln1_parts) {
+          const float *gg = ln_ones_, *bb = ln_zeros_;
           const int Mi = static_cast<int>(M);
           const float* src = as_f32ptr(t0);
           const int in16 = s16 ? 1 : 0;
@@ -712,6 +809,8 @@ int Engine::build(Prepared& P, bool dry) {
           d.act = n1; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.qkv.w; d.Cout = 3 * C; d.mode = EPI_QKV; d.out_bf16 = qk; d.ld_out = 2 * C; d.out_vt = vt;
           d.qk_cols = 2 * C;
+          d.bias = s.qkv.b; d.bias_cols = C;   // only q keeps the image of norm1's beta (finalize)
+          if (ln1_parts) { d.ln_in = ln1_stats; d.ln_stride = static_cast<long long>(M); d.ln_parts = ln1_parts; d.ln_eps = 1e-5f; }
           d.out16_bf16 = 1;   // Q | K | V^T feed the flash-attention kernels, which work in bf16 (P lives far below the fp16 range)
           d.block_n = (C % 160 == 0) ? 160 : ((C % 128 == 0) ? 128 : 64);
           add_gemm(tag + ".qkv", d);
@@ -727,6 +826,7 @@ int Engine::build(Prepared& P, bool dry) {
           launches += 1;
         }
         Act t1 = new_act(false, M * (diverged ? 1 : 2) * C, C, h.H, h.W);
+        const size_t M_t1 = M * (diverged ? 1 : 2);   // rows of t1 (the CFG-pair prefix writes it in two halves)
         for (int half = 0; half < (diverged ? 1 : 2); ++half) {
           // x1 = to_out(attn) + b + x ; x2 = x1 + to_out2(to_v2(ctx))  (single-key cross-attention, folded).
           // CFG pair plan: this is where the context enters -- the shared activations feed one GEMM per half, each
@@ -741,6 +841,9 @@ int Engine::build(Prepared& P, bool dry) {
           if (s16) dst.b16 = t1.b16 + static_cast<size_t>(half) * M * C;
           else dst.f32 = t1.f32 + static_cast<size_t>(half) * M * C;
           set_out(d, dst);
+          if (half == 0) ln3_parts = want_ln_stats(d, M_t1, &ln3_stats);
+          else if (ln3_parts) { d.ln_stats_out = ln3_stats; d.ln_stats_stride = static_cast<long long>(M_t1); }
+          if (ln3_parts) d.ln_stats_out = ln3_stats + static_cast<size_t>(half) * M;
           add_gemm(tag + (half ? ".attn1.to_out+attn2[cond]" : ".attn1.to_out+attn2"), d);
         }
         if (!diverged) {
@@ -778,9 +881,9 @@ int Engine::build(Prepared& P, bool dry) {
           Bc = BcFull;
           M = static_cast<size_t>(Bc) * N;
         }
-        bf16* n3 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
-        {
-          const float *gg = s.ln3.g, *bb = s.ln3.b;
+        bf16* n3 = ln3_parts ? t1.b16 : static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        if (!ln3_parts) {
+          const float *gg = ln_ones_, *bb = ln_zeros_;
           const int Mi = static_cast<int>(M);
           const float* src = as_f32ptr(t1);
           const int in16 = s16 ? 1 : 0;
@@ -792,6 +895,7 @@ int Engine::build(Prepared& P, bool dry) {
           ConvGemmDesc d{};
           d.act = n3; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.ff1.w; d.Cout = 8 * C; d.mode = EPI_GEGLU; d.bias = s.ff1.b; d.out_bf16 = gg; d.ld_out = 4 * C;
+          if (ln3_parts) { d.ln_in = ln3_stats; d.ln_stride = static_cast<long long>(M); d.ln_parts = ln3_parts; d.ln_eps = 1e-5f; }
           add_gemm(tag + ".ff.geglu", d);
         }
         bf16* t2 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));

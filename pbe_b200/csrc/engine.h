@@ -113,6 +113,10 @@ class WeightLoader {
   int make_norm(const std::string& prefix, int c, NormW* n);
   int upload_f32(const std::vector<float>& v, float** dst);
   int upload_bf16(const std::vector<float>& v, bf16** dst);
+  float round_operand(float v) const;   // v rounded to the 16-bit operand format and back
+  // LayerNorm fold (norm1 -> qkv, norm3 -> GEGLU projection): gamma into the weight columns, rows centred, beta into the bias
+  void fold_layernorm(std::vector<float>& w, std::vector<float>& bias, const std::vector<float>& gamma,
+                      const std::vector<float>& beta, int rows, int c) const;
   std::unordered_map<std::string, HostTensor> host_;
   int fmt_f16_ = operand_f16();   // operand format the weights are repacked in (fixed at construction)
   bool finalized_ = false;
@@ -147,6 +151,9 @@ class Engine : public WeightLoader {
     return operand_f16() != 0;
   }();
   // nearest-2x upsample + 3x3 conv as four sub-pixel phase convs (16-bit stream only); PBE_SUBPIXEL_UP=0: the literal form
+  // LayerNorm statistics from the producing GEMM's epilogue, applied in the consuming GEMM's epilogue (16-bit stream only);
+  // PBE_LN_FOLD=0: a standalone normalise-only LayerNorm pass in front of the same (gamma / beta folded) GEMMs
+  int ln_fold_ = [] { const char* e = getenv("PBE_LN_FOLD"); return e == nullptr ? 1 : atoi(e); }();
   int subpixel_up_ = [] { const char* e = getenv("PBE_SUBPIXEL_UP"); return e == nullptr ? 1 : atoi(e); }();   // 2: at every size (tests)
   std::string last_error;
 
@@ -172,6 +179,7 @@ class Engine : public WeightLoader {
   // context-dependent state (folded single-key cross-attention, K4)
   float* ctx_vecs_ = nullptr;  // [ctx_Bc, ctx_total_]
   float* ctx_tmp_ = nullptr;
+  float *ln_ones_ = nullptr, *ln_zeros_ = nullptr;   // unit affine for the normalise-only LayerNorm pass
   int ctx_Bc_ = 0;
 
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Prepared>> prepared_;

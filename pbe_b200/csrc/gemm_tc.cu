@@ -92,6 +92,16 @@ __device__ __forceinline__ void geglu_block(f32x2* a, const f32x2* g) {
   for (int i = 0; i < NP; ++i) a[i] = mul2(a[i], mul2(g[i], u[i]));
 }
 
+// LayerNorm fold, writing side: add eight rounded 16-bit outputs of a row to its packed (sum, sum of squares) accumulators
+__device__ __forceinline__ void ln_accumulate(const uint4& pk, f32x2& s2, f32x2& q2, int f16) {
+  const float2 a = unpack_op2(pk.x, f16), b = unpack_op2(pk.y, f16), c = unpack_op2(pk.z, f16), d = unpack_op2(pk.w, f16);
+  const f32x2 va = pk2(a.x, a.y), vb = pk2(b.x, b.y), vc = pk2(c.x, c.y), vd = pk2(d.x, d.y);
+  s2 = add2(s2, va); q2 = fma2(va, va, q2);
+  s2 = add2(s2, vb); q2 = fma2(vb, vb, q2);
+  s2 = add2(s2, vc); q2 = fma2(vc, vc, q2);
+  s2 = add2(s2, vd); q2 = fma2(vd, vd, q2);
+}
+
 // Work-unit coordinates (split slice, n tile, w / h / batch tile) advanced incrementally: unit += gridDim.x is a
 // mixed-radix addition with carries (a dozen integer ops) instead of five runtime divisions per tile and role
 // (ncu on the short-K GEMMs: index arithmetic was ~half of the epilogue's instruction stream).
@@ -328,10 +338,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int bar_id = 1 + ws;
     const bool elected = ((ew & 3) == 0) && lane == 0;
     const int row = q * 32 + lane;
-    const bool geglu = (p.mode == EPI_GEGLU);
+    constexpr bool geglu = BLOCK_N == 256;   // the 256-wide tile exists for the GEGLU epilogue only (build_gemm_plan enforces it)
+    // epilogue features as locals that fold to constants in the GEGLU kernel: its epilogue (16-bit output, bias, optional
+    // LayerNorm fold -- nothing else) then compiles without the residual / fp32 / statistics / V^T paths and their registers
+    const bool e_has_res = !geglu && p.has_res, e_has_o32 = !geglu && p.has_o32, e_has_o16 = geglu || p.has_o16;
+    const bool e_qkv = !geglu && p.mode == EPI_QKV;
+    float* const e_stats_out = geglu ? nullptr : p.stats_out;
+    float2* const e_ln_stats_out = geglu ? nullptr : p.ln_stats_out;
+    const int e_act = geglu ? 0 : p.act;
     const int chunk_cols = 32;
     const int nchunks = geglu ? (BLOCK_N / 2) / 32 : BLOCK_N / 32;
-    const int out_cols_total = geglu ? p.n_total / 2 : (p.mode == EPI_QKV ? p.qk_cols : p.n_total);
+    const int out_cols_total = geglu ? p.n_total / 2 : (e_qkv ? p.qk_cols : p.n_total);
     const int tile_out_cols = geglu ? BLOCK_N / 2 : BLOCK_N;
     const uint32_t slot_base = smem_base + PIPE_BYTES;
     uint8_t* slot_gen_base = smem_gen + PIPE_BYTES;
@@ -342,11 +359,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (CL == 2) mbar_arrive_cluster(lead_tmem_empty0 + 8u * b);
       else mbar_arrive(tmem_empty_bar(b));
     };
-    const float* __restrict__ rowbias = p.rowbias;
+    const float* __restrict__ rowbias = geglu ? nullptr : p.rowbias;
     bf16* __restrict__ out_bf16 = p.out_bf16;
 
     const int nb_pad = p.tiles_n * p.tn;
-    auto tile_is_vt = [&](int n_tile) { return p.mode == EPI_QKV && n_tile * BLOCK_N >= p.qk_cols; };
+    auto tile_is_vt = [&](int n_tile) { return e_qkv && n_tile * BLOCK_N >= p.qk_cols; };
     auto chunk_valid = [&](int n_tile, int c) { return c < nchunks && n_tile * tile_out_cols + c * chunk_cols < out_cols_total; };
 
     // ---- prefetch iterator (elected thread): walks the chunks this warp-set will consume, in order ----
@@ -359,7 +376,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   n0 = (pf_tc.ni * mn + cn) * p.tn;
         if (!tile_is_vt(n_tile) && chunk_valid(n_tile, pf_c)) {
           const int slot = ws * 2 + (pf_seq & 1);
-          if (p.has_res) {
+          if (e_has_res) {
             mbar_expect_tx(res_full_bar(slot), p.res16 ? SLOT_BYTES / 2 : SLOT_BYTES);   // 16-bit residual: 128 rows x 64 B
             tma_load_4d(slot_base + slot * SLOT_BYTES, &tmR, res_full_bar(slot), n_tile * tile_out_cols + pf_c * chunk_cols,
                         w0, h0, n0);
@@ -377,7 +394,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pf_c = (ws + pf_ti) & 1;
       }
     };
-    if (elected && p.has_res) {
+    if (elected && e_has_res) {
       pf_issue_next();
       pf_issue_next();
     }
@@ -396,6 +413,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool bias_any = (p.bias != nullptr) || (rowbias != nullptr);
     int bpf_key = -1;
     float bpf0 = 0.0f, bpf1 = 0.0f;
+    const bool ln_on = p.ln_in != nullptr;
     // columns [col0, col0 + 32) (+ the gate columns col0 + BLOCK_N/2 for GEGLU) of sample on_w
     auto bias_fetch = [&](int key, int col0, int on_w) {
       bpf_key = key;
@@ -415,11 +433,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int seq = 0;  // chunks consumed by this warp-set
     // debug counters of CTA 0, epilogue warp 3 (not the electing warp): total, waiting for an accumulator, slot, barrier
     const bool edbg = p.debug != 0 && blockIdx.x == 0 && warp == 3 && lane == 0;
-    long long e_all = edbg ? clock64() : 0, e_full = 0, e_slot = 0, e_bar = 0, e_ld = 0, e_pack = 0, e_fence = 0, e_chunks = 0, tc0 = 0;
+    // debug counters accumulate straight into g_gemm_dbg (zeroed by the host): no registers held across the chunk loop
+    const unsigned e_all = edbg ? static_cast<unsigned>(clock()) : 0u;
+    unsigned tc0 = 0u, te = 0u;
+    auto dbg_add = [&](int i, unsigned d) { g_gemm_dbg[i] += d; };
     // position of my accumulator row inside a tile: constant over all tiles
     const int wl = row % p.tw;
     const int hl = (row / p.tw) % p.th;
     const int nl = row / (p.tw * p.th);
+    float2 lnp0 = make_float2(0.f, 0.f), lnp1 = lnp0, lnp2 = lnp0, lnp3 = lnp0;   // LayerNorm-fold row partials of the next tile
+    int lnp_tile = -1;
     TileCoord tc = tile_coord_from_unit(vblock, tstep);
     for (int tile = vblock; tile < total_tiles; tile += vgrid, ++ti, tile_coord_advance(tc, tstep)) {
       const int buf = ti & 1;
@@ -437,9 +460,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool my_valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Nb);
       const long long my_m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
 
-      long long te = edbg ? clock64() : 0;
+      // LayerNorm fold, reading side: this row's (sum, sum of squares) partials -> rstd and -mean * rstd.  The loads are
+      // issued before the accumulator wait and summed in a fixed order (part 0, 1, ...).
+      float ln_r = 1.0f;
+      if (ln_on) {
+        float s_sum = 0.0f, s_sq = 0.0f;
+        if (lnp_tile == tile) {   // prefetched while the previous tile was processed (rows with at most four partials)
+          s_sum = ((lnp0.x + lnp1.x) + lnp2.x) + lnp3.x;
+          s_sq = ((lnp0.y + lnp1.y) + lnp2.y) + lnp3.y;
+        } else if (my_valid) {
+          const float2* lp = p.ln_in + my_m;
+          float2 t0 = __ldg(lp), t1 = __ldg(lp + p.ln_stride), t2 = make_float2(0.f, 0.f), t3 = make_float2(0.f, 0.f);
+          if (p.ln_parts > 2) { t2 = __ldg(lp + 2 * p.ln_stride); t3 = __ldg(lp + 3 * p.ln_stride); }
+          s_sum = ((t0.x + t1.x) + t2.x) + t3.x;
+          s_sq = ((t0.y + t1.y) + t2.y) + t3.y;
+          for (int part = 4; part < p.ln_parts; ++part) {
+            const float2 t = __ldg(lp + static_cast<long long>(part) * p.ln_stride);
+            s_sum += t.x; s_sq += t.y;
+          }
+        }
+        const float mean = s_sum * p.ln_inv_c;
+        const float var = fmaxf(fmaf(s_sq, p.ln_inv_c, -mean * mean), 0.0f);
+        ln_r = rsqrtf(var + p.ln_eps);
+        // the next tile's partials: loads in flight during this whole tile, summed (in the same order) at its start
+        if (p.ln_parts <= 4 && next_tile_ok) {
+          const int ow2 = (tcn.wi * mw + cw) * p.tw + wl, oh2 = (tcn.hi * mh + ch) * p.th + hl, on2 = (tcn.ni * mn + cn) * p.tn + nl;
+          lnp0 = lnp1 = lnp2 = lnp3 = make_float2(0.f, 0.f);
+          if (ow2 < p.Wo && oh2 < p.Ho && on2 < p.Nb) {
+            const float2* lp = p.ln_in + (static_cast<long long>(on2) * p.Ho + oh2) * p.Wo + ow2;
+            lnp0 = __ldg(lp); lnp1 = __ldg(lp + p.ln_stride);
+            if (p.ln_parts > 2) { lnp2 = __ldg(lp + 2 * p.ln_stride); lnp3 = __ldg(lp + 3 * p.ln_stride); }
+          }
+          lnp_tile = tile + vgrid;
+        }
+      }
+      // writing side: this thread's row statistics over the chunks it handles in this tile
+      f32x2 ln_s2 = pk2(0.0f, 0.0f), ln_q2 = pk2(0.0f, 0.0f);
+      if (edbg) te = static_cast<unsigned>(clock());
       mbar_wait(tmem_full_bar(buf), (ti >> 1) & 1);
-      if (edbg) e_full += clock64() - te;
+      if (edbg) dbg_add(6, static_cast<unsigned>(clock()) - te);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
       const int c_first = (ws + ti) & 1;
@@ -453,6 +512,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = c_first; c <= last_c; c += 2) {
           uint32_t v[32];
           tmem_ld_x32(taddr + c * 32, v);
+          const bool vt_bias = p.bias != nullptr && n_base < p.bias_cols;
+          if (vt_bias) {   // v projection with a bias (VAE attention; none in the U-Net): through the per-warp scratch, as below
+            if (bpf_key != tile * 8 + c) bias_fetch(tile * 8 + c, n_base + c * 32, on_w);
+            const float cb = bpf0 + bpf1;
+            if (c + 2 <= last_c) bias_fetch(tile * 8 + c + 2, n_base + (c + 2) * 32, on_w);
+            else if (next_tile_ok) bias_fetch((tile + vgrid) * 8 + next_c_first, tcn.nt * BLOCK_N + next_c_first * 32, next_on_w);
+            __syncwarp();
+            wscr[lane] = cb;
+            __syncwarp();
+          }
           tmem_ld_wait();
           if (c == last_c) {
             tc_fence_before();
@@ -467,9 +536,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long tok = p.vt_tokens ? my_m - smp * ntok : static_cast<long long>(oh) * p.Wo + ow;
             const int vC = p.n_total - p.qk_cols;
             bf16* dst = p.out_vt + (smp * vC + (n_base + c * 32 - p.qk_cols)) * tokens + tok;
-            if (p.bias != nullptr) {   // v projection with a bias (VAE attention; the U-Net's to_v has none)
+            // rstd * acc (LayerNorm fold; rstd = 1 without it) + bias
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n_base + c * 32 + j));
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a = vt_bias ? *reinterpret_cast<const float4*>(wscr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[j + 0] = __float_as_uint(fmaf(ln_r, __uint_as_float(v[j + 0]), a.x));
+              v[j + 1] = __float_as_uint(fmaf(ln_r, __uint_as_float(v[j + 1]), a.y));
+              v[j + 2] = __float_as_uint(fmaf(ln_r, __uint_as_float(v[j + 2]), a.z));
+              v[j + 3] = __float_as_uint(fmaf(ln_r, __uint_as_float(v[j + 3]), a.w));
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -484,12 +558,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (last_c < 0 && lane == 0) tmem_empty_arrive(buf);
 #pragma unroll 1
       for (int c = c_first; c <= last_c; c += 2, ++seq) {
-        if (edbg) { tc0 = clock64(); ++e_chunks; }
+        if (edbg) { tc0 = static_cast<unsigned>(clock()); dbg_add(11, 1u); }
         const int slot = ws * 2 + (seq & 1);
         const uint32_t slot_addr = slot_base + slot * SLOT_BYTES;
         uint8_t* slot_gen = slot_gen_base + slot * SLOT_BYTES;
         float o[32];
-        if (geglu) {
+        if constexpr (geglu) {
           constexpr int HALF = BLOCK_N / 2;
           uint32_t va[32], vg[32];
           tmem_ld_x32(taddr + c * 32, va);
@@ -517,6 +591,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // eight output pairs per block, evaluated stage by stage: every dependent step of the GELU polynomial has
           // seven independent neighbours to hide its latency behind (two warps per scheduler cannot)
 #pragma unroll
+          const f32x2 r2 = pk2(ln_r, ln_r);
+#pragma unroll
           for (int j0 = 0; j0 < 32; j0 += 16) {
             f32x2 av[8], gv[8];
 #pragma unroll
@@ -524,10 +600,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float4 ba = *reinterpret_cast<const float4*>(bscr + j0 + 4 * i);
               const float4 bg = *reinterpret_cast<const float4*>(bscr + 32 + j0 + 4 * i);
               const int j = j0 + 4 * i;
-              av[2 * i] = add2(pk2(__uint_as_float(va[j + 0]), __uint_as_float(va[j + 1])), pk2(ba.x, ba.y));
-              av[2 * i + 1] = add2(pk2(__uint_as_float(va[j + 2]), __uint_as_float(va[j + 3])), pk2(ba.z, ba.w));
-              gv[2 * i] = add2(pk2(__uint_as_float(vg[j + 0]), __uint_as_float(vg[j + 1])), pk2(bg.x, bg.y));
-              gv[2 * i + 1] = add2(pk2(__uint_as_float(vg[j + 2]), __uint_as_float(vg[j + 3])), pk2(bg.z, bg.w));
+              // LayerNorm fold: rstd * acc + bias' (rstd = 1 without it: the fma is then exactly the add)
+              av[2 * i] = fma2(r2, pk2(__uint_as_float(va[j + 0]), __uint_as_float(va[j + 1])), pk2(ba.x, ba.y));
+              av[2 * i + 1] = fma2(r2, pk2(__uint_as_float(va[j + 2]), __uint_as_float(va[j + 3])), pk2(ba.z, ba.w));
+              gv[2 * i] = fma2(r2, pk2(__uint_as_float(vg[j + 0]), __uint_as_float(vg[j + 1])), pk2(bg.x, bg.y));
+              gv[2 * i + 1] = fma2(r2, pk2(__uint_as_float(vg[j + 2]), __uint_as_float(vg[j + 3])), pk2(bg.z, bg.w));
             }
             geglu_block<8>(av, gv);
 #pragma unroll
@@ -537,7 +614,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld_x32(taddr + c * 32, v);
           const int col = n_base + c * 32;
-          if (bias_uniform && bias_any) {
+          const bool tile_bias = bias_uniform && bias_any && n_base < p.bias_cols;   // (QKV with a folded LayerNorm: only Q has a bias)
+          if (tile_bias) {
             if (bpf_key != tile * 8 + c) bias_fetch(tile * 8 + c, col, on_w);   // warp-uniform; normally prefetched a chunk ago
             const float cb = bpf0 + bpf1;
             if (c + 2 <= last_c) bias_fetch(tile * 8 + c + 2, n_base + (c + 2) * 32, on_w);
@@ -556,11 +634,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (bias_any) a = *reinterpret_cast<const float4*>(wscr + j);
-              o[j + 0] = __uint_as_float(v[j + 0]) + a.x;
-              o[j + 1] = __uint_as_float(v[j + 1]) + a.y;
-              o[j + 2] = __uint_as_float(v[j + 2]) + a.z;
-              o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
+              if (tile_bias) a = *reinterpret_cast<const float4*>(wscr + j);
+              // rstd * acc + bias (LayerNorm fold); rstd = 1 without it and the fma is exactly the add
+              o[j + 0] = fmaf(ln_r, __uint_as_float(v[j + 0]), a.x);
+              o[j + 1] = fmaf(ln_r, __uint_as_float(v[j + 1]), a.y);
+              o[j + 2] = fmaf(ln_r, __uint_as_float(v[j + 2]), a.z);
+              o[j + 3] = fmaf(ln_r, __uint_as_float(v[j + 3]), a.w);
             }
           } else {   // tiles whose warps straddle samples (tiny feature maps): per-thread loads
 #pragma unroll
@@ -577,19 +656,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o[j + 3] = __uint_as_float(v[j + 3]) + a.w;
             }
           }
-          if (p.act == 1) {   // quick_gelu (CLIP MLP): x * sigmoid(1.702 x)
+          if (e_act == 1) {   // quick_gelu (CLIP MLP): x * sigmoid(1.702 x)
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __fdividef(o[j], 1.0f + __expf(-1.702f * o[j]));
           }
         }
         // the slot is ours once the residual prefetch (or the plain arrive that stands in for it) has landed
-        if (edbg) { te = clock64(); e_ld += te - tc0; }
+        if (edbg) { te = static_cast<unsigned>(clock()); dbg_add(8, te - tc0); }
         // Without a residual nothing is prefetched into the slot: it is free once the store issued from it two
         // chunks ago has read it, which the storing warp checks before it joins the previous chunk's barrier (below).
-        if (p.has_res) mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
-        if (edbg) { tc0 = clock64(); e_slot += tc0 - te; }
+        if (e_has_res) mbar_wait(res_full_bar(slot), (seq >> 1) & 1);
+        if (edbg) { tc0 = static_cast<unsigned>(clock()); dbg_add(12, tc0 - te); }
         uint8_t* my_row128 = slot_gen + row * 128;
-        if (p.has_res && p.res16) {
+        if (e_has_res && p.res16) {
           // 16-bit residual stream: the box landed in the compact [128 rows x 64 B] layout (64B swizzle) the 16-bit output
           // uses -- a thread reads its own row here and overwrites exactly those bytes below: no barrier in between
           const uint8_t* rrow = slot_gen + row * 64;
@@ -601,19 +680,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             o[8 * u + 0] += r0.x; o[8 * u + 1] += r0.y; o[8 * u + 2] += r1.x; o[8 * u + 3] += r1.y;
             o[8 * u + 4] += r2.x; o[8 * u + 5] += r2.y; o[8 * u + 6] += r3.x; o[8 * u + 7] += r3.y;
           }
-        } else if (p.has_res) {
+        } else if (e_has_res) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float4 rr = *reinterpret_cast<const float4*>(my_row128 + ((u ^ (row & 7)) << 4));
             o[4 * u + 0] += rr.x; o[4 * u + 1] += rr.y; o[4 * u + 2] += rr.z; o[4 * u + 3] += rr.w;
           }
         }
-        if (p.has_o32) {
+        if (e_has_o32) {
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             *reinterpret_cast<float4*>(my_row128 + ((u ^ (row & 7)) << 4)) =
                 make_float4(o[4 * u + 0], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-          if (p.stats_out != nullptr) {
+          if (e_stats_out != nullptr) {
             // GroupNorm statistics of the tensor being written: lane = column, walk my warp's 32 rows of the slot
             // (conflict-free: one 128-B row per step).  Fixed order, no atomics -> bit-reproducible.
             __syncwarp();
@@ -641,11 +720,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s0 += x0; q0 = fmaf(x0, x0, q0); s1 += x1; q1 = fmaf(x1, x1, q1);
                 s2 += x2; q2 = fmaf(x2, x2, q2); s3 += x3; q3 = fmaf(x3, x3, q3);
               }
-              *reinterpret_cast<float2*>(p.stats_out + (((m_first >> 5) + on_first * p.stats_sample_extra + p.stats_block_off) * p.n_total + col) * 2) =
+              *reinterpret_cast<float2*>(e_stats_out + (((m_first >> 5) + on_first * p.stats_sample_extra + p.stats_block_off) * p.n_total + col) * 2) =
                   make_float2((s0 + s1) + (s2 + s3), (q0 + q1) + (q2 + q3));
             }
           }
-          if (p.has_o16 && my_valid) {  // rare side copy (feeds a stride-2 conv): direct 64-B row store
+          if (e_has_o16 && my_valid) {  // rare side copy (feeds a stride-2 conv): direct 64-B row store
             const int col = n_base + c * 32;
             bf16* dst = out_bf16 + my_m * p.ld_out + col;
             if (((p.n_total | p.ld_out) & 7) != 0) {  // narrow / unaligned rows: scalar stores
@@ -667,7 +746,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         } else {
           // 16-bit-only output: compact [128 rows x 64 B] layout (64B swizzle) overlaps other rows' fp32 residual
-          if (p.has_res && !p.res16) named_bar_sync(bar_id, 128);
+          if (e_has_res && !p.res16) named_bar_sync(bar_id, 128);
           uint8_t* my_row64 = slot_gen + row * 64;
           if (p.out16_f16) {   // warp-uniform: one conversion per pair on either path
 #pragma unroll
@@ -678,6 +757,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               pk.z = pack_f16x2(o[8 * u + 4], o[8 * u + 5]);
               pk.w = pack_f16x2(o[8 * u + 6], o[8 * u + 7]);
               *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+              if (e_ln_stats_out != nullptr) ln_accumulate(pk, ln_s2, ln_q2, 1);
             }
           } else {
 #pragma unroll
@@ -688,9 +768,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               pk.z = pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
               pk.w = pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
               *reinterpret_cast<uint4*>(my_row64 + ((u ^ ((row >> 1) & 3)) << 4)) = pk;
+              if (e_ln_stats_out != nullptr) ln_accumulate(pk, ln_s2, ln_q2, 0);
             }
           }
-          if (p.stats_out != nullptr) {
+          if (e_stats_out != nullptr) {
             // GroupNorm statistics of the 16-bit tensor being written, taken from the ROUNDED values in the slot (they are
             // the statistics of what the next GroupNorm will read): lane = column, walk my warp's 32 rows.  Fixed order.
             __syncwarp();
@@ -716,19 +797,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s0 += xa; q0 = fmaf(xa, xa, q0);
                 s1 += xb; q1 = fmaf(xb, xb, q1);
               }
-              *reinterpret_cast<float2*>(p.stats_out + (((m_first >> 5) + on_first * p.stats_sample_extra + p.stats_block_off) * p.n_total + col) * 2) = make_float2(s0 + s1, q0 + q1);
+              *reinterpret_cast<float2*>(e_stats_out + (((m_first >> 5) + on_first * p.stats_sample_extra + p.stats_block_off) * p.n_total + col) * 2) = make_float2(s0 + s1, q0 + q1);
             }
           }
         }
-        if (edbg) { te = clock64(); e_pack += te - tc0; }
+        if (edbg) { te = static_cast<unsigned>(clock()); dbg_add(9, te - tc0); }
         fence_async_smem();
         const int ocol = n_tile * tile_out_cols + c * chunk_cols;
-        if (edbg) { tc0 = clock64(); e_fence += tc0 - te; te = tc0; }
-        if (p.has_res) {
+        if (edbg) { tc0 = static_cast<unsigned>(clock()); dbg_add(10, tc0 - te); te = tc0; }
+        if (e_has_res) {
           named_bar_sync(bar_id, 128);
-          if (edbg) e_bar += clock64() - te;
+          if (edbg) dbg_add(13, static_cast<unsigned>(clock()) - te);
           if (elected) {
-            if (p.has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
+            if (e_has_o32) tma_store_4d(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
             else tma_store_4d(&tmO16, slot_addr, ocol, w0, h0, n0);
             tma_store_commit();
             tma_store_wait_read0();  // slot may be overwritten again
@@ -741,19 +822,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // stall on the store just issued, no single-lane code between two barriers.
           if (store_warp) tma_store_wait_read0();
           named_bar_sync(bar_id, 128);
-          if (edbg) e_bar += clock64() - te;
+          if (edbg) dbg_add(13, static_cast<unsigned>(clock()) - te);
           if (store_warp) {
-            if (p.has_o32) tma_store_4d_commit_elect(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
+            if (e_has_o32) tma_store_4d_commit_elect(&tmO32, slot_addr, ocol, w0, h0, n0 + tc.s * nb_pad);
             else tma_store_4d_commit_elect(&tmO16, slot_addr, ocol, w0, h0, n0);
           }
         }
       }
+      if (e_ln_stats_out != nullptr && my_valid) {   // LayerNorm fold, writing side: partial (n tile, chunk parity) of my row
+        float s0, s1, q0, q1;
+        upk2(ln_s2, s0, s1);
+        upk2(ln_q2, q0, q1);
+        e_ln_stats_out[static_cast<long long>(n_tile * 2 + c_first) * p.ln_stats_stride + my_m] = make_float2(s0 + s1, q0 + q1);
+      }
     }
     if (edbg) {
-      g_gemm_dbg[5] = clock64() - e_all;
-      g_gemm_dbg[6] = e_full;
-      g_gemm_dbg[7] = (e_slot << 32) | (e_bar & 0xffffffffll);
-      g_gemm_dbg[8] = e_ld; g_gemm_dbg[9] = e_pack; g_gemm_dbg[10] = e_fence; g_gemm_dbg[11] = e_chunks;
+      g_gemm_dbg[5] = static_cast<unsigned>(clock()) - e_all;
+      g_gemm_dbg[7] = (g_gemm_dbg[12] << 32) | (g_gemm_dbg[13] & 0xffffffffll);
     }
     if (store_warp) tma_store_wait_all();
   }
@@ -913,8 +998,15 @@ int gemm_reset_debug_counters() {
   return 0;
 }
 
+int gemm_ln_parts(const ConvGemmDesc& d) {
+  const int bn = auto_block_n(d);
+  if (d.mode != EPI_STD || d.out_f32 != nullptr || d.epi_act != 0 || bn == 256 || bn < 64 || d.Cout % bn != 0 || d.up_phase) return 0;
+  return 2 * (d.Cout / bn);
+}
+
 int gemm_split_k(const ConvGemmDesc& d) {
   if (d.mode != EPI_STD || d.Cout % 4 != 0 || d.epi_act != 0) return 1;   // the reduce kernel applies no activation
+  if (d.ln_stats_out != nullptr) return 1;   // LayerNorm-fold row statistics come out of the GEMM's own epilogue
   int tw, th, tn;
   const int Wo = d.W / d.stride, Ho = d.H / d.stride;
   const int nb = d.split_batch ? d.split_batch : d.Nb;
@@ -1008,6 +1100,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   p.bias = d.bias;
   p.rowbias = d.rowbias;
   p.rowbias_ld = d.rowbias_ld ? d.rowbias_ld : d.Cout;
+  p.bias_cols = d.bias_cols > 0 ? d.bias_cols : d.Cout;
   p.residual = d.residual16 ? reinterpret_cast<const float*>(d.residual16) : d.residual;
   p.res16 = d.residual16 != nullptr;
   PBE_REQUIRE(!(d.residual16 && (d.residual || d.out_f32)), "a 16-bit residual goes with a 16-bit-only output");
@@ -1023,6 +1116,22 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     p.out16_f16 = (f16 && !d.out16_bf16) ? 1 : 0;
   }
   PBE_REQUIRE(d.epi_act == 0 || d.mode == EPI_STD, "activation epilogue needs mode STD");
+  if (d.ln_stats_out != nullptr) {
+    PBE_REQUIRE(gemm_ln_parts(d) > 0 && d.out_bf16 != nullptr && d.ln_stats_stride >= static_cast<long long>(d.Nb) * (d.H / d.stride) * (d.W / d.stride),
+                "LayerNorm-fold row statistics: plain epilogue, 16-bit-only output, full n tiles");
+    p.ln_stats_out = d.ln_stats_out;
+    p.ln_stats_stride = d.ln_stats_stride;
+  }
+  if (d.ln_in != nullptr) {
+    PBE_REQUIRE(d.bias != nullptr && d.ln_parts >= 2 && d.ln_parts % 2 == 0 && d.rowbias == nullptr && d.residual == nullptr &&
+                    d.residual16 == nullptr && d.out_f32 == nullptr && d.epi_act == 0 && d.ksize == 1 && d.splitk_ws == nullptr,
+                "LayerNorm-fold consumer: 1x1 GEMM with a (folded) bias, 16-bit output, no residual / split-K");
+    p.ln_in = d.ln_in;
+    p.ln_stride = d.ln_stride;
+    p.ln_parts = d.ln_parts;
+    p.ln_inv_c = 1.0f / static_cast<float>(d.C);
+    p.ln_eps = d.ln_eps;
+  }
   p.ld_out = d.ld_out ? d.ld_out : (d.mode == EPI_GEGLU ? d.Cout / 2 : d.Cout);
 
   const int bn = auto_block_n(d);
@@ -1045,6 +1154,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
   plan->red.out16_f16 = p.out16_f16;
   PBE_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
   if (d.mode == EPI_GEGLU) PBE_REQUIRE(bn == 256 && d.Cout % 256 == 0, "GEGLU needs BLOCK_N=256 | Cout");
+  PBE_REQUIRE((bn == 256) == (d.mode == EPI_GEGLU), "the 256-wide tile is the GEGLU tile (its kernel compiles only that epilogue)");
   if (d.mode == EPI_QKV) PBE_REQUIRE(d.qk_cols % bn == 0 && d.Cout % bn == 0, "QKV split must align with BLOCK_N");
   plan->block_n = bn;
   p.n_tiles = (d.Cout + bn - 1) / bn;

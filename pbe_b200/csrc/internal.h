@@ -89,6 +89,14 @@ struct ConvGemmParams {
   int qk_cols;
   int vt_tokens;          // EPI_QKV: tokens per sample of the V^T store when the activation is one flat row range (0: H*W)
   int act;                // EPI_STD: 0 none, 1 quick_gelu x * sigmoid(1.702 x) (CLIP MLP), applied after the biases
+  // LayerNorm folded around the GEMMs of a transformer block (engine.cu): the GEMM that WRITES a row-normalised tensor emits
+  // per-row partial (sum, sum of squares) of its rounded 16-bit output, one float2 per (n tile, chunk parity) -> ln_stats_out
+  // [2 * n_tiles][ln_stats_stride]; the GEMM that READS it multiplies the raw tensor by gamma-scaled, row-CENTRED weights
+  // (sum over k of W'[n][k] = 0, so x W'^T = (x - mean) W'^T: the mean needs no term of its own) and finishes LayerNorm per
+  // row in its epilogue: out = rstd * acc + bias'[n]  (attention.py:270-276 norm1 / norm3)
+  float2* ln_stats_out; long long ln_stats_stride;
+  const float2* ln_in; long long ln_stride; int ln_parts; float ln_inv_c, ln_eps;
+  int bias_cols;          // `bias` applies to columns [0, bias_cols) only (n tiles beyond it skip the bias machinery)
   uint32_t idesc_fmt;     // operand-format bits of the MMA instruction descriptor (bf16: A and B format 1; fp16: 0)
   int out16_f16;          // 16-bit outputs (out_bf16 / out_vt) are written as fp16 (else bf16)
 };
@@ -170,6 +178,11 @@ struct ConvGemmDesc {
                            // tensor [Nb,H,W,C], `wt` the phase's four combined taps [4][Cout][C], and the outputs / statistics
                            // address the FULL-resolution tensor [Nb,2H,2W,Cout] at pixels (2i+a, 2j+b).  4/9 of the FLOPs of
                            // the literal form, no upsampled copy of the input.
+  // LayerNorm fold (see ConvGemmParams): producer side -- per-row partial statistics of the 16-bit output; forces split_k = 1
+  float2* ln_stats_out; long long ln_stats_stride;   // [2 * n_tiles][ln_stats_stride] (stride in rows; >= rows of this GEMM)
+  // consumer side -- `act` is the raw (un-normalised) tensor, `wt` carries gamma, `bias` carries beta (and the layer's own bias)
+  const float2* ln_in; long long ln_stride; int ln_parts; float ln_eps;
+  int bias_cols;           // 0 -> Cout: `bias` applies to columns [0, bias_cols) only (must be a multiple of the n tile)
   int out16_bf16;          // 1: the 16-bit outputs are bf16 whatever the operand format (Q | K | V^T read by the flash kernels)
   int operands_bf16;       // 1: act / wt are bf16 whatever the operand format
 };
@@ -180,6 +193,9 @@ int gemm_read_debug_counters16(long long* out16);
 int gemm_split_k(const ConvGemmDesc& d);
 // True when the epilogue can emit per-32-row column statistics for this geometry (no split-K, aligned tiles).
 bool gemm_can_fuse_stats(const ConvGemmDesc& d);
+// Number of per-row partials (2 * n tiles) a GEMM with ln_stats_out writes, or 0 when this GEMM cannot emit them
+// (needs the plain epilogue, a 16-bit-only output, full n tiles of at least two 32-column chunks).
+int gemm_ln_parts(const ConvGemmDesc& d);
 size_t gemm_splitk_ws_bytes(const ConvGemmDesc& d);
 
 int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan);

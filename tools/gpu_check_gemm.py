@@ -73,7 +73,7 @@ if __name__ == "__main__":
     allok &= run_case("gemm_k256", 1, 1, 512, 256, 1, 1, 128, block_n=128)
     allok &= run_case("gemm_bn64", 1, 1, 512, 256, 1, 1, 64, block_n=64)
     allok &= run_case("gemm_bn160", 1, 1, 512, 320, 1, 1, 320, block_n=160)
-    allok &= run_case("gemm_bn256", 1, 1, 512, 320, 1, 1, 512, block_n=256)
+    # (BLOCK_N = 256 is the GEGLU tile; a plain epilogue on it is refused by build_gemm_plan)
     allok &= run_case("gemm_bn32", 1, 1, 300, 320, 1, 1, 16, block_n=32)
     allok &= run_case("gemm_ragged_m", 1, 1, 1000, 128, 1, 1, 128, block_n=128, use_rowbias=True, use_res=True)
     # convs
