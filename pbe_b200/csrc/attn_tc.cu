@@ -29,7 +29,7 @@ namespace pbe {
 
 namespace {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;   // flash_attn_kernel: TMA warp, MMA warp, EIGHT softmax warps (two threads per query row)
 constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 128;   // keys per tile
 constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16
@@ -72,7 +72,11 @@ __device__ __noinline__ void rescale_o_rows(uint32_t taddr, int dv, float alpha)
   tmem_st_wait();
 }
 
-template <int DK_CHUNKS, int KV_STAGES>
+// VROWS: rows (value channels, dv <= VROWS) a V^T stage is sized for -- at d = 80 a 96-row stage lets THREE K / V stages fit
+// next to Q.  With two, tile j + 2 could only be requested once P.V(j) had released its stage, i.e. one tile of compute
+// ahead of its use: the loop ran at the TMA round trip (~2 us per 128-key tile, 3.4 x the MUFU floor of its exponentials)
+// whatever the softmax warps did -- doubling them changed nothing (tools/attn_probe.py 16 1024 8 80: 115 us either way).
+template <int DK_CHUNKS, int KV_STAGES, int VROWS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                   const __grid_constant__ AttnParams p) {
@@ -88,7 +92,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   const uint32_t sQ = smem_base;
   const uint32_t sK = sQ + DK_CHUNKS * CHUNK_BYTES;                     // KV_STAGES x DK_CHUNKS chunks
   const uint32_t sV = sK + KV_STAGES * DK_CHUNKS * CHUNK_BYTES;         // KV_STAGES x 2 chunks of (dv x 64)
-  const uint32_t sBar = sV + KV_STAGES * 2 * 160 * 128;                 // V region sized for dv <= 160
+  const uint32_t sBar = sV + KV_STAGES * 2 * VROWS * 128;               // V region sized for dv <= VROWS
   uint8_t* bar_gen = smem_gen + (sBar - smem_base);
 
   const uint32_t q_full = sBar;
@@ -99,9 +103,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   auto s_free = [&](int b) { return sBar + 8u * (3 + 3 * KV_STAGES + b); };
   const uint32_t p_full = sBar + 8u * (5 + 3 * KV_STAGES);
   const uint32_t pv_done = sBar + 8u * (6 + 3 * KV_STAGES);
+  // K stages are released by QK^T(j) itself -- a whole tile before P.V(j) releases the V stage -- so K runs a tile further ahead
+  auto k_empty = [&](int s) { return sBar + 8u * (8 + 3 * KV_STAGES + s); };
   const uint32_t tmem_ptr_addr = sBar + 8u * (7 + 3 * KV_STAGES);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (7 + 3 * KV_STAGES));
   volatile int* cta_flagged = reinterpret_cast<volatile int*>(bar_gen + 8 * (7 + 3 * KV_STAGES) + 4);
+  // exchange between the two threads of a query row: [tile parity][0 maxima | 1 row sums][key half][row]
+  float* xch = reinterpret_cast<float*>(bar_gen + 8 * (8 + 4 * KV_STAGES));
 
   const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
@@ -118,12 +126,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       mbar_init(k_full(s), 1);
       mbar_init(v_full(s), 1);
       mbar_init(kv_empty(s), 1);
+      mbar_init(k_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full(i), 1);
-      mbar_init(s_free(i), 4);
+      mbar_init(s_free(i), 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     *cta_flagged = 0;
     fence_barrier_init();
@@ -150,16 +159,21 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         for (int kc = 0; kc < DK_CHUNKS; ++kc)
           tma_load_4d(sQ + kc * CHUNK_BYTES, &tmQK, q_full, kc * 64, head, q0, b);
       }
-      for (int j = 0; j < T; ++j) {
-        const int st = (base + j) % KV_STAGES;
-        const uint32_t ph = ((base + j) / KV_STAGES) & 1;
-        mbar_wait(kv_empty(st), ph ^ 1u);
-        mbar_expect_tx(k_full(st), DK_CHUNKS * CHUNK_BYTES);
-        for (int kc = 0; kc < DK_CHUNKS; ++kc)
-          tma_load_4d(sK + (st * DK_CHUNKS + kc) * CHUNK_BYTES, &tmQK, k_full(st), kc * 64, p.heads + head, j * KT, b);
-        mbar_expect_tx(v_full(st), 2 * v_chunk_bytes);
-        for (int jj = 0; jj < 2; ++jj)
-          tma_load_3d(sV + st * 2 * 160 * 128 + jj * v_chunk_bytes, &tmV, v_full(st), j * KT + jj * 64, head * p.d, b);
+      for (int step = 0; step <= T; ++step) {   // K of tile `step`, then V of tile `step - 1`: K is needed (and freed) a tile earlier
+        if (step < T) {
+          const int j = step, st = (base + j) % KV_STAGES;
+          mbar_wait(k_empty(st), (((base + j) / KV_STAGES) & 1) ^ 1u);
+          mbar_expect_tx(k_full(st), DK_CHUNKS * CHUNK_BYTES);
+          for (int kc = 0; kc < DK_CHUNKS; ++kc)
+            tma_load_4d(sK + (st * DK_CHUNKS + kc) * CHUNK_BYTES, &tmQK, k_full(st), kc * 64, p.heads + head, j * KT, b);
+        }
+        if (step >= 1) {
+          const int j = step - 1, st = (base + j) % KV_STAGES;
+          mbar_wait(kv_empty(st), (((base + j) / KV_STAGES) & 1) ^ 1u);
+          mbar_expect_tx(v_full(st), 2 * v_chunk_bytes);
+          for (int jj = 0; jj < 2; ++jj)
+            tma_load_3d(sV + st * 2 * VROWS * 128 + jj * v_chunk_bytes, &tmV, v_full(st), j * KT + jj * 64, head * p.d, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -180,6 +194,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           umma_bf16_ss_elect(tmem_base + sb * 128, adesc, bdesc, idesc_qk, ks > 0 ? 1u : 0u);
         }
         umma_commit_elect(s_full(sb));
+        umma_commit_elect(k_empty(st));   // the K stage is free once these MMAs have read it
       }
       __syncwarp();
     };
@@ -195,54 +210,70 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       {
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
-          const uint64_t bdesc = umma_desc_sw128(sV + st * 2 * 160 * 128 + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
+          const uint64_t bdesc = umma_desc_sw128(sV + st * 2 * VROWS * 128 + (ks >> 2) * v_chunk_bytes) + 2u * (ks & 3);
           umma_bf16_ts_elect(tmem_O, tmem_base + 448 + 8u * ks, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit_elect(kv_empty(st));
+        umma_commit_elect(kv_empty(st));   // the V stage
         umma_commit_elect(pv_done);
       }
       __syncwarp();
       if (KV_STAGES < 2 && j + 1 < T) issue_qk(j + 1);
     }
   } else {
-    // ================= softmax / correction / output (warps 2..5) =================
-    // One query row per thread, all 128 logits of the tile in registers.  As in flash_attn2_kernel (see there): the exact
-    // row maximum is taken for tile 0 only; later tiles use a reference that follows  ref + ATT2_BIAS + log2(row sum)  of
-    // the previous tile (an upper bound of its maximum, by at most 7) and only moves when that exceeds it by 2^8 -- no
-    // maximum pass, O is rescaled (and the tensor core waited for) only then; FFMA2 / FADD2 packed math; bf16 P goes to
-    // tensor memory and is the A operand of P.V (no shared-memory round trip).
+    // ================= softmax / correction / output (warps 2..9) =================
+    // TWO threads per query row, 64 keys of the tile each (warps 2..5: keys 0..63, warps 6..9: keys 64..127; warp w and
+    // w + 4 hold the same 32 rows).  One row per thread left each scheduler a single softmax warp: ncu of the 32 x 32 level
+    // showed the kernel latency-bound (XU pipe 31 %, issue slots 18 %, profiles/r01_ncu_attn1_v6_summary.txt).  With two
+    // warps per scheduler the exponentials of one hide the dependent chains of the other, and the 64 live logits leave
+    // room in the 168 registers a 10-warp CTA gets.  The halves meet twice per tile through 4 KB of shared memory and a
+    // 64-thread named barrier per row quarter: the exact maximum (tile 0 / exact pass) and the tile's row sum, which both
+    // threads add in the same order, so both carry the same reference, the same running sum and take the same decisions.
+    // As in flash_attn2_kernel: the exact row maximum is taken for tile 0 only; later tiles use a reference that follows
+    // ref + ATT2_BIAS + log2(row sum) of the previous tile and only moves when that exceeds it by 2^8; FFMA2 / FADD2 packed
+    // math; bf16 P goes to tensor memory and is the A operand of P.V.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tmem_P = tmem_base + 448;
+    constexpr int HK = KT / 2;   // keys per thread and tile
     float mrs = 0.0f;         // reference maximum, log2 units
     float l_run = 0.0f;
     float sm1 = 0.0f, rf1 = 0.0f;   // row sum of the previous tile and the reference it was computed against
     const float sl2 = p.scale_log2;
     const f32x2 sl2_2 = pk2(sl2, sl2);
+    // O columns of this thread in the rare rescale and in the output: 16-column chunks, alternating between the halves
+    auto rescale_mine = [&](float alpha) {
+      for (int c = half * 16; c < p.dv; c += 32) rescale_o_rows(tmem_O + lane_off + c, 16, alpha);
+    };
 
+    // My half of S(j) is requested from tensor memory at the END of tile j - 1, before P(j - 1) is handed over: tcgen05.ld
+    // executes in order with the MMAs, so a load issued after p_full would sit behind P.V(j - 1) and QK^T(j + 1) (~700 clk)
+    // while the softmax warps idle -- and P.V(j) cannot start before they finish.  (Measured at N = 1024, d = 80: the tile
+    // time was the SUM of the tensor work and the exponentials, 2.1 k cycles, not their maximum.)
+    float s[HK];   // the tile's logits, then its exponentials: loaded into, transformed in and packed from the same registers
+    auto request_s = [&](int jb2) {
+      const int sb2 = jb2 & 1;
+      mbar_wait(s_full(sb2), (jb2 >> 1) & 1);
+      tc_fence_after();
+      tmem_ld_x32_f(tmem_base + lane_off + sb2 * 128 + half * HK, s);
+      tmem_ld_x32_f(tmem_base + lane_off + sb2 * 128 + half * HK + 32, s + 32);
+    };
+    request_s(base);
     for (int j = 0; j < T; ++j) {
       const int jb = base + j;
       const int sb = jb & 1;
-      mbar_wait(s_full(sb), (jb >> 1) & 1);
-      tc_fence_after();
-      float s[KT];
-#pragma unroll
-      for (int c = 0; c < KT; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + lane_off + sb * 128 + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
-      }
+      float* xmax = xch + (jb & 1) * 512;
+      float* xsum = xmax + 256;
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(sb));
 
-      const int kvalid = p.N - j * KT;  // keys valid in this tile
-      if (kvalid < KT) {
+      const int kvalid = p.N - j * KT - half * HK;  // keys of my half that are valid in this tile
+      if (kvalid < HK) {
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
+        for (int i = 0; i < HK; ++i)
           if (i >= kvalid) s[i] = -INFINITY;
       }
       float alpha = 1.0f;
@@ -250,11 +281,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         // exact row maximum: tile 0 always; every tile in the exact re-run of a flagged item (classic online softmax)
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < KT; i += 4) {
+        for (int i = 0; i < HK; i += 4) {
           mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
           mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
         }
-        const float mt = fmaxf(mx0, mx1) * sl2;
+        xmax[half * 128 + row] = fmaxf(mx0, mx1);
+        named_bar_sync(1 + q, 64);
+        const float mt = fmaxf(xmax[row], xmax[128 + row]) * sl2;
         if (j == 0) {
           mrs = mt;
         } else if (__any_sync(0xffffffffu, mt > mrs)) {
@@ -263,7 +296,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           mrs = m_new;
           mbar_wait(pv_done, (jb - 1) & 1);
           tc_fence_after();
-          rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
+          rescale_mine(alpha);
         }
       } else {
         const float est = rf1 + ATT2_BIAS + __log2f(sm1);
@@ -273,14 +306,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
           mrs = m_new;
           mbar_wait(pv_done, (jb - 1) & 1);
           tc_fence_after();
-          rescale_o_rows(tmem_O + lane_off, p.dv, alpha);
+          rescale_mine(alpha);
         }
       }
       const float mneg = -mrs - ATT2_BIAS;
       const f32x2 mneg_2 = pk2(mneg, mneg);
       f32x2 acc0 = pk2(0.0f, 0.0f), acc1 = acc0;
 #pragma unroll
-      for (int i = 0; i < KT; i += 4) {
+      for (int i = 0; i < HK; i += 4) {
         float x0, x1, x2, x3;
         upk2(fma2(pk2(s[i], s[i + 1]), sl2_2, mneg_2), x0, x1);
         upk2(fma2(pk2(s[i + 2], s[i + 3]), sl2_2, mneg_2), x2, x3);
@@ -291,26 +324,34 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       float t0, t1, t2, t3;
       upk2(acc0, t0, t1);
       upk2(acc1, t2, t3);
-      const float tsum = (t0 + t1) + (t2 + t3);
-      l_run = l_run * alpha + tsum;
-      sm1 = tsum;
-      rf1 = mrs;
+      xsum[half * 128 + row] = (t0 + t1) + (t2 + t3);
 
       if (j > 0) {   // P is single-buffered: P.V(j-1) must have read it (pass 1, tile 0: waited for in pass 0's epilogue)
         mbar_wait(pv_done, (jb - 1) & 1);
         tc_fence_after();
       }
 #pragma unroll
-      for (int c = 0; c < KT; c += 32) {
+      for (int c = 0; c < HK; c += 32) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[c + 2 * i], s[c + 2 * i + 1]);
-        tmem_st_x16(tmem_P + lane_off + (c >> 1), pk);
+        tmem_st_x16(tmem_P + lane_off + ((half * HK + c) >> 1), pk);
       }
       tmem_st_wait();
+      // ahead of P.V(j) in the tensor core's queue (see above) -- when QK^T(j + 1) has been issued ahead of P.V(j) at all:
+      // with a single K / V stage it follows P.V(j), and waiting for it here would wait for ourselves
+      if (KV_STAGES >= 2 && j + 1 < T) request_s(jb + 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (KV_STAGES < 2 && j + 1 < T) request_s(jb + 1);
+
+      // the tile's row sum: both halves, added in the same order by both threads (the P.V MMA is already running)
+      named_bar_sync(1 + q, 64);
+      const float tsum = xsum[row] + xsum[128 + row];
+      l_run = l_run * alpha + tsum;
+      sm1 = tsum;
+      rf1 = mrs;
     }
 
     // ---- final: O / l -> out[b, q0+row, head*d + :] ----
@@ -323,7 +364,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       if (__any_sync(0xffffffffu, bad) && lane == 0) *cta_flagged = 1;
     }
     bf16* orow = p.out + (static_cast<long long>(b) * p.N + tok) * p.C + head * p.d;
-    for (int c = 0; c < p.dv; c += 16) {
+    for (int c = half * 16; c < p.dv; c += 32) {
       uint32_t o[16];
       tmem_ld_x16(tmem_O + lane_off + c, o);
       tmem_ld_wait();
@@ -1368,27 +1409,28 @@ int launch_attn3(const AttnPlan& plan, cudaStream_t stream) {
   }
 }
 
-template <int DK_CHUNKS, int KV_STAGES>
+template <int DK_CHUNKS, int KV_STAGES, int VROWS>
 constexpr size_t attn_smem_bytes() {
-  return 1024 + DK_CHUNKS * CHUNK_BYTES + KV_STAGES * DK_CHUNKS * CHUNK_BYTES + KV_STAGES * 2 * 160 * 128 +
-         8 * (8 + 3 * KV_STAGES);
+  return 1024 + DK_CHUNKS * CHUNK_BYTES + KV_STAGES * DK_CHUNKS * CHUNK_BYTES + KV_STAGES * 2 * VROWS * 128 +
+         8 * (8 + 4 * KV_STAGES) + 4096;
 }
 
-template <int DK_CHUNKS, int KV_STAGES>
+template <int DK_CHUNKS, int KV_STAGES, int VROWS>
 int launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
-  constexpr size_t smem = attn_smem_bytes<DK_CHUNKS, KV_STAGES>();
+  constexpr size_t smem = attn_smem_bytes<DK_CHUNKS, KV_STAGES, VROWS>();
   static_assert(smem <= 227 * 1024, "attention smem");
   if (!attr_set) {
-    PBE_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<DK_CHUNKS, KV_STAGES>,
+    PBE_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<DK_CHUNKS, KV_STAGES, VROWS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
   AttnParams p;
   fill_params(plan, &p);
+  PBE_REQUIRE(p.dv <= VROWS, "value rows exceed the V stage of this instantiation");
   if (attn_two_pass()) { p.two_pass = 1; p.flags = nullptr; }
   else if (!attn_rerun()) p.flags = nullptr;
-  PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
+  PBE_CHECK_CUDA(launch_k(flash_attn_kernel<DK_CHUNKS, KV_STAGES, VROWS>, dim3(plan.grid), dim3(ATT_THREADS), smem, stream, plan.tmQ, plan.tmV, p));
   PBE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1465,9 +1507,9 @@ int launch_attn_plan(const AttnPlan& plan, cudaStream_t stream) {
   static const int which = env_int("PBE_ATTN_KERNEL", 3);
   if (chunks == 1 && plan.N > QT) return which == 2 ? launch_attn2(plan, stream) : launch_attn3(plan, stream);
   switch (chunks) {
-    case 1: return launch_attn_t<1, 2>(plan, stream);
-    case 2: return launch_attn_t<2, 2>(plan, stream);
-    case 3: return launch_attn_t<3, 1>(plan, stream);
+    case 1: return launch_attn_t<1, 3, 64>(plan, stream);
+    case 2: return plan.d <= 96 ? launch_attn_t<2, 3, 96>(plan, stream) : launch_attn_t<2, 2, 128>(plan, stream);
+    case 3: return launch_attn_t<3, 1, 160>(plan, stream);
     default: set_error("launch_attn_plan: head dim too large"); return -1;
   }
 }

@@ -1035,7 +1035,16 @@ int Engine::prepare(int Bc, int H, int W, bool pair) {
   auto it = prepared_.find(key);
   if (it != prepared_.end()) {
     cur_ = it->second.get();
+    cur_->last_use = ++use_clock_;
     return 0;
+  }
+  // a plan holds its arenas (> 1 GB at CFG batch 16) and a CUDA graph: keep the most recently used few
+  while (prepared_.size() >= kMaxPlans) {
+    auto victim = prepared_.begin();
+    for (auto jt = prepared_.begin(); jt != prepared_.end(); ++jt)
+      if (jt->second->last_use < victim->second->last_use) victim = jt;
+    if (cur_ == victim->second.get()) cur_ = nullptr;
+    prepared_.erase(victim);
   }
   auto P = std::make_unique<Prepared>();
   P->Bc = Bc; P->H = H; P->W = W; P->pair = pair;
@@ -1052,6 +1061,7 @@ int Engine::prepare(int Bc, int H, int W, bool pair) {
   rc = build(*P, false);
   if (rc) { set_error(last_error); return rc; }
   cur_ = P.get();
+  cur_->last_use = ++use_clock_;
   prepared_[key] = std::move(P);
   return 0;
 }

@@ -89,6 +89,7 @@ struct Prepared {
   float* eps_stage = nullptr;  // [Bc, out_ch, H, W]
   cudaGraphExec_t graph = nullptr;
   int launches = 0;  // kernels per forward
+  unsigned long long last_use = 0;   // Engine::prepare's LRU clock
   ~Prepared();
 };
 
@@ -184,6 +185,8 @@ class Engine : public WeightLoader {
 
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Prepared>> prepared_;
   Prepared* cur_ = nullptr;
+  static constexpr size_t kMaxPlans = 6;   // launch plans kept per engine (least recently used evicted)
+  unsigned long long use_clock_ = 0;
   cudaStream_t cap_stream_ = nullptr;
 };
 
