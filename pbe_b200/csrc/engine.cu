@@ -1,10 +1,11 @@
 // U-Net engine implementation.  See engine.h.
 //
-// Data layout in HBM: activations are NHWC.  The residual stream between blocks is fp32 (statistics for
-// GroupNorm / LayerNorm are computed from it in fp32); every GEMM operand is bf16 (written by the norm kernels or by
-// the previous GEMM's epilogue); accumulation is fp32 in TMEM.  Weights are repacked once at load:
-// conv OIHW fp32 -> [tap][O][I] bf16, Linear [O,I] -> bf16, q/k/v fused to one [3C,C] matrix, GEGLU value/gate rows
-// interleaved per 128-column tile, all 22 ResBlock emb_layers concatenated into one fp32 matrix.
+// Data layout in HBM: activations are NHWC.  Every GEMM operand and the residual stream between ops are 16-bit in the
+// library's operand format (fp16 by default; PBE_STREAM=fp32 keeps an fp32 stream); statistics for GroupNorm / LayerNorm are
+// fp32, taken from the rounded values in the producing GEMM's epilogue; accumulation is fp32 in TMEM.  Weights are repacked
+// once at load: conv OIHW fp32 -> [tap][O][I] 16-bit, Linear [O,I] -> 16-bit, q/k/v fused to one [3C,C] matrix with norm1
+// folded in, the GEGLU projection (value/gate rows interleaved per 256-column tile) with norm3 folded in, the Upsample convs
+// additionally as four sub-pixel phase kernels, all 22 ResBlock emb_layers concatenated into one matrix.
 #include "engine.h"
 
 #include <math.h>

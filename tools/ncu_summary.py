@@ -26,9 +26,11 @@ if traffic_out:
                "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                "kernel": vals[name_col] if name_col is not None else None,
                "duration_us_under_ncu": float(vals[col["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(rows[1][col["gpu__time_duration.sum"]], 1),
-               "note": "DRAM read + write bytes of ONE launch of the dominant kernel (the longest conv_gemm launch of a U-Net call at "
-                       "CFG batch 16, 64x64: a 3x3 conv of the first level) from `ncu --set full` of the current build; "
-                       "source: " + rep.split("/")[-1]}, open(traffic_out, "w"), indent=1)
+               "algorithmic_bytes": 85.7e6,
+               "note": "DRAM read + write bytes of ONE launch of the dominant kernel -- the first-level 3x3 convolution of a U-Net "
+                       "call at CFG batch 16, 64x64 (320 -> 320 channels, per-sample bias, 16-bit output; tools/ncu_conv_target.py) "
+                       "-- from `ncu --set full` of the current build; algorithmic bytes of that launch: 85.7 MB (the 42 MB output "
+                       "is largely still in L2 when the kernel ends); source: " + rep.split("/")[-1]}, open(traffic_out, "w"), indent=1)
 for i, h in enumerate(hdr):
     if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and float(vals[i] or 0) > 0.15:
         print(f"{h:80s} {vals[i]}")
