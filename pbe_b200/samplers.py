@@ -136,6 +136,11 @@ class _SamplerBase:
         """U-Net evaluation on the (possibly CFG-doubled) batch.  On the fast path under CFG the input holds the B shared
         samples once (see _build_input / _dup) and the engine evaluates the pair (UNetModel.run_cfg_pair)."""
         if unet is not None:
+            # the folded context is state of the shared engine: if anything (an img_callback calling apply_model, a second
+            # sampler on the same model) has set another one since this loop set its own, put ours back first
+            if getattr(self, "_ctx_mine", None) is not None and unet.context_version != self._ctx_mine[0]:
+                unet.set_context(self._ctx_mine[1])
+                self._ctx_mine = (unet.context_version, self._ctx_mine[1])
             if eps_out.shape[0] == 2 * x9_in.shape[0]:
                 return unet.run_cfg_pair(x9_in, t_in[:x9_in.shape[0]], out=eps_out)
             return unet.run(x9_in, t_in, out=eps_out)
@@ -279,8 +284,10 @@ class PLMSSampler(_SamplerBase):
         dup = 2 if cfg else 1
         self._check_inputs(img, z_inp, m_inp, shape)
         _, C, H, W = img.shape
+        self._ctx_mine = None
         if unet is not None:
             unet.set_context(c_in)
+            self._ctx_mine = (unet.context_version, c_in)
         in_dup = 1 if unet is not None else dup     # the engine takes the CFG pair's shared input once
         x9 = torch.empty((in_dup * b, C + z_inp.shape[1] + m_inp.shape[1], H, W), device=device, dtype=torch.float32)
         eps_buf = torch.empty((dup * b, C, H, W), device=device, dtype=torch.float32)
@@ -405,8 +412,10 @@ class DDIMSampler(_SamplerBase):
         dup = 2 if cfg else 1
         self._check_inputs(img, z_inp, m_inp, shape)
         _, C, H, W = img.shape
+        self._ctx_mine = None
         if unet is not None:
             unet.set_context(c_in)
+            self._ctx_mine = (unet.context_version, c_in)
         in_dup = 1 if unet is not None else dup     # the engine takes the CFG pair's shared input once
         x9 = torch.empty((in_dup * b, C + z_inp.shape[1] + m_inp.shape[1], H, W), device=device, dtype=torch.float32)
         eps_buf = torch.empty((dup * b, C, H, W), device=device, dtype=torch.float32)

@@ -223,6 +223,13 @@ class UNetModel(nn.Module):
         with torch.cuda.device(ctx.device):
             _lib.check(_lib.load().pbe_set_context(self._engine, ctx.data_ptr(), ctx.shape[0], st), "pbe_set_context")
         self._ctx_batch = ctx.shape[0]
+        self._ctx_version = getattr(self, "_ctx_version", 0) + 1     # samplers compare this to notice a context they did not set
+
+    @property
+    def context_version(self) -> int:
+        """Incremented by every :meth:`set_context` (and ``forward``): a sampling loop that set its context remembers the
+        value and re-applies its own context when a callback / another caller on the same stream has changed it since."""
+        return getattr(self, "_ctx_version", 0)
 
     def run(self, x: torch.Tensor, timesteps: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """eps = UNet(x, t) with the context set by :meth:`set_context`. x: [Bc, in_ch, H, W] fp32 CUDA."""

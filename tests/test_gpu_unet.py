@@ -137,6 +137,31 @@ def test_small_plms50_psnr_vs_reference_golden(small, dev, golden_dir):
     assert torch.equal(out, out2)
 
 
+def test_sampler_keeps_its_context_when_a_callback_uses_the_model(small, dev):
+    """The folded cross-attention context is state of the shared engine.  An ``img_callback`` that calls
+    ``apply_model`` with another context in the middle of the loop changes it; the sampler notices (context_version) and
+    puts its own back before its next U-Net call: the result is bit-identical to the undisturbed run."""
+    from pbe_b200.samplers import PLMSSampler
+    cfg, sd, req, model = small
+    d = lambda t: t.to(dev)
+    kw = dict(S=6, conditioning=d(req["c"]), batch_size=2, shape=[4, 32, 32], verbose=False, unconditional_guidance_scale=5.0,
+              unconditional_conditioning=d(req["uc"]), eta=0.0, x_T=d(req["x_T"]),
+              test_model_kwargs=dict(inpaint_image=d(req["z_inpaint"]), inpaint_mask=d(req["mask"])))
+    smp = PLMSSampler(model)
+    ref, _ = smp.sample(**kw)
+    g = torch.Generator().manual_seed(5)
+    other = torch.randn(3, 1, 768, generator=g).to(dev)
+    calls = []
+
+    def intruder(i):
+        x = torch.randn(3, 9, 32, 32, generator=g).to(dev)
+        calls.append(model.apply_model(x, torch.full((3,), 500, dtype=torch.int64, device=dev), other))
+
+    out, _ = smp.sample(callback=intruder, **kw)
+    assert len(calls) >= 6
+    assert torch.equal(out, ref)
+
+
 def test_small_plms_per_step_eps_vs_oracle(small, dev):
     """Teacher-forced per-step parity: feed the oracle trajectory's x_t to the CUDA U-Net at every step."""
     from oracle import sampler_ref as S
