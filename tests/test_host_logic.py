@@ -297,3 +297,42 @@ def test_product_package_never_imports_the_oracle():
             elif isinstance(node, ast.ImportFrom):
                 names = [node.module or ""]
             assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+
+
+def test_layernorm_fold_algebra():
+    """The identity behind the LayerNorm fold of DESIGN.md 3.3 (Engine::fold_layernorm, csrc/engine.cu), in fp64 on the host:
+    with W''[o][i] = W[o][i] g[i] - mean_i(W[o][:] g) and b'[o] = b[o] + sum_i W[o][i] beta[i],
+        Linear(LayerNorm(x)) = rstd * (W'' x_raw) + b'          (attention.py:270-276, norm1 -> to_q/k/v, norm3 -> ff.net.0.proj)
+    for rows whose mean is far from zero too (the centred rows make the mean term vanish instead of cancelling it), and the
+    treatment of beta's image under q | k | v: k's share is constant over the keys of a query row (softmax-invariant), v's
+    share passes through the attention and becomes W_out b_v (attention.py:207-230)."""
+    g = torch.Generator().manual_seed(3)
+    C, O, M = 64, 48, 37
+    x = torch.randn(M, C, generator=g, dtype=torch.float64) * 0.7 + torch.randn(M, 1, generator=g, dtype=torch.float64) * 25.0
+    W = torch.randn(O, C, generator=g, dtype=torch.float64) / C ** 0.5
+    b = torch.randn(O, generator=g, dtype=torch.float64)
+    gamma = 1.0 + 0.3 * torch.randn(C, generator=g, dtype=torch.float64)
+    beta = 0.2 * torch.randn(C, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5), W, b)
+    Wg = W * gamma
+    W2 = Wg - Wg.mean(dim=1, keepdim=True)
+    b2 = b + W @ beta
+    assert W2.sum(dim=1).abs().max() < 1e-12
+    s, q = x.sum(dim=1), (x * x).sum(dim=1)                       # the producing epilogue's row statistics
+    mean = s / C
+    rstd = torch.rsqrt(q / C - mean * mean + 1e-5)
+    out = rstd[:, None] * (x @ W2.T) + b2
+    assert (out - ref).abs().max() < 1e-9 * ref.abs().max() * 25.0 ** 2  # the variance formula loses mean^2 / var digits, nothing else
+
+    # q | k | v: dropping b_k and moving b_v behind the attention leaves softmax(q k^T) v W_out^T unchanged
+    d = 16
+    Wq, Wk, Wv, Wo = (torch.randn(d, C, generator=g, dtype=torch.float64) / C ** 0.5 for _ in range(4))
+    Wo = torch.randn(C, d, generator=g, dtype=torch.float64) / d ** 0.5
+    ln = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)
+    qf, kf, vf = ln @ Wq.T, ln @ Wk.T, ln @ Wv.T
+    att_ref = torch.softmax(qf @ kf.T * d ** -0.5, dim=-1) @ vf @ Wo.T
+    z = (x - mean[:, None]) * rstd[:, None] * gamma                # LayerNorm without beta
+    bq, bv = Wq @ beta, Wv @ beta
+    q2, k2, v2 = z @ Wq.T + bq, z @ Wk.T, z @ Wv.T                 # k without its bias, v without its bias
+    att = torch.softmax(q2 @ k2.T * d ** -0.5, dim=-1) @ v2 @ Wo.T + Wo @ bv
+    assert (att - att_ref).abs().max() < 1e-9
