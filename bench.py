@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 # PBE_NCCL_DEBUG overrides.  stdout carries exactly ONE line, the JSON result: libraries write to file descriptor 1 behind
 # Python's back (NCCL prints its log there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
 # private duplicate of the original stdout.
-os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
+# (an NCCL_DEBUG preset by the image -- the GPU boxes export a quieter level -- is overridden: the rank check needs INFO)
+os.environ["NCCL_DEBUG"] = os.environ.get("PBE_NCCL_DEBUG", "INFO")
 _JSON_OUT = os.fdopen(os.dup(1), "w")
 sys.stdout.flush()
 os.dup2(2, 1)
