@@ -162,6 +162,27 @@ def test_sampler_keeps_its_context_when_a_callback_uses_the_model(small, dev):
     assert torch.equal(out, ref)
 
 
+def test_engine_keeps_a_bounded_number_of_plans(small, dev):
+    """Launch plans (arenas + CUDA graph, > 1 GB each at the benchmark size) are cached per (CFG batch, H, W) and the engine
+    keeps its six most recently used: ten shapes through one engine, then the first again -- rebuilt after its
+    eviction, bit-identical to its first run."""
+    cfg, sd, req, model = small
+    g = torch.Generator().manual_seed(21)
+    shapes = [(2, 32, 32), (1, 32, 32), (3, 32, 32), (2, 16, 16), (4, 32, 32), (2, 32, 16), (1, 16, 16), (5, 32, 32), (2, 16, 32),
+              (6, 32, 32)]
+    first = None
+    for i, (B, h, w) in enumerate(shapes + shapes[:1]):
+        gi = torch.Generator().manual_seed(100 + (i % len(shapes)))
+        x = torch.randn(B, 9, h, w, generator=gi).to(dev)
+        t = torch.randint(0, 1000, (B,), generator=gi).to(dev)
+        c = torch.randn(B, 1, 768, generator=gi).to(dev)
+        e = model.apply_model(x, t, c).clone()
+        assert torch.isfinite(e).all()
+        if i == 0:
+            first = e
+    assert torch.equal(e, first)
+
+
 def test_small_plms_per_step_eps_vs_oracle(small, dev):
     """Teacher-forced per-step parity: feed the oracle trajectory's x_t to the CUDA U-Net at every step."""
     from oracle import sampler_ref as S
