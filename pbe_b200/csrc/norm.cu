@@ -10,6 +10,8 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace pbe {
@@ -307,6 +309,71 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
   }
 }
 
+// The same pass for the 16-bit stream, eight channels per thread: one 16-byte load and one 16-byte store per pixel and
+// thread, byte pointers advanced by a constant per pixel, SiLU as h + h * tanh(h) with h = x / 2 (packed FMUL2, two
+// MUFU.TANH, packed FFMA2: 2 issue slots per element instead of 5; tanh.approx is 2^-11 relative, the size of the 16-bit
+// rounding the result gets next -- the v1 eps error against the fp32 reference is unchanged at 1.34e-3).  The 4-channel
+// kernel above spent ~20 issue slots per element (64-bit index arithmetic per pixel, five-slot SiLU, one conversion
+// per element) and ran at 4 TB/s, issue-bound (profiles/r02_ncu_gnapply_v4_summary.txt); the raw concat copy needs no
+// conversion at all here (same bits).
+constexpr int GN8_UNROLL = 4;
+__device__ __forceinline__ void silu2_tanh(float& a, float& b) {
+  float h0, h1, t0, t1;
+  upk2(mul2(pk2(a, b), pk2(0.5f, 0.5f)), h0, h1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  upk2(fma2(pk2(h0, h1), pk2(t0, t1), pk2(h0, h1)), a, b);
+}
+__global__ void __launch_bounds__(1024) gn_apply8_kernel(const unsigned short* __restrict__ x0, int C0,
+                                                         const unsigned short* __restrict__ x1, int C1, int HW, int rows_par,
+                                                         const float2* __restrict__ ab, int silu, bf16* __restrict__ y,
+                                                         bf16* __restrict__ raw, int f16) {
+  griddep_enter();
+  const int C = C0 + C1;
+  const int vpp = C / 8;
+  const int t = threadIdx.x;
+  const int prow = t / vpp;
+  const int c = (t - prow * vpp) * 8;
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * (rows_par * GN8_UNROLL) + prow;
+  const char* sp;
+  size_t sstep;
+  if (c < C0) {
+    sp = reinterpret_cast<const char*>(x0 + (static_cast<size_t>(b) * HW + p_begin) * C0 + c);
+    sstep = static_cast<size_t>(rows_par) * C0 * 2;
+  } else {
+    sp = reinterpret_cast<const char*>(x1 + (static_cast<size_t>(b) * HW + p_begin) * C1 + (c - C0));
+    sstep = static_cast<size_t>(rows_par) * C1 * 2;
+  }
+  const size_t ooff = ((static_cast<size_t>(b) * HW + p_begin) * C + c) * 2, ostep = static_cast<size_t>(rows_par) * C * 2;
+  // every load first: the pixels' data, then the eight (scale, shift) pairs of my channels
+  uint4 r[GN8_UNROLL];
+#pragma unroll
+  for (int u = 0; u < GN8_UNROLL; ++u)
+    r[u] = (p_begin + u * rows_par < HW) ? __ldg(reinterpret_cast<const uint4*>(sp + u * sstep)) : make_uint4(0u, 0u, 0u, 0u);
+  const float4* abp = reinterpret_cast<const float4*>(ab + static_cast<size_t>(b) * C + c);
+  const float4 s0 = __ldg(abp), s1 = __ldg(abp + 1), s2 = __ldg(abp + 2), s3 = __ldg(abp + 3);   // (a, b) of channels c .. c + 7
+  const f32x2 a01 = pk2(s0.x, s0.z), b01 = pk2(s0.y, s0.w), a23 = pk2(s1.x, s1.z), b23 = pk2(s1.y, s1.w);
+  const f32x2 a45 = pk2(s2.x, s2.z), b45 = pk2(s2.y, s2.w), a67 = pk2(s3.x, s3.z), b67 = pk2(s3.y, s3.w);
+  char* yp = reinterpret_cast<char*>(y) + ooff;
+  char* rp = raw != nullptr ? reinterpret_cast<char*>(raw) + ooff : nullptr;
+#pragma unroll
+  for (int u = 0; u < GN8_UNROLL; ++u) {
+    if (p_begin + u * rows_par < HW) {
+      const float2 v01 = unpack_op2(r[u].x, f16), v23 = unpack_op2(r[u].y, f16), v45 = unpack_op2(r[u].z, f16), v67 = unpack_op2(r[u].w, f16);
+      float o0, o1, o2, o3, o4, o5, o6, o7;
+      upk2(fma2(pk2(v01.x, v01.y), a01, b01), o0, o1);
+      upk2(fma2(pk2(v23.x, v23.y), a23, b23), o2, o3);
+      upk2(fma2(pk2(v45.x, v45.y), a45, b45), o4, o5);
+      upk2(fma2(pk2(v67.x, v67.y), a67, b67), o6, o7);
+      if (silu) { silu2_tanh(o0, o1); silu2_tanh(o2, o3); silu2_tanh(o4, o5); silu2_tanh(o6, o7); }
+      *reinterpret_cast<uint4*>(yp + u * ostep) =
+          make_uint4(pack_op2(o0, o1, f16), pack_op2(o2, o3, f16), pack_op2(o4, o5, f16), pack_op2(o6, o7, f16));
+      if (rp != nullptr) *reinterpret_cast<uint4*>(rp + u * ostep) = r[u];
+    }
+  }
+}
+
 // Low-resolution GroupNorm in ONE kernel: grid (32 groups, Nb); the (sample, group) slice (HW pixels x C/32 channels,
 // <= 80 KB of fp32) is staged in shared memory, so x is read once from HBM, statistics are an exact two-pass
 // (mean, then centred sum of squares; fixed-order reductions) and the normalised bf16 operand is written straight
@@ -543,6 +610,17 @@ int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
     PBE_CHECK_CUDA(cudaGetLastError());
     PBE_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(a.Nb), dim3(GN_THREADS), 0, stream, partial, slabs, a.HW, C, a.gamma, a.beta, a.eps, ab));
     PBE_CHECK_CUDA(cudaGetLastError());
+  }
+  static const bool apply8 = [] { const char* e = getenv("PBE_GN_APPLY8"); return e == nullptr || atoi(e) != 0; }();
+  if (a.in16 && apply8 && a.C0 % 8 == 0 && a.C1 % 8 == 0) {
+    const int vpp8 = C / 8;
+    const int rp8 = vpp8 >= 256 ? 1 : 256 / vpp8;
+    const int ppb = rp8 * GN8_UNROLL;
+    PBE_CHECK_CUDA(launch_k(gn_apply8_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.Nb)), dim3(vpp8 * rp8), 0, stream,
+        reinterpret_cast<const unsigned short*>(a.x0), a.C0, reinterpret_cast<const unsigned short*>(a.x1), a.C1, a.HW, rp8, ab, a.silu, a.y,
+        a.raw, operand_f16()));
+    PBE_CHECK_CUDA(cudaGetLastError());
+    return 0;
   }
   const int vpp = C / 4;
   const int rows_par = vpp >= 256 ? 1 : 256 / vpp;
