@@ -370,6 +370,48 @@ int Engine::finalize() {
     }
     if ((e = make_conv(tb + ".ff.net.2", 1, 4 * c, c, &s.ff2))) return e;
     if ((e = make_conv(pfx + ".proj_out", 1, c, c, &s.proj_out))) return e;
+    if (ff_proj_merge_) {
+      // x3 = W_ff2 g + b_ff2 + x2 has one reader, proj_out, and nothing non-linear in between (attention.py:276, 335-336):
+      //   proj_out(x3) = (W_po W_ff2) g + W_po x2 + (W_po b_ff2 + b_po)
+      // = one GEMM with K = 4c + c over the buffer [ g | x2 ] -- the same FLOPs as the two, one epilogue, one launch and
+      // one [M, c] round trip fewer, and x3 is never rounded to 16 bits.  The product is taken in fp64 on the device and
+      // rounded once to the operand format.
+      const HostTensor *WF, *BF, *WP, *BP;
+      if ((e = get(tb + ".ff.net.2.weight", &WF))) return e;
+      if ((e = get(tb + ".ff.net.2.bias", &BF))) return e;
+      if ((e = get(pfx + ".proj_out.weight", &WP))) return e;
+      if ((e = get(pfx + ".proj_out.bias", &BP))) return e;
+      const size_t inner = static_cast<size_t>(4) * c;
+      if (WF->data.size() != inner * c || WP->data.size() != static_cast<size_t>(c) * c || BF->data.size() != static_cast<size_t>(c) ||
+          BP->data.size() != static_cast<size_t>(c)) {
+        set_error("ff.net.2 / proj_out of " + pfx + " have wrong size");
+        return -4;
+      }
+      float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+      PBE_CHECK_CUDA(cudaMalloc(&dA, WP->data.size() * sizeof(float)));
+      PBE_CHECK_CUDA(cudaMalloc(&dB, WF->data.size() * sizeof(float)));
+      PBE_CHECK_CUDA(cudaMalloc(&dC, WF->data.size() * sizeof(float)));
+      PBE_CHECK_CUDA(cudaMemcpy(dA, WP->data.data(), WP->data.size() * sizeof(float), cudaMemcpyHostToDevice));
+      PBE_CHECK_CUDA(cudaMemcpy(dB, WF->data.data(), WF->data.size() * sizeof(float), cudaMemcpyHostToDevice));
+      if ((e = launch_matmul_f64acc(dA, dB, dC, c, c, static_cast<int>(inner), nullptr))) return e;
+      std::vector<float> prod(WF->data.size());
+      PBE_CHECK_CUDA(cudaMemcpy(prod.data(), dC, prod.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      PBE_CHECK_CUDA(cudaFree(dA));
+      PBE_CHECK_CUDA(cudaFree(dB));
+      PBE_CHECK_CUDA(cudaFree(dC));
+      const size_t kk = inner + c;
+      std::vector<float> w(static_cast<size_t>(c) * kk), b(c);
+      for (int o = 0; o < c; ++o) {
+        memcpy(&w[o * kk], &prod[o * inner], inner * sizeof(float));
+        memcpy(&w[o * kk + inner], &WP->data[static_cast<size_t>(o) * c], c * sizeof(float));
+        double acc = BP->data[o];
+        for (int i = 0; i < c; ++i) acc += static_cast<double>(WP->data[static_cast<size_t>(o) * c + i]) * BF->data[i];
+        b[o] = static_cast<float>(acc);
+      }
+      if ((e = upload_bf16(w, &s.ffproj.w))) return e;
+      if ((e = upload_f32(b, &s.ffproj.b))) return e;
+      s.ffproj.cin = s.ffproj.cin_pad = static_cast<int>(kk); s.ffproj.cout = c; s.ffproj.k = 1;
+    }
     {  // single-key cross-attention folds to to_out(to_v(ctx)); to_q / to_k / norm2 are dead (attention.py:207-230)
       const HostTensor *V2, *O2, *B2;
       if ((e = get(tb + ".attn2.to_v.weight", &V2))) return e;
@@ -826,8 +868,23 @@ int Engine::build(Prepared& P, bool dry) {
         } else {
           launches += 1;
         }
-        Act t1 = new_act(false, M * (diverged ? 1 : 2) * C, C, h.H, h.W);
         const size_t M_t1 = M * (diverged ? 1 : 2);   // rows of t1 (the CFG-pair prefix writes it in two halves)
+        // ff.net.2 + proj_out as one GEMM (engine.h: ff_proj_merge_): t1 (= x2) lives in columns [4C, 5C) of the buffer whose
+        // columns [0, 4C) receive the GEGLU output, so [ g | x2 ] is ONE K = 5C operand.  Needs the LayerNorm fold on t1
+        // (its only other reader is then the GEGLU GEMM, through a pitched tensor map).
+        bool merge = false;
+        if (s16 && ln_fold_ && ff_proj_merge_ && s.ffproj.w != nullptr) {
+          ConvGemmDesc probe{};
+          probe.Nb = Bc; probe.H = h.H; probe.W = h.W; probe.C = C; probe.ksize = 1; probe.stride = 1; probe.Cout = C; probe.mode = EPI_STD;
+          const int parts = gemm_ln_parts(probe);
+          merge = parts > 0 && parts <= 16;
+        }
+        const int catld = 5 * C;
+        bf16* cat = merge ? static_cast<bf16*>(SA(M_t1 * catld * sizeof(bf16))) : nullptr;
+        Act t1{nullptr, nullptr, C, h.H, h.W};
+        if (merge) { t1.b16 = cat + 4 * C; t1.has16 = true; }
+        else t1 = new_act(false, M_t1 * C, C, h.H, h.W);
+        const size_t t1_ld = merge ? static_cast<size_t>(catld) : static_cast<size_t>(C);
         for (int half = 0; half < (diverged ? 1 : 2); ++half) {
           // x1 = to_out(attn) + b + x ; x2 = x1 + to_out2(to_v2(ctx))  (single-key cross-attention, folded).
           // CFG pair plan: this is where the context enters -- the shared activations feed one GEMM per half, each
@@ -839,9 +896,10 @@ int Engine::build(Prepared& P, bool dry) {
           d.rowbias_ld = C;
           set_res(d, t0);
           Act dst = t1;
-          if (s16) dst.b16 = t1.b16 + static_cast<size_t>(half) * M * C;
+          if (s16) dst.b16 = t1.b16 + static_cast<size_t>(half) * M * t1_ld;
           else dst.f32 = t1.f32 + static_cast<size_t>(half) * M * C;
           set_out(d, dst);
+          if (merge) { d.ld_out = catld; d.res_ld = C; }
           if (half == 0) ln3_parts = want_ln_stats(d, M_t1, &ln3_stats);
           else if (ln3_parts) { d.ln_stats_out = ln3_stats; d.ln_stats_stride = static_cast<long long>(M_t1); }
           if (ln3_parts) d.ln_stats_out = ln3_stats + static_cast<size_t>(half) * M;
@@ -891,16 +949,18 @@ int Engine::build(Prepared& P, bool dry) {
           add_op_meta(tag + ".ln3", 1, [=](cudaStream_t st) { return launch_layernorm(src, gg, bb, n3, Mi, C, 1e-5f, st, nullptr, 0, in16); },
                       "layernorm", 0.0, static_cast<double>(M) * C * (esz + 2.0));
         }
-        bf16* gg = static_cast<bf16*>(SA(M * 4 * C * sizeof(bf16)));
+        if (merge && !ln3_parts) { err = -5; last_error = "ff / proj_out merge without LayerNorm-fold statistics at " + tag; return err; }
+        bf16* gg = merge ? cat : static_cast<bf16*>(SA(M * 4 * C * sizeof(bf16)));
         {
           ConvGemmDesc d{};
           d.act = n3; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
           d.wt = s.ff1.w; d.Cout = 8 * C; d.mode = EPI_GEGLU; d.bias = s.ff1.b; d.out_bf16 = gg; d.ld_out = 4 * C;
+          if (merge) { d.act_ld = catld; d.ld_out = catld; }
           if (ln3_parts) { d.ln_in = ln3_stats; d.ln_stride = static_cast<long long>(M); d.ln_parts = ln3_parts; d.ln_eps = 1e-5f; }
           add_gemm(tag + ".ff.geglu", d);
         }
-        bf16* t2 = static_cast<bf16*>(SA(M * C * sizeof(bf16)));
-        {
+        bf16* t2 = merge ? nullptr : static_cast<bf16*>(SA(M * C * sizeof(bf16)));
+        if (!merge) {
           ConvGemmDesc d{};
           d.act = gg; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = 4 * C; d.ksize = 1; d.stride = 1;
           d.wt = s.ff2.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.ff2.b; d.out_bf16 = t2;
@@ -911,12 +971,12 @@ int Engine::build(Prepared& P, bool dry) {
         if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * C * sizeof(bf16))); o.has16 = true; }
         {
           ConvGemmDesc d{};
-          d.act = t2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = C; d.ksize = 1; d.stride = 1;
-          d.wt = s.proj_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = s.proj_out.b;
+          d.act = merge ? cat : t2; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = merge ? catld : C; d.ksize = 1; d.stride = 1;
+          d.wt = merge ? s.ffproj.w : s.proj_out.w; d.Cout = C; d.mode = EPI_STD; d.bias = merge ? s.ffproj.b : s.proj_out.b;
           set_res(d, h);
           set_out(d, o);
           want_stats(d, o, true);
-          add_gemm(tag + ".proj_out", d);
+          add_gemm(tag + (merge ? ".ff.out+proj_out" : ".proj_out"), d);
         }
         h = o;
         break;

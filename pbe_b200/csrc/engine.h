@@ -41,6 +41,7 @@ struct STW {
   int c = 0, heads = 0, d = 0;
   NormW gn, ln1, ln3;
   ConvW proj_in, qkv, to_out, ff1, ff2, proj_out;
+  ConvW ffproj;          // proj_out o ff.net.2 as ONE GEMM over [ GEGLU output | x2 ]: [c][5c] = [ W_po W_ff2 | W_po ] (engine.cu)
   float* wv2 = nullptr;  // attn2.to_v  [c, ctx]
   float* wo2 = nullptr;  // attn2.to_out.0.weight [c, c]
   float* bo2 = nullptr;  // attn2.to_out.0.bias
@@ -155,6 +156,10 @@ class Engine : public WeightLoader {
   // LayerNorm statistics from the producing GEMM's epilogue, applied in the consuming GEMM's epilogue (16-bit stream only);
   // PBE_LN_FOLD=0: a standalone normalise-only LayerNorm pass in front of the same (gamma / beta folded) GEMMs
   int ln_fold_ = [] { const char* e = getenv("PBE_LN_FOLD"); return e == nullptr ? 1 : atoi(e); }();
+  // ff.net.2 -> (+x2) -> proj_out is linear end to end (attention.py:276, 335-336): one GEMM with K = 5C over the buffer that
+  // holds the GEGLU output and x2 side by side, weights composed at load time (16-bit stream + LayerNorm fold only);
+  // PBE_FF_PROJ_MERGE=0: the two GEMMs of the literal form
+  int ff_proj_merge_ = [] { const char* e = getenv("PBE_FF_PROJ_MERGE"); return e == nullptr ? 1 : atoi(e); }();
   int subpixel_up_ = [] { const char* e = getenv("PBE_SUBPIXEL_UP"); return e == nullptr ? 1 : atoi(e); }();   // 2: at every size (tests)
   std::string last_error;
 

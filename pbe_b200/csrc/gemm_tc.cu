@@ -1136,6 +1136,7 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
 
   const int bn = auto_block_n(d);
   p.split_k = (d.splitk_ws != nullptr) ? gemm_split_k(d) : 1;
+  PBE_REQUIRE(d.res_ld == 0 || p.split_k == 1, "res_ld excludes split-K (the reduce kernel reads residual and output at one pitch)");
   p.debug = getenv("PBE_GEMM_DEBUG") ? 1 : 0;
   p.stats_out = nullptr;
   p.stats_sample_extra = 0; p.stats_block_off = 0;
@@ -1237,8 +1238,12 @@ int build_gemm_plan(const ConvGemmDesc& d, GemmPlan* plan) {
     const size_t ph_off = d.up_phase ? (static_cast<size_t>((d.up_phase - 1) >> 1) * 2 * Wo + ((d.up_phase - 1) & 1)) * ld : 0;
     PBE_REQUIRE(!(d.up_phase && p.has_o16 && p.has_o32), "sub-pixel phase conv writes one output tensor");
     int rc = 0;
-    if (p.has_res && p.res16) rc = make_tmap(&plan->tmR, d.residual16, false, 4, dims, s16, box, 64);
-    else if (p.has_res) rc = make_tmap(&plan->tmR, d.residual, true, 4, dims, s32, box, 128);
+    const uint64_t rl = d.res_ld ? static_cast<uint64_t>(d.res_ld) : ld;   // the residual's own row pitch
+    PBE_REQUIRE(d.res_ld == 0 || (d.res_ld % 8 == 0 && d.res_ld >= out_cols && !d.up_phase), "res_ld: >= output columns, multiple of 8");
+    const uint64_t r32[3] = {rl * 4, Wo * rl * 4, Ho * Wo * rl * 4};
+    const uint64_t r16[3] = {rl * 2, Wo * rl * 2, Ho * Wo * rl * 2};
+    if (p.has_res && p.res16) rc = make_tmap(&plan->tmR, d.residual16, false, 4, dims, d.res_ld ? r16 : s16, box, 64);
+    else if (p.has_res) rc = make_tmap(&plan->tmR, d.residual, true, 4, dims, d.res_ld ? r32 : s32, box, 128);
     if (rc) return rc;
     if (p.has_o32) rc = make_tmap(&plan->tmO32, d.out_f32 + ph_off, true, 4, dims, s32, box, 128);
     if (rc) return rc;

@@ -160,6 +160,8 @@ struct ConvGemmDesc {
   float* out_f32;
   bf16* out_bf16;
   int ld_out;  // 0 -> Cout (or Cout/2 for GEGLU)
+  int res_ld;  // elements between consecutive rows of the residual (0 -> the output's leading dimension): an output that is a
+               // column slice of a wider tensor next to a contiguous residual (no split-K)
   bf16* out_vt;
   int qk_cols;
   int block_n;  // 0 -> auto
@@ -273,6 +275,9 @@ int launch_vae_pack_input(const float* z, const float* Wp, const float* bp, bf16
 int launch_softmax_rows(const float* S, bf16* P, long long rows, int N, float scale, cudaStream_t stream);
 // fp32 -> bf16 cast of a flat buffer
 int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
+
+// C[M, N] = A[M, K] . B[K, N] (row-major fp32, fp64 accumulation): weight products composed at load time
+int launch_matmul_f64acc(const float* A, const float* B, float* C, int M, int K, int N, cudaStream_t stream);
 
 // x NCHW fp32 [Nb, Cin, H, W] -> NHWC bf16 [Nb, H, W, Cpad] (channels >= Cin zero)
 int launch_pack_input(const float* x, bf16* y, int Nb, int Cin, int H, int W, int Cpad, cudaStream_t stream);

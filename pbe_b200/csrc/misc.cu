@@ -480,6 +480,32 @@ int launch_cast_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
   return 0;
 }
 
+// C[M, N] = A[M, K] . B[K, N], fp32 in / out, fp64 accumulation: products of two weight matrices at load time (engine.cu:
+// proj_out . ff.net.2 -- the composed matrix is rounded ONCE to the 16-bit operand format afterwards)
+__global__ void __launch_bounds__(256) matmul_f64acc_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                            float* __restrict__ C, int M, int K, int N) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    sa[ty][tx] = (row < M && k0 + tx < K) ? A[static_cast<size_t>(row) * K + k0 + tx] : 0.0f;
+    sb[ty][tx] = (k0 + ty < K && col < N) ? B[static_cast<size_t>(k0 + ty) * N + col] : 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) acc = fma(static_cast<double>(sa[ty][kk]), static_cast<double>(sb[kk][tx]), acc);
+    __syncthreads();
+  }
+  if (row < M && col < N) C[static_cast<size_t>(row) * N + col] = static_cast<float>(acc);
+}
+
+int launch_matmul_f64acc(const float* A, const float* B, float* C, int M, int K, int N, cudaStream_t stream) {
+  PBE_REQUIRE(M > 0 && K > 0 && N > 0, "matmul sizes");
+  matmul_f64acc_kernel<<<dim3((N + 15) / 16, (M + 15) / 16), dim3(256), 0, stream>>>(A, B, C, M, K, N);   // load time: never under PDL
+  PBE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_pack_input(const float* x, bf16* y, int Nb, int Cin, int H, int W, int Cpad, cudaStream_t stream) {
   PBE_REQUIRE(Cpad % 8 == 0 && Cpad >= Cin, "padded channel count");
   const long long total = static_cast<long long>(Nb) * H * W;

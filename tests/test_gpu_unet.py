@@ -369,11 +369,13 @@ torch.save(e2.cpu(), {str(out)!r})
 
 
 @pytest.mark.parametrize("env", [dict(PBE_SUBPIXEL_UP="2"), dict(PBE_SUBPIXEL_UP="0"), dict(PBE_STREAM="fp32"),
-                                 dict(PBE_OPERANDS="bf16"), dict(PBE_OPERANDS="bf16", PBE_STREAM="fp32"), dict(PBE_LN_FOLD="0")])
+                                 dict(PBE_OPERANDS="bf16"), dict(PBE_OPERANDS="bf16", PBE_STREAM="fp32"), dict(PBE_LN_FOLD="0"),
+                                 dict(PBE_FF_PROJ_MERGE="0")])
 def test_engine_variants_vs_oracle(small, dev, tmp_path, env):
     """The engine's build-time switches, each in its own process (they are read once): the sub-pixel form of upsample + conv
     forced at every level (PBE_SUBPIXEL_UP=2; by default only launches that fill the GPU use it) or off, the round-1 fp32
-    residual stream, bf16 operands, LayerNorm as a normalise-only pass instead of statistics folded into the GEMM epilogues.  Every variant is held to the parity bar against the fp32 oracle (odd batch, distinct
+    residual stream, bf16 operands, LayerNorm as a normalise-only pass instead of statistics folded into the GEMM epilogues, ff.net.2 and proj_out as the two GEMMs of
+    the literal form instead of one GEMM over [ GEGLU output | x2 ] with composed weights.  Every variant is held to the parity bar against the fp32 oracle (odd batch, distinct
     timesteps), and the fp16 variants to a much tighter one."""
     import subprocess
     import sys

@@ -336,3 +336,27 @@ def test_layernorm_fold_algebra():
     q2, k2, v2 = z @ Wq.T + bq, z @ Wk.T, z @ Wv.T                 # k without its bias, v without its bias
     att = torch.softmax(q2 @ k2.T * d ** -0.5, dim=-1) @ v2 @ Wo.T + Wo @ bv
     assert (att - att_ref).abs().max() < 1e-9
+
+
+def test_ff_proj_out_merge_algebra():
+    """The identity behind the merged ff.net.2 / proj_out GEMM of DESIGN.md 3.6 (Engine::finalize, csrc/engine.cu), in fp64 on the
+    host: nothing non-linear sits between the feed-forward's output Linear, its residual add and the SpatialTransformer's
+    proj_out (attention.py:276 `x = self.ff(self.norm3(x)) + x`, 335-336 `x = self.proj_out(x); return x + x_in`), so
+        proj_out(ff2(g) + x2) + x_in = [ W_po W_ff2 | W_po ] [ g | x2 ]^T + (W_po b_ff2 + b_po) + x_in
+    -- one GEMM with K = 4C + C over the buffer that holds the GEGLU output and x2 side by side."""
+    g = torch.Generator().manual_seed(5)
+    C, M = 32, 29
+    gg = torch.randn(M, 4 * C, generator=g, dtype=torch.float64)
+    x2 = torch.randn(M, C, generator=g, dtype=torch.float64)
+    x_in = torch.randn(M, C, generator=g, dtype=torch.float64)
+    Wf = torch.randn(C, 4 * C, generator=g, dtype=torch.float64) / (4 * C) ** 0.5
+    bf = torch.randn(C, generator=g, dtype=torch.float64)
+    Wp = torch.randn(C, C, generator=g, dtype=torch.float64) / C ** 0.5
+    bp = torch.randn(C, generator=g, dtype=torch.float64)
+    lin = torch.nn.functional.linear
+    ref = lin(lin(gg, Wf, bf) + x2, Wp, bp) + x_in
+    Wm = torch.cat([Wp @ Wf, Wp], dim=1)
+    bm = Wp @ bf + bp
+    out = lin(torch.cat([gg, x2], dim=1), Wm, bm) + x_in
+    assert Wm.shape == (C, 5 * C)
+    assert (out - ref).abs().max() < 1e-12 * max(1.0, ref.abs().max().item())
