@@ -41,6 +41,7 @@ Prepared::~Prepared() {
 Engine::~Engine() {
   prepared_.clear();
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
+  if (side_stream_) cudaStreamDestroy(side_stream_);
 }
 
 WeightLoader::~WeightLoader() {
@@ -581,6 +582,7 @@ int Engine::build(Prepared& P, bool dry) {
   P.persist.reset(dry);
   P.scratch.reset(dry);
   P.ops.clear();
+  P.op_flags.clear();
   P.op_names.clear();
   int launches = 0;
   auto PA = [&](size_t bytes) { return P.persist.alloc(bytes); };
@@ -592,6 +594,7 @@ int Engine::build(Prepared& P, bool dry) {
                          const std::string& family, double flops, double bytes) {
     if (!dry) {
       P.ops.push_back(std::move(fn));
+      P.op_flags.push_back(0);
       P.op_names.push_back(name);
       P.op_family.push_back(family);
       P.op_flops.push_back(flops);
@@ -663,6 +666,18 @@ int Engine::build(Prepared& P, bool dry) {
       add_gemm("emb_layers(all)", d);
     }
   }
+
+  // the ops so far depend on t only: in the captured graph they form a branch beside conv_in / the first GroupNorm and join
+  // the main line at the first consumer of emb_all, the first ResBlock's conv1 (run_op_list)
+  if (!dry) {
+    for (uint8_t& f : P.op_flags) f = OP_SIDE;
+    P.op_flags[0] |= OP_FORK;
+  }
+  bool emb_joined = false, dup_on_side = false;
+  // latency-bound plans (CFG batch <= 4) also run a ResBlock's 1x1 skip convolution beside its conv1 / GroupNorm (it reads
+  // the block's input only); a full GPU gains nothing from the concurrency
+  const bool skip_on_side = BcFull <= 4;
+  auto flag_last = [&](uint8_t f) { if (!dry && !P.op_flags.empty()) P.op_flags.back() |= f; };
 
   // The residual stream between ops (block outputs, skip tensors, ResBlock h, transformer t0 / t1) is 16-bit in the
   // operand format (fp16 by default) -- what the reference itself carries under torch.autocast -- unless PBE_STREAM=fp32:
@@ -770,6 +785,19 @@ int Engine::build(Prepared& P, bool dry) {
         g1.stats1 = (skip.C > 0 && skip.has_stats) ? skip.stats : nullptr;
         if (skip.C > 0 && !(h.has_stats && skip.has_stats)) g1.stats0 = g1.stats1 = nullptr;
         add_gn(tag + ".gn1", g1);
+        Act resid = h;
+        auto emit_skip = [&](bool side) {
+          Act sk = new_act(false, M * r.cout, r.cout, h.H, h.W);
+          ConvGemmDesc d{};
+          d.act = raw_needed ? raw : h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 1; d.stride = 1;
+          d.wt = r.skip.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.skip.b;
+          set_out(d, sk);
+          add_gemm(tag + ".skip", d);
+          if (side) flag_last(OP_SIDE | OP_FORK);
+          resid = sk;
+        };
+        const bool skip_side = r.has_skip && skip_on_side && graph_lanes_;
+        if (skip_side) emit_skip(true);   // a branch of the graph beside conv1 / gn2, joined in front of conv2
         Act h1act = new_act(false, M * r.cout, r.cout, h.H, h.W);
         {
           ConvGemmDesc d{};
@@ -779,6 +807,7 @@ int Engine::build(Prepared& P, bool dry) {
           set_out(d, h1act);
           want_stats(d, h1act, false);
           add_gemm(tag + ".conv1", d);
+          if (!emb_joined) { flag_last(OP_JOIN); emb_joined = true; }   // first reader of emb_all
         }
         bf16* a2 = static_cast<bf16*>(SA(M * r.cout * sizeof(bf16)));
         GroupNormArgs g2{};
@@ -787,16 +816,7 @@ int Engine::build(Prepared& P, bool dry) {
         g2.gamma = r.gn2.g; g2.beta = r.gn2.b; g2.eps = 1e-5f; g2.silu = 1; g2.y = a2; g2.raw = nullptr;
         g2.stats0 = h1act.has_stats ? h1act.stats : nullptr;
         add_gn(tag + ".gn2", g2);
-        Act resid = h;
-        if (r.has_skip) {
-          Act sk = new_act(false, M * r.cout, r.cout, h.H, h.W);
-          ConvGemmDesc d{};
-          d.act = raw_needed ? raw : h.b16; d.Nb = Bc; d.H = h.H; d.W = h.W; d.C = cin; d.ksize = 1; d.stride = 1;
-          d.wt = r.skip.w; d.Cout = r.cout; d.mode = EPI_STD; d.bias = r.skip.b;
-          set_out(d, sk);
-          add_gemm(tag + ".skip", d);
-          resid = sk;
-        }
+        if (r.has_skip && !skip_side) emit_skip(false);
         Act o = new_act(true, M * (diverged ? 1 : 2) * r.cout, r.cout, h.H, h.W);
         if (next_is_down) { o.b16 = static_cast<bf16*>(PA(M * (diverged ? 1 : 2) * r.cout * sizeof(bf16))); o.has16 = true; }
         {
@@ -807,6 +827,7 @@ int Engine::build(Prepared& P, bool dry) {
           set_out(d, o);
           want_stats(d, o, true);
           add_gemm(tag + ".conv2", d);
+          if (skip_side) flag_last(OP_JOIN);
         }
         h = o;
         break;
@@ -911,6 +932,14 @@ int Engine::build(Prepared& P, bool dry) {
           std::vector<Act*> dup;
           for (Act& a0 : hs) dup.push_back(&a0);
           dup.push_back(&h);
+          // (copies of tensors nobody reads before this transformer's last GEMM: a branch of the graph beside the GEMMs in between)
+          bool first_dup = true;
+          auto dup_lane = [&]() {
+            if (!graph_lanes_) return;
+            flag_last(first_dup ? (OP_SIDE | OP_FORK) : OP_SIDE);
+            first_dup = false;
+            dup_on_side = true;
+          };
           for (Act* a0 : dup) {
             const size_t elems = static_cast<size_t>(Bc) * a0->H * a0->W * a0->C;
             if (a0->f32) {
@@ -919,6 +948,7 @@ int Engine::build(Prepared& P, bool dry) {
                 PBE_CHECK_CUDA(cudaMemcpyAsync(f + elems, f, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
                 return 0;
               });
+              dup_lane();
             }
             if (a0->has_stats) {
               const size_t sel = static_cast<size_t>(Bc) * a0->H * a0->W / 32 * a0->C * 2;
@@ -927,6 +957,7 @@ int Engine::build(Prepared& P, bool dry) {
                 PBE_CHECK_CUDA(cudaMemcpyAsync(sp + sel, sp, sel * sizeof(float), cudaMemcpyDeviceToDevice, st));
                 return 0;
               });
+              dup_lane();
             }
             if (a0->has16) {
               bf16* bp = a0->b16;
@@ -934,6 +965,7 @@ int Engine::build(Prepared& P, bool dry) {
                 PBE_CHECK_CUDA(cudaMemcpyAsync(bp + elems, bp, elems * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
                 return 0;
               });
+              dup_lane();
             }
           }
           diverged = true;
@@ -977,6 +1009,7 @@ int Engine::build(Prepared& P, bool dry) {
           set_out(d, o);
           want_stats(d, o, true);
           add_gemm(tag + (merge ? ".ff.out+proj_out" : ".proj_out"), d);
+          if (dup_on_side) { flag_last(OP_JOIN); dup_on_side = false; }   // reads the duplicated h
         }
         h = o;
         break;
@@ -1169,8 +1202,10 @@ int Engine::profile_forward(const float* x, const int64_t* t, float* eps, int Bc
 }
 
 int run_op_list(const std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<std::string>& names,
-                cudaStream_t stream, bool use_graph, cudaGraphExec_t* graph, cudaStream_t* cap_stream) {
+                cudaStream_t stream, bool use_graph, cudaGraphExec_t* graph, cudaStream_t* cap_stream,
+                const std::vector<uint8_t>* flags, cudaStream_t* side_stream) {
   int rc;
+  const bool lanes = flags != nullptr && flags->size() == ops.size() && side_stream != nullptr;
   if (!use_graph) {
     for (size_t i = 0; i < ops.size(); ++i) {
       rc = ops[i](stream);
@@ -1189,16 +1224,64 @@ int run_op_list(const std::vector<std::function<int(cudaStream_t)>>& ops, const 
     // the instantiated graph is then launched on the caller's stream.
     if (*cap_stream == nullptr) PBE_CHECK_CUDA(cudaStreamCreateWithFlags(cap_stream, cudaStreamNonBlocking));
     cudaGraph_t g = nullptr;
+    // Side lane (OP_SIDE ops): a second capture stream, i.e. a branch of the graph.  OP_FORK: the side lane first waits for
+    // everything issued on the main lane so far; OP_JOIN (a main-lane op): the main lane first waits for the side lane.  The
+    // captured events become plain graph edges; the eager paths above simply run the list in order, which satisfies both.
+    // Ops next to a fork / join are launched without programmatic dependent launch (full edges only on those nodes).
+    std::vector<cudaEvent_t> events;
+    auto new_event = [&](cudaEvent_t* e) -> int {
+      PBE_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+      events.push_back(*e);
+      return 0;
+    };
+    if (lanes && *side_stream == nullptr) PBE_CHECK_CUDA(cudaStreamCreateWithFlags(side_stream, cudaStreamNonBlocking));
     PBE_CHECK_CUDA(cudaStreamBeginCapture(*cap_stream, cudaStreamCaptureModeThreadLocal));
+    bool side_open = false;   // the side lane holds work the main lane has not joined yet
+    auto fail = [&](int code) {
+      cudaStreamEndCapture(*cap_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      for (cudaEvent_t e : events) cudaEventDestroy(e);
+      pdl_suppress(false);
+      return code;
+    };
     for (size_t i = 0; i < ops.size(); ++i) {
-      rc = ops[i](*cap_stream);
-      if (rc) {
-        cudaStreamEndCapture(*cap_stream, &g);
-        if (g) cudaGraphDestroy(g);
-        return rc;
+      const uint8_t f = lanes ? (*flags)[i] : 0;
+      cudaStream_t st = *cap_stream;
+      bool edge = false;
+      if (f & OP_SIDE) {
+        st = *side_stream;
+        if ((f & OP_FORK) || !side_open) {
+          cudaEvent_t e;
+          if (new_event(&e) || cudaEventRecord(e, *cap_stream) != cudaSuccess || cudaStreamWaitEvent(*side_stream, e, 0) != cudaSuccess) {
+            set_error("graph fork failed at " + names[i]);
+            return fail(-2);
+          }
+          side_open = true;
+          edge = true;
+        }
+      } else if ((f & OP_JOIN) && side_open) {
+        cudaEvent_t e;
+        if (new_event(&e) || cudaEventRecord(e, *side_stream) != cudaSuccess || cudaStreamWaitEvent(*cap_stream, e, 0) != cudaSuccess) {
+          set_error("graph join failed at " + names[i]);
+          return fail(-2);
+        }
+        side_open = false;
+        edge = true;
+      }
+      pdl_suppress(edge);
+      rc = ops[i](st);
+      pdl_suppress(false);
+      if (rc) return fail(rc);
+    }
+    if (side_open) {   // every branch ends in the main lane before the capture does
+      cudaEvent_t e;
+      if (new_event(&e) || cudaEventRecord(e, *side_stream) != cudaSuccess || cudaStreamWaitEvent(*cap_stream, e, 0) != cudaSuccess) {
+        set_error("graph join failed at the end of the op list");
+        return fail(-2);
       }
     }
     PBE_CHECK_CUDA(cudaStreamEndCapture(*cap_stream, &g));
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
     PBE_CHECK_CUDA(cudaGraphInstantiate(graph, g, 0));
     cudaGraphDestroy(g);
   }
@@ -1220,7 +1303,7 @@ int Engine::forward_pair(const float* x, const int64_t* t, float* eps, int B, in
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage, t, static_cast<size_t>(B) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
   PBE_CHECK_CUDA(cudaMemcpyAsync(P.t_stage + B, t, static_cast<size_t>(B) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
   pdl_set_scope(Bc <= 4 ? 1 : 0);
-  rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_);
+  rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_, graph_lanes_ ? &P.op_flags : nullptr, &side_stream_);
   pdl_set_scope(-1);
   if (rc) return rc;
   PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),
@@ -1239,7 +1322,7 @@ int Engine::forward(const float* x, const int64_t* t, float* eps, int Bc, int H,
                                  stream));
   // latency-bound small batches gain from programmatic dependent launch, throughput batches lose (tmap.cu: pdl_enabled)
   pdl_set_scope(Bc <= 4 ? 1 : 0);
-  rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_);
+  rc = run_op_list(P.ops, P.op_names, stream, use_graph, &P.graph, &cap_stream_, graph_lanes_ ? &P.op_flags : nullptr, &side_stream_);
   pdl_set_scope(-1);
   if (rc) return rc;
   PBE_CHECK_CUDA(cudaMemcpyAsync(eps, P.eps_stage, static_cast<size_t>(Bc) * cfg_.out_channels * H * W * sizeof(float),

@@ -81,6 +81,7 @@ struct Prepared {
   bool pair = false;   // CFG pair plan: samples [0, Bc/2) and [Bc/2, Bc) share x and t (see Engine::forward_pair)
   Arena persist, scratch;
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<uint8_t> op_flags;       // graph lanes (OP_SIDE / OP_FORK / OP_JOIN, run_op_list)
   std::vector<std::string> op_names;
   std::vector<std::string> op_family;  // kernel family: conv_gemm, attention, groupnorm, layernorm, ...
   std::vector<double> op_flops;        // algorithmic FLOPs (2*MAC) of the op, 0 for non-GEMM ops
@@ -97,8 +98,14 @@ struct Prepared {
 // Runs a launch plan: the first call runs every op eagerly once (function attributes are set outside capture), captures
 // the list on a private stream and instantiates a CUDA graph; every call then replays the graph on the caller's stream.
 // With use_graph = false the ops are simply launched one by one.
+// `flags` (one per op, optional): lanes of the captured graph.  OP_SIDE ops are captured on a second stream, i.e. as a branch
+// beside the main line; OP_FORK (with OP_SIDE) makes the branch wait for everything on the main line so far, OP_JOIN (a
+// main-line op) makes the main line wait for the branch.  An op on one lane must not depend on ops of the other lane that
+// lie between its fork and its join.  The eager paths run the list in order.
+enum : uint8_t { OP_SIDE = 1, OP_FORK = 2, OP_JOIN = 4 };
 int run_op_list(const std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<std::string>& names,
-                cudaStream_t stream, bool use_graph, cudaGraphExec_t* graph, cudaStream_t* cap_stream);
+                cudaStream_t stream, bool use_graph, cudaGraphExec_t* graph, cudaStream_t* cap_stream,
+                const std::vector<uint8_t>* flags = nullptr, cudaStream_t* side_stream = nullptr);
 
 // Host-side weight staging shared by the U-Net engine and the VAE decoder: tensors arrive by reference state-dict name,
 // are repacked at finalize() and uploaded once.
@@ -193,6 +200,11 @@ class Engine : public WeightLoader {
   static constexpr size_t kMaxPlans = 6;   // launch plans kept per engine (least recently used evicted)
   unsigned long long use_clock_ = 0;
   cudaStream_t cap_stream_ = nullptr;
+  cudaStream_t side_stream_ = nullptr;   // capture-time second lane (run_op_list)
+  // Branches of the captured graph: the timestep-embedding ops (they depend on t only) run beside conv_in and the first
+  // GroupNorm and join at the first ResBlock's conv1; in small-batch plans a ResBlock's 1x1 skip convolution runs beside
+  // its conv1 / GroupNorm.  PBE_GRAPH_LANES=0: one line.
+  int graph_lanes_ = [] { const char* e = getenv("PBE_GRAPH_LANES"); return e == nullptr ? 1 : atoi(e); }();
 };
 
 }  // namespace pbe

@@ -127,6 +127,7 @@ struct GemmPlan {
 // the captured CUDA graph) then overlap the successor's prologue with the predecessor's tail; every kernel of this
 // library calls griddep_wait() (ptx.cuh) before it touches memory its predecessor may still be writing.
 bool pdl_enabled();
+void pdl_suppress(bool on);   // true: launches on this thread go without PDL whatever the scope / environment says (run_op_list)
 void pdl_set_scope(int v);   // 1 / 0: the launches (and graph captures) that follow on this thread use / do not use PDL; -1: default
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -84,14 +84,17 @@ void set_operand_f16(int f16) { g_operand_f16 = f16 ? 1 : 0; }
 
 namespace {
 thread_local int g_pdl_scope = -1;   // -1: no preference from the engine that is building / capturing a launch plan
+thread_local bool g_pdl_suppress = false;
 }
 void pdl_set_scope(int v) { g_pdl_scope = v; }
+void pdl_suppress(bool on) { g_pdl_suppress = on; }
 
 bool pdl_enabled() {
   // Measured on B200 inside the captured graph: PDL gives +1.7 % at CFG batch 2 (4.20 -> 4.13 ms per U-Net call) but
   // -1.5 % at CFG batch 16 (17.25 -> 17.60 ms).  So the U-Net engine asks for it (pdl_set_scope) only while it captures
   // small-batch plans; PBE_PDL=0 / 1 overrides everything.
   static const int env = [] { const char* e = getenv("PBE_PDL"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
+  if (g_pdl_suppress) return false;   // a graph node next to a fork / join of the capture lanes: full dependencies only
   if (env >= 0) return env == 1;
   return g_pdl_scope == 1;
 }
