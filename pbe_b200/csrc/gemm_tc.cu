@@ -1276,7 +1276,6 @@ int launch_gemm_plan(const GemmPlan& plan, cudaStream_t stream) {
   int rc = launch_main(plan, stream);
   if (rc) return rc;
   if (plan.red.S > 1) {
-    PdlSmallScope pdl_small;
     const long long n4 = plan.red.M * (plan.red.N / 4);
     PBE_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, stream, plan.red));
     PBE_CHECK_CUDA(cudaGetLastError());

@@ -128,17 +128,7 @@ struct GemmPlan {
 // library calls griddep_wait() (ptx.cuh) before it touches memory its predecessor may still be writing.
 bool pdl_enabled();
 void pdl_suppress(bool on);   // true: launches on this thread go without PDL whatever the scope / environment says (run_op_list)
-void pdl_set_scope(int v);
-// PBE_PDL_SMALL=1: the single-wave helper kernels (GroupNorm finalize / apply / one-kernel form, split-K reduce) are launched
-// with programmatic dependent launch in every plan -- their launch latency hides behind the tail of the kernel in front --
-// while the GEMM / attention kernels of throughput plans stay without it (measured neutral to negative there, tmap.cu)
-bool pdl_small_kernels();
-void pdl_force(bool on);
-struct PdlSmallScope {
-  bool on;
-  PdlSmallScope() : on(pdl_small_kernels()) { if (on) pdl_force(true); }
-  ~PdlSmallScope() { if (on) pdl_force(false); }
-};   // 1 / 0: the launches (and graph captures) that follow on this thread use / do not use PDL; -1: default
+void pdl_set_scope(int v);   // 1 / 0: the launches (and graph captures) that follow on this thread use / do not use PDL; -1: default
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -579,7 +579,6 @@ int gn_num_launches(const GroupNormArgs& a) {
 }
 
 int launch_groupnorm(const GroupNormArgs& a, cudaStream_t stream) {
-  PdlSmallScope pdl_small;
   const int C = a.C0 + a.C1;
   PBE_REQUIRE(C % 64 == 0 && C <= GN_MAX_C, "GroupNorm channels must be a multiple of 64, <= 2560");
   PBE_REQUIRE(a.C0 % 4 == 0 && a.C1 % 4 == 0, "GroupNorm concat halves must be multiples of 4 channels");

@@ -85,12 +85,6 @@ void set_operand_f16(int f16) { g_operand_f16 = f16 ? 1 : 0; }
 namespace {
 thread_local int g_pdl_scope = -1;   // -1: no preference from the engine that is building / capturing a launch plan
 thread_local bool g_pdl_suppress = false;
-thread_local bool g_pdl_force = false;
-}
-void pdl_force(bool on) { g_pdl_force = on; }
-bool pdl_small_kernels() {
-  static const bool on = [] { const char* e = getenv("PBE_PDL_SMALL"); return e != nullptr && atoi(e) != 0; }();
-  return on;
 }
 void pdl_set_scope(int v) { g_pdl_scope = v; }
 void pdl_suppress(bool on) { g_pdl_suppress = on; }
@@ -102,7 +96,6 @@ bool pdl_enabled() {
   static const int env = [] { const char* e = getenv("PBE_PDL"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
   if (g_pdl_suppress) return false;   // a graph node next to a fork / join of the capture lanes: full dependencies only
   if (env >= 0) return env == 1;
-  if (g_pdl_force) return true;
   return g_pdl_scope == 1;
 }
 
